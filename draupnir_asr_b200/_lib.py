@@ -1,0 +1,62 @@
+"""ctypes binding of libdraupnir_b200.so (C ABI in include/draupnir_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a symbol is absent the import of any product
+module fails loudly.  `build.py` (called by `__graft_entry__.build()`) produces the library in-tree.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdraupnir_b200.so")
+
+ABI_VERSION = 1
+
+_i32, _i64, _f64, _p = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/draupnir_b200.h one to one
+SIGNATURES = {
+    "drp_abi_version": (_i32, []),
+    "drp_tree_prepare": (_i32, [_p, _p, _i32, _p, _p, _p, _p, _p, _p]),
+    "drp_lca_workspace_bytes": (_i64, [_i32, _i32]),
+    "drp_lca_patristic_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i32, _p, _p, _p, _p, _i64, _p]),
+    "drp_ou_cov_fwd_f64": (_i32, [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p]),
+    "drp_ou_cov_bwd_f64": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _p]),
+    "drp_potrf_batched_f64": (_i32, [_p, _i32, _i32, _i32, _p, _p]),
+    "drp_ou_workspace_ld": (_i64, [_i32, _i32]),
+    "drp_ou_workspace_elems": (_i64, [_i32, _i32, _i32]),
+    "drp_ou_prior_f64": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "drp_mvn_logprob_f64": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "drp_mvn_grad_cov_f64": (_i32, [_p, _i32, _i32, _p, _p, _p]),
+    "drp_potri_batched_f64": (_i32, [_p, _i32, _i32, _p, _p, _p, _p]),
+    "drp_ou_conditional_f64": (_i32, [_p, _i64, _p, _i32, _i32, _p, _p, _p, _p, _i32, _f64, _p, _p, _p, _p, _p]),
+    "drp_cat_loglik_partials": (_i64, [_i64]),
+    "drp_cat_loglik_fwd_f64": (_i32, [_p, _p, _i32, _i64, _i32, _p, _p, _p, _p]),
+    "drp_cat_loglik_bwd_f64": (_i32, [_p, _p, _i32, _p, _p, _i64, _i32, _p, _p]),
+}
+
+
+class DraupnirB200LibraryError(ImportError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise DraupnirB200LibraryError(
+            f"{LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise DraupnirB200LibraryError(f"{LIB_PATH} does not export {name}; rebuild it") from e
+        fn.restype, fn.argtypes = res, args
+    v = lib.drp_abi_version()
+    if v != ABI_VERSION:
+        raise DraupnirB200LibraryError(f"{LIB_PATH} has ABI {v}, this package expects {ABI_VERSION}; rebuild it")
+    return lib
+
+
+lib = _load()

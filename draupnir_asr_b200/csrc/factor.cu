@@ -1,0 +1,251 @@
+// Batched blocked partial Cholesky — the engine behind the OU prior, its gradients and the conditional posterior.
+//
+// Replaces (reference, S/ = /root/reference/draupnir/src/draupnir/):
+//   torch.linalg.cholesky inside MultivariateNormal.__init__      S/models.py:118
+//   solve_triangular in MultivariateNormal.log_prob               S/models.py:118 (torch _batch_mahalanobis)
+//   autograd cholesky_backward / triangular_solve_backward        (K5 in SURVEY.md §2b)
+//   torch.linalg.inv x3 + matmul x2 in conditional_sampling*      S/models.py:167,188,190,193,214,235,237,239
+//
+// One primitive does all of it: eliminate the first `nfactor` columns of a lower-stored symmetric matrix
+//
+//            [ K    .    . ]   rows 0..n-1     (covariance)
+//        M = [ x^T  0    . ]   row  n          (right-hand side)
+//            [ B    0    C ]   rows n+1..      (B = I for the prior, K_ab for the conditional; C = 0 or K_aa)
+//
+// which leaves  row n        = y^T = (L^-1 x)^T,        M[n][n]      = -y^T y              (Mahalanobis)
+//               M[n+1+i][n]  = -(B K^-1 x)_i            (= -alpha_i or -mu_i)
+//               M[n+1+i][n+1+j] = C - B K^-1 B^T        (= -K^-1   or  Sigma_a|b)
+// i.e. the solve, the inverse and the Schur complement are all by-products of the same trailing updates, and the
+// only kernels are potf2 (diagonal block), trsm (panel rows) and syrk (trailing update).  With B = I the rows of
+// B below the current panel are still exactly zero, so the active extent grows with the panel (`grow_base`) and
+// the flop count is the optimal n^3/3 + 2n^3/3.
+//
+// Layout: row-major, leading dimension `ld`, batch stride `bs` (elements); only entries with col <= row are
+// read or written.  fp64 throughout (the reference dtype).  The trailing update runs on the fp64 tensor pipe
+// (mma.sync m8n8k4); see DESIGN.md for the tcgen05 split-integer variant.
+#include "common.cuh"
+#include "factor.cuh"
+
+namespace {
+
+constexpr int NB  = DRP_NB;    // panel width
+constexpr int PLD = NB + 1;    // padded row stride of smem panels (conflict-free thread-per-row access)
+constexpr int PR  = 128;       // rows per CTA in trsm
+constexpr int TS  = 64;        // syrk tile
+constexpr int SLD = 68;        // syrk smem row stride: (row*68 + tig) mod 16 distinct over a half warp
+
+// ---------------------------------------------------------------------------------------------------------------
+// potf2: factor the nb x nb diagonal block at (c0, c0).  One CTA of 64 threads per matrix, thread i owns row i.
+// Left-looking by columns: L[i][c] = (A[i][c] - sum_{p<c} L[i][p] L[c][p]) / L[c][c].
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) potf2_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb,
+                                                   int32_t* __restrict__ info)
+{
+    __shared__ double S[NB * PLD];
+    __shared__ double dsh;
+    double* A = Mb + (int64_t)blockIdx.x * bs + (int64_t)c0 * ld + c0;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < nb * nb; idx += 64) {
+        const int i = idx / nb, j = idx - i * nb;
+        S[i * PLD + j] = (j <= i) ? A[(int64_t)i * ld + j] : 0.0;
+    }
+    __syncthreads();
+    double* row = S + tid * PLD;
+    int bad = 0;
+    for (int c = 0; c < nb; ++c) {
+        double acc = 0.0;
+        if (tid >= c && tid < nb) {
+            const double* rc = S + c * PLD;
+            double a0 = row[c], a1 = 0.0;
+            int p = 0;
+            for (; p + 1 < c; p += 2) {
+                a0 = fma(-row[p], rc[p], a0);
+                a1 = fma(-row[p + 1], rc[p + 1], a1);
+            }
+            if (p < c) a0 = fma(-row[p], rc[p], a0);
+            acc = a0 + a1;
+            if (tid == c) dsh = acc;
+        }
+        __syncthreads();
+        const double piv = dsh;
+        if (!(piv > 0.0) && bad == 0) bad = c + 1;
+        const double d = sqrt(piv);
+        if (tid == c) row[c] = d;
+        else if (tid > c && tid < nb) row[c] = acc / d;
+        __syncthreads();
+    }
+    for (int idx = tid; idx < nb * nb; idx += 64) {
+        const int i = idx / nb, j = idx - i * nb;
+        if (j <= i) A[(int64_t)i * ld + j] = S[i * PLD + j];
+    }
+    if (bad && tid == 0 && info) atomicCAS(info + blockIdx.x, 0, c0 + bad);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// trsm: rows r in [c0+nb, R): X[r][c0:c0+nb] <- X L_jj^-T.  Thread-per-row forward substitution in smem.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PR) trsm_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb, int R)
+{
+    extern __shared__ double sm[];
+    double* S = sm;                  // [NB][PLD] factored diagonal block
+    double* invd = S + NB * PLD;     // [NB]
+    double* X = invd + NB;           // [PR][PLD]
+    double* A = Mb + (int64_t)blockIdx.y * bs;
+    const int tid = threadIdx.x;
+    const int r0 = c0 + nb + blockIdx.x * PR;
+    const int nrows = min(PR, R - r0);
+    for (int idx = tid; idx < nb * nb; idx += PR) {
+        const int i = idx / nb, j = idx - i * nb;
+        S[i * PLD + j] = (j <= i) ? A[(int64_t)(c0 + i) * ld + c0 + j] : 0.0;
+    }
+    for (int idx = tid; idx < nrows * nb; idx += PR) {
+        const int i = idx / nb, j = idx - i * nb;
+        X[i * PLD + j] = A[(int64_t)(r0 + i) * ld + c0 + j];
+    }
+    __syncthreads();
+    if (tid < nb) invd[tid] = 1.0 / S[tid * PLD + tid];
+    __syncthreads();
+    if (tid < nrows) {
+        double* xr = X + tid * PLD;
+        for (int c = 0; c < nb; ++c) {
+            const double* lc = S + c * PLD;
+            double a0 = xr[c], a1 = 0.0;
+            int p = 0;
+            for (; p + 1 < c; p += 2) {
+                a0 = fma(-xr[p], lc[p], a0);
+                a1 = fma(-xr[p + 1], lc[p + 1], a1);
+            }
+            if (p < c) a0 = fma(-xr[p], lc[p], a0);
+            xr[c] = (a0 + a1) * invd[c];
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nrows * nb; idx += PR) {
+        const int i = idx / nb, j = idx - i * nb;
+        A[(int64_t)(r0 + i) * ld + c0 + j] = X[i * PLD + j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// syrk: C[r][c] -= sum_k P[r][k] P[c][k] for r, c in [c1, R), c <= r, c < col_limit; P = columns c0..c0+nb.
+// 64x64 output tile per CTA, 4 warps (2x2) of 32x32, fp64 mma.sync m8n8k4.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) syrk_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb, int c1,
+                                                   int R, int col_limit)
+{
+    const int tj = blockIdx.x, ti = blockIdx.y;
+    if (tj > ti) return;
+    extern __shared__ double sm[];
+    double* As = sm;
+    double* Bs = (ti == tj) ? As : sm + TS * SLD;
+    double* A = Mb + (int64_t)blockIdx.z * bs;
+    const int tid = threadIdx.x;
+    const int r0 = c1 + ti * TS, q0 = c1 + tj * TS;
+    for (int idx = tid; idx < TS * NB; idx += 128) {
+        const int r = idx / NB, k = idx - r * NB;
+        As[r * SLD + k] = (r0 + r < R && k < nb) ? A[(int64_t)(r0 + r) * ld + c0 + k] : 0.0;
+    }
+    if (ti != tj) {
+        for (int idx = tid; idx < TS * NB; idx += 128) {
+            const int r = idx / NB, k = idx - r * NB;
+            Bs[r * SLD + k] = (q0 + r < R && k < nb) ? A[(int64_t)(q0 + r) * ld + c0 + k] : 0.0;
+        }
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double* ap = As + (wm * 32 + gid) * SLD + tig;
+    const double* bp = Bs + (wn * 32 + gid) * SLD + tig;
+    const int kmax = (nb + 3) & ~3;
+    for (int k = 0; k < kmax; k += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = ap[i * 8 * SLD + k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = bp[j * 8 * SLD + k];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    const int cmax = min(R, col_limit);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = r0 + wm * 32 + i * 8 + gid;
+        if (row >= R) continue;
+        double* crow = A + (int64_t)row * ld;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = q0 + wn * 32 + j * 8 + 2 * tig;
+            if (col <= row && col < cmax) crow[col] -= acc[i][j][0];
+            if (col + 1 <= row && col + 1 < cmax) crow[col + 1] -= acc[i][j][1];
+        }
+    }
+}
+
+}  // namespace
+
+static const int TRSM_SMEM = (NB * PLD + NB + PR * PLD) * (int)sizeof(double);
+static const int SYRK_SMEM = 2 * TS * SLD * (int)sizeof(double);
+
+int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_full, int grow_base, int col_limit,
+                   int32_t* info, cudaStream_t st)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM);
+        cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM);
+        attr_done = true;
+    }
+    if (info) cudaMemsetAsync(info, 0, sizeof(int32_t) * z, st);
+    for (int c0 = 0; c0 < nfactor; c0 += NB) {
+        const int nb = min(NB, nfactor - c0);
+        const int c1 = c0 + nb;
+        const int R = grow_base > 0 ? min(R_full, grow_base + c1) : R_full;
+        potf2_kernel<<<z, 64, 0, st>>>(M, ld, bs, c0, nb, info);
+        const int below = R - c1;
+        if (below > 0) {
+            dim3 g((below + PR - 1) / PR, z);
+            trsm_kernel<<<g, PR, TRSM_SMEM, st>>>(M, ld, bs, c0, nb, R);
+            const int T = (below + TS - 1) / TS;
+            const int cl = min(R, col_limit) - c1;
+            if (cl > 0) {
+                const int Tc = min(T, (cl + TS - 1) / TS);
+                dim3 gs(Tc, T, z);
+                syrk_kernel<<<gs, 128, SYRK_SMEM, st>>>(M, ld, bs, c0, nb, c1, R, col_limit);
+            }
+        }
+    }
+    return drp_launch_status();
+}
+
+// Plain batched Cholesky of z dense n x n matrices (lower), optionally zeroing the strict upper triangle so the
+// result equals torch.linalg.cholesky's.  Replaces the call inside MultivariateNormal.__init__ (S/models.py:118).
+namespace {
+__global__ void zero_upper_kernel(double* __restrict__ A, int n, int64_t ld, int64_t bs)
+{
+    const int r = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n && c > r) A[(int64_t)blockIdx.z * bs + (int64_t)r * ld + c] = 0.0;
+}
+}  // namespace
+
+DRP_API int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info, void* stream)
+{
+    if (!A) return -1;
+    if (n <= 0) return -2;
+    if (z <= 0) return -3;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = drp_factor_run(A, n, (int64_t)n * n, z, n, n, 0, n, info, st);
+    if (rc) return rc;
+    if (zero_upper) {
+        dim3 g((n + 255) / 256, n, z);
+        zero_upper_kernel<<<g, 256, 0, st>>>(A, n, n, (int64_t)n * n);
+    }
+    return drp_launch_status();
+}

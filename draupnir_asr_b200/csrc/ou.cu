@@ -1,0 +1,376 @@
+// Ornstein-Uhlenbeck covariance assembly, multivariate-normal log-prob with analytic gradients, and the
+// conditional internal|leaves posterior — all on top of the partial-Cholesky engine in factor.cu.
+//
+// Reference (S/ = /root/reference/draupnir/src/draupnir/):
+//   OUKernel_Fast.forward                       S/models_utils.py:303-311   K_z = sf_z^2 exp(-t/lam_z) + sn_z^2 I
+//   DRAUPNIRModelClass.gp_prior                 S/models.py:85-121          sum_z log N(x_z; 0, K_z)
+//   conditional_sampling / conditional_samplingMAP   S/models.py:149-242    p(z_internal | z_leaves)
+#include "common.cuh"
+#include "factor.cuh"
+
+namespace {
+
+constexpr double LOG_2PI = 1.8378770664093454835606594728112;
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2: dense OU covariance [z,n,n].  One thread per (row, col); the distance is loaded once and reused for all z
+// latent dimensions, every store is a coalesced 8-byte-per-lane row segment.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ou_cov_fwd_kernel(const double* __restrict__ D, int64_t ldd, int n,
+                                                         const double* __restrict__ sf, const double* __restrict__ sn,
+                                                         const double* __restrict__ lam, int z, double* __restrict__ K)
+{
+    extern __shared__ double hp[];   // [3][z]: sf^2, sn^2, -1/lam
+    for (int i = threadIdx.x; i < z; i += blockDim.x) {
+        hp[i] = sf[i] * sf[i];
+        hp[z + i] = sn[i] * sn[i];
+        hp[2 * z + i] = -1.0 / lam[i];
+    }
+    __syncthreads();
+    const int r = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const double d = D[(int64_t)r * ldd + c];
+    double* out = K + (int64_t)r * n + c;
+    const int64_t bs = (int64_t)n * n;
+    for (int zz = 0; zz < z; ++zz) {
+        double v = hp[zz] * exp(d * hp[2 * z + zz]);
+        if (r == c) v += hp[z + zz];
+        out[zz * bs] = v;
+    }
+}
+
+// Backward of K2 given G = dLoss/dK [z,n,n]:  partial sums of G.E, G.E.D and diag(G) per (z, row).
+__global__ void __launch_bounds__(256) ou_cov_bwd_kernel(const double* __restrict__ D, int64_t ldd, int n,
+                                                         const double* __restrict__ lam, const double* __restrict__ G,
+                                                         double* __restrict__ part /*[z][n][3]*/)
+{
+    __shared__ double red[32];
+    const int r = blockIdx.x, zz = blockIdx.y;
+    const double nil = -1.0 / lam[zz];
+    const double* g = G + ((int64_t)zz * n + r) * n;
+    const double* drow = D + (int64_t)r * ldd;
+    double sE = 0.0, sED = 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        const double d = drow[c];
+        const double t = g[c] * exp(d * nil);
+        sE += t;
+        sED += t * d;
+    }
+    sE = block_sum(sE, red);
+    sED = block_sum(sED, red);
+    if (threadIdx.x == 0) {
+        double* p = part + ((int64_t)zz * n + r) * 3;
+        p[0] = sE;
+        p[1] = sED;
+        p[2] = g[r];
+    }
+}
+
+// Deterministic second stage: out[z][k] = sum_r part[z][r][k].
+__global__ void __launch_bounds__(256) reduce3_kernel(const double* __restrict__ part, int n, double* __restrict__ out)
+{
+    __shared__ double red[32];
+    const int zz = blockIdx.x;
+    for (int k = 0; k < 3; ++k) {
+        double s = 0.0;
+        for (int r = threadIdx.x; r < n; r += blockDim.x) s += part[((int64_t)zz * n + r) * 3 + k];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) out[zz * 3 + k] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Assembly of the augmented matrix (see factor.cu) straight from the patristic distances.  Lower part only.
+//   identity != 0 : second block = I (prior: yields -K^-1 and -alpha)
+//   identity == 0 : second block = K_ab / K_aa gathered through idx[n..n+ni) (conditional posterior)
+// idx (nullable) maps position -> node row of D; rows/cols 0..n-1 are the conditioning (leaf) nodes.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ou_assemble_kernel(const double* __restrict__ D, int64_t ldd,
+                                                          const int32_t* __restrict__ idx, int n, int n2, int identity,
+                                                          const double* __restrict__ sf, const double* __restrict__ sn,
+                                                          const double* __restrict__ lam, const double* __restrict__ x,
+                                                          int z, double* __restrict__ M, int64_t ld, int64_t bs)
+{
+    const int r = blockIdx.y;
+    if ((int)(blockIdx.x * blockDim.x) > r) return;
+    extern __shared__ double hp[];
+    for (int i = threadIdx.x; i < z; i += blockDim.x) {
+        hp[i] = sf[i] * sf[i];
+        hp[z + i] = sn[i] * sn[i];
+        hp[2 * z + i] = -1.0 / lam[i];
+    }
+    __syncthreads();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > r) return;
+    double* out = M + (int64_t)r * ld + c;
+    // node behind a row/col position (-1: the x row/col)
+    const int pr = r < n ? r : (r == n ? -1 : r - 1);
+    const int pc = c < n ? c : (c == n ? -1 : c - 1);
+    if (pr < 0 || pc < 0) {                       // right-hand-side row, or the (unused) column n
+        for (int zz = 0; zz < z; ++zz) out[zz * bs] = (pr < 0 && c < n) ? x[(int64_t)zz * n + c] : 0.0;
+        return;
+    }
+    if (identity && r > n) {                      // [ I | 0 ] block
+        const double v = (c < n && c == r - n - 1) ? 1.0 : 0.0;
+        for (int zz = 0; zz < z; ++zz) out[zz * bs] = v;
+        return;
+    }
+    const int a = idx ? idx[pr] : pr, b = idx ? idx[pc] : pc;
+    const double d = D[(int64_t)a * ldd + b];
+    const bool diag = (pr == pc);
+    for (int zz = 0; zz < z; ++zz) {
+        double v = hp[zz] * exp(d * hp[2 * z + zz]);
+        if (diag) v += hp[z + zz];
+        out[zz * bs] = v;
+    }
+    (void)n2;
+}
+
+// Same augmented layout from an explicit covariance batch K [z,n,n] (general MultivariateNormal).
+__global__ void __launch_bounds__(256) cov_assemble_kernel(const double* __restrict__ K, int n, const double* __restrict__ x,
+                                                           double* __restrict__ M, int64_t ld, int64_t bs)
+{
+    const int r = blockIdx.y, zz = blockIdx.z;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > r) return;
+    double v;
+    if (r < n) v = K[((int64_t)zz * n + r) * n + c];
+    else if (r == n) v = c < n ? x[(int64_t)zz * n + c] : 0.0;
+    else v = (c < n && c == r - n - 1) ? 1.0 : 0.0;
+    M[zz * bs + (int64_t)r * ld + c] = v;
+}
+
+// logp[z] = -1/2 (n log 2pi + y^T y) - sum_i log L_ii   (torch MultivariateNormal.log_prob)
+__global__ void __launch_bounds__(256) mvn_finish_kernel(const double* __restrict__ M, int64_t ld, int64_t bs, int n,
+                                                         double* __restrict__ logp)
+{
+    __shared__ double red[32];
+    const double* A = M + (int64_t)blockIdx.x * bs;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += log(A[(int64_t)i * ld + i]);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) {
+        const double maha = -A[(int64_t)n * ld + n];
+        logp[blockIdx.x] = -0.5 * ((double)n * LOG_2PI + maha) - s;
+    }
+}
+
+// alpha[z][i] = -M[n+1+i][n]
+__global__ void alpha_extract_kernel(const double* __restrict__ M, int64_t ld, int64_t bs, int n, int cnt,
+                                     double* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) out[(int64_t)blockIdx.y * cnt + i] = -M[(int64_t)blockIdx.y * bs + (int64_t)(n + 1 + i) * ld + n];
+}
+
+// K5: hyper-parameter gradient sums.  With G = 1/2 (alpha alpha^T - K^-1) = dlogp/dK:
+//   part[z][r] = ( sum_c G_rc E_rc , sum_c G_rc E_rc D_rc , G_rr )   over the full row r (by symmetry 2x lower).
+// K^-1 is read once from the factored matrix (-M[n+1+i][n+1+j], lower), E is recomputed from D.
+__global__ void __launch_bounds__(256) ou_grad_kernel(const double* __restrict__ M, int64_t ld, int64_t bs, int n,
+                                                      const double* __restrict__ D, int64_t ldd,
+                                                      const double* __restrict__ lam, double* __restrict__ part)
+{
+    __shared__ double red[32];
+    const int r = blockIdx.x, zz = blockIdx.y;
+    const double* A = M + (int64_t)zz * bs;
+    const double nil = -1.0 / lam[zz];
+    const double ar = -A[(int64_t)(n + 1 + r) * ld + n];
+    const double* krow = A + (int64_t)(n + 1 + r) * ld + n + 1;
+    const double* drow = D + (int64_t)r * ldd;
+    double sE = 0.0, sED = 0.0, gd = 0.0;
+    for (int c = threadIdx.x; c <= r; c += blockDim.x) {
+        const double ac = -A[(int64_t)(n + 1 + c) * ld + n];
+        const double g = 0.5 * (ar * ac + krow[c]);          // krow = -Kinv
+        const double d = drow[c];
+        const double w = (c == r) ? 1.0 : 2.0;
+        const double t = w * g * exp(d * nil);
+        sE += t;
+        sED += t * d;
+        if (c == r) gd = g;
+    }
+    sE = block_sum(sE, red);
+    sED = block_sum(sED, red);
+    gd = block_sum(gd, red);
+    if (threadIdx.x == 0) {
+        double* p = part + ((int64_t)zz * n + r) * 3;
+        p[0] = sE;
+        p[1] = sED;
+        p[2] = gd;
+    }
+}
+
+// G[z][i][j] = gscale[z] * 1/2 (alpha_i alpha_j - Kinv_ij), full symmetric (gradient w.r.t. an explicit covariance).
+__global__ void __launch_bounds__(256) mvn_grad_cov_kernel(const double* __restrict__ M, int64_t ld, int64_t bs, int n,
+                                                           const double* __restrict__ gscale, double* __restrict__ G)
+{
+    const int r = blockIdx.y, zz = blockIdx.z;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const double* A = M + (int64_t)zz * bs;
+    const int hi = max(r, c), lo = min(r, c);
+    const double ar = -A[(int64_t)(n + 1 + r) * ld + n], ac = -A[(int64_t)(n + 1 + c) * ld + n];
+    const double mk = A[(int64_t)(n + 1 + hi) * ld + n + 1 + lo];
+    G[((int64_t)zz * n + r) * n + c] = (gscale ? gscale[zz] : 1.0) * 0.5 * (ar * ac + mk);
+}
+
+// Symmetric extraction of the trailing block: out[z][i][j] = sign * M[n+1+max][n+1+min] + jitter.
+__global__ void __launch_bounds__(256) block_extract_kernel(const double* __restrict__ M, int64_t ld, int64_t bs, int n,
+                                                            int cnt, double sign, double jitter, double* __restrict__ out)
+{
+    const int r = blockIdx.y, zz = blockIdx.z;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cnt) return;
+    const int hi = max(r, c), lo = min(r, c);
+    out[((int64_t)zz * cnt + r) * cnt + c] =
+        sign * M[(int64_t)zz * bs + (int64_t)(n + 1 + hi) * ld + n + 1 + lo] + jitter;
+}
+
+}  // namespace
+
+// ------------------------------------------------- entry points -----------------------------------------------
+
+DRP_API int64_t drp_ou_workspace_ld(int n, int n2) { return ((int64_t)n + 1 + n2 + 7) & ~(int64_t)7; }
+
+// elements (doubles) of the augmented workspace for z matrices: rows n+1+n2, leading dimension as above
+DRP_API int64_t drp_ou_workspace_elems(int n, int n2, int z)
+{
+    return (int64_t)z * (n + 1 + n2) * drp_ou_workspace_ld(n, n2);
+}
+
+DRP_API int drp_ou_cov_fwd_f64(const double* D, int64_t ldd, int n, const double* sf, const double* sn, const double* lam,
+                               int z, double* K, void* stream)
+{
+    if (!D) return -1;
+    if (n <= 0 || ldd < n) return -3;
+    if (!sf || !sn || !lam) return -4;
+    if (z <= 0) return -7;
+    if (!K) return -8;
+    dim3 g((n + 255) / 256, n);
+    ou_cov_fwd_kernel<<<g, 256, 3 * z * sizeof(double), (cudaStream_t)stream>>>(D, ldd, n, sf, sn, lam, z, K);
+    return drp_launch_status();
+}
+
+// out[z][3] = (sum G.E, sum G.E.D, trace G); the caller applies d_sf = 2 sf S0, d_lam = sf^2 S1 / lam^2, d_sn = 2 sn S2.
+// part: workspace of z*n*3 doubles.
+DRP_API int drp_ou_cov_bwd_f64(const double* D, int64_t ldd, int n, const double* lam, int z, const double* G, double* part,
+                               double* out, void* stream)
+{
+    if (!D) return -1;
+    if (n <= 0 || ldd < n) return -3;
+    if (!lam) return -4;
+    if (z <= 0) return -5;
+    if (!G || !part || !out) return -6;
+    cudaStream_t st = (cudaStream_t)stream;
+    ou_cov_bwd_kernel<<<dim3(n, z), 256, 0, st>>>(D, ldd, n, lam, G, part);
+    reduce3_kernel<<<z, 256, 0, st>>>(part, n, out);
+    return drp_launch_status();
+}
+
+// Fused OU prior: logp[z] = log N(x_z; 0, K_z(D; sf, sn, lam)) and, if want_grad, alpha = K^-1 x [z,n] and the
+// gradient sums gsum[z][3] (see drp_ou_cov_bwd_f64) of dlogp/dK.  The covariance never exists as a separate tensor.
+//   M    workspace of drp_ou_workspace_elems(n, want_grad ? n : 0, z) doubles
+//   part workspace of z*n*3 doubles (want_grad only)
+DRP_API int drp_ou_prior_f64(const double* D, int64_t ldd, int n, const double* sf, const double* sn, const double* lam,
+                             const double* x, int z, int want_grad, double* logp, double* alpha, double* gsum, double* M,
+                             double* part, int32_t* info, void* stream)
+{
+    if (!D) return -1;
+    if (n <= 0 || ldd < n) return -3;
+    if (!sf || !sn || !lam || !x) return -4;
+    if (z <= 0) return -8;
+    if (!logp || !M) return -10;
+    if (want_grad && (!alpha || !gsum || !part)) return -11;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n2 = want_grad ? n : 0;
+    const int R = n + 1 + n2;
+    const int64_t ld = drp_ou_workspace_ld(n, n2), bs = (int64_t)R * ld;
+    dim3 g((R + 255) / 256, R);
+    ou_assemble_kernel<<<g, 256, 3 * z * sizeof(double), st>>>(D, ldd, nullptr, n, n2, 1, sf, sn, lam, x, z, M, ld, bs);
+    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, st);
+    if (rc) return rc;
+    mvn_finish_kernel<<<z, 256, 0, st>>>(M, ld, bs, n, logp);
+    if (want_grad) {
+        alpha_extract_kernel<<<dim3((n + 255) / 256, z), 256, 0, st>>>(M, ld, bs, n, n, alpha);
+        ou_grad_kernel<<<dim3(n, z), 256, 0, st>>>(M, ld, bs, n, D, ldd, lam, part);
+        reduce3_kernel<<<z, 256, 0, st>>>(part, n, gsum);
+    }
+    return drp_launch_status();
+}
+
+// General batched MVN log-prob from an explicit covariance K [z,n,n] (zero mean handled by the caller: pass x - mu).
+// want_grad: alpha [z,n] and Kinv-based G are available afterwards through drp_mvn_grad_cov_f64 on the same M.
+DRP_API int drp_mvn_logprob_f64(const double* K, const double* x, int n, int z, int want_grad, double* logp, double* alpha,
+                                double* M, int32_t* info, void* stream)
+{
+    if (!K || !x) return -1;
+    if (n <= 0) return -3;
+    if (z <= 0) return -4;
+    if (!logp || !M) return -6;
+    if (want_grad && !alpha) return -7;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n2 = want_grad ? n : 0;
+    const int R = n + 1 + n2;
+    const int64_t ld = drp_ou_workspace_ld(n, n2), bs = (int64_t)R * ld;
+    cov_assemble_kernel<<<dim3((R + 255) / 256, R, z), 256, 0, st>>>(K, n, x, M, ld, bs);
+    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, st);
+    if (rc) return rc;
+    mvn_finish_kernel<<<z, 256, 0, st>>>(M, ld, bs, n, logp);
+    if (want_grad) alpha_extract_kernel<<<dim3((n + 255) / 256, z), 256, 0, st>>>(M, ld, bs, n, n, alpha);
+    return drp_launch_status();
+}
+
+// G[z,n,n] = gscale[z] * dlogp_z/dK_z from a workspace factored by drp_mvn_logprob_f64 / drp_ou_prior_f64 (want_grad=1).
+DRP_API int drp_mvn_grad_cov_f64(const double* M, int n, int z, const double* gscale, double* G, void* stream)
+{
+    if (!M) return -1;
+    if (n <= 0 || z <= 0) return -2;
+    if (!G) return -5;
+    const int R = 2 * n + 1;
+    const int64_t ld = drp_ou_workspace_ld(n, n), bs = (int64_t)R * ld;
+    mvn_grad_cov_kernel<<<dim3((n + 255) / 256, n, z), 256, 0, (cudaStream_t)stream>>>(M, ld, bs, n, gscale, G);
+    return drp_launch_status();
+}
+
+// K^-1 of z SPD matrices via the same elimination (potri equivalent); Kinv [z,n,n] full symmetric.
+DRP_API int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, double* M, int32_t* info, void* stream)
+{
+    if (!K) return -1;
+    if (n <= 0 || z <= 0) return -2;
+    if (!Kinv || !M) return -4;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = 2 * n + 1;
+    const int64_t ld = drp_ou_workspace_ld(n, n), bs = (int64_t)R * ld;
+    cudaMemsetAsync(Kinv, 0, sizeof(double) * (size_t)z * n, st);   // borrowed as the zero right-hand side x
+    cov_assemble_kernel<<<dim3((R + 255) / 256, R, z), 256, 0, st>>>(K, n, Kinv, M, ld, bs);
+    int rc = drp_factor_run(M, ld, bs, z, n, R, n + 1, R, info, st);
+    if (rc) return rc;
+    block_extract_kernel<<<dim3((n + 255) / 256, n, z), 256, 0, st>>>(M, ld, bs, n, n, -1.0, 0.0, Kinv);
+    return drp_launch_status();
+}
+
+// Conditional posterior of the OU process at the `ni` nodes int_idx given values x_leaf [z,n] at the nodes leaf_idx:
+//   mean [z,ni] = K_ab K_bb^-1 x_b,   cov [z,ni,ni] = K_aa - K_ab K_bb^-1 K_ba + jitter   (cov nullable: mean only)
+// Mathematically identical to the precision-partition form of S/models.py:167-193 (Bishop B.49-50).
+//   idx = [leaf_idx (n) | int_idx (ni)] rows of D;  M workspace of drp_ou_workspace_elems(n, ni, z) doubles.
+DRP_API int drp_ou_conditional_f64(const double* D, int64_t ldd, const int32_t* idx, int n, int ni, const double* sf,
+                                   const double* sn, const double* lam, const double* x_leaf, int z, double jitter,
+                                   double* mean, double* cov, double* M, int32_t* info, void* stream)
+{
+    if (!D) return -1;
+    if (!idx) return -3;
+    if (n <= 0 || ni <= 0) return -4;
+    if (!sf || !sn || !lam || !x_leaf) return -6;
+    if (z <= 0) return -10;
+    if (!mean || !M) return -12;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = n + 1 + ni;
+    const int64_t ld = drp_ou_workspace_ld(n, ni), bs = (int64_t)R * ld;
+    ou_assemble_kernel<<<dim3((R + 255) / 256, R), 256, 3 * z * sizeof(double), st>>>(D, ldd, idx, n, ni, 0, sf, sn, lam,
+                                                                                  x_leaf, z, M, ld, bs);
+    int rc = drp_factor_run(M, ld, bs, z, n, R, 0, cov ? R : n + 1, info, st);
+    if (rc) return rc;
+    alpha_extract_kernel<<<dim3((ni + 255) / 256, z), 256, 0, st>>>(M, ld, bs, n, ni, mean);
+    if (cov) block_extract_kernel<<<dim3((ni + 255) / 256, ni, z), 256, 0, st>>>(M, ld, bs, n, ni, 1.0, jitter, cov);
+    return drp_launch_status();
+}

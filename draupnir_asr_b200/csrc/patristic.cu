@@ -1,0 +1,133 @@
+// K1: all-pairs patristic (path-length) and cladistic (edge-count) distances + LCA indices on the GPU.
+//
+// Replaces the offline builder of the reference (S/ = /root/reference/draupnir/src/draupnir/):
+//   calculate_patristic_distance            S/utils.py:496-579   (O(N^2) ete3 get_distance loop, n <= 200)
+//   Rscript Calculate_Patristic.R           S/Calculate_Patristic.R:9   (ape::dist.nodes, n > 200)
+//
+// Nodes are BFS level-order ids (root 0, parent[v] < v; S/utils.py:864).  d(i,j) = r_i + r_j - 2 r_lca(i,j) with
+// r = distance to the root.  The LCA of (i, j) is the first node on i's ancestor chain whose subtree (a contiguous
+// preorder interval) contains j, found by binary search over the chain held in shared memory: O(log depth) per pair,
+// no N x log N tables, output written once, coalesced, in the reference's row-major level-order layout.
+#include "common.cuh"
+
+namespace {
+
+// Sequential O(N) tree preparation by one thread block (N <= 16k nodes fits in shared memory many times over;
+// the work is a dependent chain, so a single lane does it).  parent[v] < v makes one forward pass enough.
+__global__ void tree_prepare_kernel(const int32_t* __restrict__ parent, const double* __restrict__ branch, int N,
+                                    int32_t* __restrict__ depth, double* __restrict__ root_dist,
+                                    int32_t* __restrict__ pre, int32_t* __restrict__ size, int32_t* __restrict__ next_free)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    depth[0] = 0;
+    root_dist[0] = 0.0;
+    for (int v = 1; v < N; ++v) {
+        const int p = parent[v];
+        depth[v] = depth[p] + 1;
+        root_dist[v] = root_dist[p] + branch[v];
+    }
+    for (int v = 0; v < N; ++v) size[v] = 1;
+    for (int v = N - 1; v >= 1; --v) size[parent[v]] += size[v];
+    // preorder entry index: every subtree becomes the contiguous interval [pre, pre + size)
+    pre[0] = 0;
+    next_free[0] = 1;
+    for (int v = 1; v < N; ++v) {
+        const int p = parent[v];
+        pre[v] = next_free[p];
+        next_free[p] += size[v];
+        next_free[v] = pre[v] + 1;
+    }
+}
+
+struct ChainEntry {
+    int32_t lo, hi;    // preorder interval [lo, hi) of the ancestor's subtree
+    int32_t id, depth;
+    double rd;         // root distance of the ancestor
+};
+
+constexpr int CHAIN_SMEM = 1024;   // ancestors held in shared memory; deeper chains spill to the global workspace
+
+// One CTA per requested row node.
+__global__ void __launch_bounds__(256) lca_patristic_kernel(const int32_t* __restrict__ parent, const int32_t* __restrict__ depth,
+                                                            const double* __restrict__ root_dist, const int32_t* __restrict__ pre,
+                                                            const int32_t* __restrict__ size, const int32_t* __restrict__ rows,
+                                                            const int32_t* __restrict__ cols, int nc,
+                                                            int32_t* __restrict__ lca_out, double* __restrict__ dist_out,
+                                                            double* __restrict__ clad_out, ChainEntry* __restrict__ spill,
+                                                            int spill_stride)
+{
+    __shared__ ChainEntry chain_s[CHAIN_SMEM];
+    const int i = rows ? rows[blockIdx.x] : blockIdx.x;
+    const int len = depth[i] + 1;
+    ChainEntry* chain = len <= CHAIN_SMEM ? chain_s : spill + (int64_t)blockIdx.x * spill_stride;
+    // ancestor k of i: walk is sequential, but only `len` steps; lane 0 does it, everyone else waits.
+    if (threadIdx.x == 0) {
+        int a = i;
+        for (int k = 0; k < len; ++k) {
+            ChainEntry e;
+            e.lo = pre[a];
+            e.hi = e.lo + size[a];
+            e.id = a;
+            e.depth = depth[a];
+            e.rd = root_dist[a];
+            chain[k] = e;
+            a = parent[a];
+        }
+    }
+    __syncthreads();
+    if (len > CHAIN_SMEM) __threadfence_block();
+    const double ri = root_dist[i];
+    const int di = depth[i];
+    const int64_t obase = (int64_t)blockIdx.x * nc;
+    for (int b = threadIdx.x; b < nc; b += blockDim.x) {
+        const int j = cols ? cols[b] : b;
+        const int p = pre[j];
+        // smallest k with lo_k <= p < hi_k (intervals are nested, the root's always matches)
+        int lo = 0, hi = len - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const ChainEntry e = chain[mid];
+            if (e.lo <= p && p < e.hi) hi = mid;
+            else lo = mid + 1;
+        }
+        const ChainEntry e = chain[lo];
+        if (lca_out) lca_out[obase + b] = e.id;
+        if (dist_out) dist_out[obase + b] = (ri - e.rd) + (root_dist[j] - e.rd);
+        if (clad_out) clad_out[obase + b] = (double)(di + depth[j] - 2 * e.depth);
+    }
+}
+
+}  // namespace
+
+// depth/root_dist/pre/size/scratch: device arrays of N elements each (scratch is clobbered).
+// Requires only parent[v] < v (any topological numbering; the reference's level order satisfies it).
+DRP_API int drp_tree_prepare(const int32_t* parent, const double* branch, int32_t n_nodes, int32_t* depth, double* root_dist,
+                             int32_t* pre, int32_t* size, int32_t* scratch, void* stream)
+{
+    if (!parent || !branch) return -1;
+    if (n_nodes <= 0) return -3;
+    if (!depth || !root_dist || !pre || !size || !scratch) return -4;
+    tree_prepare_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(parent, branch, n_nodes, depth, root_dist, pre, size, scratch);
+    return drp_launch_status();
+}
+
+// bytes of spill workspace needed for `nr` rows when the deepest node has `max_depth` edges to the root
+DRP_API int64_t drp_lca_workspace_bytes(int32_t nr, int32_t max_depth)
+{
+    return max_depth + 1 <= CHAIN_SMEM ? 0 : (int64_t)nr * (max_depth + 1) * (int64_t)sizeof(ChainEntry);
+}
+
+// rows/cols: node ids to pair up (nullable = all nodes 0..nr-1 / 0..nc-1).  Any of the three outputs may be null.
+DRP_API int drp_lca_patristic_f64(const int32_t* parent, const int32_t* depth, const double* root_dist, const int32_t* pre,
+                                  const int32_t* size, int32_t n_nodes, int32_t max_depth, const int32_t* rows, int32_t nr,
+                                  const int32_t* cols, int32_t nc, int32_t* lca_out, double* dist_out, double* clad_out,
+                                  void* ws, int64_t ws_bytes, void* stream)
+{
+    if (!parent || !depth || !root_dist || !pre || !size) return -1;
+    if (n_nodes <= 0) return -6;
+    if (nr <= 0 || nc <= 0) return -9;
+    if (ws_bytes < drp_lca_workspace_bytes(nr, max_depth) || (ws_bytes > 0 && !ws)) return -16;
+    lca_patristic_kernel<<<nr, 256, 0, (cudaStream_t)stream>>>(parent, depth, root_dist, pre, size, rows, cols, nc, lca_out,
+                                                                dist_out, clad_out, (ChainEntry*)ws, max_depth + 1);
+    return drp_launch_status();
+}

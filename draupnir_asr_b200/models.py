@@ -1,0 +1,277 @@
+"""DRAUPNIR model classes with the reference's names, constructor, sample sites and method signatures
+(S/models.py, S/ = /root/reference/draupnir/src/draupnir/), computing on the sm_100a kernels.
+
+What changes under the API:
+* `gp_prior`: the `latent_z` site is an `OUProcessPrior` — covariance assembly, batched Cholesky, triangular solve,
+  log-determinant and every gradient are one fused pipeline; the `[z,n,n]` covariance is never materialised.
+* conditional sampling uses the Schur complement on the leaf block instead of three dense inversions.
+* the `aa_sequences` site scores un-normalised decoder scores with one fused log-sum-exp/gather/reduce kernel.
+* the BLOSUM embedding is evaluated once per alignment column instead of once per (node, column).
+"""
+from __future__ import annotations
+
+from abc import abstractmethod
+from collections import namedtuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .backend import pyro, dist
+from .models_utils import *  # noqa: F401,F403  (the reference does the same, S/models.py:13)
+from .models_utils import EmbedComplex, OUKernel_Fast, RNNDecoder_Tiling
+from .utils import require_cuda, squeeze_tensor
+
+SamplingOutput = namedtuple("SamplingOutput", ["aa_sequences", "latent_space", "logits", "phis", "psis", "mean_phi",
+                                               "mean_psi", "kappa_phi", "kappa_psi"])  # S/models.py:17
+
+
+class DRAUPNIRModelClass(nn.Module):
+    """S/models.py:19-288."""
+
+    def __init__(self, ModelLoad):
+        super(DRAUPNIRModelClass, self).__init__()
+        self.args = ModelLoad.args
+        self.num_epochs = ModelLoad.args.num_epochs
+        self.gru_hidden_dim = ModelLoad.gru_hidden_dim
+        self.embedding_dim = ModelLoad.args.embedding_dim
+        self.position_embedding_dim = ModelLoad.args.position_embedding_dim
+        self.pretrained_params = ModelLoad.pretrained_params
+        self.z_dim = ModelLoad.z_dim
+        self.leaves_nodes = ModelLoad.leaves_nodes
+        self.n_tree_levels = ModelLoad.n_tree_levels
+        self.align_seq_len = ModelLoad.align_seq_len
+        self.aa_probs = ModelLoad.build_config.aa_probs
+        self.edge_info = ModelLoad.graph_coo
+        self.nodes_representations_array = ModelLoad.nodes_representations_array
+        self.dgl_graph = ModelLoad.dgl_graph
+        self.children_dict = ModelLoad.children_dict
+        self.closest_leaves_dict = ModelLoad.closest_leaves_dict
+        self.descendants_dict = ModelLoad.descendants_dict
+        self.clades_dict_all = ModelLoad.clades_dict_all
+        self.max_indel_size = ModelLoad.args.max_indel_size
+        self.rnn_input_size = self.z_dim
+        self.use_attention = False
+        self.batch_first = True
+        self.leaves_testing = ModelLoad.leaves_testing
+        self.batch_by_clade = ModelLoad.args.batch_by_clade
+        self.device = require_cuda(ModelLoad.device)
+        self.kappa_addition = ModelLoad.args.kappa_addition
+        self.aa_frequencies = ModelLoad.aa_frequencies
+        self.blosum = ModelLoad.blosum
+        self.blosum_max = ModelLoad.blosum_max
+        self.blosum_weighted = ModelLoad.blosum_weighted
+        self.dataset_train_blosum = ModelLoad.dataset_train_blosum
+        self.variable_score = ModelLoad.variable_score
+        self.internal_nodes = ModelLoad.internal_nodes
+        self.batch_size = ModelLoad.build_config.batch_size
+        self.plating = ModelLoad.args.plating
+        self.plate_size = ModelLoad.build_config.plate_subsample_size
+        self.plate_unordered = ModelLoad.plate_unordered
+        self.one_hot_encoding = ModelLoad.one_hot_encoding
+        self.n_leaves_batch = self.batch_size
+        self.n_internal_batch = self.batch_size
+        self.n_leaves = len(self.leaves_nodes)
+        self.n_internal = len(self.internal_nodes)
+        self.n_all = self.n_leaves + self.n_internal
+        self.num_layers = 1
+        # S/models.py:66 — never registered with pyro.module, i.e. a constant of the model
+        self.h_0_MODEL = nn.Parameter(torch.randn(self.gru_hidden_dim, dtype=torch.float64), requires_grad=False)
+        self._one = None
+        self._pos_cache = {}
+        for name in ("blosum_weighted", "dataset_train_blosum", "internal_nodes", "leaves_nodes", "aa_frequencies",
+                     "blosum", "blosum_max"):
+            t = getattr(self, name)
+            if isinstance(t, torch.Tensor):
+                setattr(self, name, t.to(self.device))
+        self.to(self.device)
+
+    @abstractmethod
+    def guide(self, family_data, patristic_matrix, cladistic_matrix, data_blosum, batch_blosum, guide_map_estimates):
+        raise NotImplementedError
+
+    @abstractmethod
+    def model(self, family_data, patristic_matrix, cladistic_matrix, data_blosum, batch_blosum, guide_map_estimates):
+        raise NotImplementedError
+
+    @abstractmethod
+    def sample(self, map_estimates, n_samples, family_data_test, patristic_matrix, cladistic_matrix, use_test=True):
+        raise NotImplementedError
+
+    def get_class(self):
+        full_name = self.__class__
+        return str(full_name).split(".")[-1].replace("'>", "")
+
+    # -------------------------------------------------------------------------------------------------------------
+    def _hyper_priors(self, eps: float):
+        """The four HalfNormal sites of S/models.py:89-92 (sampled/replayed through pyro, +eps as the reference)."""
+        if self._one is None or self._one.device != self.h_0_MODEL.device:
+            self._one = torch.ones((), dtype=torch.float64, device=self.h_0_MODEL.device)
+        alpha = pyro.sample("alpha", dist.HalfNormal(self._one).expand_by([3, ]).to_event(1)) + eps
+        sigma_f = pyro.sample("sigma_f", dist.HalfNormal(alpha[0]).expand_by([self.z_dim, ]).to_event(1)) + eps
+        sigma_n = pyro.sample("sigma_n", dist.HalfNormal(alpha[1]).expand_by([self.z_dim, ]).to_event(1)) + eps
+        lambd = pyro.sample("lambd", dist.HalfNormal(alpha[2]).expand_by([self.z_dim, ]).to_event(1)) + eps
+        return (squeeze_tensor(1, alpha), squeeze_tensor(1, sigma_f), squeeze_tensor(1, sigma_n),
+                squeeze_tensor(1, lambd))
+
+    def gp_prior(self, patristic_matrix_sorted):
+        """Ornstein-Uhlenbeck process prior over the latent space (S/models.py:85-121).  Returns `[n, z]`."""
+        alpha, sigma_f, sigma_n, lambd = self._hyper_priors(1e-6)
+        patristic_matrix = patristic_matrix_sorted[1:, 1:]
+        n_expected = self.n_all if self.leaves_testing else self.n_leaves
+        assert patristic_matrix.shape == (n_expected, n_expected), \
+            f"Expected shape {(self.z_dim, n_expected, n_expected)}, got {(self.z_dim,) + tuple(patristic_matrix.shape)}"
+        latent_space = pyro.sample("latent_z",
+                                   dist.OUProcessPrior(patristic_matrix, sigma_f, sigma_n, lambd).to_event(1))  # [z, n]
+        return latent_space.T
+
+    def gp_prior_batched(self, patristic_matrix_sorted):
+        """S/models.py:122-142 — same prior on a batch slice of the tree, without the +1e-6."""
+        alpha, sigma_f, sigma_n, lambd = self._hyper_priors(0.0)
+        patristic_matrix = patristic_matrix_sorted[1:, 1:]
+        assert patristic_matrix.shape == (self.n_leaves_batch, self.n_leaves_batch)
+        latent_space = pyro.sample("latent_z",
+                                   dist.OUProcessPrior(patristic_matrix, sigma_f, sigma_n, lambd).to_event(1))
+        return latent_space.T
+
+    def map_sampling(self, map_estimates, patristic_matrix_full):
+        """S/models.py:143-148."""
+        test_indexes = (patristic_matrix_full[1:, 0][..., None] == self.internal_nodes).any(-1)
+        latent_space_internal = map_estimates["latent_z"][:, test_indexes].T
+        assert latent_space_internal.shape == (self.n_internal, self.z_dim)
+        return latent_space_internal
+
+    # -------------------------------------------------------------------------------------------------------------
+    def _positions(self, patristic_matrix, internal_nodes):
+        """Row positions of the internal / leaf nodes inside `patristic_matrix[1:,1:]` (S/models.py:157); cached
+        because the mask is a constant of the data set and `nonzero` synchronises."""
+        key = (patristic_matrix.data_ptr(), tuple(patristic_matrix.shape), internal_nodes.data_ptr())
+        hit = self._pos_cache.get(key)
+        if hit is None:
+            ids = patristic_matrix[1:, 0]
+            internal_indexes = (ids[..., None] == internal_nodes.to(ids.device)).any(-1)
+            hit = (torch.nonzero(~internal_indexes).reshape(-1), torch.nonzero(internal_indexes).reshape(-1))
+            self._pos_cache = {key: hit}
+        return hit
+
+    def _conditional(self, map_estimates, patristic_matrix, internal_nodes, n_internal, eps, jitter, want_cov):
+        sigma_f = squeeze_tensor(1, map_estimates["sigma_f"]) + eps
+        sigma_n = squeeze_tensor(1, map_estimates["sigma_n"]) + eps
+        lambd = squeeze_tensor(1, map_estimates["lambd"]) + eps
+        leaf_pos, int_pos = self._positions(patristic_matrix, internal_nodes)
+        assert int_pos.numel() == n_internal
+        xb = map_estimates["latent_z"]
+        if self.leaves_testing:
+            leaves_indexes = (patristic_matrix[1:, 0][..., None] == self.leaves_nodes.to(xb.device)).any(-1)
+            xb = xb[:, leaves_indexes]
+        return ops.ou_conditional(patristic_matrix[1:, 1:], leaf_pos, int_pos, sigma_f.detach(), sigma_n.detach(),
+                                  lambd.detach(), xb.detach(), jitter=jitter, want_cov=want_cov)
+
+    def conditional_sampling(self, map_estimates, patristic_matrix):
+        """One draw of the internal nodes given the leaves (S/models.py:149-196; Bishop B.49-50).  The reference adds
+        1e-6 to every entry of the conditional covariance (:193); so does this."""
+        assert patristic_matrix[1:, 1:].shape == (self.n_all, self.n_all), \
+            "Remember to use the entire/full patristic matrix for conditional sampling!"
+        mean, cov = self._conditional(map_estimates, patristic_matrix, self.internal_nodes, self.n_internal, 0.0, 1e-6, True)
+        latent_space = dist.MultivariateNormal(mean, cov).to_event(1).sample().T
+        assert latent_space.shape == (self.n_internal, self.z_dim)
+        return latent_space
+
+    def conditional_samplingMAP(self, map_estimates, patristic_matrix):
+        """Conditional MEAN of the internal nodes (S/models.py:197-242).  The reference also draws and discards one
+        sample (:239); that draw only advances the RNG and is not reproduced."""
+        assert patristic_matrix[1:, 1:].shape == (self.n_all, self.n_all), \
+            "Remember to use the entire/full patristic matrix for conditional sampling!"
+        mean, _ = self._conditional(map_estimates, patristic_matrix, self.internal_nodes, self.n_internal, 0.0, 0.0, False)
+        assert mean.shape == (self.z_dim, self.n_internal)
+        return mean.T
+
+    def conditional_sampling_batch(self, map_estimates, patristic_matrix):
+        """S/models.py:243-287 (batched variant: +1e-6 on the hyper-parameters, no jitter on the covariance)."""
+        internal = self.internal_nodes_batch
+        mean, cov = self._conditional(map_estimates, patristic_matrix, internal, len(internal), 1e-6, 0.0, True)
+        return dist.MultivariateNormal(mean, cov).to_event(1).sample().T
+
+
+class DRAUPNIRModel_classic(DRAUPNIRModelClass):
+    """S/models.py:289-401 — whole-tree model, GRU mapping function, BLOSUM embeddings."""
+
+    def __init__(self, ModelLoad):
+        DRAUPNIRModelClass.__init__(self, ModelLoad)
+        self.rnn_input_size = self.z_dim + self.aa_probs
+        self.num_layers = 1
+        self.decoder = RNNDecoder_Tiling(self.align_seq_len, self.aa_probs, self.gru_hidden_dim, self.z_dim,
+                                         self.rnn_input_size, self.kappa_addition, self.num_layers, self.pretrained_params)
+        self.embed = EmbedComplex(self.aa_probs, self.embedding_dim, self.pretrained_params)
+        self.to(device=self.device, dtype=torch.float64)
+
+    def _decoder_input(self, latent_space):
+        """`[n, L, z + aa_probs]` GRU input of S/models.py:339-342; the embedding runs once on `[L, aa_probs]`."""
+        n = latent_space.shape[0]
+        blosum = self.embed(self.blosum_weighted)                                     # [L, A]
+        return torch.cat((latent_space[:, None, :].expand(n, self.align_seq_len, self.z_dim),
+                          blosum[None].expand(n, self.align_seq_len, self.aa_probs)), dim=2)
+
+    def _hidden(self, n):
+        return self.h_0_MODEL.expand(self.decoder.num_layers * 2, n, self.gru_hidden_dim).contiguous()
+
+    def _likelihood(self, latent_space, aminoacid_sequences):
+        x = self._decoder_input(latent_space)
+        scores = self.decoder.scores(input=x, hidden=self._hidden(latent_space.shape[0]))
+        pyro.sample("aa_sequences", dist.Categorical(logits=scores), obs=aminoacid_sequences)
+
+    def model_variational(self, family_data, patristic_matrix_sorted, cladistic_matrix, data_blosum, batch_blosum=None,
+                          guide_map_estimates=None):
+        """S/models.py:300-325."""
+        aminoacid_sequences = family_data[:, 2:, 0]
+        pyro.module("embeddings", self.embed)
+        pyro.module("decoder", self.decoder)
+        with pyro.plate("plate_batch", dim=-1, device=self.device):
+            latent_space = self.gp_prior(patristic_matrix_sorted)
+            with pyro.plate("plate_len", dim=-2):
+                self._likelihood(latent_space, aminoacid_sequences)
+
+    def model_delta_map(self, family_data, patristic_matrix_sorted, cladistic_matrix, data_blosum, batch_blosum=None,
+                        guide_map_estimates=None):
+        """S/models.py:328-352."""
+        aminoacid_sequences = family_data[:, 2:, 0]
+        pyro.module("embeddings", self.embed)
+        pyro.module("decoder", self.decoder)
+        latent_space = self.gp_prior(patristic_matrix_sorted)
+        with pyro.plate("plate_len", aminoacid_sequences.shape[1], dim=-1), \
+                pyro.plate("plate_seq", aminoacid_sequences.shape[0], dim=-2):
+            self._likelihood(latent_space, aminoacid_sequences)
+
+    def model(self, family_data, patristic_matrix_sorted, cladistic_matrix, data_blosum, batch_blosum, guide_map_estimates):
+        """S/models.py:355-359."""
+        if self.args.select_guide == "delta_map":
+            self.model_delta_map(family_data, patristic_matrix_sorted, cladistic_matrix, data_blosum, batch_blosum,
+                                 guide_map_estimates)
+        else:
+            self.model_variational(family_data, patristic_matrix_sorted, cladistic_matrix, data_blosum, batch_blosum,
+                                   guide_map_estimates)
+
+    @torch.no_grad()
+    def sample(self, map_estimates, n_samples, family_data_test, patristic_matrix, cladistic_matrix, use_argmax=False,
+               use_test=True, use_test2=False):
+        """S/models.py:361-401."""
+        if use_test2:
+            assert patristic_matrix[1:, 1:].shape == (self.n_all, self.n_all)
+            latent_space = self.conditional_samplingMAP(map_estimates, patristic_matrix)
+            n_nodes = self.n_internal
+        elif use_test:
+            assert patristic_matrix[1:, 1:].shape == (self.n_all, self.n_all)
+            latent_space = self.conditional_sampling(map_estimates, patristic_matrix)
+            n_nodes = self.n_internal
+        else:
+            latent_space = map_estimates["latent_z"].T
+            assert latent_space.shape == (self.n_leaves, self.z_dim)
+            n_nodes = self.n_leaves
+        logits = self.decoder.forward(input=self._decoder_input(latent_space), hidden=self._hidden(n_nodes))
+        if use_argmax:
+            aa_sequences = torch.argmax(logits, dim=2).unsqueeze(0)
+        else:
+            aa_sequences = dist.Categorical(logits=logits).sample([n_samples])
+        return SamplingOutput(aa_sequences=aa_sequences.detach(), latent_space=latent_space.detach(),
+                              logits=logits.detach(), phis=None, psis=None, mean_phi=None, mean_psi=None, kappa_phi=None,
+                              kappa_psi=None)

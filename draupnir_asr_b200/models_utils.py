@@ -1,0 +1,114 @@
+"""Numerical building blocks with the reference's names and constructor signatures (S/models_utils.py, S/ =
+/root/reference/draupnir/src/draupnir/).  Parameter names equal the reference's so `Model_state_dict.p` /
+`Guide_state_dict.p` checkpoints interchange."""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class RNNEncoder(nn.Module):
+    """S/models_utils.py:22-65 — biGRU encoder of the variational guide."""
+
+    def __init__(self, align_seq_len, aa_prob, n_leaves, gru_hidden_dim, z_dim, rnn_input_size, kappa_addition, num_layers,
+                 pretrained_params):
+        super().__init__()
+        self.gru_hidden_dim, self.z_dim, self.n_leaves = gru_hidden_dim, z_dim, n_leaves
+        self.rnn_input_size, self.align_seq_len, self.aa_prob = rnn_input_size, align_seq_len, aa_prob
+        self.num_layers, self.kappa_addition = num_layers, kappa_addition
+        self.nndim = int(self.gru_hidden_dim / 2)
+        self.fc1 = nn.Linear(self.gru_hidden_dim, self.nndim)
+        self.linear_means = nn.Linear(self.nndim, self.z_dim)
+        self.linear_std = nn.Linear(self.nndim, self.z_dim)
+        self.softplus = nn.Softplus()
+        self.rnn = nn.GRU(input_size=self.rnn_input_size, hidden_size=self.gru_hidden_dim, batch_first=True,
+                          bidirectional=True, num_layers=self.num_layers, dropout=0.0)
+
+    def forward(self, input, hidden):
+        rnn_hidden_states, rnn_final_bidirectional = self.rnn(input, hidden)
+        H = self.gru_hidden_dim
+        rnn_hidden_states = rnn_hidden_states[:, :, :H] + rnn_hidden_states[:, :, H:]
+        rnn_final_hidden_state = self.fc1(rnn_hidden_states[:, -1])
+        z_loc = self.linear_means(rnn_final_hidden_state)
+        z_scale = self.softplus(self.linear_std(rnn_final_hidden_state))
+        return {"z_loc": z_loc, "z_scale": z_scale, "rnn_final_bidirectional": rnn_final_bidirectional,
+                "rnn_hidden_states": rnn_hidden_states, "rnn_final_hidden_state": rnn_final_hidden_state}
+
+
+class RNNDecoder_Tiling(nn.Module):
+    """S/models_utils.py:67-99 — biGRU -> fc1 -> linear_probs -> LogSoftmax."""
+
+    def __init__(self, align_seq_len, aa_prob, gru_hidden_dim, z_dim, rnn_input_size, kappa_addition, num_layers,
+                 pretrained_params):
+        super().__init__()
+        self.gru_hidden_dim, self.z_dim, self.rnn_input_size = gru_hidden_dim, z_dim, rnn_input_size
+        self.align_seq_len, self.aa_prob, self.num_layers, self.kappa_addition = align_seq_len, aa_prob, num_layers, kappa_addition
+        self.logsoftmax = nn.LogSoftmax(dim=-1)
+        self.fc1 = nn.Linear(2 * self.gru_hidden_dim, self.gru_hidden_dim)
+        self.linear_probs = nn.Linear(self.gru_hidden_dim, self.aa_prob)
+        self.rnn = nn.GRU(input_size=self.rnn_input_size, hidden_size=self.gru_hidden_dim, batch_first=True,
+                          bidirectional=True, num_layers=self.num_layers, dropout=0.0)
+
+    def scores(self, input, hidden):
+        """Un-normalised per-site scores `[n,L,A]`; the training path feeds these straight to the fused
+        categorical log-likelihood kernel (log_softmax is idempotent, so the ELBO is unchanged)."""
+        rnn_output, _ = self.rnn(input, hidden)
+        return self.linear_probs(self.fc1(rnn_output))
+
+    def forward(self, input, hidden):
+        return self.logsoftmax(self.scores(input, hidden))
+
+
+class EmbedComplex(nn.Module):
+    """S/models_utils.py:226-237."""
+
+    def __init__(self, aa_probs, embedding_dim, pretrained_params):
+        super().__init__()
+        self.aa_probs, self.embedding_dim = aa_probs, embedding_dim
+        self.softmax = nn.Softmax(dim=-1)
+        self.fc1 = nn.Linear(self.aa_probs, self.embedding_dim)
+        self.fc2 = nn.Linear(self.embedding_dim, self.aa_probs)
+
+    def forward(self, input):
+        return self.softmax(self.fc2(self.fc1(input)))
+
+
+class EmbedComplexEncoder(EmbedComplex):
+    """S/models_utils.py:238-249 (same arithmetic as EmbedComplex)."""
+
+
+class GPKernel(ABC):
+    """S/models_utils.py:251-257."""
+
+    @abstractmethod
+    def preforward(self, t1: torch.Tensor, t2: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    @abstractmethod
+    def forward(self, t: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+
+class OUKernel_Fast(GPKernel):
+    """S/models_utils.py:286-311 — K_z = sigma_f_z^2 exp(-t / lamb_z) + sigma_n_z^2 I as ONE fused kernel
+    (`drp_ou_cov_fwd_f64`) with an analytic backward, instead of six element-wise passes."""
+
+    def __init__(self, sigma_f, sigma_n, lamb):
+        self.sigma_f, self.sigma_n, self.lamb = sigma_f, sigma_n, lamb
+
+    def preforward(self, t1: torch.Tensor, t2: torch.Tensor) -> torch.Tensor:
+        return torch.zeros((1,), device=t1.device)
+
+    def forward(self, t: torch.Tensor) -> torch.Tensor:
+        return ops.ou_cov(t, self.sigma_f, self.sigma_n, self.lamb)
+
+
+def compute_sites_entropies(logits, node_names):
+    """S/models_utils.py:409-427 (consumer of the decoder's logits; kept for API completeness)."""
+    prob = torch.exp(logits) / (1 + torch.exp(logits))
+    seq_entropies = -torch.sum(prob * torch.log(prob), dim=2)
+    return torch.cat((node_names[:, None], seq_entropies), dim=1)

@@ -1,0 +1,322 @@
+"""PyTorch custom ops over the C ABI (raw device pointers + the current CUDA stream; torch is only the allocator).
+
+Every function requires CUDA fp64 tensors and raises otherwise — there is no CPU path in the product.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes
+from typing import List, Optional, Tuple
+
+import torch
+
+from ._lib import lib
+
+_DEFERRED: Optional[List[Tuple[torch.Tensor, str]]] = None
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _rc(rc: int, name: str):
+    if rc != 0:
+        what = f"argument group {-rc} invalid" if rc < 0 else f"CUDA error {rc - 1000}"
+        raise RuntimeError(f"{name} failed: {what}")
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float64) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (draupnir_asr_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t
+
+
+def _matrix_view(D: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+    """Accepts strided row-major views such as `patristic_matrix_sorted[1:, 1:]` without copying."""
+    _req(D, name)
+    if D.dim() != 2:
+        raise RuntimeError(f"{name}: expected a 2-D matrix")
+    if D.stride(1) != 1:
+        D = D.contiguous()
+    return D, D.stride(0)
+
+
+@contextlib.contextmanager
+def defer_info_checks():
+    """Inside the block, pivot-failure flags are queued instead of synchronising; the block's owner calls
+    `flush_info_checks()` where it synchronises anyway (SVI.step reads the loss there)."""
+    global _DEFERRED
+    prev, _DEFERRED = _DEFERRED, []
+    try:
+        yield
+    finally:
+        pending, _DEFERRED = _DEFERRED, prev
+        _raise_if_failed(pending)
+
+
+def _raise_if_failed(pending):
+    for info, what in pending:
+        bad = torch.nonzero(info)
+        if bad.numel():
+            b = int(bad[0, 0])
+            raise torch.linalg.LinAlgError(
+                f"{what}: (Batch element {b}): The factorization could not be completed because the input is not "
+                f"positive-definite (the leading minor of order {int(info[b])} is not positive-definite).")
+
+
+def _info_done(info: torch.Tensor, what: str):
+    if _DEFERRED is not None:
+        _DEFERRED.append((info, what))
+    else:
+        _raise_if_failed([(info, what)])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K2  OUKernel_Fast.forward
+# ------------------------------------------------------------------------------------------------------------------
+class _OUCov(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, D, sf, sn, lam):
+        Dv, ldd = _matrix_view(D, "t")
+        n, z = Dv.shape[0], sf.shape[0]
+        sf, sn, lam = (_req(v, k).contiguous() for v, k in ((sf, "sigma_f"), (sn, "sigma_n"), (lam, "lamb")))
+        K = torch.empty((z, n, n), dtype=torch.float64, device=D.device)
+        _rc(lib.drp_ou_cov_fwd_f64(_p(Dv), ldd, n, _p(sf), _p(sn), _p(lam), z, _p(K), _stream()), "drp_ou_cov_fwd_f64")
+        ctx.save_for_backward(Dv, sf, sn, lam)
+        return K
+
+    @staticmethod
+    def backward(ctx, G):
+        Dv, sf, sn, lam = ctx.saved_tensors
+        n, z = Dv.shape[0], sf.shape[0]
+        G = G.contiguous()
+        part = torch.empty((z, n, 3), dtype=torch.float64, device=G.device)
+        out = torch.empty((z, 3), dtype=torch.float64, device=G.device)
+        _rc(lib.drp_ou_cov_bwd_f64(_p(Dv), Dv.stride(0), n, _p(lam), z, _p(G), _p(part), _p(out), _stream()),
+            "drp_ou_cov_bwd_f64")
+        return None, 2.0 * sf * out[:, 0], 2.0 * sn * out[:, 2], sf * sf * out[:, 1] / (lam * lam)
+
+
+def ou_cov(t: torch.Tensor, sigma_f: torch.Tensor, sigma_n: torch.Tensor, lamb: torch.Tensor) -> torch.Tensor:
+    """`[z,n,n]` OU covariance sf^2 exp(-t/lam) + sn^2 I (S/models_utils.py:303-311)."""
+    return _OUCov.apply(t, sigma_f, sigma_n, lamb)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K3  Cholesky, potri
+# ------------------------------------------------------------------------------------------------------------------
+def potrf(A: torch.Tensor, check: bool = True) -> torch.Tensor:
+    """Batched lower Cholesky factor with zeros above the diagonal, like `torch.linalg.cholesky` (out of place)."""
+    _req(A, "A")
+    n = A.shape[-1]
+    L = A.reshape(-1, n, n).clone()
+    info = torch.empty(L.shape[0], dtype=torch.int32, device=A.device)
+    _rc(lib.drp_potrf_batched_f64(_p(L), n, L.shape[0], 1, _p(info), _stream()), "drp_potrf_batched_f64")
+    if check:
+        _info_done(info, "linalg.cholesky")
+    return L.reshape(A.shape)
+
+
+def potri(K: torch.Tensor) -> torch.Tensor:
+    """Inverse of a batch of SPD matrices through the partial-Cholesky engine."""
+    _req(K, "K")
+    n = K.shape[-1]
+    Kc = K.reshape(-1, n, n).contiguous()
+    z = Kc.shape[0]
+    out = torch.empty_like(Kc)
+    M = torch.empty(lib.drp_ou_workspace_elems(n, n, z), dtype=torch.float64, device=K.device)
+    info = torch.empty(z, dtype=torch.int32, device=K.device)
+    _rc(lib.drp_potri_batched_f64(_p(Kc), n, z, _p(out), _p(M), _p(info), _stream()), "drp_potri_batched_f64")
+    _info_done(info, "potri")
+    return out.reshape(K.shape)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K3+K4+K5  fused OU prior  log N(x_z; 0, K_z(D))
+# ------------------------------------------------------------------------------------------------------------------
+class _OUPrior(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, D, sf, sn, lam, x):
+        Dv, ldd = _matrix_view(D, "patristic_matrix")
+        sf, sn, lam, x = (_req(v, k).contiguous() for v, k in ((sf, "sigma_f"), (sn, "sigma_n"), (lam, "lambd"),
+                                                                  (x, "latent_z")))
+        z, n = x.shape
+        if Dv.shape != (n, n) or sf.shape != (z,) or sn.shape != (z,) or lam.shape != (z,):
+            raise RuntimeError(f"ou_prior_logp: inconsistent shapes D{tuple(Dv.shape)} x{tuple(x.shape)} sf{tuple(sf.shape)}")
+        want = any(ctx.needs_input_grad[1:])
+        dev = x.device
+        logp = torch.empty(z, dtype=torch.float64, device=dev)
+        info = torch.empty(z, dtype=torch.int32, device=dev)
+        M = torch.empty(lib.drp_ou_workspace_elems(n, n if want else 0, z), dtype=torch.float64, device=dev)
+        alpha = gsum = part = None
+        if want:
+            alpha = torch.empty((z, n), dtype=torch.float64, device=dev)
+            gsum = torch.empty((z, 3), dtype=torch.float64, device=dev)
+            part = torch.empty((z, n, 3), dtype=torch.float64, device=dev)
+        _rc(lib.drp_ou_prior_f64(_p(Dv), ldd, n, _p(sf), _p(sn), _p(lam), _p(x), z, int(want), _p(logp), _p(alpha),
+                                 _p(gsum), _p(M), _p(part), _p(info), _stream()), "drp_ou_prior_f64")
+        _info_done(info, "linalg.cholesky")
+        if want:
+            ctx.save_for_backward(sf, sn, lam, alpha, gsum)
+        return logp
+
+    @staticmethod
+    def backward(ctx, g):
+        sf, sn, lam, alpha, gsum = ctx.saved_tensors
+        d_sf = g * 2.0 * sf * gsum[:, 0]
+        d_sn = g * 2.0 * sn * gsum[:, 2]
+        d_lam = g * sf * sf * gsum[:, 1] / (lam * lam)
+        d_x = -g[:, None] * alpha
+        return None, d_sf, d_sn, d_lam, d_x
+
+
+def ou_prior_logp(patristic: torch.Tensor, sigma_f, sigma_n, lambd, latent_z) -> torch.Tensor:
+    """`[z]` log-densities of the zero-mean OU process prior at `latent_z [z,n]` (S/models.py:100-118), with
+    analytic gradients w.r.t. sigma_f, sigma_n, lambd and latent_z.  The covariance is never materialised."""
+    return _OUPrior.apply(patristic, sigma_f, sigma_n, lambd, latent_z)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K4/K5  general MVN log-prob from an explicit covariance
+# ------------------------------------------------------------------------------------------------------------------
+class _MVNLogProb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, K, x):
+        K, x = _req(K, "covariance_matrix").contiguous(), _req(x, "value").contiguous()
+        z, n = x.shape
+        want = any(ctx.needs_input_grad)
+        dev = x.device
+        logp = torch.empty(z, dtype=torch.float64, device=dev)
+        info = torch.empty(z, dtype=torch.int32, device=dev)
+        M = torch.empty(lib.drp_ou_workspace_elems(n, n if want else 0, z), dtype=torch.float64, device=dev)
+        alpha = torch.empty((z, n), dtype=torch.float64, device=dev) if want else None
+        _rc(lib.drp_mvn_logprob_f64(_p(K), _p(x), n, z, int(want), _p(logp), _p(alpha), _p(M), _p(info), _stream()),
+            "drp_mvn_logprob_f64")
+        _info_done(info, "linalg.cholesky")
+        if want:
+            ctx.save_for_backward(alpha, M)
+            ctx.n = n
+        return logp
+
+    @staticmethod
+    def backward(ctx, g):
+        alpha, M = ctx.saved_tensors
+        z, n = alpha.shape
+        g = g.contiguous()
+        dK = None
+        if ctx.needs_input_grad[0]:
+            dK = torch.empty((z, n, n), dtype=torch.float64, device=g.device)
+            _rc(lib.drp_mvn_grad_cov_f64(_p(M), n, z, _p(g), _p(dK), _stream()), "drp_mvn_grad_cov_f64")
+        return dK, -g[:, None] * alpha
+
+
+def mvn_logprob(covariance_matrix: torch.Tensor, value: torch.Tensor) -> torch.Tensor:
+    """`[z]` zero-mean MVN log-densities for `covariance_matrix [z,n,n]`, `value [z,n]`."""
+    return _MVNLogProb.apply(covariance_matrix, value)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K6  conditional posterior
+# ------------------------------------------------------------------------------------------------------------------
+def ou_conditional(patristic_full: torch.Tensor, leaf_pos: torch.Tensor, internal_pos: torch.Tensor, sigma_f, sigma_n,
+                   lambd, x_leaf, jitter: float = 0.0, want_cov: bool = True):
+    """Mean `[z,ni]` (and covariance `[z,ni,ni]` + jitter) of the OU process at `internal_pos` given `x_leaf [z,n]`
+    at `leaf_pos` (positions = rows of `patristic_full`).  Schur-complement form of S/models.py:167-193."""
+    Dv, ldd = _matrix_view(patristic_full, "patristic_matrix")
+    sf, sn, lam, x = (_req(v, k).contiguous() for v, k in ((sigma_f, "sigma_f"), (sigma_n, "sigma_n"), (lambd, "lambd"),
+                                                              (x_leaf, "latent_z")))
+    z, n = x.shape
+    ni = int(internal_pos.numel())
+    dev = x.device
+    idx = torch.cat((leaf_pos.reshape(-1), internal_pos.reshape(-1))).to(device=dev, dtype=torch.int32).contiguous()
+    assert idx.numel() == n + ni
+    mean = torch.empty((z, ni), dtype=torch.float64, device=dev)
+    cov = torch.empty((z, ni, ni), dtype=torch.float64, device=dev) if want_cov else None
+    info = torch.empty(z, dtype=torch.int32, device=dev)
+    M = torch.empty(lib.drp_ou_workspace_elems(n, ni, z), dtype=torch.float64, device=dev)
+    _rc(lib.drp_ou_conditional_f64(_p(Dv), ldd, _p(idx), n, ni, _p(sf), _p(sn), _p(lam), _p(x), z, float(jitter), _p(mean),
+                                   _p(cov), _p(M), _p(info), _stream()), "drp_ou_conditional_f64")
+    _info_done(info, "linalg.inv")
+    return mean, cov
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K10  categorical log-likelihood
+# ------------------------------------------------------------------------------------------------------------------
+class _CatLogLik(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores, obs):
+        scores = _req(scores, "logits").contiguous()
+        if obs.dtype not in (torch.float64, torch.int64) or not obs.is_cuda:
+            raise RuntimeError("cat_loglik: obs must be a CUDA fp64 or int64 tensor")
+        obs = obs.contiguous()
+        A = scores.shape[-1]
+        rows = scores.numel() // A
+        if obs.numel() != rows:
+            raise RuntimeError(f"cat_loglik: {obs.numel()} observations for {rows} sites")
+        dev = scores.device
+        out = torch.empty((), dtype=torch.float64, device=dev)
+        lse = torch.empty(rows, dtype=torch.float64, device=dev)
+        part = torch.empty(lib.drp_cat_loglik_partials(rows), dtype=torch.float64, device=dev)
+        f64 = int(obs.dtype == torch.float64)
+        _rc(lib.drp_cat_loglik_fwd_f64(_p(scores), _p(obs), f64, rows, A, _p(out), _p(lse), _p(part), _stream()),
+            "drp_cat_loglik_fwd_f64")
+        ctx.save_for_backward(scores, obs, lse)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        scores, obs, lse = ctx.saved_tensors
+        A = scores.shape[-1]
+        rows = scores.numel() // A
+        g = g.contiguous().reshape(1)
+        ds = torch.empty_like(scores)
+        _rc(lib.drp_cat_loglik_bwd_f64(_p(scores), _p(obs), int(obs.dtype == torch.float64), _p(lse), _p(g), rows, A, _p(ds),
+                                       _stream()), "drp_cat_loglik_bwd_f64")
+        return ds, None
+
+
+def cat_loglik(scores: torch.Tensor, obs: torch.Tensor) -> torch.Tensor:
+    """Scalar sum over sites of log softmax(scores)[obs] (S/models.py:352)."""
+    return _CatLogLik.apply(scores, obs)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K1  patristic / cladistic / LCA
+# ------------------------------------------------------------------------------------------------------------------
+def tree_distances(parent: torch.Tensor, branch: torch.Tensor, rows: Optional[torch.Tensor] = None,
+                   cols: Optional[torch.Tensor] = None, want_lca: bool = False, want_cladistic: bool = False,
+                   want_patristic: bool = True):
+    """All-pairs (or rows x cols) patristic / cladistic distances and LCA ids of a tree given as level-order
+    `parent [N] int32` (root: -1) and `branch [N] fp64` device tensors.  Returns (patristic, cladistic, lca)."""
+    if not parent.is_cuda or parent.dtype != torch.int32:
+        raise RuntimeError("tree_distances: parent must be a CUDA int32 tensor")
+    _req(branch, "branch")
+    dev = parent.device
+    N = int(parent.numel())
+    parent, branch = parent.contiguous(), branch.contiguous()
+    depth = torch.empty(N, dtype=torch.int32, device=dev)
+    pre, size, scratch = torch.empty_like(depth), torch.empty_like(depth), torch.empty_like(depth)
+    rdist = torch.empty(N, dtype=torch.float64, device=dev)
+    _rc(lib.drp_tree_prepare(_p(parent), _p(branch), N, _p(depth), _p(rdist), _p(pre), _p(size), _p(scratch), _stream()),
+        "drp_tree_prepare")
+    max_depth = int(depth.max())
+    rows_t = None if rows is None else rows.to(device=dev, dtype=torch.int32).contiguous()
+    cols_t = None if cols is None else cols.to(device=dev, dtype=torch.int32).contiguous()
+    nr = N if rows_t is None else int(rows_t.numel())
+    nc = N if cols_t is None else int(cols_t.numel())
+    wsb = lib.drp_lca_workspace_bytes(nr, max_depth)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb else None
+    pat = torch.empty((nr, nc), dtype=torch.float64, device=dev) if want_patristic else None
+    cla = torch.empty((nr, nc), dtype=torch.float64, device=dev) if want_cladistic else None
+    lca = torch.empty((nr, nc), dtype=torch.int32, device=dev) if want_lca else None
+    _rc(lib.drp_lca_patristic_f64(_p(parent), _p(depth), _p(rdist), _p(pre), _p(size), N, max_depth, _p(rows_t), nr,
+                                  _p(cols_t), nc, _p(lca), _p(pat), _p(cla), _p(ws), wsb, _stream()),
+        "drp_lca_patristic_f64")
+    return pat, cla, lca

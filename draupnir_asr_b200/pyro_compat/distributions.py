@@ -1,0 +1,213 @@
+"""`pyro.distributions` subset: torch distributions + the Pyro mixin (`expand_by`, `to_event`), `Delta`, and the two
+B200-accelerated distributions of the DRAUPNIR path.
+
+* `MultivariateNormal` / `Categorical` given CUDA fp64 tensors score through the sm_100a kernels
+  (`ops.mvn_logprob`, `ops.cat_loglik`); `OUProcessPrior` is the fused form that never materialises the covariance.
+* Given CPU tensors the generic classes are plain `torch.distributions` (that is all Pyro's are); the DRAUPNIR model
+  classes themselves refuse CPU tensors, so there is no CPU route through the product path.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributions as td
+from torch.distributions import constraints
+from torch.distributions.utils import _sum_rightmost
+
+
+def _accel(t: torch.Tensor) -> bool:
+    return isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64
+
+
+class TorchDistributionMixin:
+    def expand_by(self, sample_shape):
+        return self.expand(torch.Size(sample_shape) + self.batch_shape)
+
+    def to_event(self, reinterpreted_batch_ndims=None):
+        if reinterpreted_batch_ndims is None:
+            reinterpreted_batch_ndims = len(self.batch_shape)
+        if reinterpreted_batch_ndims == 0:
+            return self
+        return Independent(self, reinterpreted_batch_ndims)
+
+    def mask(self, mask):
+        raise NotImplementedError("mask() is not used on the DRAUPNIR path")
+
+    def __call__(self, sample_shape=torch.Size()):
+        return self.rsample(sample_shape) if self.has_rsample else self.sample(sample_shape)
+
+
+class Independent(td.Independent, TorchDistributionMixin):
+    def log_prob_sum(self, value):
+        f = getattr(self.base_dist, "log_prob_sum", None)
+        return f(value) if f is not None else self.log_prob(value).sum()
+
+
+class HalfNormal(td.HalfNormal, TorchDistributionMixin):
+    pass
+
+
+class Normal(td.Normal, TorchDistributionMixin):
+    pass
+
+
+class Delta(td.Distribution, TorchDistributionMixin):
+    """Point mass (pyro.distributions.Delta): log_prob is `log_density` at the value, -inf elsewhere."""
+    has_rsample = True
+    arg_constraints = {"v": constraints.dependent, "log_density": constraints.real}
+    support = constraints.real
+
+    def __init__(self, v, log_density=0.0, event_dim=0, validate_args=None):
+        if event_dim > v.dim():
+            raise ValueError(f"Expected event_dim <= v.dim(), actual {event_dim} vs {v.dim()}")
+        batch_dim = v.dim() - event_dim
+        self.v = v
+        self.log_density = log_density
+        super().__init__(v.shape[:batch_dim], v.shape[batch_dim:], validate_args=False)
+
+    def expand(self, batch_shape, _instance=None):
+        batch_shape = torch.Size(batch_shape)
+        return Delta(self.v.expand(batch_shape + self.event_shape), self.log_density, len(self.event_shape))
+
+    def rsample(self, sample_shape=torch.Size()):
+        shape = torch.Size(sample_shape) + self.v.shape
+        return self.v.expand(shape)
+
+    def log_prob(self, x):
+        lp = (x == self.v).to(x.dtype).log()
+        lp = _sum_rightmost(lp, len(self.event_shape))
+        return lp + self.log_density
+
+    @property
+    def mean(self):
+        return self.v
+
+
+class MultivariateNormal(td.Distribution, TorchDistributionMixin):
+    """`dist.MultivariateNormal(loc, covariance_matrix)` (S/models.py:118,193,239).  CUDA fp64: batched blocked
+    Cholesky + solve + analytic gradients on the GPU kernels; otherwise torch's implementation."""
+    has_rsample = True
+    arg_constraints = {"loc": constraints.real_vector, "covariance_matrix": constraints.positive_definite}
+    support = constraints.real_vector
+
+    def __new__(cls, loc, covariance_matrix=None, precision_matrix=None, scale_tril=None, validate_args=None):
+        if covariance_matrix is not None and _accel(covariance_matrix) and covariance_matrix.dim() == 3:
+            return super().__new__(cls)
+        return _TorchMVN(loc, covariance_matrix=covariance_matrix, precision_matrix=precision_matrix,
+                         scale_tril=scale_tril, validate_args=validate_args)
+
+    def __init__(self, loc, covariance_matrix=None, precision_matrix=None, scale_tril=None, validate_args=None):
+        z, n = covariance_matrix.shape[0], covariance_matrix.shape[-1]
+        self.covariance_matrix = covariance_matrix
+        self.loc = loc.expand(z, n) if loc.dim() <= 2 else loc
+        self._scale_tril = None
+        super().__init__(torch.Size([z]), torch.Size([n]), validate_args=False)
+
+    @property
+    def scale_tril(self):
+        if self._scale_tril is None:
+            from .. import ops
+            self._scale_tril = ops.potrf(self.covariance_matrix)
+        return self._scale_tril
+
+    @property
+    def mean(self):
+        return self.loc
+
+    def log_prob(self, value):
+        from .. import ops
+        return ops.mvn_logprob(self.covariance_matrix, (value - self.loc).reshape(self.loc.shape))
+
+    def rsample(self, sample_shape=torch.Size()):
+        shape = torch.Size(sample_shape) + self.loc.shape
+        eps = torch.randn(shape, dtype=self.loc.dtype, device=self.loc.device)
+        return self.loc + (self.scale_tril * eps.unsqueeze(-2)).sum(-1)
+
+
+class _TorchMVN(td.MultivariateNormal, TorchDistributionMixin):
+    pass
+
+
+class Categorical(td.Distribution, TorchDistributionMixin):
+    """`dist.Categorical(logits=...)` (S/models.py:352,389).  CUDA fp64 logits: the summed log-likelihood and its
+    gradient are one fused kernel each (`log_prob_sum`), and the constructor does not touch the logits."""
+    has_enumerate_support = True
+    arg_constraints = {"logits": constraints.real_vector}
+
+    def __new__(cls, probs=None, logits=None, validate_args=None):
+        if logits is not None and _accel(logits):
+            return super().__new__(cls)
+        return _TorchCategorical(probs=probs, logits=logits, validate_args=validate_args)
+
+    def __init__(self, probs=None, logits=None, validate_args=None):
+        self.raw_logits = logits
+        super().__init__(logits.shape[:-1], torch.Size(), validate_args=False)
+
+    @property
+    def logits(self):
+        return torch.log_softmax(self.raw_logits, dim=-1)
+
+    @property
+    def probs(self):
+        return torch.softmax(self.raw_logits, dim=-1)
+
+    @property
+    def support(self):
+        return constraints.integer_interval(0, self.raw_logits.shape[-1] - 1)
+
+    def log_prob_sum(self, value):
+        from .. import ops
+        return ops.cat_loglik(self.raw_logits, value)
+
+    def log_prob(self, value):
+        return self.logits.gather(-1, value.long().unsqueeze(-1)).squeeze(-1)
+
+    def sample(self, sample_shape=torch.Size()):
+        sample_shape = torch.Size(sample_shape)
+        A = self.raw_logits.shape[-1]
+        flat = self.probs.reshape(-1, A)
+        draws = torch.multinomial(flat, max(sample_shape.numel(), 1), True).T
+        return draws.reshape(sample_shape + self.batch_shape)
+
+
+class _TorchCategorical(td.Categorical, TorchDistributionMixin):
+    pass
+
+
+class OUProcessPrior(td.Distribution, TorchDistributionMixin):
+    """z independent zero-mean Ornstein-Uhlenbeck processes over the tree: N(0, sf_z^2 exp(-D/lam_z) + sn_z^2 I).
+
+    Equivalent to `MultivariateNormal(zeros(1,n), OUKernel_Fast(sf,sn,lam).forward(D))` (S/models.py:101-118) but
+    assembly, Cholesky, solve, log-det and all gradients are one fused GPU pipeline (`ops.ou_prior_logp`)."""
+    has_rsample = True
+    arg_constraints = {}
+    support = constraints.real_vector
+
+    def __init__(self, patristic, sigma_f, sigma_n, lambd, validate_args=None):
+        self.patristic, self.sigma_f, self.sigma_n, self.lambd = patristic, sigma_f, sigma_n, lambd
+        super().__init__(torch.Size([sigma_f.shape[0]]), torch.Size([patristic.shape[0]]), validate_args=False)
+
+    @property
+    def covariance_matrix(self):
+        from .. import ops
+        return ops.ou_cov(self.patristic, self.sigma_f, self.sigma_n, self.lambd)
+
+    @property
+    def mean(self):
+        return torch.zeros(self.batch_shape + self.event_shape, dtype=self.sigma_f.dtype, device=self.sigma_f.device)
+
+    def log_prob(self, value):
+        from .. import ops
+        return ops.ou_prior_logp(self.patristic, self.sigma_f, self.sigma_n, self.lambd, value)
+
+    def rsample(self, sample_shape=torch.Size()):
+        from .. import ops
+        L = ops.potrf(self.covariance_matrix.detach())
+        shape = torch.Size(sample_shape) + self.batch_shape + self.event_shape
+        eps = torch.randn(shape, dtype=L.dtype, device=L.device)
+        return (L * eps.unsqueeze(-2)).sum(-1)
+
+
+__all__ = ["HalfNormal", "Normal", "Delta", "MultivariateNormal", "Categorical", "Independent", "OUProcessPrior",
+           "TorchDistributionMixin", "constraints"]

@@ -1,0 +1,116 @@
+"""Caller-side glue: the namedtuples `S/main.py:45-59` hands to the model classes and a builder that wires a synthetic
+problem into model + guide + SVI the way `draupnir_train` does (S/main.py:991-1059).  Host logic only."""
+from __future__ import annotations
+
+from collections import namedtuple
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import torch
+
+from .backend import pyro
+from .guides import DRAUPNIRGUIDES
+from .models import DRAUPNIRModel_classic
+from .pyro_compat.infer import SVI, Trace_ELBO
+from .pyro_compat.infer.autoguide import AutoDelta, init_to_value
+from .pyro_compat.optim import ClippedAdam
+from .synthetic import SyntheticProblem
+
+# S/main.py:54-59
+ModelLoad = namedtuple("ModelLoad", ["z_dim", "align_seq_len", "device", "args", "build_config", "leaves_nodes",
+                                     "n_tree_levels", "gru_hidden_dim", "pretrained_params", "aa_frequencies", "blosum",
+                                     "blosum_max", "blosum_weighted", "dataset_train_blosum", "variable_score",
+                                     "internal_nodes", "graph_coo", "nodes_representations_array", "dgl_graph",
+                                     "children_dict", "closest_leaves_dict", "descendants_dict", "clades_dict_all",
+                                     "leaves_testing", "plate_unordered", "one_hot_encoding"])
+BuildConfig = namedtuple("BuildConfig", ["alignment_file", "use_ancestral", "n_test", "build_graph", "aa_probs", "triTSNE",
+                                         "align_seq_len", "leaves_testing", "batch_size", "plate_subsample_size",
+                                         "script_dir", "no_testing"])
+
+# S/main.py:2761-2779
+DEFAULT_CONFIG = {"lr": 1e-3, "beta1": 0.9, "beta2": 0.999, "eps": 1e-8, "weight_decay": 0.0, "clip_norm": 10.0,
+                  "lrd": 1.0, "z_dim": 30, "gru_hidden_dim": 60}
+
+
+def default_args(select_guide: str, num_epochs: int = 1, embedding_dim: int = 50, device="cuda"):
+    """The argparse fields of Draupnir_example.py:62-143 that reach the model/guide constructors."""
+    return SimpleNamespace(num_epochs=num_epochs, embedding_dim=embedding_dim, position_embedding_dim=30,
+                           max_indel_size=5, batch_by_clade=False, kappa_addition=5, plating=False, use_cuda=True,
+                           select_guide=select_guide, plate_unordered=False, device=device, use_scheduler=False)
+
+
+def model_load_from_problem(problem: SyntheticProblem, select_guide: str, device, z_dim=30, gru_hidden_dim=60,
+                            embedding_dim=50) -> ModelLoad:
+    dev = torch.device(device)
+    build = BuildConfig(alignment_file=None, use_ancestral=True, n_test=0, build_graph=False, aa_probs=problem.aa_probs,
+                        triTSNE=False, align_seq_len=problem.align_seq_len, leaves_testing=False,
+                        batch_size=problem.n_leaves,      # S/main.py:146: batch_size 1 => number of sequences
+                        plate_subsample_size=None, script_dir=None, no_testing=False)
+    to = lambda t: t.to(dev)
+    return ModelLoad(z_dim=z_dim, align_seq_len=problem.align_seq_len, device=dev,
+                     args=default_args(select_guide, embedding_dim=embedding_dim, device=dev), build_config=build,
+                     leaves_nodes=to(problem.leaves_nodes), n_tree_levels=int(problem.tree.depth.max()) + 1,
+                     gru_hidden_dim=gru_hidden_dim, pretrained_params=None, aa_frequencies=to(problem.aa_frequencies),
+                     blosum=to(problem.blosum), blosum_max=to(problem.blosum_max),
+                     blosum_weighted=to(problem.blosum_weighted), dataset_train_blosum=to(problem.dataset_train_blosum),
+                     variable_score=to(problem.variable_score), internal_nodes=to(problem.internal_nodes), graph_coo=None,
+                     nodes_representations_array=None, dgl_graph=None, children_dict=None, closest_leaves_dict=None,
+                     descendants_dict=None, clades_dict_all=None, leaves_testing=False, plate_unordered=False,
+                     one_hot_encoding=False)
+
+
+class Run(SimpleNamespace):
+    """model (`Draupnir`), `guide`, `svi`, `optim` and the device-resident step inputs of one training run."""
+
+    def step_args(self):
+        return (self.dataset_train, self.patristic_matrix_train, None, self.dataset_train_blosum, None, None)
+
+    def step(self) -> float:
+        return self.svi.step(*self.step_args())
+
+
+def build_run(problem: SyntheticProblem, select_guide: str, device="cuda", init: Optional[Dict[str, torch.Tensor]] = None,
+              z_dim=30, gru_hidden_dim=60, embedding_dim=50, config: Optional[dict] = None, seed: int = 0) -> Run:
+    """Mirror of `draupnir_train`'s setup (S/main.py:991-1059): ModelLoad -> DRAUPNIRModel_classic -> guide
+    (`AutoDelta` for delta_map, `DRAUPNIRGUIDES` otherwise) -> Trace_ELBO -> ClippedAdam -> SVI."""
+    assert select_guide in ("delta_map", "variational")
+    cfg = dict(DEFAULT_CONFIG, **(config or {}))
+    pyro.clear_param_store()
+    pyro.enable_validation(False)
+    gen_state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    try:
+        ml = model_load_from_problem(problem, select_guide, device, z_dim, gru_hidden_dim, embedding_dim)
+        Draupnir = DRAUPNIRModel_classic(ml)
+        if select_guide == "delta_map":
+            values = None if init is None else {k: v.to(ml.device) for k, v in init.items()}
+            guide = AutoDelta(Draupnir.model, init_loc_fn=init_to_value(values=values))
+        else:
+            guide = DRAUPNIRGUIDES(Draupnir.model, ml, Draupnir)
+            if init is not None:
+                with torch.no_grad():
+                    for k in ("alpha", "sigma_f", "sigma_n", "lambd"):
+                        getattr(guide, f"{k}_unconstrained").copy_(init[k].reshape(-1, 1).log().to(ml.device))
+    finally:
+        torch.random.set_rng_state(gen_state)
+    optim = ClippedAdam({"lr": cfg["lr"], "betas": (cfg["beta1"], cfg["beta2"]), "eps": cfg["eps"],
+                         "weight_decay": cfg["weight_decay"], "clip_norm": cfg["clip_norm"], "lrd": cfg["lrd"]})
+    svi = SVI(Draupnir.model, guide, optim, Trace_ELBO())
+    dev = ml.device
+    return Run(Draupnir=Draupnir, guide=guide, svi=svi, optim=optim, model_load=ml, device=dev,
+               dataset_train=problem.dataset_train.to(dev), patristic_matrix_train=problem.patristic_matrix_train.to(dev),
+               patristic_matrix_full=problem.patristic_matrix_full.to(dev),
+               dataset_train_blosum=problem.dataset_train_blosum.to(dev), problem=problem, select_guide=select_guide)
+
+
+def load_networks(run: Run, state: Dict[str, Dict[str, torch.Tensor]]):
+    """Copy identically named network weights (decoder / embed / encoder / embeddingencoder / h_0_*) into a run —
+    parity tests inject one set of weights into both the oracle and this implementation."""
+    with torch.no_grad():
+        run.Draupnir.decoder.load_state_dict(state["decoder"])
+        run.Draupnir.embed.load_state_dict(state["embed"])
+        run.Draupnir.h_0_MODEL.copy_(state["h_0_MODEL"])
+        if run.select_guide == "variational":
+            run.guide.encoder.load_state_dict(state["encoder"])
+            run.guide.embeddingencoder.load_state_dict(state["embeddingencoder"])
+            run.guide.h_0_GUIDE.copy_(state["h_0_GUIDE"])

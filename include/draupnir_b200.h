@@ -1,0 +1,84 @@
+/* draupnir_b200 — C ABI of libdraupnir_b200.so (sm_100a).
+ *
+ * The drop-in boundary for DRAUPNIR's per-step tree-OU prior + ELBO likelihood path.  The reference
+ * (LysSanzMoreta/DRAUPNIR_ASR) is pure Python and has no FFI of its own; each entry point below replaces the torch
+ * call(s) cited next to it (S/ = draupnir/src/draupnir/ in the reference tree) and is what a ctypes stub in the
+ * reference would bind (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into row-major contiguous storage unless a leading dimension is given;
+ *   - the caller owns every buffer including workspaces (sizes from the *_workspace_* helpers); the library
+ *     allocates nothing and keeps no state, so calls are re-entrant per stream and CUDA-graph capturable;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value: 0 ok, -k = argument group k invalid, 1000+e = CUDA runtime error e;
+ *   - `info[z]` (int32, device): 0, or the 1-based index of the first non-positive pivot of matrix z (LAPACK potrf
+ *     convention).  The reference's behaviour on that condition is torch.linalg.LinAlgError; the Python wrapper
+ *     raises the same class.
+ *   - fp64 ("_f64") is the reference dtype (Draupnir_example.py:146,154).
+ */
+#ifndef DRAUPNIR_B200_H
+#define DRAUPNIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ABI version (bumped on any signature change). */
+int drp_abi_version(void);
+
+/* ---- K1  patristic builder: S/utils.py:496-579 (ete3 get_distance loop) and S/Calculate_Patristic.R:9 --------- */
+/* Tree given as parent[] / branch[] with parent[v] < v (level-order ids, root 0, S/utils.py:864).                  */
+int drp_tree_prepare(const int32_t* parent, const double* branch, int32_t n_nodes, int32_t* depth, double* root_dist,
+                     int32_t* pre, int32_t* size, int32_t* scratch, void* stream);
+int64_t drp_lca_workspace_bytes(int32_t nr, int32_t max_depth);
+/* rows/cols nullable (= all nodes).  lca_out int32 [nr,nc], dist_out / clad_out fp64 [nr,nc], each nullable.       */
+int drp_lca_patristic_f64(const int32_t* parent, const int32_t* depth, const double* root_dist, const int32_t* pre,
+                          const int32_t* size, int32_t n_nodes, int32_t max_depth, const int32_t* rows, int32_t nr,
+                          const int32_t* cols, int32_t nc, int32_t* lca_out, double* dist_out, double* clad_out, void* ws,
+                          int64_t ws_bytes, void* stream);
+
+/* ---- K2  OUKernel_Fast.forward: S/models_utils.py:303-311 ------------------------------------------------------ */
+/* D [n,n] with leading dimension ldd (so patristic_matrix_sorted[1:,1:] needs no copy); K [z,n,n].                 */
+int drp_ou_cov_fwd_f64(const double* D, int64_t ldd, int n, const double* sf, const double* sn, const double* lam, int z,
+                       double* K, void* stream);
+/* out[z][3] = (sum G.E, sum G.E.D, trace G) for G = dLoss/dK; part: z*n*3 doubles of workspace.                    */
+int drp_ou_cov_bwd_f64(const double* D, int64_t ldd, int n, const double* lam, int z, const double* G, double* part,
+                       double* out, void* stream);
+
+/* ---- K3  torch.linalg.cholesky inside MultivariateNormal.__init__: S/models.py:118 ----------------------------- */
+int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info, void* stream);
+
+/* ---- K3+K4+K5  gp_prior's latent_z site, fused: S/models.py:100-118 -------------------------------------------- */
+int64_t drp_ou_workspace_ld(int n, int n2);
+int64_t drp_ou_workspace_elems(int n, int n2, int z);
+/* logp[z] = log N(x_z; 0, sf_z^2 exp(-D/lam_z) + sn_z^2 I).  want_grad: alpha[z,n] = K^-1 x and gsum[z][3]
+ * (as drp_ou_cov_bwd_f64 with G = dlogp/dK).  M: drp_ou_workspace_elems(n, want_grad ? n : 0, z) doubles.          */
+int drp_ou_prior_f64(const double* D, int64_t ldd, int n, const double* sf, const double* sn, const double* lam,
+                     const double* x, int z, int want_grad, double* logp, double* alpha, double* gsum, double* M,
+                     double* part, int32_t* info, void* stream);
+
+/* ---- K4/K5  MultivariateNormal(0, K).log_prob(x) for an explicit covariance batch ------------------------------ */
+int drp_mvn_logprob_f64(const double* K, const double* x, int n, int z, int want_grad, double* logp, double* alpha,
+                        double* M, int32_t* info, void* stream);
+int drp_mvn_grad_cov_f64(const double* M, int n, int z, const double* gscale, double* G, void* stream);
+int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, double* M, int32_t* info, void* stream);
+
+/* ---- K6  conditional_sampling / conditional_samplingMAP: S/models.py:149-242 ----------------------------------- */
+/* idx = [leaf rows of D (n) | internal rows of D (ni)]; mean [z,ni]; cov [z,ni,ni] nullable (+jitter everywhere).  */
+int drp_ou_conditional_f64(const double* D, int64_t ldd, const int32_t* idx, int n, int ni, const double* sf,
+                           const double* sn, const double* lam, const double* x_leaf, int z, double jitter, double* mean,
+                           double* cov, double* M, int32_t* info, void* stream);
+
+/* ---- K10  Categorical(logits).log_prob(obs).sum(): S/models.py:352 (+ LogSoftmax S/models_utils.py:98) --------- */
+int64_t drp_cat_loglik_partials(int64_t rows);
+int drp_cat_loglik_fwd_f64(const double* scores, const void* obs, int obs_is_f64, int64_t rows, int A, double* out,
+                           double* lse, double* part, void* stream);
+int drp_cat_loglik_bwd_f64(const double* scores, const void* obs, int obs_is_f64, const double* lse, const double* g,
+                           int64_t rows, int A, double* dscores, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRAUPNIR_B200_H */

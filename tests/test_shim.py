@@ -1,0 +1,111 @@
+"""Host logic of the Pyro-compatible runtime, on CPU with toy models (the DRAUPNIR classes themselves need the GPU)."""
+import pytest
+import torch
+
+import draupnir_asr_b200.pyro_compat as pyro
+from draupnir_asr_b200.pyro_compat import distributions as dist, poutine
+from draupnir_asr_b200.pyro_compat.infer import SVI, Trace_ELBO
+from draupnir_asr_b200.pyro_compat.infer.autoguide import AutoDelta, init_to_value
+from draupnir_asr_b200.pyro_compat.nn import PyroModule, PyroParam
+from draupnir_asr_b200.pyro_compat.optim import ClippedAdam
+from oracle import draupnir_oracle as O
+
+torch.set_default_dtype(torch.float64)
+
+
+def _model(data):
+    s = pyro.sample("s", dist.HalfNormal(torch.tensor(1.0)).expand_by([2]).to_event(1)) + 1e-6
+    mu = pyro.sample("mu", dist.Normal(torch.zeros(()), s[0]))
+    with pyro.plate("d", len(data)):
+        pyro.sample("x", dist.Normal(mu, s[1]), obs=data)
+
+
+def test_trace_replay_and_elbo_sum():
+    pyro.clear_param_store()
+    data = torch.tensor([0.3, 1.2, -0.4])
+    init = {"s": torch.tensor([0.8, 1.1]), "mu": torch.tensor(0.25)}
+    guide = AutoDelta(_model, init_loc_fn=init_to_value(values=init))
+    loss = Trace_ELBO().differentiable_loss(_model, guide, data)
+    want = (torch.distributions.HalfNormal(torch.tensor(1.0)).log_prob(init["s"]).sum()
+            + torch.distributions.Normal(0.0, init["s"][0] + 1e-6).log_prob(init["mu"])
+            + torch.distributions.Normal(init["mu"], init["s"][1] + 1e-6).log_prob(data).sum())
+    assert torch.allclose(loss, -want, rtol=1e-14)
+    # positive sites live in log space, real sites are stored as they are
+    assert torch.allclose(guide.s_unconstrained.detach(), init["s"].log())
+    assert torch.allclose(guide.mu_unconstrained.detach(), init["mu"])
+
+
+def test_svi_step_equals_oracle_clipped_adam():
+    pyro.clear_param_store()
+    data = torch.tensor([0.3, 1.2, -0.4, 2.0])
+    init = {"s": torch.tensor([0.8, 1.1]), "mu": torch.tensor(0.25)}
+    guide = AutoDelta(_model, init_loc_fn=init_to_value(values=init))
+    svi = SVI(_model, guide, ClippedAdam({"lr": 0.05, "clip_norm": 0.7, "lrd": 0.99}), Trace_ELBO())
+    us, um = init["s"].log().clone().requires_grad_(True), init["mu"].clone().requires_grad_(True)
+    ref = O.ClippedAdam([us, um], lr=0.05, clip_norm=0.7, lrd=0.99)
+    for _ in range(4):
+        got = svi.step(data)
+        s = us.exp() + 1e-6
+        want = -(torch.distributions.HalfNormal(torch.tensor(1.0)).log_prob(us.exp()).sum()
+                 + torch.distributions.Normal(0.0, s[0]).log_prob(um)
+                 + torch.distributions.Normal(um, s[1]).log_prob(data).sum())
+        want.backward()
+        ref.step()
+        assert abs(got - float(want)) < 1e-12
+    assert torch.allclose(guide.s_unconstrained.detach(), us.detach(), rtol=1e-12)
+    assert torch.allclose(guide.mu_unconstrained.detach(), um.detach(), rtol=1e-12)
+
+
+def test_sizeless_plate_is_a_noop_and_subsampling_is_refused():
+    with pyro.plate("plate_batch", dim=-1):
+        assert True
+    with pytest.raises(NotImplementedError):
+        pyro.plate("p", 10, subsample_size=3)
+
+
+def test_delta_sites_score_zero_and_keep_shape():
+    v = torch.tensor([[0.5], [1.5], [2.5]])
+    d = dist.Delta(v).to_event(1)
+    assert d.batch_shape == (3,) and d.event_shape == (1,)
+    assert torch.equal(d.rsample(), v) and float(d.log_prob(v).sum()) == 0.0
+
+
+def test_pyro_module_registers_parameters_and_svi_updates_them():
+    pyro.clear_param_store()
+    lin = torch.nn.Linear(2, 1)
+    x, y = torch.randn(16, 2), torch.randn(16)
+
+    def model(x, y):
+        pyro.module("lin", lin)
+        pyro.sample("y", dist.Normal(lin(x).squeeze(-1), torch.tensor(1.0)).to_event(1), obs=y)
+
+    def guide(x, y):
+        return {}
+
+    before = lin.weight.detach().clone()
+    SVI(model, guide, ClippedAdam({"lr": 0.1}), Trace_ELBO()).step(x, y)
+    assert "lin$$$weight" in pyro.get_param_store() and not torch.equal(before, lin.weight.detach())
+    assert lin.weight.grad is None                                    # gradients are zeroed after the step
+
+
+def test_pyro_param_attribute_is_constrained_and_traced():
+    class G(PyroModule):
+        def __init__(self):
+            super().__init__()
+            self.alpha = PyroParam(torch.tensor([[0.5], [2.0]]), constraint=torch.distributions.constraints.positive)
+
+    g = G()
+    assert torch.allclose(g.alpha, torch.tensor([[0.5], [2.0]])) and "alpha_unconstrained" in dict(g.named_parameters())
+    with poutine.trace() as tr:
+        _ = g.alpha
+    (key, site), = tr.trace.param_sites()
+    assert site["unconstrained"] is g.alpha_unconstrained and key == "alpha@param"
+
+
+def test_install_as_pyro_makes_reference_imports_work():
+    assert pyro.install_as_pyro() in (True, False)
+    import pyro as p2
+    import pyro.distributions as d2
+    from pyro.infer import SVI as S2, Trace_ELBO as T2  # noqa: F401
+    from pyro.contrib.easyguide import EasyGuide  # noqa: F401
+    assert hasattr(p2, "sample") and hasattr(d2, "HalfNormal")
