@@ -11,13 +11,16 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdraupnir_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _i32, _i64, _f64, _p = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 
 # name -> (restype, argtypes); mirrors include/draupnir_b200.h one to one
 SIGNATURES = {
     "drp_abi_version": (_i32, []),
+    "drp_launch_count": (_i64, []),
+    "drp_timing_enable": (_i32, [_i32]),
+    "drp_timing_read": (_i32, [_p, _p, _p]),
     "drp_tree_prepare": (_i32, [_p, _p, _i32, _p, _p, _p, _p, _p, _p]),
     "drp_lca_workspace_bytes": (_i64, [_i32, _i32]),
     "drp_lca_patristic_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i32, _p, _p, _p, _p, _i64, _p]),

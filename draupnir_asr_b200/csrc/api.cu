@@ -1,4 +1,81 @@
-// ABI bookkeeping for libdraupnir_b200.so (see include/draupnir_b200.h).
+// ABI bookkeeping + instrumentation for libdraupnir_b200.so (see include/draupnir_b200.h).
 #include "common.cuh"
+#include "instrument.cuh"
+#include <atomic>
+#include <mutex>
+#include <vector>
 
-DRP_API int drp_abi_version(void) { return 1; }
+namespace {
+std::atomic<long long> g_launches[DRP_K_CLASSES];
+std::atomic<int> g_timing{0};
+std::mutex g_mu;
+struct Span { cudaEvent_t a, b; };
+std::vector<Span> g_spans[DRP_K_CLASSES];
+double g_work[DRP_K_CLASSES];
+cudaEvent_t g_pending[DRP_K_CLASSES];
+}  // namespace
+
+void drp_instr_begin(int k, double work, cudaStream_t st)
+{
+    g_launches[k].fetch_add(1, std::memory_order_relaxed);
+    if (!g_timing.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_work[k] += work;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    g_pending[k] = e;
+}
+
+void drp_instr_end(int k, cudaStream_t st)
+{
+    if (!g_timing.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    g_spans[k].push_back({g_pending[k], e});
+}
+
+DRP_API int drp_abi_version(void) { return 2; }
+
+// Cumulative number of kernels this library has launched (all classes).
+DRP_API int64_t drp_launch_count(void)
+{
+    long long s = 0;
+    for (int k = 0; k < DRP_K_CLASSES; ++k) s += g_launches[k].load();
+    return (int64_t)s;
+}
+
+// Enable (1) / disable (0) CUDA-event timing of every launch; enabling clears previous records.
+DRP_API int drp_timing_enable(int on)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int k = 0; k < DRP_K_CLASSES; ++k) {
+        for (auto& s : g_spans[k]) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+        g_spans[k].clear();
+        g_work[k] = 0.0;
+    }
+    g_timing.store(on ? 1 : 0);
+    return 0;
+}
+
+// Synchronises the device and fills, per kernel class k < DRP_K_CLASSES (8): ms[k] summed device time,
+// launches[k] timed launches, work[k] summed algorithmic flops (classes 0-2) or bytes (classes 3-6).
+DRP_API int drp_timing_read(double* ms, int64_t* launches, double* work)
+{
+    if (!ms || !launches || !work) return -1;
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int k = 0; k < DRP_K_CLASSES; ++k) {
+        double t = 0.0;
+        for (auto& s : g_spans[k]) {
+            float f = 0.f;
+            if (cudaEventElapsedTime(&f, s.a, s.b) == cudaSuccess) t += f;
+        }
+        ms[k] = t;
+        launches[k] = (int64_t)g_spans[k].size();
+        work[k] = g_work[k];
+    }
+    return 0;
+}

@@ -9,6 +9,7 @@
 // then owns one site.  The observations arrive as fp64 (the reference keeps residues in the fp64 dataset tensor and
 // casts with .long() inside log_prob) or as int64.
 #include "common.cuh"
+#include "instrument.cuh"
 
 namespace {
 
@@ -92,9 +93,15 @@ DRP_API int drp_cat_loglik_fwd_f64(const double* scores, const void* obs, int ob
         cudaFuncSetAttribute(cat_fwd_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 65 * 8);
         attr_done = true;
     }
-    if (obs_is_f64) cat_fwd_kernel<double><<<nb, 256, sm, st>>>(scores, (const double*)obs, rows, A, lse, part);
+    if (obs_is_f64) {
+        DRP_LAUNCH(DRP_K_CATLIK, ((double)rows * (A * 8.0 + 16.0)), st);
+        cat_fwd_kernel<double><<<nb, 256, sm, st>>>(scores, (const double*)obs, rows, A, lse, part);
+    }
     else cat_fwd_kernel<int64_t><<<nb, 256, sm, st>>>(scores, (const int64_t*)obs, rows, A, lse, part);
-    sum_kernel<<<1, 256, 0, st>>>(part, nb, out);
+    {
+        DRP_LAUNCH(DRP_K_CATLIK, ((double)nb * 8.0), st);
+        sum_kernel<<<1, 256, 0, st>>>(part, nb, out);
+    }
     return drp_launch_status();
 }
 
@@ -109,7 +116,10 @@ DRP_API int drp_cat_loglik_bwd_f64(const double* scores, const void* obs, int ob
     const int64_t total = rows * A;
     int64_t nb64 = (total + 255) / 256;
     const int nb = nb64 > 148 * 16 ? 148 * 16 : (int)nb64;
-    if (obs_is_f64) cat_bwd_kernel<double><<<nb, 256, 0, st>>>(scores, (const double*)obs, lse, g, rows, A, dscores);
+    if (obs_is_f64) {
+        DRP_LAUNCH(DRP_K_CATLIK, ((double)rows * (A * 16.0 + 16.0)), st);
+        cat_bwd_kernel<double><<<nb, 256, 0, st>>>(scores, (const double*)obs, lse, g, rows, A, dscores);
+    }
     else cat_bwd_kernel<int64_t><<<nb, 256, 0, st>>>(scores, (const int64_t*)obs, lse, g, rows, A, dscores);
     return drp_launch_status();
 }

@@ -25,6 +25,7 @@
 // (mma.sync m8n8k4); see DESIGN.md for the tcgen05 split-integer variant.
 #include "common.cuh"
 #include "factor.cuh"
+#include "instrument.cuh"
 
 namespace {
 
@@ -207,16 +208,25 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
         const int nb = min(NB, nfactor - c0);
         const int c1 = c0 + nb;
         const int R = grow_base > 0 ? min(R_full, grow_base + c1) : R_full;
-        potf2_kernel<<<z, 64, 0, st>>>(M, ld, bs, c0, nb, info);
+        {
+            DRP_LAUNCH(DRP_K_POTF2, (double)z * nb * nb * nb / 3.0, st);
+            potf2_kernel<<<z, 64, 0, st>>>(M, ld, bs, c0, nb, info);
+        }
         const int below = R - c1;
         if (below > 0) {
             dim3 g((below + PR - 1) / PR, z);
-            trsm_kernel<<<g, PR, TRSM_SMEM, st>>>(M, ld, bs, c0, nb, R);
+            {
+                DRP_LAUNCH(DRP_K_TRSM, (double)z * below * nb * nb, st);
+                trsm_kernel<<<g, PR, TRSM_SMEM, st>>>(M, ld, bs, c0, nb, R);
+            }
             const int T = (below + TS - 1) / TS;
             const int cl = min(R, col_limit) - c1;
             if (cl > 0) {
                 const int Tc = min(T, (cl + TS - 1) / TS);
                 dim3 gs(Tc, T, z);
+                // algorithmic flops: 2*nb per updated entry of the lower trapezoid rows [c1,R) x cols [c1,c1+cl)
+                const double entries = (double)cl * (cl + 1) / 2.0 + (double)(below - cl) * cl;
+                DRP_LAUNCH(DRP_K_SYRK, (double)z * entries * 2.0 * nb, st);
                 syrk_kernel<<<gs, 128, SYRK_SMEM, st>>>(M, ld, bs, c0, nb, c1, R, col_limit);
             }
         }
@@ -245,6 +255,7 @@ DRP_API int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32
     if (rc) return rc;
     if (zero_upper) {
         dim3 g((n + 255) / 256, n, z);
+        DRP_LAUNCH(DRP_K_OTHER, (double)z * n * n * 4.0, st);
         zero_upper_kernel<<<g, 256, 0, st>>>(A, n, n, (int64_t)n * n);
     }
     return drp_launch_status();

@@ -6,6 +6,7 @@
 //   DRAUPNIRModelClass.gp_prior                 S/models.py:85-121          sum_z log N(x_z; 0, K_z)
 //   conditional_sampling / conditional_samplingMAP   S/models.py:149-242    p(z_internal | z_leaves)
 #include "common.cuh"
+#include "instrument.cuh"
 #include "factor.cuh"
 
 namespace {
@@ -241,13 +242,17 @@ DRP_API int64_t drp_ou_workspace_elems(int n, int n2, int z)
 DRP_API int drp_ou_cov_fwd_f64(const double* D, int64_t ldd, int n, const double* sf, const double* sn, const double* lam,
                                int z, double* K, void* stream)
 {
+    cudaStream_t st = (cudaStream_t)stream;
     if (!D) return -1;
     if (n <= 0 || ldd < n) return -3;
     if (!sf || !sn || !lam) return -4;
     if (z <= 0) return -7;
     if (!K) return -8;
     dim3 g((n + 255) / 256, n);
-    ou_cov_fwd_kernel<<<g, 256, 3 * z * sizeof(double), (cudaStream_t)stream>>>(D, ldd, n, sf, sn, lam, z, K);
+    {
+        DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)n * n * 8.0 * (z + 1)), st);
+        ou_cov_fwd_kernel<<<g, 256, 3 * z * sizeof(double), (cudaStream_t)stream>>>(D, ldd, n, sf, sn, lam, z, K);
+    }
     return drp_launch_status();
 }
 
@@ -262,8 +267,14 @@ DRP_API int drp_ou_cov_bwd_f64(const double* D, int64_t ldd, int n, const double
     if (z <= 0) return -5;
     if (!G || !part || !out) return -6;
     cudaStream_t st = (cudaStream_t)stream;
-    ou_cov_bwd_kernel<<<dim3(n, z), 256, 0, st>>>(D, ldd, n, lam, G, part);
-    reduce3_kernel<<<z, 256, 0, st>>>(part, n, out);
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)n * n * 8.0 * (z + 1)), st);
+        ou_cov_bwd_kernel<<<dim3(n, z), 256, 0, st>>>(D, ldd, n, lam, G, part);
+    }
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 24.0), st);
+        reduce3_kernel<<<z, 256, 0, st>>>(part, n, out);
+    }
     return drp_launch_status();
 }
 
@@ -286,14 +297,29 @@ DRP_API int drp_ou_prior_f64(const double* D, int64_t ldd, int n, const double* 
     const int R = n + 1 + n2;
     const int64_t ld = drp_ou_workspace_ld(n, n2), bs = (int64_t)R * ld;
     dim3 g((R + 255) / 256, R);
-    ou_assemble_kernel<<<g, 256, 3 * z * sizeof(double), st>>>(D, ldd, nullptr, n, n2, 1, sf, sn, lam, x, z, M, ld, bs);
+    {
+        DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)z * R * (R + 1) * 4.0), st);
+        ou_assemble_kernel<<<g, 256, 3 * z * sizeof(double), st>>>(D, ldd, nullptr, n, n2, 1, sf, sn, lam, x, z, M, ld, bs);
+    }
     int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, st);
     if (rc) return rc;
-    mvn_finish_kernel<<<z, 256, 0, st>>>(M, ld, bs, n, logp);
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 8.0), st);
+        mvn_finish_kernel<<<z, 256, 0, st>>>(M, ld, bs, n, logp);
+    }
     if (want_grad) {
-        alpha_extract_kernel<<<dim3((n + 255) / 256, z), 256, 0, st>>>(M, ld, bs, n, n, alpha);
-        ou_grad_kernel<<<dim3(n, z), 256, 0, st>>>(M, ld, bs, n, D, ldd, lam, part);
-        reduce3_kernel<<<z, 256, 0, st>>>(part, n, gsum);
+        {
+            DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 16.0), st);
+            alpha_extract_kernel<<<dim3((n + 255) / 256, z), 256, 0, st>>>(M, ld, bs, n, n, alpha);
+        }
+        {
+            DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * n * 4.0 + (double)n * n * 4.0), st);
+            ou_grad_kernel<<<dim3(n, z), 256, 0, st>>>(M, ld, bs, n, D, ldd, lam, part);
+        }
+        {
+            DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 24.0), st);
+            reduce3_kernel<<<z, 256, 0, st>>>(part, n, gsum);
+        }
     }
     return drp_launch_status();
 }
@@ -312,23 +338,36 @@ DRP_API int drp_mvn_logprob_f64(const double* K, const double* x, int n, int z, 
     const int n2 = want_grad ? n : 0;
     const int R = n + 1 + n2;
     const int64_t ld = drp_ou_workspace_ld(n, n2), bs = (int64_t)R * ld;
-    cov_assemble_kernel<<<dim3((R + 255) / 256, R, z), 256, 0, st>>>(K, n, x, M, ld, bs);
+    {
+        DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)z * R * (R + 1) * 4.0 + (double)z * n * n * 4.0), st);
+        cov_assemble_kernel<<<dim3((R + 255) / 256, R, z), 256, 0, st>>>(K, n, x, M, ld, bs);
+    }
     int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, st);
     if (rc) return rc;
-    mvn_finish_kernel<<<z, 256, 0, st>>>(M, ld, bs, n, logp);
-    if (want_grad) alpha_extract_kernel<<<dim3((n + 255) / 256, z), 256, 0, st>>>(M, ld, bs, n, n, alpha);
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 8.0), st);
+        mvn_finish_kernel<<<z, 256, 0, st>>>(M, ld, bs, n, logp);
+    }
+    if (want_grad) {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 16.0), st);
+        alpha_extract_kernel<<<dim3((n + 255) / 256, z), 256, 0, st>>>(M, ld, bs, n, n, alpha);
+    }
     return drp_launch_status();
 }
 
 // G[z,n,n] = gscale[z] * dlogp_z/dK_z from a workspace factored by drp_mvn_logprob_f64 / drp_ou_prior_f64 (want_grad=1).
 DRP_API int drp_mvn_grad_cov_f64(const double* M, int n, int z, const double* gscale, double* G, void* stream)
 {
+    cudaStream_t st = (cudaStream_t)stream;
     if (!M) return -1;
     if (n <= 0 || z <= 0) return -2;
     if (!G) return -5;
     const int R = 2 * n + 1;
     const int64_t ld = drp_ou_workspace_ld(n, n), bs = (int64_t)R * ld;
-    mvn_grad_cov_kernel<<<dim3((n + 255) / 256, n, z), 256, 0, (cudaStream_t)stream>>>(M, ld, bs, n, gscale, G);
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * n * 12.0), st);
+        mvn_grad_cov_kernel<<<dim3((n + 255) / 256, n, z), 256, 0, (cudaStream_t)stream>>>(M, ld, bs, n, gscale, G);
+    }
     return drp_launch_status();
 }
 
@@ -342,10 +381,16 @@ DRP_API int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, d
     const int R = 2 * n + 1;
     const int64_t ld = drp_ou_workspace_ld(n, n), bs = (int64_t)R * ld;
     cudaMemsetAsync(Kinv, 0, sizeof(double) * (size_t)z * n, st);   // borrowed as the zero right-hand side x
-    cov_assemble_kernel<<<dim3((R + 255) / 256, R, z), 256, 0, st>>>(K, n, Kinv, M, ld, bs);
+    {
+        DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)z * R * (R + 1) * 4.0 + (double)z * n * n * 4.0), st);
+        cov_assemble_kernel<<<dim3((R + 255) / 256, R, z), 256, 0, st>>>(K, n, Kinv, M, ld, bs);
+    }
     int rc = drp_factor_run(M, ld, bs, z, n, R, n + 1, R, info, st);
     if (rc) return rc;
-    block_extract_kernel<<<dim3((n + 255) / 256, n, z), 256, 0, st>>>(M, ld, bs, n, n, -1.0, 0.0, Kinv);
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * n * 12.0), st);
+        block_extract_kernel<<<dim3((n + 255) / 256, n, z), 256, 0, st>>>(M, ld, bs, n, n, -1.0, 0.0, Kinv);
+    }
     return drp_launch_status();
 }
 
@@ -366,11 +411,20 @@ DRP_API int drp_ou_conditional_f64(const double* D, int64_t ldd, const int32_t* 
     cudaStream_t st = (cudaStream_t)stream;
     const int R = n + 1 + ni;
     const int64_t ld = drp_ou_workspace_ld(n, ni), bs = (int64_t)R * ld;
-    ou_assemble_kernel<<<dim3((R + 255) / 256, R), 256, 3 * z * sizeof(double), st>>>(D, ldd, idx, n, ni, 0, sf, sn, lam,
+    {
+        DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)z * R * (R + 1) * 4.0), st);
+        ou_assemble_kernel<<<dim3((R + 255) / 256, R), 256, 3 * z * sizeof(double), st>>>(D, ldd, idx, n, ni, 0, sf, sn, lam,
                                                                                   x_leaf, z, M, ld, bs);
+    }
     int rc = drp_factor_run(M, ld, bs, z, n, R, 0, cov ? R : n + 1, info, st);
     if (rc) return rc;
-    alpha_extract_kernel<<<dim3((ni + 255) / 256, z), 256, 0, st>>>(M, ld, bs, n, ni, mean);
-    if (cov) block_extract_kernel<<<dim3((ni + 255) / 256, ni, z), 256, 0, st>>>(M, ld, bs, n, ni, 1.0, jitter, cov);
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 16.0), st);
+        alpha_extract_kernel<<<dim3((ni + 255) / 256, z), 256, 0, st>>>(M, ld, bs, n, ni, mean);
+    }
+    if (cov) {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * n * 12.0), st);
+        block_extract_kernel<<<dim3((ni + 255) / 256, ni, z), 256, 0, st>>>(M, ld, bs, n, ni, 1.0, jitter, cov);
+    }
     return drp_launch_status();
 }

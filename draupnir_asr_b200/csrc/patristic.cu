@@ -9,6 +9,7 @@
 // preorder interval) contains j, found by binary search over the chain held in shared memory: O(log depth) per pair,
 // no N x log N tables, output written once, coalesced, in the reference's row-major level-order layout.
 #include "common.cuh"
+#include "instrument.cuh"
 
 namespace {
 
@@ -104,10 +105,14 @@ __global__ void __launch_bounds__(256) lca_patristic_kernel(const int32_t* __res
 DRP_API int drp_tree_prepare(const int32_t* parent, const double* branch, int32_t n_nodes, int32_t* depth, double* root_dist,
                              int32_t* pre, int32_t* size, int32_t* scratch, void* stream)
 {
+    cudaStream_t st = (cudaStream_t)stream;
     if (!parent || !branch) return -1;
     if (n_nodes <= 0) return -3;
     if (!depth || !root_dist || !pre || !size || !scratch) return -4;
-    tree_prepare_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(parent, branch, n_nodes, depth, root_dist, pre, size, scratch);
+    {
+        DRP_LAUNCH(DRP_K_PATRISTIC, ((double)n_nodes * 40.0), st);
+        tree_prepare_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(parent, branch, n_nodes, depth, root_dist, pre, size, scratch);
+    }
     return drp_launch_status();
 }
 
@@ -123,11 +128,15 @@ DRP_API int drp_lca_patristic_f64(const int32_t* parent, const int32_t* depth, c
                                   const int32_t* cols, int32_t nc, int32_t* lca_out, double* dist_out, double* clad_out,
                                   void* ws, int64_t ws_bytes, void* stream)
 {
+    cudaStream_t st = (cudaStream_t)stream;
     if (!parent || !depth || !root_dist || !pre || !size) return -1;
     if (n_nodes <= 0) return -6;
     if (nr <= 0 || nc <= 0) return -9;
     if (ws_bytes < drp_lca_workspace_bytes(nr, max_depth) || (ws_bytes > 0 && !ws)) return -16;
-    lca_patristic_kernel<<<nr, 256, 0, (cudaStream_t)stream>>>(parent, depth, root_dist, pre, size, rows, cols, nc, lca_out,
+    {
+        DRP_LAUNCH(DRP_K_PATRISTIC, ((double)nr * nc * ((dist_out ? 8.0 : 0.0) + (clad_out ? 8.0 : 0.0) + (lca_out ? 4.0 : 0.0))), st);
+        lca_patristic_kernel<<<nr, 256, 0, (cudaStream_t)stream>>>(parent, depth, root_dist, pre, size, rows, cols, nc, lca_out,
                                                                 dist_out, clad_out, (ChainEntry*)ws, max_depth + 1);
+    }
     return drp_launch_status();
 }

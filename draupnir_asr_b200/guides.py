@@ -57,10 +57,27 @@ class DRAUPNIRGUIDES(EasyGuide):
         return self.guide_noplating(family_data, patristic_matrix, cladistic_matrix, data_blosum, batch_blosum=None)
 
     def _encode(self, data_blosum):
+        shard = getattr(self.draupnir, "shard", None)
+        n = data_blosum.shape[0]
+        if shard is not None:        # encoder is data-parallel over contiguous blocks of leaves
+            data_blosum = data_blosum[shard.leaf_lo:shard.leaf_hi]
         aminoacid_sequences = self.embeddingencoder(data_blosum)
         encoder_h_0 = self.h_0_GUIDE.expand(self.encoder.num_layers * 2, aminoacid_sequences.shape[0],
                                             self.draupnir.gru_hidden_dim).contiguous()
-        return self.encoder(aminoacid_sequences, encoder_h_0), aminoacid_sequences.shape[0]
+        out = self.encoder(aminoacid_sequences, encoder_h_0)
+        if shard is not None:        # one all-gather of [z_loc | z_scale] rebuilds the [n, z] posterior parameters
+            z = out["z_loc"].shape[1]
+            both = shard.gather_leaf_rows(torch.cat((out["z_loc"], out["z_scale"]), dim=1))
+            out = dict(out, z_loc=both[:, :z], z_scale=both[:, z:])
+        return out, n
+
+    def _latent_site(self, out):
+        shard = getattr(self.draupnir, "shard", None)
+        q = dist.Normal(out["z_loc"].T, out["z_scale"].T)
+        if shard is None:
+            return pyro.sample("latent_z", q)
+        with pyro.poutine.scale(scale=shard.replicated_scale):   # q(z) is replicated: scored on rank 0 only
+            return pyro.sample("latent_z", q)
 
     @staticmethod
     def _result(alpha, sigma_n, sigma_f, lambd, latent_z, out):
@@ -77,7 +94,7 @@ class DRAUPNIRGUIDES(EasyGuide):
         pyro.module("embeddingsencoder", self.embeddingencoder)
         with pyro.plate("plate_batch", dim=-1, device=self.draupnir.device):
             out, n = self._encode(self.dataset_train_blosum)
-            latent_z = pyro.sample("latent_z", dist.Normal(out["z_loc"].T, out["z_scale"].T))
+            latent_z = self._latent_site(out)
             assert latent_z.shape == (self.draupnir.z_dim, n)
         return self._result(alpha, sigma_n, sigma_f, lambd, latent_z, out)
 
@@ -92,6 +109,6 @@ class DRAUPNIRGUIDES(EasyGuide):
             sigma_f = pyro.sample("sigma_f", dist.Delta(self.sigma_f).to_event(1))
             lambd = pyro.sample("lambd", dist.Delta(self.lambd).to_event(1))
             out, n = self._encode(data_blosum)
-            latent_z = pyro.sample("latent_z", dist.Normal(out["z_loc"].T, out["z_scale"].T))
+            latent_z = self._latent_site(out)
             assert latent_z.shape == (self.draupnir.z_dim, n)
         return self._result(alpha, sigma_n, sigma_f, lambd, latent_z, out)

@@ -79,6 +79,7 @@ class DRAUPNIRModelClass(nn.Module):
         self.h_0_MODEL = nn.Parameter(torch.randn(self.gru_hidden_dim, dtype=torch.float64), requires_grad=False)
         self._one = None
         self._pos_cache = {}
+        self.shard = None          # zshard.ShardContext when the run is spread over several GPUs
         for name in ("blosum_weighted", "dataset_train_blosum", "internal_nodes", "leaves_nodes", "aa_frequencies",
                      "blosum", "blosum_max"):
             t = getattr(self, name)
@@ -107,6 +108,12 @@ class DRAUPNIRModelClass(nn.Module):
         """The four HalfNormal sites of S/models.py:89-92 (sampled/replayed through pyro, +eps as the reference)."""
         if self._one is None or self._one.device != self.h_0_MODEL.device:
             self._one = torch.ones((), dtype=torch.float64, device=self.h_0_MODEL.device)
+        if self.shard is not None:   # replicated sites are scored on rank 0 only (zshard.py)
+            with pyro.poutine.scale(scale=self.shard.replicated_scale):
+                return self._hyper_prior_sites(eps)
+        return self._hyper_prior_sites(eps)
+
+    def _hyper_prior_sites(self, eps: float):
         alpha = pyro.sample("alpha", dist.HalfNormal(self._one).expand_by([3, ]).to_event(1)) + eps
         sigma_f = pyro.sample("sigma_f", dist.HalfNormal(alpha[0]).expand_by([self.z_dim, ]).to_event(1)) + eps
         sigma_n = pyro.sample("sigma_n", dist.HalfNormal(alpha[1]).expand_by([self.z_dim, ]).to_event(1)) + eps
@@ -121,8 +128,9 @@ class DRAUPNIRModelClass(nn.Module):
         n_expected = self.n_all if self.leaves_testing else self.n_leaves
         assert patristic_matrix.shape == (n_expected, n_expected), \
             f"Expected shape {(self.z_dim, n_expected, n_expected)}, got {(self.z_dim,) + tuple(patristic_matrix.shape)}"
-        latent_space = pyro.sample("latent_z",
-                                   dist.OUProcessPrior(patristic_matrix, sigma_f, sigma_n, lambd).to_event(1))  # [z, n]
+        z_slice = None if self.shard is None else (self.shard.z_lo, self.shard.z_hi)
+        latent_space = pyro.sample("latent_z", dist.OUProcessPrior(patristic_matrix, sigma_f, sigma_n, lambd,
+                                                                   z_slice=z_slice).to_event(1))  # [z, n]
         return latent_space.T
 
     def gp_prior_batched(self, patristic_matrix_sorted):
@@ -216,6 +224,9 @@ class DRAUPNIRModel_classic(DRAUPNIRModelClass):
         return self.h_0_MODEL.expand(self.decoder.num_layers * 2, n, self.gru_hidden_dim).contiguous()
 
     def _likelihood(self, latent_space, aminoacid_sequences):
+        if self.shard is not None:   # decoder is data-parallel over contiguous blocks of leaves
+            lo, hi = self.shard.leaf_lo, self.shard.leaf_hi
+            latent_space, aminoacid_sequences = latent_space[lo:hi], aminoacid_sequences[lo:hi]
         x = self._decoder_input(latent_space)
         scores = self.decoder.scores(input=x, hidden=self._hidden(latent_space.shape[0]))
         pyro.sample("aa_sequences", dist.Categorical(logits=scores), obs=aminoacid_sequences)

@@ -184,8 +184,11 @@ class OUProcessPrior(td.Distribution, TorchDistributionMixin):
     arg_constraints = {}
     support = constraints.real_vector
 
-    def __init__(self, patristic, sigma_f, sigma_n, lambd, validate_args=None):
+    def __init__(self, patristic, sigma_f, sigma_n, lambd, z_slice=None, validate_args=None):
         self.patristic, self.sigma_f, self.sigma_n, self.lambd = patristic, sigma_f, sigma_n, lambd
+        # z_slice = (lo, hi): this process owns only these latent dimensions (multi-GPU z-sharding); log_prob then
+        # returns the densities of the slice alone, the other ranks contribute theirs
+        self.z_slice = z_slice
         super().__init__(torch.Size([sigma_f.shape[0]]), torch.Size([patristic.shape[0]]), validate_args=False)
 
     @property
@@ -199,6 +202,12 @@ class OUProcessPrior(td.Distribution, TorchDistributionMixin):
 
     def log_prob(self, value):
         from .. import ops
+        if self.z_slice is not None:
+            lo, hi = self.z_slice
+            if hi <= lo:
+                return value.new_zeros(0)
+            return ops.ou_prior_logp(self.patristic, self.sigma_f[lo:hi], self.sigma_n[lo:hi], self.lambd[lo:hi],
+                                     value[lo:hi])
         return ops.ou_prior_logp(self.patristic, self.sigma_f, self.sigma_n, self.lambd, value)
 
     def rsample(self, sample_shape=torch.Size()):

@@ -54,8 +54,9 @@ class Trace_ELBO:
 
 
 class SVI:
-    def __init__(self, model, guide, optim, loss, **kwargs):
+    def __init__(self, model, guide, optim, loss, shard=None, **kwargs):
         self.model, self.guide, self.optim, self.loss = model, guide, optim, loss
+        self.shard = shard     # zshard.ShardContext: local losses/gradients are summed over the ranks before the update
 
     def step(self, *args, **kwargs) -> float:
         """One gradient step; returns the loss as a Python float (the only host<->device synchronisation)."""
@@ -63,6 +64,8 @@ class SVI:
         with ops.defer_info_checks():
             loss = self.loss.loss_and_grads(self.model, self.guide, *args, **kwargs)
             params = _unconstrained_params(*self.loss.last_traces)
+            if self.shard is not None:
+                loss = self.shard.reduce_step(params, loss)
             self.optim(params)
             for p in params:
                 p.grad = None

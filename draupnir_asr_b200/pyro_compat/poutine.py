@@ -132,6 +132,18 @@ class block(Messenger):
             msg["stop"] = True
 
 
+class scale(Messenger):
+    """poutine.scale: multiplies the log-density of the enclosed sample sites by `scale`."""
+
+    def __init__(self, fn=None, scale: float = 1.0):
+        super().__init__(fn)
+        self.scale = scale
+
+    def _process_message(self, msg):
+        if msg["type"] == "sample":
+            msg["scale"] = msg["scale"] * self.scale
+
+
 class CondIndepStackFrame(tuple):
     def __new__(cls, name, dim, size):
         return super().__new__(cls, (name, dim, size))

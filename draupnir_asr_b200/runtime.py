@@ -68,9 +68,31 @@ class Run(SimpleNamespace):
     def step(self) -> float:
         return self.svi.step(*self.step_args())
 
+    # ---- the same call with HOST inputs: what a caller holding CPU tensors pays per step --------------------------
+    def make_host_inputs(self):
+        """Pinned host copies of the tensors `svi.step` consumes (S/train.py:75): the dataset, the leaves' patristic
+        matrix and, for the variational guide, the BLOSUM-encoded dataset."""
+        pin = lambda t: t.detach().cpu().contiguous().pin_memory()
+        host = {"dataset": pin(self.problem.dataset_train), "patristic": pin(self.problem.patristic_matrix_train)}
+        if self.select_guide == "variational":
+            host["blosum"] = pin(self.problem.dataset_train_blosum)
+        self._staging = {k: torch.empty_like(v, device=self.device) for k, v in host.items()}
+        return host
+
+    def host_bytes_per_step(self, host) -> int:
+        return int(sum(v.numel() * v.element_size() for v in host.values()))
+
+    def step_from_host(self, host) -> float:
+        """H2D of the step inputs (pinned, async, same stream) -> svi.step -> loss back to the host as a float."""
+        for k, v in host.items():
+            self._staging[k].copy_(v, non_blocking=True)
+        st = self._staging
+        return self.svi.step(st["dataset"], st["patristic"], None, st.get("blosum"), None, None)
+
 
 def build_run(problem: SyntheticProblem, select_guide: str, device="cuda", init: Optional[Dict[str, torch.Tensor]] = None,
-              z_dim=30, gru_hidden_dim=60, embedding_dim=50, config: Optional[dict] = None, seed: int = 0) -> Run:
+              z_dim=30, gru_hidden_dim=60, embedding_dim=50, config: Optional[dict] = None, seed: int = 0,
+              shard=None) -> Run:
     """Mirror of `draupnir_train`'s setup (S/main.py:991-1059): ModelLoad -> DRAUPNIRModel_classic -> guide
     (`AutoDelta` for delta_map, `DRAUPNIRGUIDES` otherwise) -> Trace_ELBO -> ClippedAdam -> SVI."""
     assert select_guide in ("delta_map", "variational")
@@ -82,6 +104,7 @@ def build_run(problem: SyntheticProblem, select_guide: str, device="cuda", init:
     try:
         ml = model_load_from_problem(problem, select_guide, device, z_dim, gru_hidden_dim, embedding_dim)
         Draupnir = DRAUPNIRModel_classic(ml)
+        Draupnir.shard = shard
         if select_guide == "delta_map":
             values = None if init is None else {k: v.to(ml.device) for k, v in init.items()}
             guide = AutoDelta(Draupnir.model, init_loc_fn=init_to_value(values=values))
@@ -95,7 +118,7 @@ def build_run(problem: SyntheticProblem, select_guide: str, device="cuda", init:
         torch.random.set_rng_state(gen_state)
     optim = ClippedAdam({"lr": cfg["lr"], "betas": (cfg["beta1"], cfg["beta2"]), "eps": cfg["eps"],
                          "weight_decay": cfg["weight_decay"], "clip_norm": cfg["clip_norm"], "lrd": cfg["lrd"]})
-    svi = SVI(Draupnir.model, guide, optim, Trace_ELBO())
+    svi = SVI(Draupnir.model, guide, optim, Trace_ELBO(), shard=shard)
     dev = ml.device
     return Run(Draupnir=Draupnir, guide=guide, svi=svi, optim=optim, model_load=ml, device=dev,
                dataset_train=problem.dataset_train.to(dev), patristic_matrix_train=problem.patristic_matrix_train.to(dev),

@@ -28,6 +28,15 @@ extern "C" {
 /* ABI version (bumped on any signature change). */
 int drp_abi_version(void);
 
+/* ---- instrumentation (bench.py: `gpu_launches` and the live per-kernel roofline) -------------------------------- */
+/* Cumulative number of kernels launched by this library.                                                            */
+int64_t drp_launch_count(void);
+/* CUDA-event timing of every launch, by kernel class: 0 syrk, 1 trsm, 2 potf2 (work = flops), 3 assembly,
+ * 4 reductions, 5 categorical, 6 patristic (work = bytes), 7 other.  enable(1) clears earlier records;
+ * read() synchronises the device and fills three arrays of 8 entries (HOST pointers).                              */
+int drp_timing_enable(int on);
+int drp_timing_read(double* ms, int64_t* launches, double* work);
+
 /* ---- K1  patristic builder: S/utils.py:496-579 (ete3 get_distance loop) and S/Calculate_Patristic.R:9 --------- */
 /* Tree given as parent[] / branch[] with parent[v] < v (level-order ids, root 0, S/utils.py:864).                  */
 int drp_tree_prepare(const int32_t* parent, const double* branch, int32_t n_nodes, int32_t* depth, double* root_dist,
