@@ -31,7 +31,8 @@ Z_DIM = 30
 METRIC = "svi_steps_per_sec"
 UNIT = "steps/s"
 FP64_TENSOR_NOMINAL_TFLOPS = 40.0          # B200 data sheet, dense fp64 (tensor and CUDA-core figures coincide)
-KCLASS = ["syrk", "trsm", "potf2", "assemble", "reduce", "catlik", "patristic", "other"]
+KCLASS = ["syrk", "trsm", "potf2", "assemble", "reduce", "catlik", "patristic", "other", "syrk_tcgen05", "slice"]
+FLOP_CLASSES = (0, 1, 2, 8)
 
 
 def log(*a):
@@ -197,9 +198,10 @@ def run_ours(args, w, rank, world, local_rank):
     l0 = lib.drp_launch_count()
     ms = timed(run.step, args.steps)
     launches = lib.drp_launch_count() - l0
-    kms = (ctypes.c_double * 8)()
-    kln = (ctypes.c_int64 * 8)()
-    kwk = (ctypes.c_double * 8)()
+    NK = lib.drp_timing_classes()
+    kms = (ctypes.c_double * NK)()
+    kln = (ctypes.c_int64 * NK)()
+    kwk = (ctypes.c_double * NK)()
     lib.drp_timing_read(kms, kln, kwk)
     lib.drp_timing_enable(0)
     barrier()
@@ -218,9 +220,9 @@ def run_ours(args, w, rank, world, local_rank):
 
     peaks = measured_peaks()
     per_class = {KCLASS[k]: {"ms_per_step": kms[k] / args.steps, "launches_per_step": kln[k] / args.steps,
-                             "work_per_step": kwk[k] / args.steps} for k in range(8) if kln[k]}
-    dom = max(range(8), key=lambda k: kms[k])
-    tensor_bound = dom in (0, 1, 2)
+                             "work_per_step": kwk[k] / args.steps} for k in range(NK) if kln[k]}
+    dom = max(range(NK), key=lambda k: kms[k])
+    tensor_bound = dom in FLOP_CLASSES
     avg_ms = kms[dom] / max(kln[dom], 1)
     work_per_launch = kwk[dom] / max(kln[dom], 1)
     achieved = work_per_launch / (avg_ms * 1e-3) / (1e12 if tensor_bound else 1e9)

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdraupnir_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _i32, _i64, _f64, _p = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 
@@ -19,6 +19,7 @@ _i32, _i64, _f64, _p = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c
 SIGNATURES = {
     "drp_abi_version": (_i32, []),
     "drp_launch_count": (_i64, []),
+    "drp_timing_classes": (_i32, []),
     "drp_timing_enable": (_i32, [_i32]),
     "drp_timing_read": (_i32, [_p, _p, _p]),
     "drp_tree_prepare": (_i32, [_p, _p, _i32, _p, _p, _p, _p, _p, _p]),
@@ -26,7 +27,9 @@ SIGNATURES = {
     "drp_lca_patristic_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i32, _p, _p, _p, _p, _i64, _p]),
     "drp_ou_cov_fwd_f64": (_i32, [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p]),
     "drp_ou_cov_bwd_f64": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _p]),
-    "drp_potrf_batched_f64": (_i32, [_p, _i32, _i32, _i32, _p, _p]),
+    "drp_factor_workspace_bytes": (_i64, [_i32, _i32]),
+    "drp_potrf_batched_f64": (_i32, [_p, _i32, _i32, _i32, _p, _p, _i64, _p]),
+    "drp_syrk_update_f64": (_i32, [_p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),
     "drp_ou_workspace_ld": (_i64, [_i32, _i32]),
     "drp_ou_workspace_elems": (_i64, [_i32, _i32, _i32]),
     "drp_ou_prior_f64": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),

@@ -37,7 +37,10 @@ void drp_instr_end(int k, cudaStream_t st)
     g_spans[k].push_back({g_pending[k], e});
 }
 
-DRP_API int drp_abi_version(void) { return 2; }
+DRP_API int drp_abi_version(void) { return 3; }
+
+// Number of kernel classes reported by drp_timing_read (length of its three arrays).
+DRP_API int drp_timing_classes(void) { return DRP_K_CLASSES; }
 
 // Cumulative number of kernels this library has launched (all classes).
 DRP_API int64_t drp_launch_count(void)
@@ -60,8 +63,8 @@ DRP_API int drp_timing_enable(int on)
     return 0;
 }
 
-// Synchronises the device and fills, per kernel class k < DRP_K_CLASSES (8): ms[k] summed device time,
-// launches[k] timed launches, work[k] summed algorithmic flops (classes 0-2) or bytes (classes 3-6).
+// Synchronises the device and fills, per kernel class k < drp_timing_classes(): ms[k] summed device time,
+// launches[k] timed launches, work[k] summed algorithmic flops (classes 0-2, 8) or bytes (classes 3-6, 9).
 DRP_API int drp_timing_read(double* ms, int64_t* launches, double* work)
 {
     if (!ms || !launches || !work) return -1;

@@ -128,10 +128,10 @@ __global__ void __launch_bounds__(PR) trsm_kernel(double* __restrict__ Mb, int64
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// syrk: C[r][c] -= sum_k P[r][k] P[c][k] for r, c in [c1, R), c <= r, c < col_limit; P = columns c0..c0+nb.
-// 64x64 output tile per CTA, 4 warps (2x2) of 32x32, fp64 mma.sync m8n8k4.
+// syrk: C[r][c] -= sum_{k in [k0, k0+K)} P[r][k] P[c][k] for r in [c1, R), c in [c1, min(R, col_limit)), c <= r.
+// 64x64 output tile per CTA, 4 warps (2x2) of 32x32, fp64 mma.sync m8n8k4, K consumed in chunks of 64.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) syrk_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb, int c1,
+__global__ void __launch_bounds__(128) syrk_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int k0, int K, int c1,
                                                    int R, int col_limit)
 {
     const int tj = blockIdx.x, ti = blockIdx.y;
@@ -142,17 +142,6 @@ __global__ void __launch_bounds__(128) syrk_kernel(double* __restrict__ Mb, int6
     double* A = Mb + (int64_t)blockIdx.z * bs;
     const int tid = threadIdx.x;
     const int r0 = c1 + ti * TS, q0 = c1 + tj * TS;
-    for (int idx = tid; idx < TS * NB; idx += 128) {
-        const int r = idx / NB, k = idx - r * NB;
-        As[r * SLD + k] = (r0 + r < R && k < nb) ? A[(int64_t)(r0 + r) * ld + c0 + k] : 0.0;
-    }
-    if (ti != tj) {
-        for (int idx = tid; idx < TS * NB; idx += 128) {
-            const int r = idx / NB, k = idx - r * NB;
-            Bs[r * SLD + k] = (q0 + r < R && k < nb) ? A[(int64_t)(q0 + r) * ld + c0 + k] : 0.0;
-        }
-    }
-    __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
     double acc[4][4][2];
@@ -162,17 +151,32 @@ __global__ void __launch_bounds__(128) syrk_kernel(double* __restrict__ Mb, int6
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const double* ap = As + (wm * 32 + gid) * SLD + tig;
     const double* bp = Bs + (wn * 32 + gid) * SLD + tig;
-    const int kmax = (nb + 3) & ~3;
-    for (int k = 0; k < kmax; k += 4) {
-        double a[4], b[4];
+    for (int kc = 0; kc < K; kc += NB) {
+        const int kb = min(NB, K - kc);
+        if (kc) __syncthreads();
+        for (int idx = tid; idx < TS * NB; idx += 128) {
+            const int r = idx / NB, k = idx - r * NB;
+            As[r * SLD + k] = (r0 + r < R && k < kb) ? A[(int64_t)(r0 + r) * ld + k0 + kc + k] : 0.0;
+        }
+        if (ti != tj) {
+            for (int idx = tid; idx < TS * NB; idx += 128) {
+                const int r = idx / NB, k = idx - r * NB;
+                Bs[r * SLD + k] = (q0 + r < R && k < kb) ? A[(int64_t)(q0 + r) * ld + k0 + kc + k] : 0.0;
+            }
+        }
+        __syncthreads();
+        const int kmax = (kb + 3) & ~3;
+        for (int k = 0; k < kmax; k += 4) {
+            double a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = ap[i * 8 * SLD + k];
+            for (int i = 0; i < 4; ++i) a[i] = ap[i * 8 * SLD + k];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = bp[j * 8 * SLD + k];
+            for (int j = 0; j < 4; ++j) b[j] = bp[j * 8 * SLD + k];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
     }
     const int cmax = min(R, col_limit);
 #pragma unroll
@@ -191,45 +195,89 @@ __global__ void __launch_bounds__(128) syrk_kernel(double* __restrict__ Mb, int6
 
 }  // namespace
 
+#include <stdlib.h>
 static const int TRSM_SMEM = (NB * PLD + NB + PR * PLD) * (int)sizeof(double);
 static const int SYRK_SMEM = 2 * TS * SLD * (int)sizeof(double);
 
+void drp_dmma_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, cudaStream_t st)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM);
+        attr_done = true;
+    }
+    const int below = R - c1;
+    const int cl = min(R, col_limit) - c1;
+    if (below <= 0 || cl <= 0) return;
+    const int T = (below + TS - 1) / TS;
+    const int Tc = min(T, (cl + TS - 1) / TS);
+    // algorithmic flops: 2*K per updated entry of the lower trapezoid rows [c1,R) x cols [c1,c1+cl)
+    const double entries = (double)cl * (cl + 1) / 2.0 + (double)(below - cl) * cl;
+    DRP_LAUNCH(DRP_K_SYRK, (double)z * entries * 2.0 * K, st);
+    syrk_kernel<<<dim3(Tc, T, z), 128, SYRK_SMEM, st>>>(M, ld, bs, k0, K, c1, R, col_limit);
+}
+
+// Trailing update: int8 tcgen05 pipe when a workspace is given and the update is large, fp64 mma.sync otherwise.
+static int trailing_update(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, void* ws,
+                           int64_t ws_bytes, cudaStream_t st)
+{
+    const int rc = drp_ozaki_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, drp_ozaki_slices(), ws, ws_bytes, st);
+    if (rc != 1) return rc;
+    drp_dmma_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, st);
+    return 0;
+}
+
+static int outer_block(int R_full, bool tensor_path)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DRP_OUTER_BLOCK");
+        v = e ? atoi(e) : 0;
+        if (v != 0 && v < NB) v = NB;
+        v = (v / NB) * NB;
+    }
+    if (v) return v;
+    return (tensor_path && R_full >= 1024) ? 256 : 128;
+}
+
+// Two-level right-looking elimination: panels of `outer_block()` columns are factored with NB-wide inner steps whose
+// trailing updates stay inside the panel; the rest of the matrix is then updated once per panel with K = panel width
+// (halves / quarters the read-modify-write traffic of the trailing matrix compared with K = NB, and gives the tensor
+// path a contraction length of 128-256).
 int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_full, int grow_base, int col_limit,
-                   int32_t* info, cudaStream_t st)
+                   int32_t* info, void* ws, int64_t ws_bytes, cudaStream_t st)
 {
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM);
-        cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM);
         attr_done = true;
     }
     if (info) cudaMemsetAsync(info, 0, sizeof(int32_t) * z, st);
-    for (int c0 = 0; c0 < nfactor; c0 += NB) {
-        const int nb = min(NB, nfactor - c0);
-        const int c1 = c0 + nb;
-        const int R = grow_base > 0 ? min(R_full, grow_base + c1) : R_full;
-        {
-            DRP_LAUNCH(DRP_K_POTF2, (double)z * nb * nb * nb / 3.0, st);
-            potf2_kernel<<<z, 64, 0, st>>>(M, ld, bs, c0, nb, info);
-        }
-        const int below = R - c1;
-        if (below > 0) {
-            dim3 g((below + PR - 1) / PR, z);
+    const bool tensor_path = ws != nullptr && drp_ozaki_slices() != 0 && ws_bytes >= drp_ozaki_workspace_bytes(R_full, z);
+    const int NBO = outer_block(R_full, tensor_path);
+    for (int C0 = 0; C0 < nfactor; C0 += NBO) {
+        const int W = min(NBO, nfactor - C0);
+        const int C1 = C0 + W;
+        const int R = grow_base > 0 ? min(R_full, grow_base + C1) : R_full;
+        for (int c0 = C0; c0 < C1; c0 += NB) {
+            const int nb = min(NB, C1 - c0);
+            const int c1 = c0 + nb;
             {
-                DRP_LAUNCH(DRP_K_TRSM, (double)z * below * nb * nb, st);
-                trsm_kernel<<<g, PR, TRSM_SMEM, st>>>(M, ld, bs, c0, nb, R);
+                DRP_LAUNCH(DRP_K_POTF2, (double)z * nb * nb * nb / 3.0, st);
+                potf2_kernel<<<z, 64, 0, st>>>(M, ld, bs, c0, nb, info);
             }
-            const int T = (below + TS - 1) / TS;
-            const int cl = min(R, col_limit) - c1;
-            if (cl > 0) {
-                const int Tc = min(T, (cl + TS - 1) / TS);
-                dim3 gs(Tc, T, z);
-                // algorithmic flops: 2*nb per updated entry of the lower trapezoid rows [c1,R) x cols [c1,c1+cl)
-                const double entries = (double)cl * (cl + 1) / 2.0 + (double)(below - cl) * cl;
-                DRP_LAUNCH(DRP_K_SYRK, (double)z * entries * 2.0 * nb, st);
-                syrk_kernel<<<gs, 128, SYRK_SMEM, st>>>(M, ld, bs, c0, nb, c1, R, col_limit);
+            const int below = R - c1;
+            if (below > 0) {
+                dim3 g((below + PR - 1) / PR, z);
+                {
+                    DRP_LAUNCH(DRP_K_TRSM, (double)z * below * nb * nb, st);
+                    trsm_kernel<<<g, PR, TRSM_SMEM, st>>>(M, ld, bs, c0, nb, R);
+                }
+                if (c1 < C1) drp_dmma_syrk(M, ld, bs, z, c0, nb, c1, R, min(col_limit, C1), st);   // inside the panel
             }
         }
+        const int rc = trailing_update(M, ld, bs, z, C0, W, C1, R, col_limit, tensor_path ? ws : nullptr, ws_bytes, st);
+        if (rc) return rc;
     }
     return drp_launch_status();
 }
@@ -245,13 +293,32 @@ __global__ void zero_upper_kernel(double* __restrict__ A, int n, int64_t ld, int
 }
 }  // namespace
 
-DRP_API int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info, void* stream)
+DRP_API int64_t drp_factor_workspace_bytes(int rows, int z) { return drp_ozaki_workspace_bytes(rows, z); }
+
+// Test hook: one trailing update C[r][c] -= sum_{k in [k0,k0+K)} P[r][k] P[c][k] (rows [c1,R), cols [c1,min(R,col_limit)),
+// c <= r) with slices = 0: fp64 mma.sync kernel, 4..7: int8 tcgen05 kernel with that many slices.  Returns 1 if the
+// tcgen05 kernel does not accept the shape.
+DRP_API int drp_syrk_update_f64(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit,
+                                int slices, void* ws, int64_t ws_bytes, void* stream)
+{
+    if (!M) return -1;
+    if (z <= 0 || K <= 0 || R <= c1) return -4;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (slices == 0) {
+        drp_dmma_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, st);
+        return drp_launch_status();
+    }
+    return drp_ozaki_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, slices, ws, ws_bytes, st);
+}
+
+DRP_API int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info, void* ws, int64_t ws_bytes,
+                                  void* stream)
 {
     if (!A) return -1;
     if (n <= 0) return -2;
     if (z <= 0) return -3;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = drp_factor_run(A, n, (int64_t)n * n, z, n, n, 0, n, info, st);
+    int rc = drp_factor_run(A, n, (int64_t)n * n, z, n, n, 0, n, info, ws, ws_bytes, st);
     if (rc) return rc;
     if (zero_upper) {
         dim3 g((n + 255) / 256, n, z);

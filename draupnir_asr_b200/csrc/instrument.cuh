@@ -13,7 +13,9 @@ enum DrpKernelClass {
     DRP_K_CATLIK = 5,    // categorical log-likelihood fwd/bwd          work = bytes
     DRP_K_PATRISTIC = 6, // LCA / patristic                             work = bytes
     DRP_K_OTHER = 7,
-    DRP_K_CLASSES = 8
+    DRP_K_SYRK_TC = 8,   // trailing update on the int8 tcgen05 pipe         work = fp64-equivalent flops
+    DRP_K_SLICE = 9,     // fp64 panel -> int8 slices for the tcgen05 update work = bytes
+    DRP_K_CLASSES = 10
 };
 
 // Call right before / after a kernel launch of class `k` doing `work` algorithmic flops or bytes.

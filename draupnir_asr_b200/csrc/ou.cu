@@ -234,9 +234,12 @@ __global__ void __launch_bounds__(256) block_extract_kernel(const double* __rest
 DRP_API int64_t drp_ou_workspace_ld(int n, int n2) { return ((int64_t)n + 1 + n2 + 7) & ~(int64_t)7; }
 
 // elements (doubles) of the augmented workspace for z matrices: rows n+1+n2, leading dimension as above
+static inline int64_t ou_matrix_elems(int n, int n2, int z) { return (int64_t)z * (n + 1 + n2) * drp_ou_workspace_ld(n, n2); }
+
+// The tail of the workspace (behind the z augmented matrices) holds the int8 slices of the tcgen05 trailing update.
 DRP_API int64_t drp_ou_workspace_elems(int n, int n2, int z)
 {
-    return (int64_t)z * (n + 1 + n2) * drp_ou_workspace_ld(n, n2);
+    return ou_matrix_elems(n, n2, z) + (drp_ozaki_workspace_bytes(n + 1 + n2, z) + 7) / 8;
 }
 
 DRP_API int drp_ou_cov_fwd_f64(const double* D, int64_t ldd, int n, const double* sf, const double* sn, const double* lam,
@@ -301,7 +304,7 @@ DRP_API int drp_ou_prior_f64(const double* D, int64_t ldd, int n, const double* 
         DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)z * R * (R + 1) * 4.0), st);
         ou_assemble_kernel<<<g, 256, 3 * z * sizeof(double), st>>>(D, ldd, nullptr, n, n2, 1, sf, sn, lam, x, z, M, ld, bs);
     }
-    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, st);
+    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, M + ou_matrix_elems(n, n2, z), drp_ozaki_workspace_bytes(R, z), st);
     if (rc) return rc;
     {
         DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 8.0), st);
@@ -342,7 +345,7 @@ DRP_API int drp_mvn_logprob_f64(const double* K, const double* x, int n, int z, 
         DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)z * R * (R + 1) * 4.0 + (double)z * n * n * 4.0), st);
         cov_assemble_kernel<<<dim3((R + 255) / 256, R, z), 256, 0, st>>>(K, n, x, M, ld, bs);
     }
-    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, st);
+    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, M + ou_matrix_elems(n, n2, z), drp_ozaki_workspace_bytes(R, z), st);
     if (rc) return rc;
     {
         DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 8.0), st);
@@ -385,7 +388,7 @@ DRP_API int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, d
         DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)z * R * (R + 1) * 4.0 + (double)z * n * n * 4.0), st);
         cov_assemble_kernel<<<dim3((R + 255) / 256, R, z), 256, 0, st>>>(K, n, Kinv, M, ld, bs);
     }
-    int rc = drp_factor_run(M, ld, bs, z, n, R, n + 1, R, info, st);
+    int rc = drp_factor_run(M, ld, bs, z, n, R, n + 1, R, info, M + ou_matrix_elems(n, n, z), drp_ozaki_workspace_bytes(R, z), st);
     if (rc) return rc;
     {
         DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * n * 12.0), st);
@@ -416,7 +419,7 @@ DRP_API int drp_ou_conditional_f64(const double* D, int64_t ldd, const int32_t* 
         ou_assemble_kernel<<<dim3((R + 255) / 256, R), 256, 3 * z * sizeof(double), st>>>(D, ldd, idx, n, ni, 0, sf, sn, lam,
                                                                                   x_leaf, z, M, ld, bs);
     }
-    int rc = drp_factor_run(M, ld, bs, z, n, R, 0, cov ? R : n + 1, info, st);
+    int rc = drp_factor_run(M, ld, bs, z, n, R, 0, cov ? R : n + 1, info, M + ou_matrix_elems(n, ni, z), drp_ozaki_workspace_bytes(R, z), st);
     if (rc) return rc;
     {
         DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 16.0), st);

@@ -1,0 +1,505 @@
+// fp64-accurate trailing update of the blocked Cholesky on the INT8 tcgen05 tensor pipe (sm_100a).
+//
+// The trailing update  C[r][c] -= sum_k P[r][k] P[c][k]  (factor.cu) is the only dense contraction on the OU-prior
+// path (torch.linalg.cholesky / cholesky_backward / linalg.inv of the reference: S/models.py:118,167-193).  tcgen05
+// has no f64 kind, so the fp64 panel P is split, row by row, into S byte slices of a fixed-point mantissa
+//
+//     P[r][k] ~= 2^(e_r - 7) * ( q0 + q1 2^-8 + ... + q_{S-1} 2^-8(S-1) ),   q0 in [-128,127] (s8), q_t in [0,255] (u8)
+//
+// (e_r = exponent of the row maximum, mantissa rounded to nearest at 8S-1 bits), and the products of slices are
+// accumulated EXACTLY in int32 by tcgen05.mma.kind::i8 into S TMEM accumulators, one per anti-diagonal d = t + u:
+//
+//     sum_k P[r][k] P[c][k] ~= 2^(e_r-7) 2^(e_c-7) * sum_{d<S} 2^-8d * ( sum_{t+u=d} sum_k q_t[r][k] q_u[c][k] )
+//
+// The epilogue recombines the S integers in fp64 (Horner, one rounding per term) and applies the update to C.  The only
+// error is the mantissa truncation (2^-(8S-1) of the row maximum) and the dropped anti-diagonals d >= S
+// (~ S 2^-8S of the product of row maxima): S = 6 gives ~1e-13, S = 7 ~1e-15 relative to |P_r|max |P_c|max, i.e. a
+// backward error at fp64 level for the factorisation (DESIGN.md "split-integer trailing update").
+//
+// Data movement: oz_slice_kernel writes the slices in global memory already in the 128-byte-swizzled K-major shared
+// memory image that tcgen05 reads, so every operand tile is ONE contiguous 16 KB / 8 KB block moved by a TMA bulk
+// copy (cp.async.bulk, completes on an mbarrier).  oz_syrk_kernel is persistent and warp-specialised:
+//   warp 0   TMA producer: the S*KBN A tiles of a 128-row strip stay resident, B tiles stream through a ring
+//   warp 1   MMA issuer (one lane): 128x64x32 int8 MMAs into TMEM, tcgen05.commit -> mbarriers
+//   warps 2-9 epilogue: tcgen05.ld of the S accumulators, fp64 recombination, masked read-modify-write of C
+#include "common.cuh"
+#include "instrument.cuh"
+#include "factor.cuh"
+#include <stdlib.h>
+
+namespace {
+
+constexpr int OZ_TM = 128;                       // tile rows  (UMMA M)
+constexpr int OZ_TN = 64;                        // tile cols  (UMMA N)
+constexpr int OZ_ROWB = 128;                     // bytes (= int8 K elements) per swizzled row of a k-block
+constexpr int OZ_A_TILE = OZ_TM * OZ_ROWB;       // 16 KB
+constexpr int OZ_B_TILE = OZ_TN * OZ_ROWB;       // 8 KB
+constexpr int OZ_CHUNK = 16;                     // column tiles per work unit (A strip reloaded per unit)
+constexpr int OZ_EPI_WARPS = 8;
+constexpr int OZ_THREADS = (2 + OZ_EPI_WARPS) * 32;
+constexpr int OZ_SMEM_MAX = 232448;              // 227 KB
+constexpr long long OZ_TIMEOUT_CYCLES = 6000000000LL;   // a stuck barrier traps instead of hanging the device
+
+template <int S, int KBN>
+struct OzCfg {
+    static constexpr int NA = S * KBN;                                   // resident A tiles per strip
+    static constexpr int A_BYTES = NA * OZ_A_TILE;
+    static constexpr int NST_RAW = (OZ_SMEM_MAX - 1024 - 256 - A_BYTES) / OZ_B_TILE;
+    static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;                // B ring stages
+    static constexpr int SMEM = 1024 + A_BYTES + NST * OZ_B_TILE + 256;
+    static constexpr int TMEM_COLS = (S * OZ_TN <= 64) ? 64 : (S * OZ_TN <= 128) ? 128 : (S * OZ_TN <= 256) ? 256 : 512;
+    static_assert(NST >= 2, "A strip does not leave room for the B ring");
+    static_assert(S * OZ_TN <= 512, "too many accumulators for TMEM");
+};
+
+struct OzParams {
+    double* M;                 // fp64 matrices, row-major
+    int64_t ld, bs;
+    const uint8_t* sl;         // slices [z][S][KBN][Rpad][128 B swizzled]
+    int64_t sl_bs;             // bytes per matrix
+    const double* scl;         // [z][Rpad]  2^(e_r - 7)
+    int Rpad, rb, c1, R, cmax;
+    int nTi, nTj, units_per_z, total_units;
+};
+
+// ------------------------------------------------ PTX wrappers ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (((++spins) & 0xFFF) == 0 && clock64() - t0 > OZ_TIMEOUT_CYCLES) __trap();
+    }
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, issued by ONE thread for the CTA (SASS: UTCIMMA)
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile, 128-byte swizzle: 8-row groups 1024 B apart (SBO), version 1 (sm_100), layout SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::i8 instruction descriptor: D = s32, A/B signed (1) or unsigned (0), both K-major, N = 64, M = 128
+__device__ __forceinline__ uint32_t umma_idesc(uint32_t a_signed, uint32_t b_signed)
+{
+    return (2u << 4) | (a_signed << 7) | (b_signed << 10) | ((uint32_t)(OZ_TN >> 3) << 17) | ((uint32_t)(OZ_TM >> 4) << 24);
+}
+
+// exact int32 -> fp64 without the conversion pipe: 2^52 + (a + 2^31) assembled in the mantissa, then one subtraction
+__device__ __forceinline__ double i32_to_f64(uint32_t a)
+{
+    return __hiloint2double(0x43300000, (int)(a ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+// work unit u -> (matrix, 128-row strip, first column tile, number of column tiles); strips longest first
+__device__ __forceinline__ void oz_decode(const OzParams& p, int u, int& zz, int& ti, int& tj0, int& ntj)
+{
+    zz = u / p.units_per_z;
+    int v = u - zz * p.units_per_z;
+    tj0 = 0;
+    ntj = 0;
+    for (ti = p.nTi - 1; ti >= 0; --ti) {
+        const int tot = min(2 * ti + 2, p.nTj);
+        const int nch = (tot + OZ_CHUNK - 1) / OZ_CHUNK;
+        if (v < nch) {
+            tj0 = v * OZ_CHUNK;
+            ntj = min(OZ_CHUNK, tot - tj0);
+            return;
+        }
+        v -= nch;
+    }
+    ti = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Slicing: one warp per row of the panel P = M[rb .. rb+Rpad) x [k0, k0+K).  Rows outside [c1, R) become zeros.
+// ---------------------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ Mb, int64_t ld, int64_t bs, int k0, int KBN,
+                                                       int rb, int c1, int R, int Rpad, uint8_t* __restrict__ sl,
+                                                       int64_t sl_bs, double* __restrict__ scl)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rr = blockIdx.x * 8 + warp;
+    const int zz = blockIdx.y;
+    if (rr >= Rpad) return;
+    const int r = rb + rr;
+    const bool live = (r >= c1 && r < R);
+    const double* src = Mb + (int64_t)zz * bs + (int64_t)r * ld + k0 + 4 * lane;
+    double x[8];
+    double m = 0.0;
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double v = (live && kb < KBN) ? src[kb * 128 + j] : 0.0;
+            x[kb * 4 + j] = v;
+            m = fmax(m, fabs(v));
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    int e = 0;
+    if (m > 0.0 && m < 1e300) frexp(m, &e);
+    if (lane == 0) scl[(int64_t)zz * Rpad + rr] = scalbn(1.0, e - 7);
+    const int sh = 8 * S - 1 - e;
+    const long long hi = (1LL << (8 * S - 1)) - 1;
+    uint8_t* dst = sl + (int64_t)zz * sl_bs;
+    const int chunk = ((lane >> 2) ^ (rr & 7)) << 4;       // 16-byte chunk of the row after the 128B swizzle
+    for (int kb = 0; kb < KBN; ++kb) {
+        long long X[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            long long q = __double2ll_rn(scalbn(x[kb * 4 + j], sh));
+            X[j] = q > hi ? hi : (q < -hi - 1 ? -hi - 1 : q);
+        }
+#pragma unroll
+        for (int t = 0; t < S; ++t) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w |= (uint32_t)((X[j] >> (8 * (S - 1 - t))) & 0xFF) << (8 * j);
+            const int64_t off = ((int64_t)(t * KBN + kb) * Rpad + rr) * OZ_ROWB + chunk + ((4 * lane) & 15);
+            *reinterpret_cast<uint32_t*>(dst + off) = w;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The update kernel.
+// ---------------------------------------------------------------------------------------------------------------
+template <int S, int KBN>
+__global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p)
+{
+    using Cfg = OzCfg<S, KBN>;
+    constexpr int NST = Cfg::NST;
+    extern __shared__ uint8_t oz_smem_raw[];
+    const uint32_t raw = smem_u32(oz_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;              // swizzle atoms need 1024-byte alignment
+    uint8_t* gen = oz_smem_raw + (base - raw);
+    const uint32_t sA = base;
+    const uint32_t sB = base + Cfg::A_BYTES;
+    const uint32_t bars = sB + NST * OZ_B_TILE;
+    const uint32_t bar_a_full = bars, bar_a_empty = bars + 8, bar_acc_full = bars + 16, bar_acc_empty = bars + 24;
+    const uint32_t bar_b_full = bars + 32, bar_b_empty = bars + 32 + 8 * NST;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + Cfg::A_BYTES + NST * OZ_B_TILE + 32 + 16 * NST);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a_full, 1);
+        mbar_init(bar_a_empty, 1);
+        mbar_init(bar_acc_full, 1);
+        mbar_init(bar_acc_empty, OZ_EPI_WARPS);
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(bar_b_full + 8 * s, 1);
+            mbar_init(bar_b_empty + 8 * s, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================ TMA producer ============================
+        if (lane == 0) {
+            uint32_t a_phase = 0, b_phase = 0;
+            int st = 0;
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+                int zz, ti, tj0, ntj;
+                oz_decode(p, u, zz, ti, tj0, ntj);
+                const uint8_t* src = p.sl + (int64_t)zz * p.sl_bs;
+                mbar_wait(bar_a_empty, a_phase ^ 1);
+                mbar_expect_tx(bar_a_full, Cfg::A_BYTES);
+                for (int a = 0; a < Cfg::NA; ++a)
+                    bulk_g2s(sA + a * OZ_A_TILE, src + ((int64_t)a * p.Rpad + (int64_t)ti * OZ_TM) * OZ_ROWB, OZ_A_TILE,
+                             bar_a_full);
+                a_phase ^= 1;
+                for (int t = 0; t < ntj; ++t) {
+                    const int64_t cc0 = (int64_t)(tj0 + t) * OZ_TN;
+                    for (int b = 0; b < Cfg::NA; ++b) {
+                        mbar_wait(bar_b_empty + 8 * st, b_phase ^ 1);
+                        mbar_expect_tx(bar_b_full + 8 * st, OZ_B_TILE);
+                        bulk_g2s(sB + st * OZ_B_TILE, src + ((int64_t)b * p.Rpad + cc0) * OZ_ROWB, OZ_B_TILE,
+                                 bar_b_full + 8 * st);
+                        if (++st == NST) {
+                            st = 0;
+                            b_phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ============================ MMA issuer ==============================
+        if (lane == 0) {
+            uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
+            int st = 0;
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+                int zz, ti, tj0, ntj;
+                oz_decode(p, u, zz, ti, tj0, ntj);
+                mbar_wait(bar_a_full, a_phase);
+                a_phase ^= 1;
+                tc_fence_after();
+                for (int t = 0; t < ntj; ++t) {
+                    mbar_wait(bar_acc_empty, acc_phase ^ 1);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int ub = 0; ub < S; ++ub) {               // slice of B (columns of the update)
+#pragma unroll 1
+                        for (int kb = 0; kb < KBN; ++kb) {
+                            mbar_wait(bar_b_full + 8 * st, b_phase);
+                            tc_fence_after();
+                            const uint64_t bdesc = umma_desc(sB + st * OZ_B_TILE);
+                            for (int ta = 0; ta + ub < S; ++ta) {      // slice of A; anti-diagonal d = ta + ub
+                                const uint64_t adesc = umma_desc(sA + (ta * KBN + kb) * OZ_A_TILE);
+                                const uint32_t idesc = umma_idesc(ta == 0, ub == 0);
+                                const uint32_t dcol = tmem + (uint32_t)((ta + ub) * OZ_TN);
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4)
+                                    umma_i8(dcol, adesc + 2 * k4, bdesc + 2 * k4, idesc, (ub | kb | k4) != 0);
+                            }
+                            umma_commit(bar_b_empty + 8 * st);
+                            if (++st == NST) {
+                                st = 0;
+                                b_phase ^= 1;
+                            }
+                        }
+                    }
+                    umma_commit(bar_acc_full);
+                    acc_phase ^= 1;
+                }
+                umma_commit(bar_a_empty);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============================ epilogue ================================
+        const int q = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int h = (warp - 2) >> 2;             // which 32 of the tile's 64 columns
+        uint32_t acc_phase = 0;
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            int zz, ti, tj0, ntj;
+            oz_decode(p, u, zz, ti, tj0, ntj);
+            const int rr = ti * OZ_TM + q * 32 + lane;
+            const int r = p.rb + rr;
+            const bool row_ok = (r >= p.c1 && r < p.R);
+            const double* sc = p.scl + (int64_t)zz * p.Rpad;
+            const double sr = sc[rr];
+            double* crow = p.M + (int64_t)zz * p.bs + (int64_t)r * p.ld;
+            for (int t = 0; t < ntj; ++t) {
+                const int cc0 = (tj0 + t) * OZ_TN + 32 * h;
+                mbar_wait(bar_acc_full, acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                double v[32];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * h);
+#pragma unroll
+                for (int d = S - 1; d >= 0; --d) {
+                    uint32_t a[32];
+                    tmem_ld32(taddr + (uint32_t)(d * OZ_TN), a);
+                    if (d == S - 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = i32_to_f64(a[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fma(v[j], 0.00390625, i32_to_f64(a[j]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty);       // accumulators may be overwritten by the next tile
+                if (row_ok) {
+                    const int c0 = p.rb + cc0;
+                    const int jmax = min(32, min(r + 1, p.cmax) - c0);
+                    const int jmin = max(0, p.c1 - c0);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j >= jmin && j < jmax) crow[c0 + j] -= v[j] * (sr * sc[cc0 + j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_COLS);
+}
+
+template <int S, int KBN>
+int oz_launch(const OzParams& p, int z, int k0, cudaStream_t st, double flops)
+{
+    using Cfg = OzCfg<S, KBN>;
+    static bool attr_done = false;
+    static int n_sm = 0;
+    if (!attr_done) {
+        cudaFuncSetAttribute(oz_syrk_kernel<S, KBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        attr_done = true;
+    }
+    {
+        DRP_LAUNCH(DRP_K_SLICE, (double)z * p.Rpad * KBN * 128 * (8.0 + S), st);
+        oz_slice_kernel<S><<<dim3((p.Rpad + 7) / 8, z), 256, 0, st>>>(p.M, p.ld, p.bs, k0, KBN, p.rb, p.c1, p.R, p.Rpad,
+                                                                     const_cast<uint8_t*>(p.sl), p.sl_bs,
+                                                                     const_cast<double*>(p.scl));
+    }
+    {
+        DRP_LAUNCH(DRP_K_SYRK_TC, flops, st);
+        const int grid = p.total_units < n_sm ? p.total_units : n_sm;
+        oz_syrk_kernel<S, KBN><<<grid, OZ_THREADS, Cfg::SMEM, st>>>(p);
+    }
+    return 0;
+}
+
+}  // namespace
+
+// Bytes of workspace drp_ozaki_syrk may need for matrices with at most R_full rows.
+int64_t drp_ozaki_workspace_bytes(int R_full, int z)
+{
+    const int64_t Rpad = (((int64_t)R_full + 127) / 128 + 1) * 128;
+    return (int64_t)z * Rpad * (12 * OZ_ROWB + 8) + 1024;
+}
+
+int drp_ozaki_slices()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DRP_OZAKI_SLICES");
+        v = e ? atoi(e) : 6;
+        if (v != 0 && (v < 4 || v > 7)) v = 6;
+    }
+    return v;
+}
+
+// Trailing update through the int8 tensor pipe.  Returns 0 when it ran, 1 when the shape/workspace does not qualify
+// (the caller then uses the fp64 mma.sync kernel), otherwise a launch error code.
+int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, int S, void* ws,
+                   int64_t ws_bytes, cudaStream_t st)
+{
+    if (S == 0 || !ws) return 1;
+    if (K != 128 && K != 256) return 1;
+    const int KBN = K / 128;
+    if (S * KBN > 12) return 1;                          // A strip must stay resident in shared memory
+    const int cmax = R < col_limit ? R : col_limit;
+    const int below = R - c1, cl = cmax - c1;
+    if (below < 384 || cl < 256) return 1;               // small updates: launch/slicing overhead dominates
+    OzParams p;
+    p.M = M;
+    p.ld = ld;
+    p.bs = bs;
+    p.rb = c1 & ~7;
+    p.c1 = c1;
+    p.R = R;
+    p.cmax = cmax;
+    p.nTi = (R - p.rb + OZ_TM - 1) / OZ_TM;
+    p.nTj = (cmax - p.rb + OZ_TN - 1) / OZ_TN;
+    p.Rpad = p.nTi * OZ_TM;
+    p.sl_bs = (int64_t)S * KBN * p.Rpad * OZ_ROWB;
+    const int64_t need = (int64_t)z * p.sl_bs + (int64_t)z * p.Rpad * 8 + 1024;
+    if (need > ws_bytes) return 1;
+    uint8_t* w = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    p.sl = w;
+    p.scl = reinterpret_cast<const double*>(w + (int64_t)z * p.sl_bs);
+    int upz = 0;
+    for (int ti = 0; ti < p.nTi; ++ti) {
+        const int tot = 2 * ti + 2 < p.nTj ? 2 * ti + 2 : p.nTj;
+        upz += (tot + OZ_CHUNK - 1) / OZ_CHUNK;
+    }
+    p.units_per_z = upz;
+    p.total_units = upz * z;
+    const double entries = (double)cl * (cl + 1) / 2.0 + (double)(below - cl) * cl;
+    const double flops = (double)z * entries * 2.0 * K;
+    int rc = 1;
+    if (KBN == 1) {
+        switch (S) {
+            case 4: rc = oz_launch<4, 1>(p, z, k0, st, flops); break;
+            case 5: rc = oz_launch<5, 1>(p, z, k0, st, flops); break;
+            case 6: rc = oz_launch<6, 1>(p, z, k0, st, flops); break;
+            case 7: rc = oz_launch<7, 1>(p, z, k0, st, flops); break;
+        }
+    } else {
+        switch (S) {
+            case 4: rc = oz_launch<4, 2>(p, z, k0, st, flops); break;
+            case 5: rc = oz_launch<5, 2>(p, z, k0, st, flops); break;
+            case 6: rc = oz_launch<6, 2>(p, z, k0, st, flops); break;
+        }
+    }
+    if (rc) return rc;
+    return drp_launch_status();
+}

@@ -117,7 +117,9 @@ def potrf(A: torch.Tensor, check: bool = True) -> torch.Tensor:
     n = A.shape[-1]
     L = A.reshape(-1, n, n).clone()
     info = torch.empty(L.shape[0], dtype=torch.int32, device=A.device)
-    _rc(lib.drp_potrf_batched_f64(_p(L), n, L.shape[0], 1, _p(info), _stream()), "drp_potrf_batched_f64")
+    wsb = lib.drp_factor_workspace_bytes(n, L.shape[0]) if n >= 1024 else 0
+    ws = torch.empty(wsb, dtype=torch.uint8, device=A.device) if wsb else None
+    _rc(lib.drp_potrf_batched_f64(_p(L), n, L.shape[0], 1, _p(info), _p(ws), wsb, _stream()), "drp_potrf_batched_f64")
     if check:
         _info_done(info, "linalg.cholesky")
     return L.reshape(A.shape)
@@ -320,3 +322,22 @@ def tree_distances(parent: torch.Tensor, branch: torch.Tensor, rows: Optional[to
                                   _p(cols_t), nc, _p(lca), _p(pat), _p(cla), _p(ws), wsb, _stream()),
         "drp_lca_patristic_f64")
     return pat, cla, lca
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# test hook: one trailing update of the blocked factorisation (fp64 mma.sync kernel or int8 tcgen05 kernel)
+# ------------------------------------------------------------------------------------------------------------------
+def syrk_update(M: torch.Tensor, k0: int, K: int, c1: int, R: int, col_limit: int, slices: int = 0) -> bool:
+    """In place on `M [z, rows, ld]`: `M[r][c] -= sum_{k0<=k<k0+K} M[r][k] M[c][k]` for `c1 <= c <= r < R`, `c < col_limit`.
+    `slices = 0` runs the fp64 mma.sync kernel, `4..7` the split-integer tcgen05 kernel.  Returns False when the tcgen05
+    kernel does not accept the shape (nothing is modified then)."""
+    _req(M, "M")
+    assert M.dim() == 3 and M.is_contiguous()
+    z, rows, ld = M.shape
+    wsb = lib.drp_factor_workspace_bytes(rows, z)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=M.device)
+    rc = lib.drp_syrk_update_f64(_p(M), ld, rows * ld, z, k0, K, c1, R, col_limit, slices, _p(ws), wsb, _stream())
+    if rc == 1:
+        return False
+    _rc(rc, "drp_syrk_update_f64")
+    return True

@@ -31,9 +31,11 @@ int drp_abi_version(void);
 /* ---- instrumentation (bench.py: `gpu_launches` and the live per-kernel roofline) -------------------------------- */
 /* Cumulative number of kernels launched by this library.                                                            */
 int64_t drp_launch_count(void);
-/* CUDA-event timing of every launch, by kernel class: 0 syrk, 1 trsm, 2 potf2 (work = flops), 3 assembly,
- * 4 reductions, 5 categorical, 6 patristic (work = bytes), 7 other.  enable(1) clears earlier records;
- * read() synchronises the device and fills three arrays of 8 entries (HOST pointers).                              */
+/* CUDA-event timing of every launch, by kernel class: 0 syrk (fp64 mma.sync), 1 trsm, 2 potf2 (work = flops),
+ * 3 assembly, 4 reductions, 5 categorical, 6 patristic (work = bytes), 7 other, 8 syrk on the int8 tcgen05 pipe
+ * (work = fp64-equivalent flops), 9 int8 slicing (work = bytes).  enable(1) clears earlier records; read()
+ * synchronises the device and fills three arrays of drp_timing_classes() entries (HOST pointers).                  */
+int drp_timing_classes(void);
 int drp_timing_enable(int on);
 int drp_timing_read(double* ms, int64_t* launches, double* work);
 
@@ -57,7 +59,14 @@ int drp_ou_cov_bwd_f64(const double* D, int64_t ldd, int n, const double* lam, i
                        double* out, void* stream);
 
 /* ---- K3  torch.linalg.cholesky inside MultivariateNormal.__init__: S/models.py:118 ----------------------------- */
-int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info, void* stream);
+/* ws (nullable): drp_factor_workspace_bytes(n, z) bytes; with it, trailing updates of large matrices run on the int8
+ * tcgen05 tensor pipe (split-integer, fp64-accurate; DRP_OZAKI_SLICES = 0 disables, 4..7 selects the slice count). */
+int64_t drp_factor_workspace_bytes(int rows, int z);
+int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info, void* ws, int64_t ws_bytes, void* stream);
+/* Test hook: ONE trailing update C[r][c] -= sum_{k0 <= k < k0+K} P[r][k] P[c][k], rows [c1,R), cols [c1,min(R,col_limit)),
+ * c <= r; slices = 0 -> fp64 mma.sync kernel, 4..7 -> int8 tcgen05 kernel.  Returns 1 if tcgen05 rejects the shape.  */
+int drp_syrk_update_f64(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, int slices,
+                        void* ws, int64_t ws_bytes, void* stream);
 
 /* ---- K3+K4+K5  gp_prior's latent_z site, fused: S/models.py:100-118 -------------------------------------------- */
 int64_t drp_ou_workspace_ld(int n, int n2);

@@ -1,0 +1,103 @@
+"""GPU parity tests of the split-integer (int8 tcgen05) trailing update against exact fp64 arithmetic on the CPU and
+against the fp64 mma.sync kernel, through the C ABI (`drp_syrk_update_f64`), plus the factorisations that use it.
+
+Error model (csrc/ozaki.cu): with S byte slices the update of entry (r, c) is exact up to
+~ K * (S + 1) * 2^-(8 S - 6) * max_k|P[r][k]| * max_k|P[c][k]|; the bounds asserted below are that model with slack."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference_update(M, k0, K, c1, R, col_limit):
+    """fp64 (long-double accumulated) result of the update on the host; only c1 <= c <= r < R, c < col_limit change."""
+    out = M.copy()
+    P = M[:, c1:R, k0:k0 + K].astype(np.longdouble)
+    U = np.einsum("zik,zjk->zij", P, P)
+    cmax = min(R, col_limit)
+    rows = np.arange(c1, R)[:, None]
+    cols = np.arange(c1, R)[None, :]
+    mask = (cols <= rows) & (cols < cmax)
+    blk = out[:, c1:R, c1:R].astype(np.longdouble)
+    blk = np.where(mask[None], blk - U, blk)
+    out[:, c1:R, c1:R] = blk.astype(np.float64)
+    return out, mask
+
+
+def _scale_bound(M, k0, K, c1, R):
+    m = np.abs(M[:, c1:R, k0:k0 + K]).max(axis=2)
+    return m[:, :, None] * m[:, None, :]
+
+
+CASES = [
+    # z, rows, ld, k0, K, c1, R, col_limit
+    (2, 900, 904, 0, 256, 256, 900, 900),
+    (3, 1000, 1003, 100, 128, 250, 997, 997),       # nothing aligned: c1 % 8 != 0, odd ld, ragged last tiles
+    (2, 1400, 1408, 128, 128, 256, 1400, 1000),     # col_limit cuts the update (conditional-mean shape)
+    (1, 2100, 2104, 512, 256, 768, 2100, 2100),     # several work units per strip
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("slices", [5, 6, 7])
+def test_tcgen05_update_matches_exact(cuda, case, slices):
+    from draupnir_asr_b200 import ops
+    z, rows, ld, k0, K, c1, R, col_limit = case
+    if slices * (K // 128) > 12:
+        pytest.skip("A strip of S*K/128 tiles does not stay resident")
+    rng = np.random.default_rng(7)
+    M = rng.standard_normal((z, rows, ld))
+    # rows of very different magnitude (identity-block rows, K rows, the x row live in one matrix)
+    M *= np.exp(rng.uniform(-12, 6, size=(z, rows, 1)))
+    M[:, c1 + 5, :] = 0.0                                                   # an all-zero panel row
+    ref, mask = _reference_update(M, k0, K, c1, R, col_limit)
+    Mg = torch.from_numpy(M).to(cuda)
+    assert ops.syrk_update(Mg, k0, K, c1, R, col_limit, slices=slices)
+    got = Mg.cpu().numpy()
+    outside = np.ones_like(M, dtype=bool)
+    outside[:, c1:R, c1:R] = ~mask[None]
+    assert np.array_equal(got[outside], M[outside])                         # nothing else is touched
+    err = np.abs(got[:, c1:R, c1:R] - ref[:, c1:R, c1:R])
+    bound = K * (slices + 1) * 2.0 ** -(8 * slices - 6) * _scale_bound(M, k0, K, c1, R)
+    bound = bound + 4 * np.finfo(np.float64).eps * np.abs(ref[:, c1:R, c1:R])   # final fp64 subtraction
+    assert np.all(err <= bound), f"max err/bound {np.max(err / np.maximum(bound, 1e-300)):.3g}"
+
+
+def test_tcgen05_update_vs_mma_sync_kernel(cuda):
+    from draupnir_asr_b200 import ops
+    z, rows, ld, k0, K, c1, R = 4, 1200, 1208, 0, 256, 256, 1200
+    g = torch.Generator().manual_seed(3)
+    M = torch.randn(z, rows, ld, generator=g, dtype=torch.float64)
+    A, B = M.to(cuda), M.to(cuda)
+    assert ops.syrk_update(A, k0, K, c1, R, R, slices=0)
+    assert ops.syrk_update(B, k0, K, c1, R, R, slices=6)
+    d = (A - B).abs().max().item()
+    assert d < 1e-9, d
+
+
+def test_small_shapes_are_declined(cuda):
+    from draupnir_asr_b200 import ops
+    M = torch.randn(1, 300, 304, dtype=torch.float64, device=cuda)
+    before = M.clone()
+    assert not ops.syrk_update(M, 0, 128, 128, 300, 300, slices=6)
+    assert torch.equal(M, before)
+
+
+@pytest.mark.parametrize("n", [1100, 1500])
+def test_potrf_large_through_tensor_path(cuda, n):
+    """Batched Cholesky big enough to take the tcgen05 trailing update: L L^T reproduces K to fp64 backward-error level
+    and matches torch's fp64 factor on the host."""
+    from draupnir_asr_b200 import ops
+    from draupnir_asr_b200 import synthetic as S
+    t = S.random_tree(n, seed=1)
+    D = torch.from_numpy(S.patristic_host(t)[np.ix_(t.leaves, t.leaves)])
+    sf = torch.tensor([1.3, 0.7], dtype=torch.float64)
+    sn = torch.tensor([0.6, 1.1], dtype=torch.float64)
+    lam = torch.tensor([0.9, 1.4], dtype=torch.float64)
+    K = sf[:, None, None] ** 2 * torch.exp(-D[None] / lam[:, None, None]) + sn[:, None, None] ** 2 * torch.eye(n, dtype=torch.float64)
+    L = ops.potrf(K.to(cuda)).cpu()
+    L_ref = torch.linalg.cholesky(K)
+    assert float((L - L_ref).abs().max() / L_ref.abs().max()) < 1e-10
+    back = float((L @ L.transpose(-1, -2) - K).abs().max() / K.abs().max())
+    assert back < 1e-12, back
