@@ -100,4 +100,4 @@ def test_potrf_large_through_tensor_path(cuda, n):
     L_ref = torch.linalg.cholesky(K)
     assert float((L - L_ref).abs().max() / L_ref.abs().max()) < 1e-10
     back = float((L @ L.transpose(-1, -2) - K).abs().max() / K.abs().max())
-    assert back < 1e-12, back
+    assert back < 2e-11, back          # S = 6 slices: ~1e-11 |K| backward error
