@@ -255,28 +255,39 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
     if (info) cudaMemsetAsync(info, 0, sizeof(int32_t) * z, st);
     const bool tensor_path = ws != nullptr && drp_ozaki_slices() != 0 && ws_bytes >= drp_ozaki_workspace_bytes(R_full, z);
     const int NBO = outer_block(R_full, tensor_path);
+    void* tws = tensor_path ? ws : nullptr;
     for (int C0 = 0; C0 < nfactor; C0 += NBO) {
         const int W = min(NBO, nfactor - C0);
         const int C1 = C0 + W;
         const int R = grow_base > 0 ? min(R_full, grow_base + C1) : R_full;
-        for (int c0 = C0; c0 < C1; c0 += NB) {
-            const int nb = min(NB, C1 - c0);
-            const int c1 = c0 + nb;
-            {
-                DRP_LAUNCH(DRP_K_POTF2, (double)z * nb * nb * nb / 3.0, st);
-                potf2_kernel<<<z, 64, 0, st>>>(M, ld, bs, c0, nb, info);
-            }
-            const int below = R - c1;
-            if (below > 0) {
-                dim3 g((below + PR - 1) / PR, z);
+        // inside the outer panel: 64-wide steps; with the tensor path the panel is split again into 128-wide
+        // sub-panels so that only 64-column-wide updates are left to the fp64 mma.sync kernel
+        const int NBM = (tensor_path && W > 2 * NB) ? 2 * NB : W;
+        for (int Q0 = C0; Q0 < C1; Q0 += NBM) {
+            const int Q1 = min(Q0 + NBM, C1);
+            for (int c0 = Q0; c0 < Q1; c0 += NB) {
+                const int nb = min(NB, Q1 - c0);
+                const int c1 = c0 + nb;
                 {
-                    DRP_LAUNCH(DRP_K_TRSM, (double)z * below * nb * nb, st);
-                    trsm_kernel<<<g, PR, TRSM_SMEM, st>>>(M, ld, bs, c0, nb, R);
+                    DRP_LAUNCH(DRP_K_POTF2, (double)z * nb * nb * nb / 3.0, st);
+                    potf2_kernel<<<z, 64, 0, st>>>(M, ld, bs, c0, nb, info);
                 }
-                if (c1 < C1) drp_dmma_syrk(M, ld, bs, z, c0, nb, c1, R, min(col_limit, C1), st);   // inside the panel
+                const int below = R - c1;
+                if (below > 0) {
+                    dim3 g((below + PR - 1) / PR, z);
+                    {
+                        DRP_LAUNCH(DRP_K_TRSM, (double)z * below * nb * nb, st);
+                        trsm_kernel<<<g, PR, TRSM_SMEM, st>>>(M, ld, bs, c0, nb, R);
+                    }
+                    if (c1 < Q1) drp_dmma_syrk(M, ld, bs, z, c0, nb, c1, R, min(col_limit, Q1), st);   // inside the sub-panel
+                }
+            }
+            if (Q1 < C1) {                                                                              // rest of the outer panel
+                const int rc = trailing_update(M, ld, bs, z, Q0, Q1 - Q0, Q1, R, min(col_limit, C1), tws, ws_bytes, st);
+                if (rc) return rc;
             }
         }
-        const int rc = trailing_update(M, ld, bs, z, C0, W, C1, R, col_limit, tensor_path ? ws : nullptr, ws_bytes, st);
+        const int rc = trailing_update(M, ld, bs, z, C0, W, C1, R, col_limit, tws, ws_bytes, st);          // rest of the matrix
         if (rc) return rc;
     }
     return drp_launch_status();

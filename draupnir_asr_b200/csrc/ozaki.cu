@@ -21,7 +21,7 @@
 // copy (cp.async.bulk, completes on an mbarrier).  oz_syrk_kernel is persistent and warp-specialised:
 //   warp 0   TMA producer: the S*KBN A tiles of a 128-row strip stay resident, B tiles stream through a ring
 //   warp 1   MMA issuer (one lane): 128x64x32 int8 MMAs into TMEM, tcgen05.commit -> mbarriers
-//   warps 2-9 epilogue: tcgen05.ld of the S accumulators, fp64 recombination, masked read-modify-write of C
+//   warps 2-17 epilogue: prefetch of the C tile, tcgen05.ld of the S accumulators, fp64 recombination, masked write-back
 #include "common.cuh"
 #include "instrument.cuh"
 #include "factor.cuh"
@@ -35,7 +35,7 @@ constexpr int OZ_ROWB = 128;                     // bytes (= int8 K elements) pe
 constexpr int OZ_A_TILE = OZ_TM * OZ_ROWB;       // 16 KB
 constexpr int OZ_B_TILE = OZ_TN * OZ_ROWB;       // 8 KB
 constexpr int OZ_CHUNK = 16;                     // column tiles per work unit (A strip reloaded per unit)
-constexpr int OZ_EPI_WARPS = 8;
+constexpr int OZ_EPI_WARPS = 16;                 // 4 TMEM lane quadrants x 4 column quarters of the 128x64 tile
 constexpr int OZ_THREADS = (2 + OZ_EPI_WARPS) * 32;
 constexpr int OZ_SMEM_MAX = 232448;              // 227 KB
 constexpr long long OZ_TIMEOUT_CYCLES = 6000000000LL;   // a stuck barrier traps instead of hanging the device
@@ -131,21 +131,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base + i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+// 16 lanes x 16 columns in the accumulator-fragment layout: thread t gets rows (t/4, t/4+8) of the 16-lane window and,
+// for each 8-column block k, columns 8k + 2(t%4), +1:  v[4k+0..1] = row t/4, v[4k+2..3] = row t/4+8.
+// A warp-wide 16-byte access to those elements touches 8 rows x 64 contiguous bytes (full sectors).
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8])
 {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile, 128-byte swizzle: 8-row groups 1024 B apart (SBO), version 1 (sm_100), layout SWIZZLE_128B
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
@@ -350,48 +347,97 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
         __syncwarp();
     } else {
         // ============================ epilogue ================================
+        // warp (q, h) owns rows 32q.. and columns 16h.. of the 128x64 tile; thread t holds, for row select i = 0..3,
+        // row 32q + t/4 + 8i and, for k = 0..1, the column pair 16h + 8k + 2(t%4), +1.  The C values are prefetched to
+        // L2 BEFORE waiting for the accumulators (their DRAM latency hides behind the tile's MMAs) and the
+        // read-modify-write happens after the accumulators have been released, overlapping the next tile's MMAs.
         const int q = warp & 3;                    // TMEM lane quadrant this warp may read
-        const int h = (warp - 2) >> 2;             // which 32 of the tile's 64 columns
+        const int h = (warp - 2) >> 2;             // which 16 of the tile's 64 columns
+        const int tr = lane >> 2, tc = 2 * (lane & 3);
+        const bool vec_ok = ((p.ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.M) & 15) == 0) && ((p.bs & 1) == 0);
         uint32_t acc_phase = 0;
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
             int zz, ti, tj0, ntj;
             oz_decode(p, u, zz, ti, tj0, ntj);
-            const int rr = ti * OZ_TM + q * 32 + lane;
-            const int r = p.rb + rr;
-            const bool row_ok = (r >= p.c1 && r < p.R);
             const double* sc = p.scl + (int64_t)zz * p.Rpad;
-            const double sr = sc[rr];
-            double* crow = p.M + (int64_t)zz * p.bs + (int64_t)r * p.ld;
+            const int rr0 = ti * OZ_TM + q * 32 + tr;
+            const int r0 = p.rb + rr0;                  // this thread's rows are r0 + 8 i
+            double* const cbase = p.M + (int64_t)zz * p.bs + (int64_t)r0 * p.ld;
+            const int64_t rstep = 8 * p.ld;
+#define OZ_CLIMIT(i) ((r0 + 8 * (i) >= p.c1 && r0 + 8 * (i) < p.R) ? min(r0 + 8 * (i) + 1, p.cmax) : 0)
             for (int t = 0; t < ntj; ++t) {
-                const int cc0 = (tj0 + t) * OZ_TN + 32 * h;
+                const int cc0 = (tj0 + t) * OZ_TN + 16 * h + tc;      // local column of this thread's first pair
+                // pull this thread's part of the C tile towards L2 while the tile's MMAs run
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int col = p.rb + cc0 + 8 * k;
+                        if (col < OZ_CLIMIT(i)) prefetch_l2(cbase + i * rstep + col);
+                    }
                 mbar_wait(bar_acc_full, acc_phase);
                 acc_phase ^= 1;
                 tc_fence_after();
-                double v[32];
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * h);
+                double v[4][4];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * h);
 #pragma unroll
                 for (int d = S - 1; d >= 0; --d) {
-                    uint32_t a[32];
-                    tmem_ld32(taddr + (uint32_t)(d * OZ_TN), a);
-                    if (d == S - 1) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = i32_to_f64(a[j]);
-                    } else {
+                    for (int half = 0; half < 2; ++half) {      // lanes 32q + 16 half ..: rows i = 2 half, 2 half + 1
+                        uint32_t a[8];
+                        tmem_ld_16x256b_x2(taddr + ((uint32_t)(16 * half) << 16) + (uint32_t)(d * OZ_TN), a);
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fma(v[j], 0.00390625, i32_to_f64(a[j]));
+                        for (int k = 0; k < 2; ++k)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const double x0 = i32_to_f64(a[4 * k + e]), x1 = i32_to_f64(a[4 * k + 2 + e]);
+                                if (d == S - 1) {
+                                    v[2 * half][2 * k + e] = x0;
+                                    v[2 * half + 1][2 * k + e] = x1;
+                                } else {
+                                    v[2 * half][2 * k + e] = fma(v[2 * half][2 * k + e], 0.00390625, x0);
+                                    v[2 * half + 1][2 * k + e] = fma(v[2 * half + 1][2 * k + e], 0.00390625, x1);
+                                }
+                            }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_acc_empty);       // accumulators may be overwritten by the next tile
-                if (row_ok) {
-                    const int c0 = p.rb + cc0;
-                    const int jmax = min(32, min(r + 1, p.cmax) - c0);
-                    const int jmin = max(0, p.c1 - c0);
+                double2 c[4][2];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j >= jmin && j < jmax) crow[c0 + j] -= v[j] * (sr * sc[cc0 + j]);
-                }
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int col = p.rb + cc0 + 8 * k;
+                        const int cl = OZ_CLIMIT(i);
+                        const double* crow = cbase + i * rstep;
+                        c[i][k] = make_double2(0.0, 0.0);
+                        if (vec_ok && col >= p.c1 && col + 1 < cl) {
+                            c[i][k] = *reinterpret_cast<const double2*>(crow + col);
+                        } else {
+                            if (col >= p.c1 && col < cl) c[i][k].x = crow[col];
+                            if (col + 1 >= p.c1 && col + 1 < cl) c[i][k].y = crow[col + 1];
+                        }
+                    }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int col = p.rb + cc0 + 8 * k;
+                        const int cl = OZ_CLIMIT(i);
+                        double* crow = cbase + i * rstep;
+                        const double sri = sc[rr0 + 8 * i];
+                        const double w0 = c[i][k].x - v[i][2 * k] * (sri * sc[cc0 + 8 * k]);
+                        const double w1 = c[i][k].y - v[i][2 * k + 1] * (sri * sc[cc0 + 8 * k + 1]);
+                        if (vec_ok && col >= p.c1 && col + 1 < cl) {
+                            *reinterpret_cast<double2*>(crow + col) = make_double2(w0, w1);
+                        } else {
+                            if (col >= p.c1 && col < cl) crow[col] = w0;
+                            if (col + 1 >= p.c1 && col + 1 < cl) crow[col + 1] = w1;
+                        }
+                    }
             }
         }
     }
@@ -458,7 +504,7 @@ int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     if (S * KBN > 12) return 1;                          // A strip must stay resident in shared memory
     const int cmax = R < col_limit ? R : col_limit;
     const int below = R - c1, cl = cmax - c1;
-    if (below < 384 || cl < 256) return 1;               // small updates: launch/slicing overhead dominates
+    if (below < 384 || cl < 128) return 1;               // small updates: launch/slicing overhead dominates
     OzParams p;
     p.M = M;
     p.ld = ld;
