@@ -31,8 +31,8 @@ Z_DIM = 30
 METRIC = "svi_steps_per_sec"
 UNIT = "steps/s"
 FP64_TENSOR_NOMINAL_TFLOPS = 40.0          # B200 data sheet, dense fp64 (tensor and CUDA-core figures coincide)
-KCLASS = ["syrk", "trsm", "potf2", "assemble", "reduce", "catlik", "patristic", "other", "syrk_tcgen05", "slice"]
-FLOP_CLASSES = (0, 1, 2, 8)
+KCLASS = ["syrk", "trsm", "potf2", "assemble", "reduce", "catlik", "patristic", "other", "syrk_tcgen05", "slice", "gru"]
+FLOP_CLASSES = (0, 1, 2, 8, 10)
 
 
 def log(*a):

@@ -37,6 +37,9 @@ SIGNATURES = {
     "drp_mvn_grad_cov_f64": (_i32, [_p, _i32, _i32, _p, _p, _p]),
     "drp_potri_batched_f64": (_i32, [_p, _i32, _i32, _p, _p, _p, _p]),
     "drp_ou_conditional_f64": (_i32, [_p, _i64, _p, _i32, _i32, _p, _p, _p, _p, _i32, _f64, _p, _p, _p, _p, _p]),
+    "drp_gru_hidden_size": (_i32, []),
+    "drp_gru_fwd_f64": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "drp_gru_bwd_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "drp_cat_loglik_partials": (_i64, [_i64]),
     "drp_cat_loglik_fwd_f64": (_i32, [_p, _p, _i32, _i64, _i32, _p, _p, _p, _p]),
     "drp_cat_loglik_bwd_f64": (_i32, [_p, _p, _i32, _p, _p, _i64, _i32, _p, _p]),

@@ -1,0 +1,383 @@
+// Bidirectional single-layer GRU recurrence (hidden size 60), forward and backward through time, fp64.
+//
+// Replaces nn.GRU inside the reference's decoder and encoder (S/ = /root/reference/draupnir/src/draupnir/):
+//   RNNDecoder_Tiling.forward      S/models_utils.py:93-99    rnn_output, _ = self.rnn(input, hidden)
+//   RNNEncoder.forward             S/models_utils.py:52-65    rnn_hidden_states, rnn_final = self.rnn(input, hidden)
+// with torch's gate conventions (gate order r, z, n):
+//   r = sigmoid(gi_r + W_hr h + b_hr)      z = sigmoid(gi_z + W_hz h + b_hz)
+//   n = tanh(gi_n + r * (W_hn h + b_hn))   h' = (1 - z) n + z h
+// `gi = W_ih x + b_ih` is the caller's business (one dense GEMM for the encoder; for the decoder the input is
+// [latent_i ; blosum_l], so gi[i,l] = U[i] + V[l] is a broadcast sum and the [n,L,51] input is never materialised).
+//
+// The recurrence is the sequential part: L dependent steps of a [rows,60]x[60,180] product plus gate math.  One CTA
+// owns 32 sequences of one direction for all L steps:
+//   * W_hh lives in REGISTERS as mma.sync.m8n8k4.f64 B-fragments (45 doubles per lane), h in shared memory;
+//   * warp w owns hidden units 8w..8w+7 of all three gates and all 32 rows, so every thread ends up holding r, z, n
+//     pre-activations of the SAME (row, unit) pairs and the gate math needs no exchange;
+//   * the per-step operand rows (gi; in the backward pass the saved gates and h_prev) are contiguous per sequence and
+//     are streamed into a shared-memory ring by TMA bulk copies (cp.async.bulk + mbarrier), issued one step ahead.
+// The backward kernel back-propagates dh through time (dh_prev = dh z + dgh W_hh, again register-resident W_hh) and
+// writes dgi; the weight gradients are dense reductions over all (sequence, step) pairs and are left to one GEMM each.
+#include "common.cuh"
+#include "instrument.cuh"
+
+namespace {
+
+constexpr int GH = 60;              // hidden size
+constexpr int G3 = 3 * GH;          // gate columns
+constexpr int GROWS = 32;           // sequences per CTA
+constexpr int GHS = 68;             // smem row stride of h   (stride mod 16 == 4: conflict-free fragment loads)
+constexpr int GDS = 180;            // smem row stride of dgh (180 mod 16 == 4)
+constexpr int GTHREADS = 256;
+constexpr long long G_TIMEOUT_CYCLES = 20000000000LL;
+
+__device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g_mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void g_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t g_mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void g_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    if (g_mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    int spins = 0;
+    while (!g_mbar_try_wait(bar, parity)) {
+        if (((++spins) & 0xFFF) == 0 && clock64() - t0 > G_TIMEOUT_CYCLES) __trap();
+    }
+}
+__device__ __forceinline__ void g_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ double sigmoid_f64(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Forward.  grid (ceil(n/32), 2 directions), 256 threads.
+//   gi    [n, L, 2, 180]   W_ih x + b_ih for both directions
+//   whh   [2, 180, 60]     bhh [2, 180]     h0 [2, n, 60]
+//   out   [n, L, 120]      hidden states (forward direction in [:60], backward in [60:], torch layout)
+//   gates [n, L, 2, 4, 60] r, z, n, (W_hn h + b_hn) for the backward pass; nullable
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GF_STAGES = 3;
+constexpr int GF_STAGE_BYTES = GROWS * G3 * 8;                                   // 46080
+constexpr int GF_SMEM = 2 * GROWS * GHS * 8 + GF_STAGES * GF_STAGE_BYTES + 64;     // h double buffer + gi ring + barriers
+
+__global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __restrict__ gi, const double* __restrict__ whh,
+                                                              const double* __restrict__ bhh, const double* __restrict__ h0,
+                                                              int n, int L, double* __restrict__ out,
+                                                              double* __restrict__ gates)
+{
+    extern __shared__ __align__(16) uint8_t gsm[];
+    double* hbuf = reinterpret_cast<double*>(gsm);                                   // [2][32][68]
+    double* ring = reinterpret_cast<double*>(gsm + 2 * GROWS * GHS * 8);              // [stages][32][180]
+    const uint32_t bars = g_smem_u32(gsm + 2 * GROWS * GHS * 8 + GF_STAGES * GF_STAGE_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    const int dir = blockIdx.y;
+    const int row0 = blockIdx.x * GROWS;
+    const int nrows = min(GROWS, n - row0);
+    const int j0 = warp * 8 + 2 * tig;            // this thread's hidden units j0, j0+1 (as C-fragment columns)
+    const bool jok = j0 < GH;
+    const int jb = warp * 8 + gid;                // hidden unit whose W_hh row this lane holds as B-fragment
+    const double* W = whh + (int64_t)dir * G3 * GH;
+
+    double B[3][15];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int ks = 0; ks < 15; ++ks) B[g][ks] = jb < GH ? W[(int64_t)(g * GH + jb) * GH + 4 * ks + tig] : 0.0;
+    double bh[3][2];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        bh[g][0] = jok ? bhh[dir * G3 + g * GH + j0] : 0.0;
+        bh[g][1] = jok ? bhh[dir * G3 + g * GH + j0 + 1] : 0.0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < GF_STAGES; ++s) g_mbar_init(bars + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // h0 -> hbuf[0] (all 60 units of the CTA's rows) and the thread's own copies
+    for (int idx = tid; idx < GROWS * GH; idx += GTHREADS) {
+        const int r = idx / GH, j = idx - r * GH;
+        hbuf[r * GHS + j] = r < nrows ? h0[((int64_t)dir * n + row0 + r) * GH + j] : 0.0;
+    }
+    __syncthreads();
+    double hold[4][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        hold[mt][0] = jok ? hbuf[(8 * mt + gid) * GHS + j0] : 0.0;
+        hold[mt][1] = jok ? hbuf[(8 * mt + gid) * GHS + j0 + 1] : 0.0;
+    }
+    auto issue = [&](int t) {      // warp 0: stream gi of step t into its ring stage (one bulk copy per sequence)
+        const int s = t % GF_STAGES;
+        const int l = dir ? L - 1 - t : t;
+        if (lane == 0) g_mbar_expect_tx(bars + 8 * s, (uint32_t)nrows * G3 * 8);
+        __syncwarp();
+        if (lane < nrows)
+            g_bulk_g2s(g_smem_u32(ring + (int64_t)s * GROWS * G3 + lane * G3),
+                       gi + (((int64_t)(row0 + lane) * L + l) * 2 + dir) * G3, G3 * 8, bars + 8 * s);
+    };
+    if (warp == 0)
+        for (int t = 0; t < min(GF_STAGES - 1, L); ++t) issue(t);
+
+    for (int t = 0; t < L; ++t) {
+        const int l = dir ? L - 1 - t : t;
+        const double* hc = hbuf + (t & 1) * GROWS * GHS;
+        double* hn = hbuf + ((t + 1) & 1) * GROWS * GHS;
+        if (warp == 0 && t + GF_STAGES - 1 < L) issue(t + GF_STAGES - 1);   // its stage was drained in step t-1
+        double acc[3][4][2];
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) acc[g][mt][0] = acc[g][mt][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 15; ++ks) {
+            double a[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) a[mt] = hc[(8 * mt + gid) * GHS + 4 * ks + tig];
+#pragma unroll
+            for (int g = 0; g < 3; ++g)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) dmma_8x8x4(acc[g][mt][0], acc[g][mt][1], a[mt], B[g][ks]);
+        }
+        const int s = t % GF_STAGES;
+        g_mbar_wait(bars + 8 * s, (uint32_t)(t / GF_STAGES) & 1u);
+        const double* gs = ring + (int64_t)s * GROWS * G3;
+        if (jok) {
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                const int r = 8 * mt + gid;
+                const double2 xr = *reinterpret_cast<const double2*>(gs + r * G3 + j0);
+                const double2 xz = *reinterpret_cast<const double2*>(gs + r * G3 + GH + j0);
+                const double2 xn = *reinterpret_cast<const double2*>(gs + r * G3 + 2 * GH + j0);
+                double hv[2], rv[2], zv[2], nv[2], qv[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double gr = (e ? xr.y : xr.x) + acc[0][mt][e] + bh[0][e];
+                    const double gz = (e ? xz.y : xz.x) + acc[1][mt][e] + bh[1][e];
+                    qv[e] = acc[2][mt][e] + bh[2][e];
+                    rv[e] = sigmoid_f64(gr);
+                    zv[e] = sigmoid_f64(gz);
+                    nv[e] = tanh((e ? xn.y : xn.x) + rv[e] * qv[e]);
+                    hv[e] = (1.0 - zv[e]) * nv[e] + zv[e] * hold[mt][e];
+                    hold[mt][e] = hv[e];
+                }
+                *reinterpret_cast<double2*>(hn + r * GHS + j0) = make_double2(hv[0], hv[1]);
+                if (r < nrows) {
+                    const int64_t site = (int64_t)(row0 + r) * L + l;
+                    *reinterpret_cast<double2*>(out + site * (2 * GH) + dir * GH + j0) = make_double2(hv[0], hv[1]);
+                    if (gates) {
+                        double* gp = gates + (site * 2 + dir) * (4 * GH) + j0;
+                        *reinterpret_cast<double2*>(gp) = make_double2(rv[0], rv[1]);
+                        *reinterpret_cast<double2*>(gp + GH) = make_double2(zv[0], zv[1]);
+                        *reinterpret_cast<double2*>(gp + 2 * GH) = make_double2(nv[0], nv[1]);
+                        *reinterpret_cast<double2*>(gp + 3 * GH) = make_double2(qv[0], qv[1]);
+                    }
+                }
+            }
+        }
+        __syncthreads();      // h of step t complete in hn; ring stage s and hc free for reuse
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward through time.  Steps run in the reverse of the forward order of the direction.
+//   dout  [n, L, 120]  gradient w.r.t. the hidden states   out / gates / h0 / whh as in the forward kernel
+//   dgi   [n, L, 2, 180]  gradient w.r.t. gi (r, z, n pre-activations); dgh = dgi with the n-part multiplied by r
+//   dh0   [2, n, 60] nullable
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GB_STAGES = 2;
+constexpr int GB_ROW_BYTES = (4 * GH + GH) * 8;                                   // saved gates + h_prev = 2400
+constexpr int GB_STAGE_BYTES = GROWS * GB_ROW_BYTES;                               // 76800
+constexpr int GB_SMEM = GROWS * GDS * 8 + GB_STAGES * GB_STAGE_BYTES + 64;
+
+__global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __restrict__ dout, const double* __restrict__ out,
+                                                              const double* __restrict__ gates, const double* __restrict__ whh,
+                                                              const double* __restrict__ h0, int n, int L,
+                                                              double* __restrict__ dgi, double* __restrict__ dh0)
+{
+    extern __shared__ __align__(16) uint8_t gsm[];
+    double* dgh = reinterpret_cast<double*>(gsm);                                    // [32][180]
+    double* ring = reinterpret_cast<double*>(gsm + GROWS * GDS * 8);                  // [stages][32][300]
+    const uint32_t bars = g_smem_u32(gsm + GROWS * GDS * 8 + GB_STAGES * GB_STAGE_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    const int dir = blockIdx.y;
+    const int row0 = blockIdx.x * GROWS;
+    const int nrows = min(GROWS, n - row0);
+    const int j0 = warp * 8 + 2 * tig;
+    const bool jok = j0 < GH;
+    const int jb = warp * 8 + gid;
+    const double* W = whh + (int64_t)dir * G3 * GH;
+    constexpr int RS = GB_ROW_BYTES / 8;          // 300 doubles per ring row: [r | z | n | q | h_prev]
+
+    double B[45];                                 // B[k][n] = W_hh[c = 4 ks + tig][j = jb]
+#pragma unroll
+    for (int ks = 0; ks < 45; ++ks) B[ks] = jb < GH ? W[(int64_t)(4 * ks + tig) * GH + jb] : 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < GB_STAGES; ++s) g_mbar_init(bars + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int idx = tid; idx < GROWS * GDS; idx += GTHREADS) dgh[idx] = 0.0;
+    __syncthreads();
+    // backward step tb = 0..L-1 handles forward step t = L-1-tb, i.e. position l = dir ? tb : L-1-tb
+    auto issue = [&](int tb) {
+        const int s = tb % GB_STAGES;
+        const int t = L - 1 - tb;
+        const int l = dir ? L - 1 - t : t;
+        const int lp = dir ? l + 1 : l - 1;       // position of h_prev (outside [0,L): h0)
+        if (lane == 0) g_mbar_expect_tx(bars + 8 * s, (uint32_t)nrows * GB_ROW_BYTES);
+        __syncwarp();
+        if (lane < nrows) {
+            const int64_t row = row0 + lane;
+            double* dst = ring + (int64_t)s * GROWS * RS + lane * RS;
+            g_bulk_g2s(g_smem_u32(dst), gates + ((row * L + l) * 2 + dir) * (4 * GH), 4 * GH * 8, bars + 8 * s);
+            const double* hp = t == 0 ? h0 + ((int64_t)dir * n + row) * GH : out + (row * L + lp) * (2 * GH) + dir * GH;
+            g_bulk_g2s(g_smem_u32(dst + 4 * GH), hp, GH * 8, bars + 8 * s);
+        }
+    };
+    if (warp == 0) issue(0);
+    double dh[4][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) dh[mt][0] = dh[mt][1] = 0.0;
+
+    for (int tb = 0; tb < L; ++tb) {
+        const int t = L - 1 - tb;
+        const int l = dir ? L - 1 - t : t;
+        if (warp == 0 && tb + 1 < L) issue(tb + 1);      // the other stage was drained before the last barrier
+        double2 dO[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int r = 8 * mt + gid;
+            dO[mt] = (jok && r < nrows) ? *reinterpret_cast<const double2*>(dout + ((int64_t)(row0 + r) * L + l) * (2 * GH) + dir * GH + j0)
+                                        : make_double2(0.0, 0.0);
+        }
+        const int s = tb % GB_STAGES;
+        g_mbar_wait(bars + 8 * s, (uint32_t)(tb / GB_STAGES) & 1u);
+        const double* gs = ring + (int64_t)s * GROWS * RS;
+        if (jok) {
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                const int r = 8 * mt + gid;
+                const double2 rr = *reinterpret_cast<const double2*>(gs + r * RS + j0);
+                const double2 zz = *reinterpret_cast<const double2*>(gs + r * RS + GH + j0);
+                const double2 nn = *reinterpret_cast<const double2*>(gs + r * RS + 2 * GH + j0);
+                const double2 qq = *reinterpret_cast<const double2*>(gs + r * RS + 3 * GH + j0);
+                const double2 hp = *reinterpret_cast<const double2*>(gs + r * RS + 4 * GH + j0);
+                double dr[2], dz[2], dn[2], dq[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double rv = e ? rr.y : rr.x, zv = e ? zz.y : zz.x, nv = e ? nn.y : nn.x, qv = e ? qq.y : qq.x;
+                    const double hv = e ? hp.y : hp.x;
+                    const double d = (e ? dO[mt].y : dO[mt].x) + dh[mt][e];
+                    dn[e] = d * (1.0 - zv) * (1.0 - nv * nv);
+                    dz[e] = d * (hv - nv) * zv * (1.0 - zv);
+                    dr[e] = dn[e] * qv * rv * (1.0 - rv);
+                    dq[e] = dn[e] * rv;
+                    dh[mt][e] = d * zv;
+                }
+                *reinterpret_cast<double2*>(dgh + r * GDS + j0) = make_double2(dr[0], dr[1]);
+                *reinterpret_cast<double2*>(dgh + r * GDS + GH + j0) = make_double2(dz[0], dz[1]);
+                *reinterpret_cast<double2*>(dgh + r * GDS + 2 * GH + j0) = make_double2(dq[0], dq[1]);
+                if (r < nrows) {
+                    double* gp = dgi + (((int64_t)(row0 + r) * L + l) * 2 + dir) * G3 + j0;
+                    *reinterpret_cast<double2*>(gp) = make_double2(dr[0], dr[1]);
+                    *reinterpret_cast<double2*>(gp + GH) = make_double2(dz[0], dz[1]);
+                    *reinterpret_cast<double2*>(gp + 2 * GH) = make_double2(dn[0], dn[1]);
+                }
+            }
+        }
+        __syncthreads();                           // dgh of this step complete; ring stage s drained
+        double acc[4][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 45; ++ks) {
+            double a[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) a[mt] = dgh[(8 * mt + gid) * GDS + 4 * ks + tig];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) dmma_8x8x4(acc[mt][0], acc[mt][1], a[mt], B[ks]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            dh[mt][0] += acc[mt][0];
+            dh[mt][1] += acc[mt][1];
+        }
+        __syncthreads();                           // everyone done reading dgh before the next step overwrites it
+    }
+    if (dh0 && jok) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int r = 8 * mt + gid;
+            if (r < nrows)
+                *reinterpret_cast<double2*>(dh0 + ((int64_t)dir * n + row0 + r) * GH + j0) = make_double2(dh[mt][0], dh[mt][1]);
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------- entry points -----------------------------------------------
+DRP_API int drp_gru_hidden_size(void) { return GH; }
+
+DRP_API int drp_gru_fwd_f64(const double* gi, const double* whh, const double* bhh, const double* h0, int n, int L, int H,
+                            double* out, double* gates, void* stream)
+{
+    if (!gi || !whh || !bhh || !h0) return -1;
+    if (n <= 0 || L <= 0) return -5;
+    if (H != GH) return -7;
+    if (!out) return -8;
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+        cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM);
+        attr_done = true;
+    }
+    {
+        DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * GH, st);
+        gru_fwd_kernel<<<dim3((n + GROWS - 1) / GROWS, 2), GTHREADS, GF_SMEM, st>>>(gi, whh, bhh, h0, n, L, out, gates);
+    }
+    return drp_launch_status();
+}
+
+DRP_API int drp_gru_bwd_f64(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
+                            int n, int L, int H, double* dgi, double* dh0, void* stream)
+{
+    if (!dout || !out || !gates || !whh || !h0) return -1;
+    if (n <= 0 || L <= 0) return -6;
+    if (H != GH) return -8;
+    if (!dgi) return -9;
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+        cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM);
+        attr_done = true;
+    }
+    {
+        DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * GH, st);
+        gru_bwd_kernel<<<dim3((n + GROWS - 1) / GROWS, 2), GTHREADS, GB_SMEM, st>>>(dout, out, gates, whh, h0, n, L, dgi, dh0);
+    }
+    return drp_launch_status();
+}

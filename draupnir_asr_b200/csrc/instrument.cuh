@@ -15,7 +15,8 @@ enum DrpKernelClass {
     DRP_K_OTHER = 7,
     DRP_K_SYRK_TC = 8,   // trailing update on the int8 tcgen05 pipe         work = fp64-equivalent flops
     DRP_K_SLICE = 9,     // fp64 panel -> int8 slices for the tcgen05 update work = bytes
-    DRP_K_CLASSES = 10
+    DRP_K_GRU = 10,      // bidirectional GRU recurrence fwd / bwd                work = recurrent-GEMM flops
+    DRP_K_CLASSES = 11
 };
 
 // Call right before / after a kernel launch of class `k` doing `work` algorithmic flops or bytes.

@@ -13,13 +13,13 @@
 
 namespace {
 
-// Sequential O(N) tree preparation by one thread block (N <= 16k nodes fits in shared memory many times over;
-// the work is a dependent chain, so a single lane does it).  parent[v] < v makes one forward pass enough.
-__global__ void tree_prepare_kernel(const int32_t* __restrict__ parent, const double* __restrict__ branch, int N,
-                                    int32_t* __restrict__ depth, double* __restrict__ root_dist,
-                                    int32_t* __restrict__ pre, int32_t* __restrict__ size, int32_t* __restrict__ next_free)
+// Tree preparation: depth, root distance, subtree size and preorder index of every node (every subtree becomes the
+// contiguous preorder interval [pre, pre + size)).  Sequential reference path: one lane, three passes; parent[v] < v
+// makes one forward pass enough.  Used for orderings that are topological but not level-order, and for N > 32768.
+__device__ void tree_prepare_sequential(const int32_t* __restrict__ parent, const double* __restrict__ branch, int N,
+                                        int32_t* __restrict__ depth, double* __restrict__ root_dist,
+                                        int32_t* __restrict__ pre, int32_t* __restrict__ size, int32_t* __restrict__ next_free)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     depth[0] = 0;
     root_dist[0] = 0.0;
     for (int v = 1; v < N; ++v) {
@@ -29,7 +29,6 @@ __global__ void tree_prepare_kernel(const int32_t* __restrict__ parent, const do
     }
     for (int v = 0; v < N; ++v) size[v] = 1;
     for (int v = N - 1; v >= 1; --v) size[parent[v]] += size[v];
-    // preorder entry index: every subtree becomes the contiguous interval [pre, pre + size)
     pre[0] = 0;
     next_free[0] = 1;
     for (int v = 1; v < N; ++v) {
@@ -37,6 +36,113 @@ __global__ void tree_prepare_kernel(const int32_t* __restrict__ parent, const do
         pre[v] = next_free[p];
         next_free[p] += size[v];
         next_free[v] = pre[v] + 1;
+    }
+}
+
+constexpr int TP_THREADS = 1024;
+constexpr int TP_PER_THREAD = 32;       // the parallel path covers N <= 32768 nodes
+
+// Parallel path for the reference's numbering (BFS level order, S/utils.py:864: nodes sorted by depth, siblings
+// adjacent): depths by pointer jumping (log2(depth) rounds), then one bottom-up sweep (subtree sizes) and one top-down
+// sweep (root distances - same summation order as the sequential path, so bit-identical - and preorder indices) over
+// the levels, each level processed by the whole CTA.  Any other numbering falls back to the sequential path.
+__global__ void __launch_bounds__(TP_THREADS) tree_prepare_kernel(const int32_t* __restrict__ parent,
+                                                                  const double* __restrict__ branch, int N,
+                                                                  int32_t* __restrict__ depth, double* __restrict__ root_dist,
+                                                                  int32_t* __restrict__ pre, int32_t* __restrict__ size,
+                                                                  int32_t* __restrict__ scratch)
+{
+    __shared__ int s_any, s_bad;
+    const int tid = threadIdx.x;
+    if (N > TP_THREADS * TP_PER_THREAD) {
+        if (tid == 0) tree_prepare_sequential(parent, branch, N, depth, root_dist, pre, size, scratch);
+        return;
+    }
+    // ---- depths: anc (in `pre`) and the edge count to it (in `depth`) double every round
+    for (int v = tid; v < N; v += TP_THREADS) {
+        pre[v] = v ? parent[v] : -1;
+        depth[v] = v ? 1 : 0;
+        scratch[v] = 0;
+    }
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    while (true) {
+        if (tid == 0) s_any = 0;
+        __syncthreads();
+        int na[TP_PER_THREAD], nc[TP_PER_THREAD];
+        int any = 0;
+#pragma unroll
+        for (int k = 0; k < TP_PER_THREAD; ++k) {
+            const int v = tid + k * TP_THREADS;
+            na[k] = -2;
+            if (v < N) {
+                const int a = pre[v];
+                if (a >= 0) {
+                    na[k] = pre[a];
+                    nc[k] = depth[a];
+                    any = 1;
+                }
+            }
+        }
+        __syncthreads();                                   // every read of this round precedes every write
+#pragma unroll
+        for (int k = 0; k < TP_PER_THREAD; ++k) {
+            const int v = tid + k * TP_THREADS;
+            if (na[k] != -2) {
+                pre[v] = na[k];
+                depth[v] += nc[k];
+            }
+        }
+        if (any) s_any = 1;
+        __syncthreads();
+        if (!s_any) break;
+    }
+    // ---- is this a level order with adjacent siblings?
+    for (int v = tid + 1; v < N; v += TP_THREADS) {
+        if (depth[v] < depth[v - 1]) s_bad = 1;
+        if (parent[v] != parent[v - 1]) atomicAdd(&scratch[parent[v]], 1);      // one block of children per parent
+    }
+    __syncthreads();
+    for (int v = tid; v < N; v += TP_THREADS)
+        if (scratch[v] > 1) s_bad = 1;
+    __syncthreads();
+    if (s_bad) {
+        if (tid == 0) tree_prepare_sequential(parent, branch, N, depth, root_dist, pre, size, scratch);
+        return;
+    }
+    // ---- level boundaries: scratch[d] = first node of depth d
+    const int maxd = depth[N - 1];
+    for (int v = tid; v < N; v += TP_THREADS) {
+        if (v == 0 || depth[v] != depth[v - 1]) scratch[depth[v]] = v;
+        size[v] = 1;
+    }
+    __syncthreads();
+    // ---- bottom-up: subtree sizes
+    for (int d = maxd; d >= 1; --d) {
+        const int lo = scratch[d], hi = d == maxd ? N : scratch[d + 1];
+        for (int v = lo + tid; v < hi; v += TP_THREADS) atomicAdd(&size[parent[v]], size[v]);
+        __syncthreads();
+    }
+    // ---- top-down: root distances and preorder indices
+    if (tid == 0) {
+        root_dist[0] = 0.0;
+        pre[0] = 0;
+    }
+    __syncthreads();
+    for (int d = 1; d <= maxd; ++d) {
+        const int lo = scratch[d], hi = d == maxd ? N : scratch[d + 1];
+        for (int v = lo + tid; v < hi; v += TP_THREADS) {
+            const int p = parent[v];
+            root_dist[v] = root_dist[p] + branch[v];
+            if (parent[v - 1] != p) {                                       // first child lays out its siblings
+                int run = pre[p] + 1;
+                for (int w = v; w < N && parent[w] == p; ++w) {
+                    pre[w] = run;
+                    run += size[w];
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -101,7 +207,7 @@ __global__ void __launch_bounds__(256) lca_patristic_kernel(const int32_t* __res
 }  // namespace
 
 // depth/root_dist/pre/size/scratch: device arrays of N elements each (scratch is clobbered).
-// Requires only parent[v] < v (any topological numbering; the reference's level order satisfies it).
+// Requires only parent[v] < v (any topological numbering); the reference's level order takes the parallel path.
 DRP_API int drp_tree_prepare(const int32_t* parent, const double* branch, int32_t n_nodes, int32_t* depth, double* root_dist,
                              int32_t* pre, int32_t* size, int32_t* scratch, void* stream)
 {
@@ -111,7 +217,7 @@ DRP_API int drp_tree_prepare(const int32_t* parent, const double* branch, int32_
     if (!depth || !root_dist || !pre || !size || !scratch) return -4;
     {
         DRP_LAUNCH(DRP_K_PATRISTIC, ((double)n_nodes * 40.0), st);
-        tree_prepare_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(parent, branch, n_nodes, depth, root_dist, pre, size, scratch);
+        tree_prepare_kernel<<<1, TP_THREADS, 0, (cudaStream_t)stream>>>(parent, branch, n_nodes, depth, root_dist, pre, size, scratch);
     }
     return drp_launch_status();
 }

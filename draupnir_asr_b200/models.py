@@ -227,8 +227,8 @@ class DRAUPNIRModel_classic(DRAUPNIRModelClass):
         if self.shard is not None:   # decoder is data-parallel over contiguous blocks of leaves
             lo, hi = self.shard.leaf_lo, self.shard.leaf_hi
             latent_space, aminoacid_sequences = latent_space[lo:hi], aminoacid_sequences[lo:hi]
-        x = self._decoder_input(latent_space)
-        scores = self.decoder.scores(input=x, hidden=self._hidden(latent_space.shape[0]))
+        scores = self.decoder.scores_structured(latent_space, self.embed(self.blosum_weighted),
+                                                hidden=self._hidden(latent_space.shape[0]))
         pyro.sample("aa_sequences", dist.Categorical(logits=scores), obs=aminoacid_sequences)
 
     def model_variational(self, family_data, patristic_matrix_sorted, cladistic_matrix, data_blosum, batch_blosum=None,
@@ -278,7 +278,7 @@ class DRAUPNIRModel_classic(DRAUPNIRModelClass):
             latent_space = map_estimates["latent_z"].T
             assert latent_space.shape == (self.n_leaves, self.z_dim)
             n_nodes = self.n_leaves
-        logits = self.decoder.forward(input=self._decoder_input(latent_space), hidden=self._hidden(n_nodes))
+        logits = self.decoder.forward_structured(latent_space, self.embed(self.blosum_weighted), hidden=self._hidden(n_nodes))
         if use_argmax:
             aa_sequences = torch.argmax(logits, dim=2).unsqueeze(0)
         else:

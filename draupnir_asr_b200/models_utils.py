@@ -29,7 +29,7 @@ class RNNEncoder(nn.Module):
                           bidirectional=True, num_layers=self.num_layers, dropout=0.0)
 
     def forward(self, input, hidden):
-        rnn_hidden_states, rnn_final_bidirectional = self.rnn(input, hidden)
+        rnn_hidden_states, rnn_final_bidirectional = ops.gru_module_forward(self.rnn, input, hidden)
         H = self.gru_hidden_dim
         rnn_hidden_states = rnn_hidden_states[:, :, :H] + rnn_hidden_states[:, :, H:]
         rnn_final_hidden_state = self.fc1(rnn_hidden_states[:, -1])
@@ -56,11 +56,30 @@ class RNNDecoder_Tiling(nn.Module):
     def scores(self, input, hidden):
         """Un-normalised per-site scores `[n,L,A]`; the training path feeds these straight to the fused
         categorical log-likelihood kernel (log_softmax is idempotent, so the ELBO is unchanged)."""
-        rnn_output, _ = self.rnn(input, hidden)
+        rnn_output, _ = ops.gru_module_forward(self.rnn, input, hidden)
+        return self.linear_probs(self.fc1(rnn_output))
+
+    def scores_structured(self, latent_space, blosum, hidden):
+        """`scores(cat(latent_space tiled over L, blosum tiled over n), hidden)` without building the `[n,L,z+A]` input
+        (S/models.py:339-342): since x[i,l] = [latent_i ; blosum_l], W_ih x + b_ih = W_z latent_i + (W_b blosum_l + b_ih)
+        is a broadcast sum of an `[n,3H]` and an `[L,3H]` term per direction."""
+        H, z = self.gru_hidden_dim, latent_space.shape[1]
+        if H != ops.GRU_HIDDEN:
+            n, L = latent_space.shape[0], blosum.shape[0]
+            x = torch.cat((latent_space[:, None, :].expand(n, L, z), blosum[None].expand(n, L, blosum.shape[1])), dim=2)
+            return self.scores(x, hidden)
+        wih, whh, bih, bhh = ops.gru_stacked_params(self.rnn)
+        U = latent_space @ wih[:, :, :z].reshape(6 * H, z).t()                               # [n, 2*3H]
+        V = torch.addmm(bih.reshape(-1), blosum, wih[:, :, z:].reshape(6 * H, -1).t())      # [L, 2*3H]
+        gi = (U[:, None, :] + V[None, :, :]).reshape(U.shape[0], V.shape[0], 2, 3 * H)
+        rnn_output = ops.gru_bidirectional(gi, whh, bhh, hidden)
         return self.linear_probs(self.fc1(rnn_output))
 
     def forward(self, input, hidden):
         return self.logsoftmax(self.scores(input, hidden))
+
+    def forward_structured(self, latent_space, blosum, hidden):
+        return self.logsoftmax(self.scores_structured(latent_space, blosum, hidden))
 
 
 class EmbedComplex(nn.Module):

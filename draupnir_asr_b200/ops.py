@@ -325,6 +325,86 @@ def tree_distances(parent: torch.Tensor, branch: torch.Tensor, rows: Optional[to
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# bidirectional GRU recurrence (decoder / encoder)
+# ------------------------------------------------------------------------------------------------------------------
+GRU_HIDDEN = lib.drp_gru_hidden_size()
+
+
+class _GRUBidir(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gi, whh, bhh, h0):
+        gi, whh, bhh, h0 = (_req(v, k).contiguous() for v, k in ((gi, "gi"), (whh, "weight_hh"), (bhh, "bias_hh"), (h0, "h0")))
+        n, L = gi.shape[0], gi.shape[1]
+        H = whh.shape[-1]
+        if gi.numel() != n * L * 2 * 3 * H or whh.shape != (2, 3 * H, H) or bhh.shape != (2, 3 * H) or h0.shape != (2, n, H):
+            raise RuntimeError(f"gru_bidirectional: inconsistent shapes gi{tuple(gi.shape)} whh{tuple(whh.shape)} "
+                               f"bhh{tuple(bhh.shape)} h0{tuple(h0.shape)}")
+        want = any(ctx.needs_input_grad)
+        out = torch.empty((n, L, 2 * H), dtype=torch.float64, device=gi.device)
+        gates = torch.empty((n, L, 2, 4, H), dtype=torch.float64, device=gi.device) if want else None
+        _rc(lib.drp_gru_fwd_f64(_p(gi), _p(whh), _p(bhh), _p(h0), n, L, H, _p(out), _p(gates), _stream()), "drp_gru_fwd_f64")
+        if want:
+            ctx.save_for_backward(out, gates, whh, h0)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        out, gates, whh, h0 = ctx.saved_tensors
+        n, L, H2 = out.shape
+        H = H2 // 2
+        dout = dout.contiguous()
+        dgi = torch.empty((n, L, 2, 3 * H), dtype=torch.float64, device=out.device)
+        dh0 = torch.empty_like(h0) if ctx.needs_input_grad[3] else None
+        _rc(lib.drp_gru_bwd_f64(_p(dout), _p(out), _p(gates), _p(whh), _p(h0), n, L, H, _p(dgi), _p(dh0), _stream()),
+            "drp_gru_bwd_f64")
+        dwhh = dbhh = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            # weight gradients: dense reductions over every (sequence, step) pair -> one GEMM per direction
+            dwhh = torch.empty_like(whh)
+            dbhh = torch.empty((2, 3 * H), dtype=torch.float64, device=out.device)
+            for d in range(2):
+                dgh = dgi[:, :, d, :].reshape(n * L, 3 * H).clone()
+                dgh[:, 2 * H:] *= gates[:, :, d, 0, :].reshape(n * L, H)
+                hprev = torch.empty((n, L, H), dtype=torch.float64, device=out.device)
+                if d == 0:
+                    hprev[:, 1:] = out[:, :-1, :H]
+                    hprev[:, 0] = h0[0]
+                else:
+                    hprev[:, :-1] = out[:, 1:, H:]
+                    hprev[:, -1] = h0[1]
+                dwhh[d] = dgh.t() @ hprev.reshape(n * L, H)
+                dbhh[d] = dgh.sum(0)
+                del dgh, hprev
+        return dgi if ctx.needs_input_grad[0] else None, dwhh, dbhh, dh0
+
+
+def gru_bidirectional(gi: torch.Tensor, weight_hh: torch.Tensor, bias_hh: torch.Tensor, h0: torch.Tensor) -> torch.Tensor:
+    """Hidden states `[n, L, 2H]` (torch's bidirectional layout) of a one-layer bidirectional GRU whose input
+    projections `gi = W_ih x + b_ih` are given as `[n, L, 2, 3H]`; `weight_hh [2,3H,H]`, `bias_hh [2,3H]`, `h0 [2,n,H]`
+    (direction 0 forward, 1 reverse; gate order r, z, n as in `nn.GRU`).  H must equal `GRU_HIDDEN`."""
+    return _GRUBidir.apply(gi, weight_hh, bias_hh, h0)
+
+
+def gru_stacked_params(rnn: torch.nn.GRU):
+    """(W_ih [2,3H,I], W_hh [2,3H,H], b_ih [2,3H], b_hh [2,3H]) of a one-layer bidirectional `nn.GRU`."""
+    assert rnn.num_layers == 1 and rnn.bidirectional and rnn.batch_first and rnn.bias
+    return (torch.stack((rnn.weight_ih_l0, rnn.weight_ih_l0_reverse)), torch.stack((rnn.weight_hh_l0, rnn.weight_hh_l0_reverse)),
+            torch.stack((rnn.bias_ih_l0, rnn.bias_ih_l0_reverse)), torch.stack((rnn.bias_hh_l0, rnn.bias_hh_l0_reverse)))
+
+
+def gru_module_forward(rnn: torch.nn.GRU, x: torch.Tensor, h0: torch.Tensor):
+    """Drop-in for `rnn(x, h0)` of a one-layer bidirectional batch-first `nn.GRU`: returns `(output, h_n)`."""
+    H = rnn.hidden_size
+    if H != GRU_HIDDEN or not x.is_cuda:
+        return rnn(x, h0)
+    wih, whh, bih, bhh = gru_stacked_params(rnn)
+    n, L, I = x.shape
+    gi = torch.addmm(bih.reshape(-1), x.reshape(n * L, I), wih.reshape(6 * H, I).t()).reshape(n, L, 2, 3 * H)
+    out = gru_bidirectional(gi, whh, bhh, h0)
+    return out, torch.stack((out[:, -1, :H], out[:, 0, H:]))
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # test hook: one trailing update of the blocked factorisation (fp64 mma.sync kernel or int8 tcgen05 kernel)
 # ------------------------------------------------------------------------------------------------------------------
 def syrk_update(M: torch.Tensor, k0: int, K: int, c1: int, R: int, col_limit: int, slices: int = 0) -> bool:

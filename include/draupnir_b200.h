@@ -33,7 +33,7 @@ int drp_abi_version(void);
 int64_t drp_launch_count(void);
 /* CUDA-event timing of every launch, by kernel class: 0 syrk (fp64 mma.sync), 1 trsm, 2 potf2 (work = flops),
  * 3 assembly, 4 reductions, 5 categorical, 6 patristic (work = bytes), 7 other, 8 syrk on the int8 tcgen05 pipe
- * (work = fp64-equivalent flops), 9 int8 slicing (work = bytes).  enable(1) clears earlier records; read()
+ * (work = fp64-equivalent flops), 9 int8 slicing (work = bytes), 10 GRU recurrence (work = flops).  enable(1) clears earlier records; read()
  * synchronises the device and fills three arrays of drp_timing_classes() entries (HOST pointers).                  */
 int drp_timing_classes(void);
 int drp_timing_enable(int on);
@@ -88,6 +88,18 @@ int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, double* M
 int drp_ou_conditional_f64(const double* D, int64_t ldd, const int32_t* idx, int n, int ni, const double* sf,
                            const double* sn, const double* lam, const double* x_leaf, int z, double jitter, double* mean,
                            double* cov, double* M, int32_t* info, void* stream);
+
+/* ---- K9  nn.GRU (bidirectional, one layer, hidden 60) inside RNNDecoder_Tiling.forward / RNNEncoder.forward:
+ *          S/models_utils.py:93-94 and :54 ----------------------------------------------------------------------- */
+/* gi [n,L,2,3H] = W_ih x + b_ih per direction (gate order r,z,n); whh [2,3H,H]; bhh [2,3H]; h0 [2,n,H];
+ * out [n,L,2H] (torch layout: forward direction first); gates [n,L,2,4,H] saved for the backward pass (nullable).
+ * H must equal drp_gru_hidden_size() (60, the reference's gru_hidden_dim: S/main.py:2777).                        */
+int drp_gru_hidden_size(void);
+int drp_gru_fwd_f64(const double* gi, const double* whh, const double* bhh, const double* h0, int n, int L, int H,
+                    double* out, double* gates, void* stream);
+/* dgi [n,L,2,3H] = dLoss/dgi; dh0 [2,n,H] nullable.  dLoss/dW_hh = sum dgh^T h_prev with dgh = dgi, n-part times r.   */
+int drp_gru_bwd_f64(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
+                    int n, int L, int H, double* dgi, double* dh0, void* stream);
 
 /* ---- K10  Categorical(logits).log_prob(obs).sum(): S/models.py:352 (+ LogSoftmax S/models_utils.py:98) --------- */
 int64_t drp_cat_loglik_partials(int64_t rows);
