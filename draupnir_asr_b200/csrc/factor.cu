@@ -34,96 +34,130 @@ constexpr int PLD = NB + 1;    // padded row stride of smem panels (conflict-fre
 constexpr int PR  = 128;       // rows per CTA in trsm
 constexpr int TS  = 64;        // syrk tile
 constexpr int SLD = 68;        // syrk smem row stride: (row*68 + tig) mod 16 distinct over a half warp
+static_assert(PR == 2 * NB, "trsm staging assumes two rows per pass");
 
 // ---------------------------------------------------------------------------------------------------------------
-// potf2: factor the nb x nb diagonal block at (c0, c0).  One CTA of 64 threads per matrix, thread i owns row i.
-// Left-looking by columns: L[i][c] = (A[i][c] - sum_{p<c} L[i][p] L[c][p]) / L[c][c].
+// potf2: factor the nb x nb diagonal block at (c0, c0).  One CTA of 64 threads per matrix; thread i keeps row i in
+// REGISTERS (fully unrolled right-looking elimination): per column one pivot broadcast, one column broadcast through
+// shared memory and a rank-1 update of the thread's own row.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) potf2_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb,
                                                    int32_t* __restrict__ info)
 {
     __shared__ double S[NB * PLD];
-    __shared__ double dsh;
+    __shared__ __align__(16) double colbuf[NB];
     double* A = Mb + (int64_t)blockIdx.x * bs + (int64_t)c0 * ld + c0;
     const int tid = threadIdx.x;
-    for (int idx = tid; idx < nb * nb; idx += 64) {
-        const int i = idx / nb, j = idx - i * nb;
-        S[i * PLD + j] = (j <= i) ? A[(int64_t)i * ld + j] : 0.0;
+    // thread tid fetches column tid of 16 rows at a time (16 independent loads in flight, coalesced across the CTA);
+    // rows / columns beyond nb: identity, so the unrolled 64-step elimination is a no-op there
+    for (int i0 = 0; i0 < NB; i0 += 16) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int i = i0 + u;
+            v[u] = (i < nb && tid <= i) ? A[(int64_t)i * ld + tid] : (i == tid ? 1.0 : 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) S[(i0 + u) * PLD + tid] = v[u];
     }
     __syncthreads();
-    double* row = S + tid * PLD;
+    double a[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) a[j] = S[tid * PLD + j];
     int bad = 0;
-    for (int c = 0; c < nb; ++c) {
-        double acc = 0.0;
-        if (tid >= c && tid < nb) {
-            const double* rc = S + c * PLD;
-            double a0 = row[c], a1 = 0.0;
-            int p = 0;
-            for (; p + 1 < c; p += 2) {
-                a0 = fma(-row[p], rc[p], a0);
-                a1 = fma(-row[p + 1], rc[p + 1], a1);
-            }
-            if (p < c) a0 = fma(-row[p], rc[p], a0);
-            acc = a0 + a1;
-            if (tid == c) dsh = acc;
-        }
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        colbuf[tid] = a[c];                                // column c of the current trailing matrix (rows >= c valid)
         __syncthreads();
-        const double piv = dsh;
+        const double piv = colbuf[c];
         if (!(piv > 0.0) && bad == 0) bad = c + 1;
-        const double d = sqrt(piv);
-        if (tid == c) row[c] = d;
-        else if (tid > c && tid < nb) row[c] = acc / d;
+        const double rd = rsqrt(piv);
+        const double l = tid >= c ? a[c] * rd : 0.0;       // rows above the pivot take no part
+        a[c] = tid == c ? piv * rd : l;
+        // unpredicated rank-1 update of the whole register row: entries right of the diagonal collect garbage that
+        // is never read back (l is forced to zero above) nor stored
+#pragma unroll
+        for (int j = c + 1; j < NB; ++j) a[j] = fma(-l, colbuf[j] * rd, a[j]);
         __syncthreads();
     }
-    for (int idx = tid; idx < nb * nb; idx += 64) {
-        const int i = idx / nb, j = idx - i * nb;
-        if (j <= i) A[(int64_t)i * ld + j] = S[i * PLD + j];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) S[tid * PLD + j] = a[j];
+    __syncthreads();
+    if (tid < nb) {
+#pragma unroll 8
+        for (int i = 0; i < NB; ++i)
+            if (i < nb && tid <= i) A[(int64_t)i * ld + tid] = S[i * PLD + tid];
     }
-    if (bad && tid == 0 && info) atomicCAS(info + blockIdx.x, 0, c0 + bad);
+    if (bad && bad <= nb && tid == 0 && info) atomicCAS(info + blockIdx.x, 0, c0 + bad);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// trsm: rows r in [c0+nb, R): X[r][c0:c0+nb] <- X L_jj^-T.  Thread-per-row forward substitution in smem.
+// trsm: rows r in [c0+nb, R): X[r][c0:c0+nb] <- X L_jj^-T.  One thread per row with the row in REGISTERS (fully
+// unrolled forward substitution, two independent accumulation chains); the factored block is read from shared memory
+// with warp-uniform (broadcast) 16-byte loads; rows are staged through shared memory for coalesced global access.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PR) trsm_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb, int R)
 {
-    extern __shared__ double sm[];
-    double* S = sm;                  // [NB][PLD] factored diagonal block
-    double* invd = S + NB * PLD;     // [NB]
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;                  // [NB][NB] factored diagonal block (identity beyond nb)
+    double* invd = S + NB * NB;      // [NB]
     double* X = invd + NB;           // [PR][PLD]
     double* A = Mb + (int64_t)blockIdx.y * bs;
     const int tid = threadIdx.x;
     const int r0 = c0 + nb + blockIdx.x * PR;
     const int nrows = min(PR, R - r0);
-    for (int idx = tid; idx < nb * nb; idx += PR) {
-        const int i = idx / nb, j = idx - i * nb;
-        S[i * PLD + j] = (j <= i) ? A[(int64_t)(c0 + i) * ld + c0 + j] : 0.0;
-    }
-    for (int idx = tid; idx < nrows * nb; idx += PR) {
-        const int i = idx / nb, j = idx - i * nb;
-        X[i * PLD + j] = A[(int64_t)(r0 + i) * ld + c0 + j];
-    }
-    __syncthreads();
-    if (tid < nb) invd[tid] = 1.0 / S[tid * PLD + tid];
-    __syncthreads();
-    if (tid < nrows) {
-        double* xr = X + tid * PLD;
-        for (int c = 0; c < nb; ++c) {
-            const double* lc = S + c * PLD;
-            double a0 = xr[c], a1 = 0.0;
-            int p = 0;
-            for (; p + 1 < c; p += 2) {
-                a0 = fma(-xr[p], lc[p], a0);
-                a1 = fma(-xr[p + 1], lc[p + 1], a1);
+    {   // two rows per pass (PR = 2 NB threads), 16 passes in flight at a time
+        const int j = tid & (NB - 1), half = tid >> 6;
+        for (int i0 = 0; i0 < NB; i0 += 32) {
+            double v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int i = i0 + 2 * u + half;
+                v[u] = (i < nb && j <= i) ? A[(int64_t)(c0 + i) * ld + c0 + j] : (i == j ? 1.0 : 0.0);
             }
-            if (p < c) a0 = fma(-xr[p], lc[p], a0);
-            xr[c] = (a0 + a1) * invd[c];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) S[(i0 + 2 * u + half) * NB + j] = v[u];
+        }
+        for (int i0 = 0; i0 < PR; i0 += 32) {
+            double v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int i = i0 + 2 * u + half;
+                v[u] = (i < nrows && j < nb) ? A[(int64_t)(r0 + i) * ld + c0 + j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) X[(i0 + 2 * u + half) * PLD + j] = v[u];
         }
     }
     __syncthreads();
-    for (int idx = tid; idx < nrows * nb; idx += PR) {
-        const int i = idx / nb, j = idx - i * nb;
-        A[(int64_t)(r0 + i) * ld + c0 + j] = X[i * PLD + j];
+    if (tid < NB) invd[tid] = 1.0 / S[tid * NB + tid];
+    __syncthreads();
+    double x[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) x[j] = X[tid * PLD + j];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        const double* lc = S + c * NB;
+        double a0 = x[c], a1 = 0.0;
+#pragma unroll
+        for (int p = 0; p + 1 < c; p += 2) {
+            const double2 l2 = *reinterpret_cast<const double2*>(lc + p);
+            a0 = fma(-x[p], l2.x, a0);
+            a1 = fma(-x[p + 1], l2.y, a1);
+        }
+        if (c & 1) a0 = fma(-x[c - 1], lc[c - 1], a0);
+        x[c] = (a0 + a1) * invd[c];
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) X[tid * PLD + j] = x[j];
+    __syncthreads();
+    {
+        const int j = tid & (NB - 1), half = tid >> 6;
+        if (j < nb) {
+#pragma unroll 8
+            for (int i = half; i < PR; i += 2)
+                if (i < nrows) A[(int64_t)(r0 + i) * ld + c0 + j] = X[i * PLD + j];
+        }
     }
 }
 
@@ -196,7 +230,7 @@ __global__ void __launch_bounds__(128) syrk_kernel(double* __restrict__ Mb, int6
 }  // namespace
 
 #include <stdlib.h>
-static const int TRSM_SMEM = (NB * PLD + NB + PR * PLD) * (int)sizeof(double);
+static const int TRSM_SMEM = (NB * NB + NB + PR * PLD) * (int)sizeof(double);
 static const int SYRK_SMEM = 2 * TS * SLD * (int)sizeof(double);
 
 void drp_dmma_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, cudaStream_t st)
@@ -279,7 +313,10 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
                         DRP_LAUNCH(DRP_K_TRSM, (double)z * below * nb * nb, st);
                         trsm_kernel<<<g, PR, TRSM_SMEM, st>>>(M, ld, bs, c0, nb, R);
                     }
-                    if (c1 < Q1) drp_dmma_syrk(M, ld, bs, z, c0, nb, c1, R, min(col_limit, Q1), st);   // inside the sub-panel
+                    if (c1 < Q1) {                                                              // inside the sub-panel
+                        const int rc = trailing_update(M, ld, bs, z, c0, nb, c1, R, min(col_limit, Q1), tws, ws_bytes, st);
+                        if (rc) return rc;
+                    }
                 }
             }
             if (Q1 < C1) {                                                                              // rest of the outer panel

@@ -335,6 +335,108 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradients of the recurrence: dW_hh[dir] = sum_p dgh[p]^T h_prev[p], db_hh[dir] = sum_p dgh[p] over all
+// (sequence, step) pairs p, with dgh = dgi except that the n-part is multiplied by r.  A [180 x 60] += [180 x K][K x 60]
+// product with K = n L, split over the grid along K; every CTA keeps its partial product in registers (fp64 mma.sync
+// accumulators), operand rows arrive by TMA bulk copies, partials are summed by a second, deterministic kernel.
+// The bias gradient rides along as column 60 of the padded h_prev tile (a column of ones).
+//   part [n_cta/2][2][184][64]
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GW_PAIRS = 32;                                   // pairs per pipeline stage (8 k-steps)
+constexpr int GW_ROW = (G3 + GH + GH);                          // doubles per staged pair: dgi | r | h_prev
+constexpr int GW_STAGE_BYTES = GW_PAIRS * GW_ROW * 8;           // 76800
+constexpr int GW_STAGES = 2;
+constexpr int GW_SMEM = GW_STAGES * GW_STAGE_BYTES + 64;
+constexpr int GW_MT = 23;                                      // 184 = 23 m-tiles cover the 180 gate columns
+
+__global__ void __launch_bounds__(GTHREADS, 1) gru_wgrad_kernel(const double* __restrict__ dgi, const double* __restrict__ gates,
+                                                                const double* __restrict__ out, const double* __restrict__ h0,
+                                                                int n, int L, double* __restrict__ part)
+{
+    extern __shared__ __align__(16) uint8_t gsm[];
+    double* ring = reinterpret_cast<double*>(gsm);
+    const uint32_t bars = g_smem_u32(gsm + GW_STAGES * GW_STAGE_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    const int dir = blockIdx.x & 1;
+    const int chunk = blockIdx.x >> 1, nchunks = gridDim.x >> 1;
+    const int64_t P = (int64_t)n * L;
+    const int64_t nblk = (P + GW_PAIRS - 1) / GW_PAIRS;
+    const int64_t b0 = nblk * chunk / nchunks, b1 = nblk * (chunk + 1) / nchunks;
+    if (tid == 0) {
+        for (int s = 0; s < GW_STAGES; ++s) g_mbar_init(bars + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t blk) {      // warp 0, one pair per lane
+        const int s = (int)((blk - b0) % GW_STAGES);
+        const int64_t p = blk * GW_PAIRS + lane;
+        const int valid = (int)min((int64_t)GW_PAIRS, P - blk * GW_PAIRS);
+        if (lane == 0) g_mbar_expect_tx(bars + 8 * s, (uint32_t)valid * GW_ROW * 8);
+        __syncwarp();
+        if (lane < valid) {
+            double* dst = ring + (int64_t)s * GW_PAIRS * GW_ROW + lane * GW_ROW;
+            const int64_t i = p / L;
+            const int l = (int)(p - i * L);
+            g_bulk_g2s(g_smem_u32(dst), dgi + (p * 2 + dir) * G3, G3 * 8, bars + 8 * s);
+            g_bulk_g2s(g_smem_u32(dst + G3), gates + (p * 2 + dir) * (4 * GH), GH * 8, bars + 8 * s);
+            const bool first = dir ? (l == L - 1) : (l == 0);          // first step of the direction: h_prev = h0
+            const double* hp = first ? h0 + ((int64_t)dir * n + i) * GH : out + (dir ? p + 1 : p - 1) * (2 * GH) + dir * GH;
+            g_bulk_g2s(g_smem_u32(dst + G3 + GH), hp, GH * 8, bars + 8 * s);
+        }
+    };
+    double acc[GW_MT][2];
+#pragma unroll
+    for (int mt = 0; mt < GW_MT; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+    if (warp == 0 && b0 < b1) issue(b0);
+    const int jb = warp * 8 + gid;                 // column of h_prev (60: ones -> bias gradient; 61..63: zero)
+    for (int64_t blk = b0; blk < b1; ++blk) {
+        const int it = (int)(blk - b0);
+        const int s = it % GW_STAGES;
+        if (warp == 0 && blk + 1 < b1) issue(blk + 1);
+        g_mbar_wait(bars + 8 * s, (uint32_t)(it / GW_STAGES) & 1u);
+        double* st = ring + (int64_t)s * GW_PAIRS * GW_ROW;
+        const int valid = (int)min((int64_t)GW_PAIRS, P - blk * GW_PAIRS);
+        if (valid < GW_PAIRS) {                    // ragged last block: rows that were not loaded must not contribute
+            for (int idx = tid; idx < (GW_PAIRS - valid) * GW_ROW; idx += GTHREADS) st[valid * GW_ROW + idx] = 0.0;
+            __syncthreads();
+        }
+#pragma unroll 2
+        for (int ks = 0; ks < GW_PAIRS / 4; ++ks) {
+            const double* row = st + (4 * ks + tig) * GW_ROW;
+            const double b = jb < GH ? row[G3 + GH + jb] : (jb == GH ? 1.0 : 0.0);
+#pragma unroll
+            for (int mt = 0; mt < GW_MT; ++mt) {
+                const int c = 8 * mt + gid;
+                double a = c < G3 ? row[c] : 0.0;
+                if (mt >= 15) a *= (c < G3 ? row[G3 + c - 2 * GH] : 0.0);       // n-part: times r
+                dmma_8x8x4(acc[mt][0], acc[mt][1], a, b);
+            }
+        }
+        __syncthreads();                           // stage s drained before it is refilled
+    }
+    double* dst = part + ((int64_t)chunk * 2 + dir) * (GW_MT * 8) * 64;
+#pragma unroll
+    for (int mt = 0; mt < GW_MT; ++mt) {
+        const int c = 8 * mt + gid, j = warp * 8 + 2 * tig;
+        *reinterpret_cast<double2*>(dst + (int64_t)c * 64 + j) = make_double2(acc[mt][0], acc[mt][1]);
+    }
+}
+
+// dwhh [2][180][60], dbhh [2][180] = sum over chunks of part (fixed order: deterministic)
+__global__ void __launch_bounds__(256) gru_wgrad_reduce_kernel(const double* __restrict__ part, int nchunks,
+                                                               double* __restrict__ dwhh, double* __restrict__ dbhh)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // over [2][180][61]
+    if (idx >= 2 * G3 * (GH + 1)) return;
+    const int j = idx % (GH + 1), c = (idx / (GH + 1)) % G3, dir = idx / ((GH + 1) * G3);
+    double s = 0.0;
+    for (int k = 0; k < nchunks; ++k) s += part[(((int64_t)k * 2 + dir) * (GW_MT * 8) + c) * 64 + j];
+    if (j < GH) dwhh[((int64_t)dir * G3 + c) * GH + j] = s;
+    else dbhh[dir * G3 + c] = s;
+}
+
 }  // namespace
 
 // ------------------------------------------------- entry points -----------------------------------------------
@@ -378,6 +480,48 @@ DRP_API int drp_gru_bwd_f64(const double* dout, const double* out, const double*
     {
         DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * GH, st);
         gru_bwd_kernel<<<dim3((n + GROWS - 1) / GROWS, 2), GTHREADS, GB_SMEM, st>>>(dout, out, gates, whh, h0, n, L, dgi, dh0);
+    }
+    return drp_launch_status();
+}
+
+// Workspace (doubles) of drp_gru_wgrad_f64.
+DRP_API int64_t drp_gru_wgrad_workspace_elems(void)
+{
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    return (int64_t)n_sm * 2 * (GW_MT * 8) * 64;
+}
+
+// dwhh [2,3H,H], dbhh [2,3H] from dgi [n,L,2,3H] (drp_gru_bwd_f64), the saved gates, the hidden states and h0.
+DRP_API int drp_gru_wgrad_f64(const double* dgi, const double* gates, const double* out, const double* h0, int n, int L,
+                              int H, double* dwhh, double* dbhh, double* ws, int64_t ws_elems, void* stream)
+{
+    if (!dgi || !gates || !out || !h0) return -1;
+    if (n <= 0 || L <= 0) return -5;
+    if (H != GH) return -7;
+    if (!dwhh || !dbhh) return -8;
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr_done = false;
+    static int n_sm = 148;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gru_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GW_SMEM);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        attr_done = true;
+    }
+    const int64_t nblk = ((int64_t)n * L + GW_PAIRS - 1) / GW_PAIRS;
+    int nchunks = n_sm / 2 > 0 ? n_sm / 2 : 1;
+    if (nchunks > nblk) nchunks = (int)nblk;
+    if (!ws || ws_elems < (int64_t)nchunks * 2 * (GW_MT * 8) * 64) return -10;
+    {
+        DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * (GH + 1), st);
+        gru_wgrad_kernel<<<2 * nchunks, GTHREADS, GW_SMEM, st>>>(dgi, gates, out, h0, n, L, ws);
+    }
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, (double)nchunks * 2 * G3 * (GH + 1) * 8.0, st);
+        gru_wgrad_reduce_kernel<<<(2 * G3 * (GH + 1) + 255) / 256, 256, 0, st>>>(ws, nchunks, dwhh, dbhh);
     }
     return drp_launch_status();
 }

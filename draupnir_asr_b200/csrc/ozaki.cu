@@ -11,7 +11,8 @@
 //
 //     sum_k P[r][k] P[c][k] ~= 2^(e_r-7) 2^(e_c-7) * sum_{d<S} 2^-8d * ( sum_{t+u=d} sum_k q_t[r][k] q_u[c][k] )
 //
-// The epilogue recombines the S integers in fp64 (Horner, one rounding per term) and applies the update to C.  The only
+// The epilogue recombines the S integers in fp64 (one fma per term, in the order the accumulators complete) and
+// applies the update to C.  The only
 // error is the mantissa truncation (2^-(8S-1) of the row maximum) and the dropped anti-diagonals d >= S
 // (~ S 2^-8S of the product of row maxima): S = 6 gives ~1e-13, S = 7 ~1e-15 relative to |P_r|max |P_c|max, i.e. a
 // backward error at fp64 level for the factorisation (DESIGN.md "split-integer trailing update").
@@ -38,6 +39,7 @@ constexpr int OZ_CHUNK = 16;                     // column tiles per work unit (
 constexpr int OZ_EPI_WARPS = 16;                 // 4 TMEM lane quadrants x 4 column quarters of the 128x64 tile
 constexpr int OZ_THREADS = (2 + OZ_EPI_WARPS) * 32;
 constexpr int OZ_SMEM_MAX = 232448;              // 227 KB
+constexpr int OZ_MAXS = 8;                       // upper bound on the slice count (barrier storage)
 constexpr long long OZ_TIMEOUT_CYCLES = 6000000000LL;   // a stuck barrier traps instead of hanging the device
 
 template <int S, int KBN>
@@ -60,6 +62,7 @@ struct OzParams {
     const double* scl;         // [z][Rpad]  2^(e_r - 7)
     int Rpad, rb, c1, R, cmax;
     int nTi, nTj, units_per_z, total_units;
+    int K;                     // real contraction length (columns of the panel); the k-blocks are zero-padded
 };
 
 // ------------------------------------------------ PTX wrappers ---------------------------------------------------
@@ -185,7 +188,7 @@ __device__ __forceinline__ void oz_decode(const OzParams& p, int u, int& zz, int
 // Slicing: one warp per row of the panel P = M[rb .. rb+Rpad) x [k0, k0+K).  Rows outside [c1, R) become zeros.
 // ---------------------------------------------------------------------------------------------------------------
 template <int S>
-__global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ Mb, int64_t ld, int64_t bs, int k0, int KBN,
+__global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ Mb, int64_t ld, int64_t bs, int k0, int Kcols, int KBN,
                                                        int rb, int c1, int R, int Rpad, uint8_t* __restrict__ sl,
                                                        int64_t sl_bs, double* __restrict__ scl)
 {
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const double v = (live && kb < KBN) ? src[kb * 128 + j] : 0.0;
+            const double v = (live && kb * 128 + 4 * lane + j < Kcols) ? src[kb * 128 + j] : 0.0;
             x[kb * 4 + j] = v;
             m = fmax(m, fabs(v));
         }
@@ -248,15 +251,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
     const uint32_t sA = base;
     const uint32_t sB = base + Cfg::A_BYTES;
     const uint32_t bars = sB + NST * OZ_B_TILE;
-    const uint32_t bar_a_full = bars, bar_a_empty = bars + 8, bar_acc_full = bars + 16, bar_acc_empty = bars + 24;
-    const uint32_t bar_b_full = bars + 32, bar_b_empty = bars + 32 + 8 * NST;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + Cfg::A_BYTES + NST * OZ_B_TILE + 32 + 16 * NST);
+    // mbarriers: A strip full/empty, accumulators drained, accumulator d complete (one per anti-diagonal), B ring
+    const uint32_t bar_a_full = bars, bar_a_empty = bars + 8, bar_acc_empty = bars + 16, bar_acc_full = bars + 24;
+    const uint32_t bar_b_full = bars + 24 + 8 * OZ_MAXS, bar_b_empty = bar_b_full + 8 * NST;
+    volatile uint32_t* tmem_slot =
+        reinterpret_cast<volatile uint32_t*>(gen + Cfg::A_BYTES + NST * OZ_B_TILE + 24 + 8 * OZ_MAXS + 16 * NST);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_a_full, 1);
         mbar_init(bar_a_empty, 1);
-        mbar_init(bar_acc_full, 1);
+        for (int d = 0; d < S; ++d) mbar_init(bar_acc_full + 8 * d, 1);
         mbar_init(bar_acc_empty, OZ_EPI_WARPS);
         for (int s = 0; s < NST; ++s) {
             mbar_init(bar_b_full + 8 * s, 1);
@@ -323,13 +328,14 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                             mbar_wait(bar_b_full + 8 * st, b_phase);
                             tc_fence_after();
                             const uint64_t bdesc = umma_desc(sB + st * OZ_B_TILE);
+                            const int k4n = min(4, (p.K - OZ_ROWB * kb + 31) >> 5);   // 32-column steps with real data
                             for (int ta = 0; ta + ub < S; ++ta) {      // slice of A; anti-diagonal d = ta + ub
                                 const uint64_t adesc = umma_desc(sA + (ta * KBN + kb) * OZ_A_TILE);
                                 const uint32_t idesc = umma_idesc(ta == 0, ub == 0);
                                 const uint32_t dcol = tmem + (uint32_t)((ta + ub) * OZ_TN);
 #pragma unroll
                                 for (int k4 = 0; k4 < 4; ++k4)
-                                    umma_i8(dcol, adesc + 2 * k4, bdesc + 2 * k4, idesc, (ub | kb | k4) != 0);
+                                    if (k4 < k4n) umma_i8(dcol, adesc + 2 * k4, bdesc + 2 * k4, idesc, (ub | kb | k4) != 0);
                             }
                             umma_commit(bar_b_empty + 8 * st);
                             if (++st == NST) {
@@ -337,8 +343,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                                 b_phase ^= 1;
                             }
                         }
+                        // anti-diagonal d = ub only receives products with B slices <= ub: it is complete now, the
+                        // epilogue may start on it while the remaining (fewer and fewer) slice pairs are multiplied
+                        umma_commit(bar_acc_full + 8 * ub);
                     }
-                    umma_commit(bar_acc_full);
                     acc_phase ^= 1;
                 }
                 umma_commit(bar_a_empty);
@@ -375,13 +383,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                         const int col = p.rb + cc0 + 8 * k;
                         if (col < OZ_CLIMIT(i)) prefetch_l2(cbase + i * rstep + col);
                     }
-                mbar_wait(bar_acc_full, acc_phase);
-                acc_phase ^= 1;
-                tc_fence_after();
                 double v[4][4];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * h);
 #pragma unroll
-                for (int d = S - 1; d >= 0; --d) {
+                for (int d = 0; d < S; ++d) {                    // in the order the anti-diagonals complete
+                    mbar_wait(bar_acc_full + 8 * d, acc_phase);
+                    tc_fence_after();
+                    const double w = 1.0 / (double)(1ull << (8 * d));                 // 2^-8d
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {      // lanes 32q + 16 half ..: rows i = 2 half, 2 half + 1
                         uint32_t a[8];
@@ -392,16 +400,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const double x0 = i32_to_f64(a[4 * k + e]), x1 = i32_to_f64(a[4 * k + 2 + e]);
-                                if (d == S - 1) {
+                                if (d == 0) {
                                     v[2 * half][2 * k + e] = x0;
                                     v[2 * half + 1][2 * k + e] = x1;
                                 } else {
-                                    v[2 * half][2 * k + e] = fma(v[2 * half][2 * k + e], 0.00390625, x0);
-                                    v[2 * half + 1][2 * k + e] = fma(v[2 * half + 1][2 * k + e], 0.00390625, x1);
+                                    v[2 * half][2 * k + e] = fma(x0, w, v[2 * half][2 * k + e]);
+                                    v[2 * half + 1][2 * k + e] = fma(x1, w, v[2 * half + 1][2 * k + e]);
                                 }
                             }
                     }
                 }
+                acc_phase ^= 1;
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_acc_empty);       // accumulators may be overwritten by the next tile
@@ -447,7 +456,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
 }
 
 template <int S, int KBN>
-int oz_launch(const OzParams& p, int z, int k0, cudaStream_t st, double flops)
+int oz_launch(const OzParams& p, int z, int k0, int Kcols, cudaStream_t st, double flops)
 {
     using Cfg = OzCfg<S, KBN>;
     static bool attr_done = false;
@@ -461,7 +470,7 @@ int oz_launch(const OzParams& p, int z, int k0, cudaStream_t st, double flops)
     }
     {
         DRP_LAUNCH(DRP_K_SLICE, (double)z * p.Rpad * KBN * 128 * (8.0 + S), st);
-        oz_slice_kernel<S><<<dim3((p.Rpad + 7) / 8, z), 256, 0, st>>>(p.M, p.ld, p.bs, k0, KBN, p.rb, p.c1, p.R, p.Rpad,
+        oz_slice_kernel<S><<<dim3((p.Rpad + 7) / 8, z), 256, 0, st>>>(p.M, p.ld, p.bs, k0, Kcols, KBN, p.rb, p.c1, p.R, p.Rpad,
                                                                      const_cast<uint8_t*>(p.sl), p.sl_bs,
                                                                      const_cast<double*>(p.scl));
     }
@@ -499,12 +508,12 @@ int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
                    int64_t ws_bytes, cudaStream_t st)
 {
     if (S == 0 || !ws) return 1;
-    if (K != 128 && K != 256) return 1;
-    const int KBN = K / 128;
+    if (K < 32 || K > 256) return 1;
+    const int KBN = K > 128 ? 2 : 1;
     if (S * KBN > 12) return 1;                          // A strip must stay resident in shared memory
     const int cmax = R < col_limit ? R : col_limit;
     const int below = R - c1, cl = cmax - c1;
-    if (below < 384 || cl < 128) return 1;               // small updates: launch/slicing overhead dominates
+    if (below < 384 || cl < 64) return 1;                // small updates: launch/slicing overhead dominates
     OzParams p;
     p.M = M;
     p.ld = ld;
@@ -513,6 +522,7 @@ int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     p.c1 = c1;
     p.R = R;
     p.cmax = cmax;
+    p.K = K;
     p.nTi = (R - p.rb + OZ_TM - 1) / OZ_TM;
     p.nTj = (cmax - p.rb + OZ_TN - 1) / OZ_TN;
     p.Rpad = p.nTi * OZ_TM;
@@ -534,16 +544,16 @@ int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     int rc = 1;
     if (KBN == 1) {
         switch (S) {
-            case 4: rc = oz_launch<4, 1>(p, z, k0, st, flops); break;
-            case 5: rc = oz_launch<5, 1>(p, z, k0, st, flops); break;
-            case 6: rc = oz_launch<6, 1>(p, z, k0, st, flops); break;
-            case 7: rc = oz_launch<7, 1>(p, z, k0, st, flops); break;
+            case 4: rc = oz_launch<4, 1>(p, z, k0, K, st, flops); break;
+            case 5: rc = oz_launch<5, 1>(p, z, k0, K, st, flops); break;
+            case 6: rc = oz_launch<6, 1>(p, z, k0, K, st, flops); break;
+            case 7: rc = oz_launch<7, 1>(p, z, k0, K, st, flops); break;
         }
     } else {
         switch (S) {
-            case 4: rc = oz_launch<4, 2>(p, z, k0, st, flops); break;
-            case 5: rc = oz_launch<5, 2>(p, z, k0, st, flops); break;
-            case 6: rc = oz_launch<6, 2>(p, z, k0, st, flops); break;
+            case 4: rc = oz_launch<4, 2>(p, z, k0, K, st, flops); break;
+            case 5: rc = oz_launch<5, 2>(p, z, k0, K, st, flops); break;
+            case 6: rc = oz_launch<6, 2>(p, z, k0, K, st, flops); break;
         }
     }
     if (rc) return rc;

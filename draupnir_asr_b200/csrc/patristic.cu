@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(TP_THREADS) tree_prepare_kernel(const int32_t*
     }
     if (tid == 0) s_bad = 0;
     __syncthreads();
-    while (true) {
+    for (int round = 0;; ++round) {
         if (tid == 0) s_any = 0;
         __syncthreads();
         int na[TP_PER_THREAD], nc[TP_PER_THREAD];
@@ -95,8 +95,15 @@ __global__ void __launch_bounds__(TP_THREADS) tree_prepare_kernel(const int32_t*
         }
         if (any) s_any = 1;
         __syncthreads();
-        if (!s_any) break;
+        const int more = s_any;
+        __syncthreads();                                   // everyone has read the flag before it is reset
+        if (!more) break;
+        if (round > 40) {                                  // 2^40 levels cannot exist: parent[] is not a forest
+            if (tid == 0) s_bad = 1;
+            break;
+        }
     }
+    __syncthreads();
     // ---- is this a level order with adjacent siblings?
     for (int v = tid + 1; v < N; v += TP_THREADS) {
         if (depth[v] < depth[v - 1]) s_bad = 1;

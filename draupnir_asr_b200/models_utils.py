@@ -57,7 +57,16 @@ class RNNDecoder_Tiling(nn.Module):
         """Un-normalised per-site scores `[n,L,A]`; the training path feeds these straight to the fused
         categorical log-likelihood kernel (log_softmax is idempotent, so the ELBO is unchanged)."""
         rnn_output, _ = ops.gru_module_forward(self.rnn, input, hidden)
-        return self.linear_probs(self.fc1(rnn_output))
+        return self._project(rnn_output)
+
+    def _project(self, rnn_output):
+        """`linear_probs(fc1(rnn_output))` (S/models_utils.py:98).  There is no non-linearity between the two layers, so
+        they are applied as ONE `[2H -> aa_prob]` affine map (W2 W1, W2 b1 + b2): a third of the flops and no
+        `[n,L,H]` intermediate; autograd still delivers the gradients of fc1 / linear_probs themselves."""
+        W = self.linear_probs.weight @ self.fc1.weight                                   # [A, 2H]
+        b = torch.addmv(self.linear_probs.bias, self.linear_probs.weight, self.fc1.bias)  # [A]
+        n, L, F = rnn_output.shape
+        return torch.addmm(b, rnn_output.reshape(n * L, F), W.t()).reshape(n, L, -1)
 
     def scores_structured(self, latent_space, blosum, hidden):
         """`scores(cat(latent_space tiled over L, blosum tiled over n), hidden)` without building the `[n,L,z+A]` input
@@ -73,7 +82,7 @@ class RNNDecoder_Tiling(nn.Module):
         V = torch.addmm(bih.reshape(-1), blosum, wih[:, :, z:].reshape(6 * H, -1).t())      # [L, 2*3H]
         gi = (U[:, None, :] + V[None, :, :]).reshape(U.shape[0], V.shape[0], 2, 3 * H)
         rnn_output = ops.gru_bidirectional(gi, whh, bhh, hidden)
-        return self.linear_probs(self.fc1(rnn_output))
+        return self._project(rnn_output)
 
     def forward(self, input, hidden):
         return self.logsoftmax(self.scores(input, hidden))

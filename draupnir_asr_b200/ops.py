@@ -359,22 +359,13 @@ class _GRUBidir(torch.autograd.Function):
             "drp_gru_bwd_f64")
         dwhh = dbhh = None
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            # weight gradients: dense reductions over every (sequence, step) pair -> one GEMM per direction
+            # weight gradients: reductions over every (sequence, step) pair, one split-K kernel + a deterministic sum
             dwhh = torch.empty_like(whh)
             dbhh = torch.empty((2, 3 * H), dtype=torch.float64, device=out.device)
-            for d in range(2):
-                dgh = dgi[:, :, d, :].reshape(n * L, 3 * H).clone()
-                dgh[:, 2 * H:] *= gates[:, :, d, 0, :].reshape(n * L, H)
-                hprev = torch.empty((n, L, H), dtype=torch.float64, device=out.device)
-                if d == 0:
-                    hprev[:, 1:] = out[:, :-1, :H]
-                    hprev[:, 0] = h0[0]
-                else:
-                    hprev[:, :-1] = out[:, 1:, H:]
-                    hprev[:, -1] = h0[1]
-                dwhh[d] = dgh.t() @ hprev.reshape(n * L, H)
-                dbhh[d] = dgh.sum(0)
-                del dgh, hprev
+            wse = lib.drp_gru_wgrad_workspace_elems()
+            ws = torch.empty(wse, dtype=torch.float64, device=out.device)
+            _rc(lib.drp_gru_wgrad_f64(_p(dgi), _p(gates), _p(out), _p(h0), n, L, H, _p(dwhh), _p(dbhh), _p(ws), wse, _stream()),
+                "drp_gru_wgrad_f64")
         return dgi if ctx.needs_input_grad[0] else None, dwhh, dbhh, dh0
 
 

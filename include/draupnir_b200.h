@@ -101,6 +101,12 @@ int drp_gru_fwd_f64(const double* gi, const double* whh, const double* bhh, cons
 int drp_gru_bwd_f64(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
                     int n, int L, int H, double* dgi, double* dh0, void* stream);
 
+/* dwhh [2,3H,H] = sum_p dgh[p]^T h_prev[p], dbhh [2,3H] = sum_p dgh[p] (autograd of nn.GRU's weight_hh / bias_hh);
+ * ws: drp_gru_wgrad_workspace_elems() doubles.                                                                   */
+int64_t drp_gru_wgrad_workspace_elems(void);
+int drp_gru_wgrad_f64(const double* dgi, const double* gates, const double* out, const double* h0, int n, int L, int H,
+                      double* dwhh, double* dbhh, double* ws, int64_t ws_elems, void* stream);
+
 /* ---- K10  Categorical(logits).log_prob(obs).sum(): S/models.py:352 (+ LogSoftmax S/models_utils.py:98) --------- */
 int64_t drp_cat_loglik_partials(int64_t rows);
 int drp_cat_loglik_fwd_f64(const double* scores, const void* obs, int obs_is_f64, int64_t rows, int A, double* out,

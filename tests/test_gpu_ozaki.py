@@ -36,6 +36,8 @@ CASES = [
     (3, 1000, 1003, 100, 128, 250, 997, 997),       # nothing aligned: c1 % 8 != 0, odd ld, ragged last tiles
     (2, 1400, 1408, 128, 128, 256, 1400, 1000),     # col_limit cuts the update (conditional-mean shape)
     (1, 2100, 2104, 512, 256, 768, 2100, 2100),     # several work units per strip
+    (2, 1100, 1104, 64, 64, 128, 1100, 192),         # K = 64 panel step: half-filled k-block, one column tile
+    (2, 1300, 1304, 0, 208, 208, 1300, 1300),        # ragged contraction length (last panel of n = 2000)
 ]
 
 
@@ -44,7 +46,7 @@ CASES = [
 def test_tcgen05_update_matches_exact(cuda, case, slices):
     from draupnir_asr_b200 import ops
     z, rows, ld, k0, K, c1, R, col_limit = case
-    if slices * (K // 128) > 12:
+    if slices * ((K + 127) // 128) > 12:
         pytest.skip("A strip of S*K/128 tiles does not stay resident")
     rng = np.random.default_rng(7)
     M = rng.standard_normal((z, rows, ld))
