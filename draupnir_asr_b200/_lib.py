@@ -29,6 +29,7 @@ SIGNATURES = {
     "drp_ou_cov_bwd_f64": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _p]),
     "drp_factor_workspace_bytes": (_i64, [_i32, _i32]),
     "drp_potrf_batched_f64": (_i32, [_p, _i32, _i32, _i32, _p, _p, _i64, _p]),
+    "drp_ozaki_set_trace": (None, [_p]),
     "drp_syrk_update_f64": (_i32, [_p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),
     "drp_ou_workspace_ld": (_i64, [_i32, _i32]),
     "drp_ou_workspace_elems": (_i64, [_i32, _i32, _i32]),
@@ -39,6 +40,7 @@ SIGNATURES = {
     "drp_ou_conditional_f64": (_i32, [_p, _i64, _p, _i32, _i32, _p, _p, _p, _p, _i32, _f64, _p, _p, _p, _p, _p]),
     "drp_gru_hidden_size": (_i32, []),
     "drp_gru_fwd_f64": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "drp_gru_fwd_uv_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "drp_gru_bwd_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "drp_gru_wgrad_workspace_elems": (_i64, []),
     "drp_gru_wgrad_f64": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),

@@ -37,57 +37,68 @@ constexpr int SLD = 68;        // syrk smem row stride: (row*68 + tig) mod 16 di
 static_assert(PR == 2 * NB, "trsm staging assumes two rows per pass");
 
 // ---------------------------------------------------------------------------------------------------------------
-// potf2: factor the nb x nb diagonal block at (c0, c0).  One CTA of 64 threads per matrix; thread i keeps row i in
-// REGISTERS (fully unrolled right-looking elimination): per column one pivot broadcast, one column broadcast through
-// shared memory and a rank-1 update of the thread's own row.
+// potf2: factor the nb x nb diagonal block at (c0, c0).  One CTA of 256 threads per matrix; thread (ty, tx) keeps the
+// 4x4 block (rows 4ty.., columns 4tx..) in registers.  Right-looking, one column per step: the owners of the column
+// publish it through shared memory, everybody applies the rank-1 update to its block.  Entries right of the diagonal
+// collect garbage that is never read back nor stored.  Compact code (16 x 4 unrolled steps): the fully unrolled
+// thread-per-row variant was instruction-fetch bound.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) potf2_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb,
-                                                   int32_t* __restrict__ info)
+__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb,
+                                                    int32_t* __restrict__ info)
 {
-    __shared__ double S[NB * PLD];
-    __shared__ __align__(16) double colbuf[NB];
+    __shared__ double colv[NB];
     double* A = Mb + (int64_t)blockIdx.x * bs + (int64_t)c0 * ld + c0;
-    const int tid = threadIdx.x;
-    // thread tid fetches column tid of 16 rows at a time (16 independent loads in flight, coalesced across the CTA);
-    // rows / columns beyond nb: identity, so the unrolled 64-step elimination is a no-op there
-    for (int i0 = 0; i0 < NB; i0 += 16) {
-        double v[16];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double a[4][4];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int i = i0 + u;
-            v[u] = (i < nb && tid <= i) ? A[(int64_t)i * ld + tid] : (i == tid ? 1.0 : 0.0);
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = 4 * ty + r, j = 4 * tx + k;
+            // rows / columns beyond nb: identity, so the 64-step elimination is a no-op there
+            a[r][k] = (i < nb && j <= i) ? A[(int64_t)i * ld + j] : (i == j ? 1.0 : 0.0);
         }
-#pragma unroll
-        for (int u = 0; u < 16; ++u) S[(i0 + u) * PLD + tid] = v[u];
-    }
-    __syncthreads();
-    double a[NB];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) a[j] = S[tid * PLD + j];
     int bad = 0;
+    for (int cb = 0; cb < NB / 4; ++cb) {
 #pragma unroll
-    for (int c = 0; c < NB; ++c) {
-        colbuf[tid] = a[c];                                // column c of the current trailing matrix (rows >= c valid)
-        __syncthreads();
-        const double piv = colbuf[c];
-        if (!(piv > 0.0) && bad == 0) bad = c + 1;
-        const double rd = rsqrt(piv);
-        const double l = tid >= c ? a[c] * rd : 0.0;       // rows above the pivot take no part
-        a[c] = tid == c ? piv * rd : l;
-        // unpredicated rank-1 update of the whole register row: entries right of the diagonal collect garbage that
-        // is never read back (l is forced to zero above) nor stored
+        for (int cc = 0; cc < 4; ++cc) {
+            const int c = 4 * cb + cc;
+            if (tx == cb) {
 #pragma unroll
-        for (int j = c + 1; j < NB; ++j) a[j] = fma(-l, colbuf[j] * rd, a[j]);
-        __syncthreads();
+                for (int r = 0; r < 4; ++r) colv[4 * ty + r] = a[r][cc];
+            }
+            __syncthreads();
+            const double piv = colv[c];
+            if (!(piv > 0.0) && bad == 0) bad = c + 1;
+            const double rd = rsqrt(piv);
+            double lr[4], lc[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) lr[r] = colv[4 * ty + r] * rd;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) lc[k] = colv[4 * tx + k] * rd;
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (4 * tx + k > c) a[r][k] = fma(-lr[r], lc[k], a[r][k]);
+            if (tx == cb) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int i = 4 * ty + r;
+                    if (i == c) a[r][cc] = piv * rd;
+                    else if (i > c) a[r][cc] = lr[r];
+                }
+            }
+        }
     }
 #pragma unroll
-    for (int j = 0; j < NB; ++j) S[tid * PLD + j] = a[j];
-    __syncthreads();
-    if (tid < nb) {
-#pragma unroll 8
-        for (int i = 0; i < NB; ++i)
-            if (i < nb && tid <= i) A[(int64_t)i * ld + tid] = S[i * PLD + tid];
-    }
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = 4 * ty + r, j = 4 * tx + k;
+            if (i < nb && j <= i) A[(int64_t)i * ld + j] = a[r][k];
+        }
     if (bad && bad <= nb && tid == 0 && info) atomicCAS(info + blockIdx.x, 0, c0 + bad);
 }
 
@@ -304,7 +315,7 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
                 const int c1 = c0 + nb;
                 {
                     DRP_LAUNCH(DRP_K_POTF2, (double)z * nb * nb * nb / 3.0, st);
-                    potf2_kernel<<<z, 64, 0, st>>>(M, ld, bs, c0, nb, info);
+                    potf2_kernel<<<z, 256, 0, st>>>(M, ld, bs, c0, nb, info);
                 }
                 const int below = R - c1;
                 if (below > 0) {

@@ -68,7 +68,34 @@ __device__ __forceinline__ void g_bulk_g2s(uint32_t dst, const void* src, uint32
                  : "memory");
 }
 
-__device__ __forceinline__ double sigmoid_f64(double x) { return 1.0 / (1.0 + exp(-x)); }
+// exp for the gate non-linearities: arguments are pre-activations (clamped to +-700, never NaN-producing), so the
+// library routine's special-case handling is dropped: n = rint(x log2 e), two-term Cody-Waite reduction, degree-13
+// Taylor polynomial on |r| <= ln2/2 (truncation 4e-18), scaling by 2^n through the exponent field.
+__device__ __forceinline__ double gate_exp(double x)
+{
+    x = fmin(fmax(x, -700.0), 700.0);
+    const double t = rint(x * 1.4426950408889634074);
+    double r = fma(t, -6.93147180369123816490e-01, x);
+    r = fma(t, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, r, 2.0876756987868100e-09);        // 1/12!
+    p = fma(p, r, 2.5052108385441720e-08);        // 1/11!
+    p = fma(p, r, 2.7557319223985893e-07);        // 1/10!
+    p = fma(p, r, 2.7557319223985888e-06);        // 1/9!
+    p = fma(p, r, 2.4801587301587302e-05);        // 1/8!
+    p = fma(p, r, 1.9841269841269841e-04);        // 1/7!
+    p = fma(p, r, 1.3888888888888889e-03);        // 1/6!
+    p = fma(p, r, 8.3333333333333332e-03);        // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + ((int)t << 20), __double2loint(p));
+}
+__device__ __forceinline__ double sigmoid_f64(double x) { return __drcp_rn(1.0 + gate_exp(-x)); }
+// tanh(x) = 1 - 2 / (1 + e^{2x}): absolute error ~1e-16 (what the recurrence needs), saturates correctly at +-1
+__device__ __forceinline__ double tanh_f64(double x) { return fma(-2.0, __drcp_rn(1.0 + gate_exp(2.0 * x)), 1.0); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Forward.  grid (ceil(n/32), 2 directions), 256 threads.
@@ -80,8 +107,13 @@ __device__ __forceinline__ double sigmoid_f64(double x) { return 1.0 / (1.0 + ex
 constexpr int GF_STAGES = 3;
 constexpr int GF_STAGE_BYTES = GROWS * G3 * 8;                                   // 46080
 constexpr int GF_SMEM = 2 * GROWS * GHS * 8 + GF_STAGES * GF_STAGE_BYTES + 64;     // h double buffer + gi ring + barriers
+constexpr int GF_SMEM_UV = GF_SMEM + GROWS * G3 * 8;                               // + the CTA's U rows
 
-__global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __restrict__ gi, const double* __restrict__ whh,
+// UV = true: gi[i][l] = U[i] + V[l] (the decoder's [latent_i ; blosum_l] input, S/models.py:339-342): `gi` then points to
+// U [n, 2, 180] and `vrow` to V [L, 2, 180]; the U rows of the CTA stay in shared memory, one V row streams per step.
+template <bool UV>
+__global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __restrict__ gi, const double* __restrict__ vrow,
+                                                              const double* __restrict__ whh,
                                                               const double* __restrict__ bhh, const double* __restrict__ h0,
                                                               int n, int L, double* __restrict__ out,
                                                               double* __restrict__ gates)
@@ -90,6 +122,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
     double* hbuf = reinterpret_cast<double*>(gsm);                                   // [2][32][68]
     double* ring = reinterpret_cast<double*>(gsm + 2 * GROWS * GHS * 8);              // [stages][32][180]
     const uint32_t bars = g_smem_u32(gsm + 2 * GROWS * GHS * 8 + GF_STAGES * GF_STAGE_BYTES);
+    double* ubuf = reinterpret_cast<double*>(gsm + GF_SMEM);                           // [32][180] (UV only)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
     const int dir = blockIdx.y;
     const int row0 = blockIdx.x * GROWS;
@@ -120,6 +153,12 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
         const int r = idx / GH, j = idx - r * GH;
         hbuf[r * GHS + j] = r < nrows ? h0[((int64_t)dir * n + row0 + r) * GH + j] : 0.0;
     }
+    if (UV) {
+        for (int idx = tid; idx < GROWS * G3; idx += GTHREADS) {
+            const int r = idx / G3, c = idx - r * G3;
+            ubuf[idx] = r < nrows ? gi[((int64_t)(row0 + r) * 2 + dir) * G3 + c] : 0.0;
+        }
+    }
     __syncthreads();
     double hold[4][2];
 #pragma unroll
@@ -130,6 +169,13 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
     auto issue = [&](int t) {      // warp 0: stream gi of step t into its ring stage (one bulk copy per sequence)
         const int s = t % GF_STAGES;
         const int l = dir ? L - 1 - t : t;
+        if (UV) {
+            if (lane == 0) {
+                g_mbar_expect_tx(bars + 8 * s, G3 * 8);
+                g_bulk_g2s(g_smem_u32(ring + (int64_t)s * GROWS * G3), vrow + ((int64_t)l * 2 + dir) * G3, G3 * 8, bars + 8 * s);
+            }
+            return;
+        }
         if (lane == 0) g_mbar_expect_tx(bars + 8 * s, (uint32_t)nrows * G3 * 8);
         __syncwarp();
         if (lane < nrows)
@@ -166,9 +212,22 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) {
                 const int r = 8 * mt + gid;
-                const double2 xr = *reinterpret_cast<const double2*>(gs + r * G3 + j0);
-                const double2 xz = *reinterpret_cast<const double2*>(gs + r * G3 + GH + j0);
-                const double2 xn = *reinterpret_cast<const double2*>(gs + r * G3 + 2 * GH + j0);
+                double2 xr, xz, xn;
+                if (UV) {
+                    const double2 ur = *reinterpret_cast<const double2*>(ubuf + r * G3 + j0);
+                    const double2 uz = *reinterpret_cast<const double2*>(ubuf + r * G3 + GH + j0);
+                    const double2 un = *reinterpret_cast<const double2*>(ubuf + r * G3 + 2 * GH + j0);
+                    const double2 vr = *reinterpret_cast<const double2*>(gs + j0);
+                    const double2 vz = *reinterpret_cast<const double2*>(gs + GH + j0);
+                    const double2 vn = *reinterpret_cast<const double2*>(gs + 2 * GH + j0);
+                    xr = make_double2(ur.x + vr.x, ur.y + vr.y);
+                    xz = make_double2(uz.x + vz.x, uz.y + vz.y);
+                    xn = make_double2(un.x + vn.x, un.y + vn.y);
+                } else {
+                    xr = *reinterpret_cast<const double2*>(gs + r * G3 + j0);
+                    xz = *reinterpret_cast<const double2*>(gs + r * G3 + GH + j0);
+                    xn = *reinterpret_cast<const double2*>(gs + r * G3 + 2 * GH + j0);
+                }
                 double hv[2], rv[2], zv[2], nv[2], qv[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -177,7 +236,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
                     qv[e] = acc[2][mt][e] + bh[2][e];
                     rv[e] = sigmoid_f64(gr);
                     zv[e] = sigmoid_f64(gz);
-                    nv[e] = tanh((e ? xn.y : xn.x) + rv[e] * qv[e]);
+                    nv[e] = tanh_f64((e ? xn.y : xn.x) + rv[e] * qv[e]);
                     hv[e] = (1.0 - zv[e]) * nv[e] + zv[e] * hold[mt][e];
                     hold[mt][e] = hv[e];
                 }
@@ -452,13 +511,36 @@ DRP_API int drp_gru_fwd_f64(const double* gi, const double* whh, const double* b
     cudaStream_t st = (cudaStream_t)stream;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+        cudaFuncSetAttribute(gru_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+        cudaFuncSetAttribute(gru_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_UV);
         cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM);
         attr_done = true;
     }
     {
         DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * GH, st);
-        gru_fwd_kernel<<<dim3((n + GROWS - 1) / GROWS, 2), GTHREADS, GF_SMEM, st>>>(gi, whh, bhh, h0, n, L, out, gates);
+        gru_fwd_kernel<false><<<dim3((n + GROWS - 1) / GROWS, 2), GTHREADS, GF_SMEM, st>>>(gi, nullptr, whh, bhh, h0, n, L, out,
+                                                                                           gates);
+    }
+    return drp_launch_status();
+}
+
+// Same recurrence with gi[i][l] = U[i] + V[l]:  U [n,2,3H], V [L,2,3H]  (the decoder's tiled input, never materialised).
+DRP_API int drp_gru_fwd_uv_f64(const double* U, const double* V, const double* whh, const double* bhh, const double* h0,
+                               int n, int L, int H, double* out, double* gates, void* stream)
+{
+    if (!U || !V || !whh || !bhh || !h0) return -1;
+    if (n <= 0 || L <= 0) return -6;
+    if (H != GH) return -8;
+    if (!out) return -9;
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gru_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_UV);
+        attr_done = true;
+    }
+    {
+        DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * GH, st);
+        gru_fwd_kernel<true><<<dim3((n + GROWS - 1) / GROWS, 2), GTHREADS, GF_SMEM_UV, st>>>(U, V, whh, bhh, h0, n, L, out, gates);
     }
     return drp_launch_status();
 }
@@ -473,7 +555,6 @@ DRP_API int drp_gru_bwd_f64(const double* dout, const double* out, const double*
     cudaStream_t st = (cudaStream_t)stream;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
         cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM);
         attr_done = true;
     }

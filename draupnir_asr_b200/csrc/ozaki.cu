@@ -59,10 +59,11 @@ struct OzParams {
     int64_t ld, bs;
     const uint8_t* sl;         // slices [z][S][KBN][Rpad][128 B swizzled]
     int64_t sl_bs;             // bytes per matrix
-    const double* scl;         // [z][Rpad]  2^(e_r - 7)
+    const int32_t* scl;        // [z][Rpad]  binary exponent e_r of the row maximum (row scale 2^(e_r - 7))
     int Rpad, rb, c1, R, cmax;
     int nTi, nTj, units_per_z, total_units;
     int K;                     // real contraction length (columns of the panel); the k-blocks are zero-padded
+    long long* trace;          // optional event trace of CTA 0 (debug; nullptr in production)
 };
 
 // ------------------------------------------------ PTX wrappers ---------------------------------------------------
@@ -107,6 +108,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+// one lane of the (fully converged) warp
+__device__ __forceinline__ uint32_t elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -158,11 +170,29 @@ __device__ __forceinline__ uint32_t umma_idesc(uint32_t a_signed, uint32_t b_sig
     return (2u << 4) | (a_signed << 7) | (b_signed << 10) | ((uint32_t)(OZ_TN >> 3) << 17) | ((uint32_t)(OZ_TM >> 4) << 24);
 }
 
+// 2^ex as a double (exponent-field construction; far out-of-range products of row scales go through scalbn)
+__device__ __forceinline__ double oz_pow2(int ex)
+{
+    return (ex > -1000 && ex < 1000) ? __hiloint2double((ex + 1023) << 20, 0) : scalbn(1.0, ex);
+}
+
 // exact int32 -> fp64 without the conversion pipe: 2^52 + (a + 2^31) assembled in the mantissa, then one subtraction
 __device__ __forceinline__ double i32_to_f64(uint32_t a)
 {
     return __hiloint2double(0x43300000, (int)(a ^ 0x80000000u)) - 4503601774854144.0;
 }
+
+// debug trace: (event id, clock) pairs appended by single threads of CTA 0
+#define OZ_TRACE(id)                                                                   \
+    do {                                                                               \
+        if (p.trace && blockIdx.x == 0) {                                              \
+            const unsigned long long _k = atomicAdd((unsigned long long*)p.trace, 1ull); \
+            if (_k < 4000) {                                                           \
+                p.trace[2 + 2 * _k] = (id);                                            \
+                p.trace[3 + 2 * _k] = clock64();                                       \
+            }                                                                          \
+        }                                                                              \
+    } while (0)
 
 // work unit u -> (matrix, 128-row strip, first column tile, number of column tiles); strips longest first
 __device__ __forceinline__ void oz_decode(const OzParams& p, int u, int& zz, int& ti, int& tj0, int& ntj)
@@ -190,7 +220,7 @@ __device__ __forceinline__ void oz_decode(const OzParams& p, int u, int& zz, int
 template <int S>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ Mb, int64_t ld, int64_t bs, int k0, int Kcols, int KBN,
                                                        int rb, int c1, int R, int Rpad, uint8_t* __restrict__ sl,
-                                                       int64_t sl_bs, double* __restrict__ scl)
+                                                       int64_t sl_bs, int32_t* __restrict__ scl)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rr = blockIdx.x * 8 + warp;
@@ -213,7 +243,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     int e = 0;
     if (m > 0.0 && m < 1e300) frexp(m, &e);
-    if (lane == 0) scl[(int64_t)zz * Rpad + rr] = scalbn(1.0, e - 7);
+    if (lane == 0) scl[(int64_t)zz * Rpad + rr] = e;
     const int sh = 8 * S - 1 - e;
     const long long hi = (1LL << (8 * S - 1)) - 1;
     uint8_t* dst = sl + (int64_t)zz * sl_bs;
@@ -286,6 +316,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                 oz_decode(p, u, zz, ti, tj0, ntj);
                 const uint8_t* src = p.sl + (int64_t)zz * p.sl_bs;
                 mbar_wait(bar_a_empty, a_phase ^ 1);
+                OZ_TRACE(100);
                 mbar_expect_tx(bar_a_full, Cfg::A_BYTES);
                 for (int a = 0; a < Cfg::NA; ++a)
                     bulk_g2s(sA + a * OZ_A_TILE, src + ((int64_t)a * p.Rpad + (int64_t)ti * OZ_TM) * OZ_ROWB, OZ_A_TILE,
@@ -295,6 +326,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                     const int64_t cc0 = (int64_t)(tj0 + t) * OZ_TN;
                     for (int b = 0; b < Cfg::NA; ++b) {
                         mbar_wait(bar_b_empty + 8 * st, b_phase ^ 1);
+                        OZ_TRACE(200 + b);
                         mbar_expect_tx(bar_b_full + 8 * st, OZ_B_TILE);
                         bulk_g2s(sB + st * OZ_B_TILE, src + ((int64_t)b * p.Rpad + cc0) * OZ_ROWB, OZ_B_TILE,
                                  bar_b_full + 8 * st);
@@ -309,50 +341,63 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
         __syncwarp();
     } else if (warp == 1) {
         // ============================ MMA issuer ==============================
-        if (lane == 0) {
-            uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
-            int st = 0;
-            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-                int zz, ti, tj0, ntj;
-                oz_decode(p, u, zz, ti, tj0, ntj);
-                mbar_wait(bar_a_full, a_phase);
-                a_phase ^= 1;
+        // The whole warp walks the loop convergently and ONE elected lane issues (elect.sync): tcgen05.mma inside
+        // divergent `lane == 0` code is wrapped by the compiler in a per-thread ELECT/branch loop that costs more
+        // issue cycles than the 32-cycle MMA itself lasts.
+        uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
+        int st = 0;
+        const bool full_k = p.K == KBN * OZ_ROWB;      // no ragged last k-block
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            int zz, ti, tj0, ntj;
+            oz_decode(p, u, zz, ti, tj0, ntj);
+            mbar_wait(bar_a_full, a_phase);
+            a_phase ^= 1;
+            tc_fence_after();
+            if (lane == 0) OZ_TRACE(300);
+            for (int t = 0; t < ntj; ++t) {
+                mbar_wait(bar_acc_empty, acc_phase ^ 1);
                 tc_fence_after();
-                for (int t = 0; t < ntj; ++t) {
-                    mbar_wait(bar_acc_empty, acc_phase ^ 1);
-                    tc_fence_after();
-#pragma unroll 1
-                    for (int ub = 0; ub < S; ++ub) {               // slice of B (columns of the update)
-#pragma unroll 1
-                        for (int kb = 0; kb < KBN; ++kb) {
-                            mbar_wait(bar_b_full + 8 * st, b_phase);
-                            tc_fence_after();
-                            const uint64_t bdesc = umma_desc(sB + st * OZ_B_TILE);
-                            const int k4n = min(4, (p.K - OZ_ROWB * kb + 31) >> 5);   // 32-column steps with real data
-                            for (int ta = 0; ta + ub < S; ++ta) {      // slice of A; anti-diagonal d = ta + ub
-                                const uint64_t adesc = umma_desc(sA + (ta * KBN + kb) * OZ_A_TILE);
-                                const uint32_t idesc = umma_idesc(ta == 0, ub == 0);
-                                const uint32_t dcol = tmem + (uint32_t)((ta + ub) * OZ_TN);
+                if (lane == 0) OZ_TRACE(310);
 #pragma unroll
-                                for (int k4 = 0; k4 < 4; ++k4)
-                                    if (k4 < k4n) umma_i8(dcol, adesc + 2 * k4, bdesc + 2 * k4, idesc, (ub | kb | k4) != 0);
+                for (int ub = 0; ub < S; ++ub) {               // slice of B (columns of the update)
+#pragma unroll
+                    for (int kb = 0; kb < KBN; ++kb) {
+                        mbar_wait(bar_b_full + 8 * st, b_phase);
+                        tc_fence_after();
+                        if (lane == 0) OZ_TRACE(400 + ub * KBN + kb);
+                        if (elect_one()) {
+                            const uint64_t bdesc = umma_desc(sB + st * OZ_B_TILE);
+                            const int k4n = full_k ? 4 : min(4, (p.K - OZ_ROWB * kb + 31) >> 5);   // 32-column steps with data
+                            // k-step outer, A slice inner: consecutive MMAs accumulate into DIFFERENT TMEM tiles
+                            // (anti-diagonals d = ta + ub).  Back-to-back MMAs into the same accumulator serialise on
+                            // the accumulate latency (~90 cycles measured, vs 32 cycles of math for a 128x64x32 MMA).
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                if (!full_k && k4 >= k4n) break;
+#pragma unroll
+                                for (int ta = 0; ta + ub < S; ++ta) {  // slice of A
+                                    const uint64_t adesc = umma_desc(sA + (ta * KBN + kb) * OZ_A_TILE);
+                                    const uint32_t idesc = umma_idesc(ta == 0, ub == 0);
+                                    const uint32_t dcol = tmem + (uint32_t)((ta + ub) * OZ_TN);
+                                    umma_i8(dcol, adesc + 2 * k4, bdesc + 2 * k4, idesc, (ub | kb | k4) != 0);
+                                }
                             }
                             umma_commit(bar_b_empty + 8 * st);
-                            if (++st == NST) {
-                                st = 0;
-                                b_phase ^= 1;
-                            }
+                            // anti-diagonal d = ub only receives products with B slices <= ub: complete after its last
+                            // k-block, so the epilogue starts on it while the remaining slice pairs are multiplied
+                            if (kb == KBN - 1) umma_commit(bar_acc_full + 8 * ub);
+                            if (kb == KBN - 1 && ub == S - 1 && t == ntj - 1) umma_commit(bar_a_empty);
                         }
-                        // anti-diagonal d = ub only receives products with B slices <= ub: it is complete now, the
-                        // epilogue may start on it while the remaining (fewer and fewer) slice pairs are multiplied
-                        umma_commit(bar_acc_full + 8 * ub);
+                        __syncwarp();
+                        if (++st == NST) {
+                            st = 0;
+                            b_phase ^= 1;
+                        }
                     }
-                    acc_phase ^= 1;
                 }
-                umma_commit(bar_a_empty);
+                acc_phase ^= 1;
             }
         }
-        __syncwarp();
     } else {
         // ============================ epilogue ================================
         // warp (q, h) owns rows 32q.. and columns 16h.. of the 128x64 tile; thread t holds, for row select i = 0..3,
@@ -367,14 +412,23 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
             int zz, ti, tj0, ntj;
             oz_decode(p, u, zz, ti, tj0, ntj);
-            const double* sc = p.scl + (int64_t)zz * p.Rpad;
+            const int32_t* sc = p.scl + (int64_t)zz * p.Rpad;
             const int rr0 = ti * OZ_TM + q * 32 + tr;
+            int er[4];                                  // row exponents: one batched load per unit
+#pragma unroll
+            for (int i = 0; i < 4; ++i) er[i] = sc[rr0 + 8 * i];
             const int r0 = p.rb + rr0;                  // this thread's rows are r0 + 8 i
             double* const cbase = p.M + (int64_t)zz * p.bs + (int64_t)r0 * p.ld;
             const int64_t rstep = 8 * p.ld;
 #define OZ_CLIMIT(i) ((r0 + 8 * (i) >= p.c1 && r0 + 8 * (i) < p.R) ? min(r0 + 8 * (i) + 1, p.cmax) : 0)
             for (int t = 0; t < ntj; ++t) {
                 const int cc0 = (tj0 + t) * OZ_TN + 16 * h + tc;      // local column of this thread's first pair
+                int ec[4];                                 // column exponents of this thread's two column pairs
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    ec[2 * k] = sc[cc0 + 8 * k];
+                    ec[2 * k + 1] = sc[cc0 + 8 * k + 1];
+                }
                 // pull this thread's part of the C tile towards L2 while the tile's MMAs run
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -389,6 +443,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                 for (int d = 0; d < S; ++d) {                    // in the order the anti-diagonals complete
                     mbar_wait(bar_acc_full + 8 * d, acc_phase);
                     tc_fence_after();
+                    if (warp == 2 && lane == 0) OZ_TRACE(500 + d);
                     const double w = 1.0 / (double)(1ull << (8 * d));                 // 2^-8d
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {      // lanes 32q + 16 half ..: rows i = 2 half, 2 half + 1
@@ -414,6 +469,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_acc_empty);       // accumulators may be overwritten by the next tile
+                if (warp == 2 && lane == 0) OZ_TRACE(600);
                 double2 c[4][2];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -437,9 +493,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                         const int col = p.rb + cc0 + 8 * k;
                         const int cl = OZ_CLIMIT(i);
                         double* crow = cbase + i * rstep;
-                        const double sri = sc[rr0 + 8 * i];
-                        const double w0 = c[i][k].x - v[i][2 * k] * (sri * sc[cc0 + 8 * k]);
-                        const double w1 = c[i][k].y - v[i][2 * k + 1] * (sri * sc[cc0 + 8 * k + 1]);
+                        const double w0 = c[i][k].x - v[i][2 * k] * oz_pow2(er[i] + ec[2 * k] - 14);
+                        const double w1 = c[i][k].y - v[i][2 * k + 1] * oz_pow2(er[i] + ec[2 * k + 1] - 14);
                         if (vec_ok && col >= p.c1 && col + 1 < cl) {
                             *reinterpret_cast<double2*>(crow + col) = make_double2(w0, w1);
                         } else {
@@ -472,7 +527,7 @@ int oz_launch(const OzParams& p, int z, int k0, int Kcols, cudaStream_t st, doub
         DRP_LAUNCH(DRP_K_SLICE, (double)z * p.Rpad * KBN * 128 * (8.0 + S), st);
         oz_slice_kernel<S><<<dim3((p.Rpad + 7) / 8, z), 256, 0, st>>>(p.M, p.ld, p.bs, k0, Kcols, KBN, p.rb, p.c1, p.R, p.Rpad,
                                                                      const_cast<uint8_t*>(p.sl), p.sl_bs,
-                                                                     const_cast<double*>(p.scl));
+                                                                     const_cast<int32_t*>(p.scl));
     }
     {
         DRP_LAUNCH(DRP_K_SYRK_TC, flops, st);
@@ -483,6 +538,10 @@ int oz_launch(const OzParams& p, int z, int k0, int Kcols, cudaStream_t st, doub
 }
 
 }  // namespace
+
+static long long* g_oz_trace = nullptr;
+// Debug hook: device buffer of >= 8002 int64 ([0] = event count) that CTA 0 of every following update appends to.
+DRP_API void drp_ozaki_set_trace(void* buf) { g_oz_trace = (long long*)buf; }
 
 // Bytes of workspace drp_ozaki_syrk may need for matrices with at most R_full rows.
 int64_t drp_ozaki_workspace_bytes(int R_full, int z)
@@ -523,6 +582,7 @@ int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     p.R = R;
     p.cmax = cmax;
     p.K = K;
+    p.trace = g_oz_trace;
     p.nTi = (R - p.rb + OZ_TM - 1) / OZ_TM;
     p.nTj = (cmax - p.rb + OZ_TN - 1) / OZ_TN;
     p.Rpad = p.nTi * OZ_TM;
@@ -531,7 +591,7 @@ int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     if (need > ws_bytes) return 1;
     uint8_t* w = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
     p.sl = w;
-    p.scl = reinterpret_cast<const double*>(w + (int64_t)z * p.sl_bs);
+    p.scl = reinterpret_cast<const int32_t*>(w + (int64_t)z * p.sl_bs);
     int upz = 0;
     for (int ti = 0; ti < p.nTi; ++ti) {
         const int tot = 2 * ti + 2 < p.nTj ? 2 * ti + 2 : p.nTj;

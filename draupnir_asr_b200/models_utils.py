@@ -80,8 +80,7 @@ class RNNDecoder_Tiling(nn.Module):
         wih, whh, bih, bhh = ops.gru_stacked_params(self.rnn)
         U = latent_space @ wih[:, :, :z].reshape(6 * H, z).t()                               # [n, 2*3H]
         V = torch.addmm(bih.reshape(-1), blosum, wih[:, :, z:].reshape(6 * H, -1).t())      # [L, 2*3H]
-        gi = (U[:, None, :] + V[None, :, :]).reshape(U.shape[0], V.shape[0], 2, 3 * H)
-        rnn_output = ops.gru_bidirectional(gi, whh, bhh, hidden)
+        rnn_output = ops.gru_bidirectional_uv(U, V, whh, bhh, hidden)
         return self._project(rnn_output)
 
     def forward(self, input, hidden):

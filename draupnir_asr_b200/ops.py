@@ -349,24 +349,67 @@ class _GRUBidir(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        out, gates, whh, h0 = ctx.saved_tensors
-        n, L, H2 = out.shape
-        H = H2 // 2
-        dout = dout.contiguous()
-        dgi = torch.empty((n, L, 2, 3 * H), dtype=torch.float64, device=out.device)
-        dh0 = torch.empty_like(h0) if ctx.needs_input_grad[3] else None
-        _rc(lib.drp_gru_bwd_f64(_p(dout), _p(out), _p(gates), _p(whh), _p(h0), n, L, H, _p(dgi), _p(dh0), _stream()),
-            "drp_gru_bwd_f64")
-        dwhh = dbhh = None
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            # weight gradients: reductions over every (sequence, step) pair, one split-K kernel + a deterministic sum
-            dwhh = torch.empty_like(whh)
-            dbhh = torch.empty((2, 3 * H), dtype=torch.float64, device=out.device)
-            wse = lib.drp_gru_wgrad_workspace_elems()
-            ws = torch.empty(wse, dtype=torch.float64, device=out.device)
-            _rc(lib.drp_gru_wgrad_f64(_p(dgi), _p(gates), _p(out), _p(h0), n, L, H, _p(dwhh), _p(dbhh), _p(ws), wse, _stream()),
-                "drp_gru_wgrad_f64")
+        dgi, dwhh, dbhh, dh0 = _gru_backward_common(ctx.saved_tensors, dout, ctx.needs_input_grad[1] or ctx.needs_input_grad[2],
+                                                    ctx.needs_input_grad[3])
         return dgi if ctx.needs_input_grad[0] else None, dwhh, dbhh, dh0
+
+
+def _gru_backward_common(ctx_saved, dout, need_w, need_h0):
+    """BPTT + weight gradients shared by the two input modes: returns (dgi, dwhh, dbhh, dh0)."""
+    out, gates, whh, h0 = ctx_saved
+    n, L, H2 = out.shape
+    H = H2 // 2
+    dout = dout.contiguous()
+    dgi = torch.empty((n, L, 2, 3 * H), dtype=torch.float64, device=out.device)
+    dh0 = torch.empty_like(h0) if need_h0 else None
+    _rc(lib.drp_gru_bwd_f64(_p(dout), _p(out), _p(gates), _p(whh), _p(h0), n, L, H, _p(dgi), _p(dh0), _stream()),
+        "drp_gru_bwd_f64")
+    dwhh = dbhh = None
+    if need_w:
+        dwhh = torch.empty_like(whh)
+        dbhh = torch.empty((2, 3 * H), dtype=torch.float64, device=out.device)
+        wse = lib.drp_gru_wgrad_workspace_elems()
+        ws = torch.empty(wse, dtype=torch.float64, device=out.device)
+        _rc(lib.drp_gru_wgrad_f64(_p(dgi), _p(gates), _p(out), _p(h0), n, L, H, _p(dwhh), _p(dbhh), _p(ws), wse, _stream()),
+            "drp_gru_wgrad_f64")
+    return dgi, dwhh, dbhh, dh0
+
+
+class _GRUBidirUV(torch.autograd.Function):
+    """Same recurrence with `gi[i, l] = U[i] + V[l]` formed inside the kernel (never materialised)."""
+
+    @staticmethod
+    def forward(ctx, U, V, whh, bhh, h0):
+        U, V, whh, bhh, h0 = (_req(v, k).contiguous() for v, k in ((U, "U"), (V, "V"), (whh, "weight_hh"), (bhh, "bias_hh"),
+                                                                    (h0, "h0")))
+        n, L, H = U.shape[0], V.shape[0], whh.shape[-1]
+        if U.numel() != n * 6 * H or V.numel() != L * 6 * H or whh.shape != (2, 3 * H, H) or bhh.shape != (2, 3 * H) \
+                or h0.shape != (2, n, H):
+            raise RuntimeError(f"gru_bidirectional_uv: inconsistent shapes U{tuple(U.shape)} V{tuple(V.shape)} "
+                               f"whh{tuple(whh.shape)} h0{tuple(h0.shape)}")
+        want = any(ctx.needs_input_grad)
+        out = torch.empty((n, L, 2 * H), dtype=torch.float64, device=U.device)
+        gates = torch.empty((n, L, 2, 4, H), dtype=torch.float64, device=U.device) if want else None
+        _rc(lib.drp_gru_fwd_uv_f64(_p(U), _p(V), _p(whh), _p(bhh), _p(h0), n, L, H, _p(out), _p(gates), _stream()),
+            "drp_gru_fwd_uv_f64")
+        if want:
+            ctx.save_for_backward(out, gates, whh, h0)
+            ctx.shapes = (U.shape, V.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dgi, dwhh, dbhh, dh0 = _gru_backward_common(ctx.saved_tensors, dout, ctx.needs_input_grad[2] or ctx.needs_input_grad[3],
+                                                    ctx.needs_input_grad[4])
+        dU = dgi.sum(1).reshape(ctx.shapes[0]) if ctx.needs_input_grad[0] else None
+        dV = dgi.sum(0).reshape(ctx.shapes[1]) if ctx.needs_input_grad[1] else None
+        return dU, dV, dwhh, dbhh, dh0
+
+
+def gru_bidirectional_uv(U: torch.Tensor, V: torch.Tensor, weight_hh, bias_hh, h0) -> torch.Tensor:
+    """`gru_bidirectional(U[:, None] + V[None], ...)` for `U [n, 2, 3H]` (or `[n, 6H]`) and `V [L, 2, 3H]` without the
+    `[n, L, 2, 3H]` intermediate: the decoder's input is `[latent_i ; blosum_l]` (S/models.py:339-342)."""
+    return _GRUBidirUV.apply(U, V, weight_hh, bias_hh, h0)
 
 
 def gru_bidirectional(gi: torch.Tensor, weight_hh: torch.Tensor, bias_hh: torch.Tensor, h0: torch.Tensor) -> torch.Tensor:

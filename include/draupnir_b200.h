@@ -65,6 +65,9 @@ int64_t drp_factor_workspace_bytes(int rows, int z);
 int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info, void* ws, int64_t ws_bytes, void* stream);
 /* Test hook: ONE trailing update C[r][c] -= sum_{k0 <= k < k0+K} P[r][k] P[c][k], rows [c1,R), cols [c1,min(R,col_limit)),
  * c <= r; slices = 0 -> fp64 mma.sync kernel, 4..7 -> int8 tcgen05 kernel.  Returns 1 if tcgen05 rejects the shape.  */
+/* Debug hook: device buffer of >= 8002 int64 ([0] = event count, then (event id, clock64) pairs) that CTA 0 of every
+ * following tcgen05 update appends to; NULL switches tracing off (the default).                                     */
+void drp_ozaki_set_trace(void* buf);
 int drp_syrk_update_f64(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, int slices,
                         void* ws, int64_t ws_bytes, void* stream);
 
@@ -97,6 +100,10 @@ int drp_ou_conditional_f64(const double* D, int64_t ldd, const int32_t* idx, int
 int drp_gru_hidden_size(void);
 int drp_gru_fwd_f64(const double* gi, const double* whh, const double* bhh, const double* h0, int n, int L, int H,
                     double* out, double* gates, void* stream);
+/* Same with gi[i][l] = U[i] + V[l], U [n,2,3H], V [L,2,3H]: the decoder's tiled input [latent_i ; blosum_l]
+ * (S/models.py:339-342) is never materialised.                                                                     */
+int drp_gru_fwd_uv_f64(const double* U, const double* V, const double* whh, const double* bhh, const double* h0, int n,
+                       int L, int H, double* out, double* gates, void* stream);
 /* dgi [n,L,2,3H] = dLoss/dgi; dh0 [2,n,H] nullable.  dLoss/dW_hh = sum dgh^T h_prev with dgh = dgi, n-part times r.   */
 int drp_gru_bwd_f64(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
                     int n, int L, int H, double* dgi, double* dh0, void* stream);

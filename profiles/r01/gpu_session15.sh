@@ -1,0 +1,10 @@
+#!/bin/bash
+# GPU session 15: compact potf2/trsm parity + bench; event trace of the tcgen05 update.
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_all.log
+tail -5 gpurun_out/t_all.log
+timeout 300 python profiles/trace_ozaki.py > gpurun_out/trace_ozaki.txt 2>&1
+grep -q "rc=0" gpurun_out/t_all.log || exit 0
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err
+ls -la gpurun_out
