@@ -36,8 +36,17 @@ KCLASS = ["syrk", "trsm", "potf2", "assemble", "reduce", "catlik", "patristic", 
 FLOP_CLASSES = (0, 1, 2, 8, 10)
 
 
+_REAL_STDOUT = None
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def measured_peaks():
@@ -146,7 +155,7 @@ def run_reference(args, w, rank, world):
             "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, w, rank, world, local_rank):
@@ -274,12 +283,18 @@ def run_ours(args, w, rank, world, local_rank):
             "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": run.host_bytes_per_step(host),
                     "d2h_bytes_per_step": 8 + 4 * Z_DIM, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "kernel_classes": per_class}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner, cuDNN notices) are sent to
+    # stderr for the duration of the run and the line is written to the saved descriptor at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

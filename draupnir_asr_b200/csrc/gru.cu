@@ -20,12 +20,12 @@
 // writes dgi; the weight gradients are dense reductions over all (sequence, step) pairs and are left to one GEMM each.
 #include "common.cuh"
 #include "instrument.cuh"
+#include <stdlib.h>
 
 namespace {
 
 constexpr int GH = 60;              // hidden size
 constexpr int G3 = 3 * GH;          // gate columns
-constexpr int GROWS = 32;           // sequences per CTA
 constexpr int GHS = 68;             // smem row stride of h   (stride mod 16 == 4: conflict-free fragment loads)
 constexpr int GDS = 180;            // smem row stride of dgh (180 mod 16 == 4)
 constexpr int GTHREADS = 256;
@@ -98,31 +98,35 @@ __device__ __forceinline__ double sigmoid_f64(double x) { return __drcp_rn(1.0 +
 __device__ __forceinline__ double tanh_f64(double x) { return fma(-2.0, __drcp_rn(1.0 + gate_exp(2.0 * x)), 1.0); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Forward.  grid (ceil(n/32), 2 directions), 256 threads.
+// Forward.  grid (ceil(n/ROWS), 2 directions), 256 threads; ROWS = 8 MT sequences per CTA (MT = 4, 2 or 1 chosen by
+// the host so that one wave of CTAs covers the batch: the recurrence is latency-bound, fewer rows = shorter steps).
 //   gi    [n, L, 2, 180]   W_ih x + b_ih for both directions
 //   whh   [2, 180, 60]     bhh [2, 180]     h0 [2, n, 60]
 //   out   [n, L, 120]      hidden states (forward direction in [:60], backward in [60:], torch layout)
 //   gates [n, L, 2, 4, 60] r, z, n, (W_hn h + b_hn) for the backward pass; nullable
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int GF_STAGES = 3;
-constexpr int GF_STAGE_BYTES = GROWS * G3 * 8;                                   // 46080
-constexpr int GF_SMEM = 2 * GROWS * GHS * 8 + GF_STAGES * GF_STAGE_BYTES + 64;     // h double buffer + gi ring + barriers
-constexpr int GF_SMEM_UV = GF_SMEM + GROWS * G3 * 8;                               // + the CTA's U rows
+__host__ __device__ constexpr int gf_smem(int rows, bool uv)        // h double buffer + gi ring + barriers (+ the CTA's U rows)
+{
+    return 2 * rows * GHS * 8 + GF_STAGES * rows * G3 * 8 + 64 + (uv ? rows * G3 * 8 : 0);
+}
 
 // UV = true: gi[i][l] = U[i] + V[l] (the decoder's [latent_i ; blosum_l] input, S/models.py:339-342): `gi` then points to
 // U [n, 2, 180] and `vrow` to V [L, 2, 180]; the U rows of the CTA stay in shared memory, one V row streams per step.
-template <bool UV>
+template <bool UV, int MT>
 __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __restrict__ gi, const double* __restrict__ vrow,
                                                               const double* __restrict__ whh,
                                                               const double* __restrict__ bhh, const double* __restrict__ h0,
                                                               int n, int L, double* __restrict__ out,
                                                               double* __restrict__ gates)
 {
+    constexpr int GROWS = 8 * MT;
+    constexpr int GF_STAGE_BYTES = GROWS * G3 * 8;
     extern __shared__ __align__(16) uint8_t gsm[];
     double* hbuf = reinterpret_cast<double*>(gsm);                                   // [2][32][68]
     double* ring = reinterpret_cast<double*>(gsm + 2 * GROWS * GHS * 8);              // [stages][32][180]
     const uint32_t bars = g_smem_u32(gsm + 2 * GROWS * GHS * 8 + GF_STAGES * GF_STAGE_BYTES);
-    double* ubuf = reinterpret_cast<double*>(gsm + GF_SMEM);                           // [32][180] (UV only)
+    double* ubuf = reinterpret_cast<double*>(gsm + gf_smem(GROWS, false));             // [rows][180] (UV only)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
     const int dir = blockIdx.y;
     const int row0 = blockIdx.x * GROWS;
@@ -160,9 +164,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
         }
     }
     __syncthreads();
-    double hold[4][2];
+    double hold[MT][2];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
         hold[mt][0] = jok ? hbuf[(8 * mt + gid) * GHS + j0] : 0.0;
         hold[mt][1] = jok ? hbuf[(8 * mt + gid) * GHS + j0 + 1] : 0.0;
     }
@@ -190,27 +194,27 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
         const double* hc = hbuf + (t & 1) * GROWS * GHS;
         double* hn = hbuf + ((t + 1) & 1) * GROWS * GHS;
         if (warp == 0 && t + GF_STAGES - 1 < L) issue(t + GF_STAGES - 1);   // its stage was drained in step t-1
-        double acc[3][4][2];
+        double acc[3][MT][2];
 #pragma unroll
         for (int g = 0; g < 3; ++g)
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) acc[g][mt][0] = acc[g][mt][1] = 0.0;
+            for (int mt = 0; mt < MT; ++mt) acc[g][mt][0] = acc[g][mt][1] = 0.0;
 #pragma unroll
         for (int ks = 0; ks < 15; ++ks) {
-            double a[4];
+            double a[MT];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) a[mt] = hc[(8 * mt + gid) * GHS + 4 * ks + tig];
+            for (int mt = 0; mt < MT; ++mt) a[mt] = hc[(8 * mt + gid) * GHS + 4 * ks + tig];
 #pragma unroll
             for (int g = 0; g < 3; ++g)
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt) dmma_8x8x4(acc[g][mt][0], acc[g][mt][1], a[mt], B[g][ks]);
+                for (int mt = 0; mt < MT; ++mt) dmma_8x8x4(acc[g][mt][0], acc[g][mt][1], a[mt], B[g][ks]);
         }
         const int s = t % GF_STAGES;
         g_mbar_wait(bars + 8 * s, (uint32_t)(t / GF_STAGES) & 1u);
         const double* gs = ring + (int64_t)s * GROWS * G3;
         if (jok) {
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) {
                 const int r = 8 * mt + gid;
                 double2 xr, xz, xn;
                 if (UV) {
@@ -266,14 +270,16 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int GB_STAGES = 2;
 constexpr int GB_ROW_BYTES = (4 * GH + GH) * 8;                                   // saved gates + h_prev = 2400
-constexpr int GB_STAGE_BYTES = GROWS * GB_ROW_BYTES;                               // 76800
-constexpr int GB_SMEM = GROWS * GDS * 8 + GB_STAGES * GB_STAGE_BYTES + 64;
+__host__ __device__ constexpr int gb_smem(int rows) { return rows * GDS * 8 + GB_STAGES * rows * GB_ROW_BYTES + 64; }
 
+template <int MT>
 __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __restrict__ dout, const double* __restrict__ out,
                                                               const double* __restrict__ gates, const double* __restrict__ whh,
                                                               const double* __restrict__ h0, int n, int L,
                                                               double* __restrict__ dgi, double* __restrict__ dh0)
 {
+    constexpr int GROWS = 8 * MT;
+    constexpr int GB_STAGE_BYTES = GROWS * GB_ROW_BYTES;
     extern __shared__ __align__(16) uint8_t gsm[];
     double* dgh = reinterpret_cast<double*>(gsm);                                    // [32][180]
     double* ring = reinterpret_cast<double*>(gsm + GROWS * GDS * 8);                  // [stages][32][300]
@@ -315,17 +321,17 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
         }
     };
     if (warp == 0) issue(0);
-    double dh[4][2];
+    double dh[MT][2];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) dh[mt][0] = dh[mt][1] = 0.0;
+    for (int mt = 0; mt < MT; ++mt) dh[mt][0] = dh[mt][1] = 0.0;
 
     for (int tb = 0; tb < L; ++tb) {
         const int t = L - 1 - tb;
         const int l = dir ? L - 1 - t : t;
         if (warp == 0 && tb + 1 < L) issue(tb + 1);      // the other stage was drained before the last barrier
-        double2 dO[4];
+        double2 dO[MT];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
             const int r = 8 * mt + gid;
             dO[mt] = (jok && r < nrows) ? *reinterpret_cast<const double2*>(dout + ((int64_t)(row0 + r) * L + l) * (2 * GH) + dir * GH + j0)
                                         : make_double2(0.0, 0.0);
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
         const double* gs = ring + (int64_t)s * GROWS * RS;
         if (jok) {
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) {
                 const int r = 8 * mt + gid;
                 const double2 rr = *reinterpret_cast<const double2*>(gs + r * RS + j0);
                 const double2 zz = *reinterpret_cast<const double2*>(gs + r * RS + GH + j0);
@@ -366,19 +372,19 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
             }
         }
         __syncthreads();                           // dgh of this step complete; ring stage s drained
-        double acc[4][2];
+        double acc[MT][2];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+        for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
 #pragma unroll
         for (int ks = 0; ks < 45; ++ks) {
-            double a[4];
+            double a[MT];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) a[mt] = dgh[(8 * mt + gid) * GDS + 4 * ks + tig];
+            for (int mt = 0; mt < MT; ++mt) a[mt] = dgh[(8 * mt + gid) * GDS + 4 * ks + tig];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) dmma_8x8x4(acc[mt][0], acc[mt][1], a[mt], B[ks]);
+            for (int mt = 0; mt < MT; ++mt) dmma_8x8x4(acc[mt][0], acc[mt][1], a[mt], B[ks]);
         }
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
             dh[mt][0] += acc[mt][0];
             dh[mt][1] += acc[mt][1];
         }
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
     }
     if (dh0 && jok) {
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
             const int r = 8 * mt + gid;
             if (r < nrows)
                 *reinterpret_cast<double2*>(dh0 + ((int64_t)dir * n + row0 + r) * GH + j0) = make_double2(dh[mt][0], dh[mt][1]);
@@ -501,6 +507,53 @@ __global__ void __launch_bounds__(256) gru_wgrad_reduce_kernel(const double* __r
 // ------------------------------------------------- entry points -----------------------------------------------
 DRP_API int drp_gru_hidden_size(void) { return GH; }
 
+// rows per CTA = 8 MT: the largest of 32 / 16 / 8 for which one wave of CTAs (2 directions) still covers the batch
+static int gru_pick_mt(int n)
+{
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    const char* e = getenv("DRP_GRU_ROWS");
+    if (e) {
+        const int r = atoi(e);
+        if (r == 8 || r == 16 || r == 32) return r / 8;
+    }
+    if (2 * ((n + 7) / 8) <= n_sm) return 1;
+    if (2 * ((n + 15) / 16) <= n_sm) return 2;
+    return 4;
+}
+
+template <bool UV, int MT>
+static void gru_fwd_launch(const double* gi, const double* v, const double* whh, const double* bhh, const double* h0, int n,
+                           int L, double* out, double* gates, cudaStream_t st)
+{
+    constexpr int smem = gf_smem(8 * MT, UV);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gru_fwd_kernel<UV, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_done = true;
+    }
+    DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * GH, st);
+    gru_fwd_kernel<UV, MT><<<dim3((n + 8 * MT - 1) / (8 * MT), 2), GTHREADS, smem, st>>>(gi, v, whh, bhh, h0, n, L, out, gates);
+}
+
+template <int MT>
+static void gru_bwd_launch(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
+                           int n, int L, double* dgi, double* dh0, cudaStream_t st)
+{
+    constexpr int smem = gb_smem(8 * MT);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gru_bwd_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_done = true;
+    }
+    DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * GH, st);
+    gru_bwd_kernel<MT><<<dim3((n + 8 * MT - 1) / (8 * MT), 2), GTHREADS, smem, st>>>(dout, out, gates, whh, h0, n, L, dgi, dh0);
+}
+
 DRP_API int drp_gru_fwd_f64(const double* gi, const double* whh, const double* bhh, const double* h0, int n, int L, int H,
                             double* out, double* gates, void* stream)
 {
@@ -509,17 +562,10 @@ DRP_API int drp_gru_fwd_f64(const double* gi, const double* whh, const double* b
     if (H != GH) return -7;
     if (!out) return -8;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(gru_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
-        cudaFuncSetAttribute(gru_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_UV);
-        cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM);
-        attr_done = true;
-    }
-    {
-        DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * GH, st);
-        gru_fwd_kernel<false><<<dim3((n + GROWS - 1) / GROWS, 2), GTHREADS, GF_SMEM, st>>>(gi, nullptr, whh, bhh, h0, n, L, out,
-                                                                                           gates);
+    switch (gru_pick_mt(n)) {
+        case 1: gru_fwd_launch<false, 1>(gi, nullptr, whh, bhh, h0, n, L, out, gates, st); break;
+        case 2: gru_fwd_launch<false, 2>(gi, nullptr, whh, bhh, h0, n, L, out, gates, st); break;
+        default: gru_fwd_launch<false, 4>(gi, nullptr, whh, bhh, h0, n, L, out, gates, st); break;
     }
     return drp_launch_status();
 }
@@ -533,14 +579,10 @@ DRP_API int drp_gru_fwd_uv_f64(const double* U, const double* V, const double* w
     if (H != GH) return -8;
     if (!out) return -9;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(gru_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_UV);
-        attr_done = true;
-    }
-    {
-        DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * GH, st);
-        gru_fwd_kernel<true><<<dim3((n + GROWS - 1) / GROWS, 2), GTHREADS, GF_SMEM_UV, st>>>(U, V, whh, bhh, h0, n, L, out, gates);
+    switch (gru_pick_mt(n)) {
+        case 1: gru_fwd_launch<true, 1>(U, V, whh, bhh, h0, n, L, out, gates, st); break;
+        case 2: gru_fwd_launch<true, 2>(U, V, whh, bhh, h0, n, L, out, gates, st); break;
+        default: gru_fwd_launch<true, 4>(U, V, whh, bhh, h0, n, L, out, gates, st); break;
     }
     return drp_launch_status();
 }
@@ -553,14 +595,10 @@ DRP_API int drp_gru_bwd_f64(const double* dout, const double* out, const double*
     if (H != GH) return -8;
     if (!dgi) return -9;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM);
-        attr_done = true;
-    }
-    {
-        DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * GH, st);
-        gru_bwd_kernel<<<dim3((n + GROWS - 1) / GROWS, 2), GTHREADS, GB_SMEM, st>>>(dout, out, gates, whh, h0, n, L, dgi, dh0);
+    switch (gru_pick_mt(n)) {
+        case 1: gru_bwd_launch<1>(dout, out, gates, whh, h0, n, L, dgi, dh0, st); break;
+        case 2: gru_bwd_launch<2>(dout, out, gates, whh, h0, n, L, dgi, dh0, st); break;
+        default: gru_bwd_launch<4>(dout, out, gates, whh, h0, n, L, dgi, dh0, st); break;
     }
     return drp_launch_status();
 }

@@ -29,8 +29,10 @@ def _ref_and_ours(n, L, I, seed, cuda):
     return ref, got
 
 
+@pytest.mark.parametrize("rows", [8, 16, 32])          # sequences per CTA (DRP_GRU_ROWS overrides the one-wave heuristic)
 @pytest.mark.parametrize("n,L,I", [(1, 1, 21), (5, 7, 51), (37, 23, 51), (64, 40, 21), (130, 33, 51)])
-def test_gru_matches_torch(cuda, n, L, I):
+def test_gru_matches_torch(cuda, monkeypatch, n, L, I, rows):
+    monkeypatch.setenv("DRP_GRU_ROWS", str(rows))
     ref, got = _ref_and_ours(n, L, I, seed=n + L, cuda=cuda)
     for k in ref:
         scale = ref[k].abs().max().clamp_min(1e-30)
@@ -38,7 +40,9 @@ def test_gru_matches_torch(cuda, n, L, I):
         assert err < 1e-11, (k, err)
 
 
-def test_no_grad_path_and_structured_decoder(cuda):
+@pytest.mark.parametrize("rows", [8, 16, 32])
+def test_no_grad_path_and_structured_decoder(cuda, monkeypatch, rows):
+    monkeypatch.setenv("DRP_GRU_ROWS", str(rows))
     from draupnir_asr_b200.models_utils import RNNDecoder_Tiling
     torch.manual_seed(3)
     n, L, z, A = 45, 31, 30, 21
