@@ -40,10 +40,6 @@ __device__ __forceinline__ void g_mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void g_mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ uint32_t g_mbar_try_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
@@ -109,12 +105,10 @@ __device__ __forceinline__ double tanh_f64(double x) { return fma(-2.0, __drcp_r
 //   out   [n, L, 120]      hidden states (forward direction in [:60], backward in [60:], torch layout)
 //   gates [n, L, 2, 4, 60] r, z, n, (W_hn h + b_hn) for the backward pass; nullable
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int GF_STAGES = 4;
-// h double buffer + gi ring (one V row per stage in UV mode) + barriers + (UV) the CTA's U rows
-__host__ __device__ constexpr int gf_stage_bytes(int rows, bool uv) { return (uv ? 1 : rows) * G3 * 8; }
-__host__ __device__ constexpr int gf_smem(int rows, bool uv)
+constexpr int GF_STAGES = 3;
+__host__ __device__ constexpr int gf_smem(int rows, bool uv)        // h double buffer + gi ring + barriers (+ the CTA's U rows)
 {
-    return 2 * rows * GHS * 8 + GF_STAGES * gf_stage_bytes(rows, uv) + 64 + (uv ? rows * G3 * 8 : 0);
+    return 2 * rows * GHS * 8 + GF_STAGES * rows * G3 * 8 + 64 + (uv ? rows * G3 * 8 : 0);
 }
 
 // UV = true: gi[i][l] = U[i] + V[l] (the decoder's [latent_i ; blosum_l] input, S/models.py:339-342): `gi` then points to
@@ -127,15 +121,12 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
                                                               double* __restrict__ gates)
 {
     constexpr int GROWS = 8 * MT;
-    constexpr int NH = MT >= 2 ? 2 : 1;          // independent row halves, each with its own hand-off barrier
-    constexpr int HM = MT / NH;                  // m-tiles per half
-    constexpr int STAGE = gf_stage_bytes(GROWS, UV) / 8;     // doubles per ring stage
+    constexpr int GF_STAGE_BYTES = GROWS * G3 * 8;
     extern __shared__ __align__(16) uint8_t gsm[];
-    double* hbuf = reinterpret_cast<double*>(gsm);                                   // [2][rows][68]
-    double* ring = reinterpret_cast<double*>(gsm + 2 * GROWS * GHS * 8);              // [stages][rows | 1][180]
-    const uint32_t bars = g_smem_u32(gsm + 2 * GROWS * GHS * 8 + GF_STAGES * STAGE * 8);   // [4] ring full, [NH] h ready
-    const uint32_t hbar = bars + 8 * GF_STAGES;
-    double* ubuf = reinterpret_cast<double*>(gsm + 2 * GROWS * GHS * 8 + GF_STAGES * STAGE * 8 + 64);   // [rows][180] (UV)
+    double* hbuf = reinterpret_cast<double*>(gsm);                                   // [2][32][68]
+    double* ring = reinterpret_cast<double*>(gsm + 2 * GROWS * GHS * 8);              // [stages][32][180]
+    const uint32_t bars = g_smem_u32(gsm + 2 * GROWS * GHS * 8 + GF_STAGES * GF_STAGE_BYTES);
+    double* ubuf = reinterpret_cast<double*>(gsm + gf_smem(GROWS, false));             // [rows][180] (UV only)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
     const int dir = blockIdx.y;
     const int row0 = blockIdx.x * GROWS;
@@ -158,7 +149,6 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
     }
     if (tid == 0) {
         for (int s = 0; s < GF_STAGES; ++s) g_mbar_init(bars + 8 * s, 1);
-        for (int h = 0; h < NH; ++h) g_mbar_init(hbar + 8 * h, GTHREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -186,100 +176,89 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
         if (UV) {
             if (lane == 0) {
                 g_mbar_expect_tx(bars + 8 * s, G3 * 8);
-                g_bulk_g2s(g_smem_u32(ring + (int64_t)s * STAGE), vrow + ((int64_t)l * 2 + dir) * G3, G3 * 8, bars + 8 * s);
+                g_bulk_g2s(g_smem_u32(ring + (int64_t)s * GROWS * G3), vrow + ((int64_t)l * 2 + dir) * G3, G3 * 8, bars + 8 * s);
             }
             return;
         }
         if (lane == 0) g_mbar_expect_tx(bars + 8 * s, (uint32_t)nrows * G3 * 8);
         __syncwarp();
         if (lane < nrows)
-            g_bulk_g2s(g_smem_u32(ring + (int64_t)s * STAGE + lane * G3),
+            g_bulk_g2s(g_smem_u32(ring + (int64_t)s * GROWS * G3 + lane * G3),
                        gi + (((int64_t)(row0 + lane) * L + l) * 2 + dir) * G3, G3 * 8, bars + 8 * s);
     };
     if (warp == 0)
-        for (int t = 0; t < min(GF_STAGES - 2, L); ++t) issue(t);
+        for (int t = 0; t < min(GF_STAGES - 1, L); ++t) issue(t);
 
-    // The two row halves are independent recurrences.  Each has its own hand-off mbarrier ("h of this step is in shared
-    // memory"): a thread arrives after its gate math and waits only before the next product of the SAME half, so warps
-    // drift apart by up to half a step and the fp64 gate math of one warp overlaps the tensor-pipe work of another
-    // instead of the whole CTA marching through product -> gates -> barrier in lock-step.
     for (int t = 0; t < L; ++t) {
         const int l = dir ? L - 1 - t : t;
         const double* hc = hbuf + (t & 1) * GROWS * GHS;
         double* hn = hbuf + ((t + 1) & 1) * GROWS * GHS;
-        // ring stage of step t+2 was last read in step t-2, which every thread has left (this warp passed the last
-        // half's barrier of step t-2 during step t-1)
-        if (warp == 0 && t + GF_STAGES - 2 < L) issue(t + GF_STAGES - 2);
-        const int s = t % GF_STAGES;
-        const double* gs = ring + (int64_t)s * STAGE;
+        if (warp == 0 && t + GF_STAGES - 1 < L) issue(t + GF_STAGES - 1);   // its stage was drained in step t-1
+        double acc[3][MT][2];
 #pragma unroll
-        for (int half = 0; half < NH; ++half) {
-            if (t > 0) g_mbar_wait(hbar + 8 * half, (uint32_t)(t - 1) & 1u);       // h(t-1) of this half is complete
-            double acc[3][HM][2];
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) acc[g][mt][0] = acc[g][mt][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 15; ++ks) {
+            double a[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) a[mt] = hc[(8 * mt + gid) * GHS + 4 * ks + tig];
 #pragma unroll
             for (int g = 0; g < 3; ++g)
 #pragma unroll
-                for (int mt = 0; mt < HM; ++mt) acc[g][mt][0] = acc[g][mt][1] = 0.0;
+                for (int mt = 0; mt < MT; ++mt) dmma_8x8x4(acc[g][mt][0], acc[g][mt][1], a[mt], B[g][ks]);
+        }
+        const int s = t % GF_STAGES;
+        g_mbar_wait(bars + 8 * s, (uint32_t)(t / GF_STAGES) & 1u);
+        const double* gs = ring + (int64_t)s * GROWS * G3;
+        if (jok) {
 #pragma unroll
-            for (int ks = 0; ks < 15; ++ks) {
-                double a[HM];
+            for (int mt = 0; mt < MT; ++mt) {
+                const int r = 8 * mt + gid;
+                double2 xr, xz, xn;
+                if (UV) {
+                    const double2 ur = *reinterpret_cast<const double2*>(ubuf + r * G3 + j0);
+                    const double2 uz = *reinterpret_cast<const double2*>(ubuf + r * G3 + GH + j0);
+                    const double2 un = *reinterpret_cast<const double2*>(ubuf + r * G3 + 2 * GH + j0);
+                    const double2 vr = *reinterpret_cast<const double2*>(gs + j0);
+                    const double2 vz = *reinterpret_cast<const double2*>(gs + GH + j0);
+                    const double2 vn = *reinterpret_cast<const double2*>(gs + 2 * GH + j0);
+                    xr = make_double2(ur.x + vr.x, ur.y + vr.y);
+                    xz = make_double2(uz.x + vz.x, uz.y + vz.y);
+                    xn = make_double2(un.x + vn.x, un.y + vn.y);
+                } else {
+                    xr = *reinterpret_cast<const double2*>(gs + r * G3 + j0);
+                    xz = *reinterpret_cast<const double2*>(gs + r * G3 + GH + j0);
+                    xn = *reinterpret_cast<const double2*>(gs + r * G3 + 2 * GH + j0);
+                }
+                double hv[2], rv[2], zv[2], nv[2], qv[2];
 #pragma unroll
-                for (int mt = 0; mt < HM; ++mt) a[mt] = hc[(8 * (half * HM + mt) + gid) * GHS + 4 * ks + tig];
-#pragma unroll
-                for (int g = 0; g < 3; ++g)
-#pragma unroll
-                    for (int mt = 0; mt < HM; ++mt) dmma_8x8x4(acc[g][mt][0], acc[g][mt][1], a[mt], B[g][ks]);
-            }
-            if (half == 0) g_mbar_wait(bars + 8 * s, (uint32_t)(t / GF_STAGES) & 1u);
-            if (jok) {
-#pragma unroll
-                for (int mt = 0; mt < HM; ++mt) {
-                    const int m = half * HM + mt;
-                    const int r = 8 * m + gid;
-                    double2 xr, xz, xn;
-                    if (UV) {
-                        const double2 ur = *reinterpret_cast<const double2*>(ubuf + r * G3 + j0);
-                        const double2 uz = *reinterpret_cast<const double2*>(ubuf + r * G3 + GH + j0);
-                        const double2 un = *reinterpret_cast<const double2*>(ubuf + r * G3 + 2 * GH + j0);
-                        const double2 vr = *reinterpret_cast<const double2*>(gs + j0);
-                        const double2 vz = *reinterpret_cast<const double2*>(gs + GH + j0);
-                        const double2 vn = *reinterpret_cast<const double2*>(gs + 2 * GH + j0);
-                        xr = make_double2(ur.x + vr.x, ur.y + vr.y);
-                        xz = make_double2(uz.x + vz.x, uz.y + vz.y);
-                        xn = make_double2(un.x + vn.x, un.y + vn.y);
-                    } else {
-                        xr = *reinterpret_cast<const double2*>(gs + r * G3 + j0);
-                        xz = *reinterpret_cast<const double2*>(gs + r * G3 + GH + j0);
-                        xn = *reinterpret_cast<const double2*>(gs + r * G3 + 2 * GH + j0);
-                    }
-                    double hv[2], rv[2], zv[2], nv[2], qv[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const double gr = (e ? xr.y : xr.x) + acc[0][mt][e] + bh[0][e];
-                        const double gz = (e ? xz.y : xz.x) + acc[1][mt][e] + bh[1][e];
-                        qv[e] = acc[2][mt][e] + bh[2][e];
-                        rv[e] = sigmoid_f64(gr);
-                        zv[e] = sigmoid_f64(gz);
-                        nv[e] = tanh_f64((e ? xn.y : xn.x) + rv[e] * qv[e]);
-                        hv[e] = (1.0 - zv[e]) * nv[e] + zv[e] * hold[m][e];
-                        hold[m][e] = hv[e];
-                    }
-                    *reinterpret_cast<double2*>(hn + r * GHS + j0) = make_double2(hv[0], hv[1]);
-                    if (r < nrows) {
-                        const int64_t site = (int64_t)(row0 + r) * L + l;
-                        *reinterpret_cast<double2*>(out + site * (2 * GH) + dir * GH + j0) = make_double2(hv[0], hv[1]);
-                        if (gates) {
-                            double* gp = gates + (site * 2 + dir) * (4 * GH) + j0;
-                            *reinterpret_cast<double2*>(gp) = make_double2(rv[0], rv[1]);
-                            *reinterpret_cast<double2*>(gp + GH) = make_double2(zv[0], zv[1]);
-                            *reinterpret_cast<double2*>(gp + 2 * GH) = make_double2(nv[0], nv[1]);
-                            *reinterpret_cast<double2*>(gp + 3 * GH) = make_double2(qv[0], qv[1]);
-                        }
+                for (int e = 0; e < 2; ++e) {
+                    const double gr = (e ? xr.y : xr.x) + acc[0][mt][e] + bh[0][e];
+                    const double gz = (e ? xz.y : xz.x) + acc[1][mt][e] + bh[1][e];
+                    qv[e] = acc[2][mt][e] + bh[2][e];
+                    rv[e] = sigmoid_f64(gr);
+                    zv[e] = sigmoid_f64(gz);
+                    nv[e] = tanh_f64((e ? xn.y : xn.x) + rv[e] * qv[e]);
+                    hv[e] = (1.0 - zv[e]) * nv[e] + zv[e] * hold[mt][e];
+                    hold[mt][e] = hv[e];
+                }
+                *reinterpret_cast<double2*>(hn + r * GHS + j0) = make_double2(hv[0], hv[1]);
+                if (r < nrows) {
+                    const int64_t site = (int64_t)(row0 + r) * L + l;
+                    *reinterpret_cast<double2*>(out + site * (2 * GH) + dir * GH + j0) = make_double2(hv[0], hv[1]);
+                    if (gates) {
+                        double* gp = gates + (site * 2 + dir) * (4 * GH) + j0;
+                        *reinterpret_cast<double2*>(gp) = make_double2(rv[0], rv[1]);
+                        *reinterpret_cast<double2*>(gp + GH) = make_double2(zv[0], zv[1]);
+                        *reinterpret_cast<double2*>(gp + 2 * GH) = make_double2(nv[0], nv[1]);
+                        *reinterpret_cast<double2*>(gp + 3 * GH) = make_double2(qv[0], qv[1]);
                     }
                 }
             }
-            g_mbar_arrive(hbar + 8 * half);        // release: this thread's part of h(t) of this half is written
         }
+        __syncthreads();      // h of step t complete in hn; ring stage s and hc free for reuse
     }
 }
 
@@ -297,7 +276,8 @@ template <int MT>
 __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __restrict__ dout, const double* __restrict__ out,
                                                               const double* __restrict__ gates, const double* __restrict__ whh,
                                                               const double* __restrict__ h0, int n, int L,
-                                                              double* __restrict__ dgi, double* __restrict__ dh0)
+                                                              double* __restrict__ dgi, double* __restrict__ dh0,
+                                                              int dgi_dirs)
 {
     constexpr int GROWS = 8 * MT;
     constexpr int GB_STAGE_BYTES = GROWS * GB_ROW_BYTES;
@@ -318,16 +298,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
     double B[45];                                 // B[k][n] = W_hh[c = 4 ks + tig][j = jb]
 #pragma unroll
     for (int ks = 0; ks < 45; ++ks) B[ks] = jb < GH ? W[(int64_t)(4 * ks + tig) * GH + jb] : 0.0;
-    constexpr int NH = MT >= 2 ? 2 : 1;          // independent row halves (see the forward kernel)
-    constexpr int HM = MT / NH;
-    const uint32_t wbar = bars + 8 * GB_STAGES;   // [NH] dgh rows of the half are written for this step
-    const uint32_t rbar = wbar + 8 * NH;          // [NH] ... and have been consumed by every warp's product
     if (tid == 0) {
         for (int s = 0; s < GB_STAGES; ++s) g_mbar_init(bars + 8 * s, 1);
-        for (int h = 0; h < NH; ++h) {
-            g_mbar_init(wbar + 8 * h, GTHREADS);
-            g_mbar_init(rbar + 8 * h, GTHREADS);
-        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -357,78 +329,67 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
     for (int tb = 0; tb < L; ++tb) {
         const int t = L - 1 - tb;
         const int l = dir ? L - 1 - t : t;
-        // the other ring stage held step tb-1, whose rows every thread has consumed (this warp passed wbar of the last
-        // half for step tb-1)
-        if (warp == 0 && tb + 1 < L) issue(tb + 1);
+        if (warp == 0 && tb + 1 < L) issue(tb + 1);      // the other stage was drained before the last barrier
+        double2 dO[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int r = 8 * mt + gid;
+            dO[mt] = (jok && r < nrows) ? *reinterpret_cast<const double2*>(dout + ((int64_t)(row0 + r) * L + l) * (2 * GH) + dir * GH + j0)
+                                        : make_double2(0.0, 0.0);
+        }
         const int s = tb % GB_STAGES;
+        g_mbar_wait(bars + 8 * s, (uint32_t)(tb / GB_STAGES) & 1u);
         const double* gs = ring + (int64_t)s * GROWS * RS;
+        if (jok) {
 #pragma unroll
-        for (int half = 0; half < NH; ++half) {
-            // ---- element-wise part: dgh / dgi of this half's rows (dh is thread-local: no cross-warp dependency)
-            double2 dO[HM];
+            for (int mt = 0; mt < MT; ++mt) {
+                const int r = 8 * mt + gid;
+                const double2 rr = *reinterpret_cast<const double2*>(gs + r * RS + j0);
+                const double2 zz = *reinterpret_cast<const double2*>(gs + r * RS + GH + j0);
+                const double2 nn = *reinterpret_cast<const double2*>(gs + r * RS + 2 * GH + j0);
+                const double2 qq = *reinterpret_cast<const double2*>(gs + r * RS + 3 * GH + j0);
+                const double2 hp = *reinterpret_cast<const double2*>(gs + r * RS + 4 * GH + j0);
+                double dr[2], dz[2], dn[2], dq[2];
 #pragma unroll
-            for (int mt = 0; mt < HM; ++mt) {
-                const int r = 8 * (half * HM + mt) + gid;
-                dO[mt] = (jok && r < nrows)
-                             ? *reinterpret_cast<const double2*>(dout + ((int64_t)(row0 + r) * L + l) * (2 * GH) + dir * GH + j0)
-                             : make_double2(0.0, 0.0);
-            }
-            if (tb > 0) g_mbar_wait(rbar + 8 * half, (uint32_t)(tb - 1) & 1u);     // dgh rows of step tb-1 fully consumed
-            if (half == 0) g_mbar_wait(bars + 8 * s, (uint32_t)(tb / GB_STAGES) & 1u);
-            if (jok) {
-#pragma unroll
-                for (int mt = 0; mt < HM; ++mt) {
-                    const int m = half * HM + mt;
-                    const int r = 8 * m + gid;
-                    const double2 rr = *reinterpret_cast<const double2*>(gs + r * RS + j0);
-                    const double2 zz = *reinterpret_cast<const double2*>(gs + r * RS + GH + j0);
-                    const double2 nn = *reinterpret_cast<const double2*>(gs + r * RS + 2 * GH + j0);
-                    const double2 qq = *reinterpret_cast<const double2*>(gs + r * RS + 3 * GH + j0);
-                    const double2 hp = *reinterpret_cast<const double2*>(gs + r * RS + 4 * GH + j0);
-                    double dr[2], dz[2], dn[2], dq[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const double rv = e ? rr.y : rr.x, zv = e ? zz.y : zz.x, nv = e ? nn.y : nn.x, qv = e ? qq.y : qq.x;
-                        const double hv = e ? hp.y : hp.x;
-                        const double d = (e ? dO[mt].y : dO[mt].x) + dh[m][e];
-                        dn[e] = d * (1.0 - zv) * (1.0 - nv * nv);
-                        dz[e] = d * (hv - nv) * zv * (1.0 - zv);
-                        dr[e] = dn[e] * qv * rv * (1.0 - rv);
-                        dq[e] = dn[e] * rv;
-                        dh[m][e] = d * zv;
-                    }
-                    *reinterpret_cast<double2*>(dgh + r * GDS + j0) = make_double2(dr[0], dr[1]);
-                    *reinterpret_cast<double2*>(dgh + r * GDS + GH + j0) = make_double2(dz[0], dz[1]);
-                    *reinterpret_cast<double2*>(dgh + r * GDS + 2 * GH + j0) = make_double2(dq[0], dq[1]);
-                    if (r < nrows) {
-                        double* gp = dgi + (((int64_t)(row0 + r) * L + l) * 2 + dir) * G3 + j0;
-                        *reinterpret_cast<double2*>(gp) = make_double2(dr[0], dr[1]);
-                        *reinterpret_cast<double2*>(gp + GH) = make_double2(dz[0], dz[1]);
-                        *reinterpret_cast<double2*>(gp + 2 * GH) = make_double2(dn[0], dn[1]);
-                    }
+                for (int e = 0; e < 2; ++e) {
+                    const double rv = e ? rr.y : rr.x, zv = e ? zz.y : zz.x, nv = e ? nn.y : nn.x, qv = e ? qq.y : qq.x;
+                    const double hv = e ? hp.y : hp.x;
+                    const double d = (e ? dO[mt].y : dO[mt].x) + dh[mt][e];
+                    dn[e] = d * (1.0 - zv) * (1.0 - nv * nv);
+                    dz[e] = d * (hv - nv) * zv * (1.0 - zv);
+                    dr[e] = dn[e] * qv * rv * (1.0 - rv);
+                    dq[e] = dn[e] * rv;
+                    dh[mt][e] = d * zv;
+                }
+                *reinterpret_cast<double2*>(dgh + r * GDS + j0) = make_double2(dr[0], dr[1]);
+                *reinterpret_cast<double2*>(dgh + r * GDS + GH + j0) = make_double2(dz[0], dz[1]);
+                *reinterpret_cast<double2*>(dgh + r * GDS + 2 * GH + j0) = make_double2(dq[0], dq[1]);
+                if (r < nrows) {
+                    double* gp = dgi + (((int64_t)(row0 + r) * L + l) * dgi_dirs + (dgi_dirs == 2 ? dir : 0)) * G3 + j0;
+                    *reinterpret_cast<double2*>(gp) = make_double2(dr[0], dr[1]);
+                    *reinterpret_cast<double2*>(gp + GH) = make_double2(dz[0], dz[1]);
+                    *reinterpret_cast<double2*>(gp + 2 * GH) = make_double2(dn[0], dn[1]);
                 }
             }
-            g_mbar_arrive(wbar + 8 * half);
-            // ---- product dgh W_hh of this half's rows
-            g_mbar_wait(wbar + 8 * half, (uint32_t)tb & 1u);
-            double acc[HM][2];
-#pragma unroll
-            for (int mt = 0; mt < HM; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
-#pragma unroll
-            for (int ks = 0; ks < 45; ++ks) {
-                double a[HM];
-#pragma unroll
-                for (int mt = 0; mt < HM; ++mt) a[mt] = dgh[(8 * (half * HM + mt) + gid) * GDS + 4 * ks + tig];
-#pragma unroll
-                for (int mt = 0; mt < HM; ++mt) dmma_8x8x4(acc[mt][0], acc[mt][1], a[mt], B[ks]);
-            }
-#pragma unroll
-            for (int mt = 0; mt < HM; ++mt) {
-                dh[half * HM + mt][0] += acc[mt][0];
-                dh[half * HM + mt][1] += acc[mt][1];
-            }
-            g_mbar_arrive(rbar + 8 * half);
         }
+        __syncthreads();                           // dgh of this step complete; ring stage s drained
+        double acc[MT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 45; ++ks) {
+            double a[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) a[mt] = dgh[(8 * mt + gid) * GDS + 4 * ks + tig];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) dmma_8x8x4(acc[mt][0], acc[mt][1], a[mt], B[ks]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            dh[mt][0] += acc[mt][0];
+            dh[mt][1] += acc[mt][1];
+        }
+        __syncthreads();                           // everyone done reading dgh before the next step overwrites it
     }
     if (dh0 && jok) {
 #pragma unroll
@@ -457,14 +418,15 @@ constexpr int GW_MT = 23;                                      // 184 = 23 m-til
 
 __global__ void __launch_bounds__(GTHREADS, 1) gru_wgrad_kernel(const double* __restrict__ dgi, const double* __restrict__ gates,
                                                                 const double* __restrict__ out, const double* __restrict__ h0,
-                                                                int n, int L, double* __restrict__ part)
+                                                                int n, int L, double* __restrict__ part, int ndir,
+                                                                int dgi_dirs)
 {
     extern __shared__ __align__(16) uint8_t gsm[];
     double* ring = reinterpret_cast<double*>(gsm);
     const uint32_t bars = g_smem_u32(gsm + GW_STAGES * GW_STAGE_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
-    const int dir = blockIdx.x & 1;
-    const int chunk = blockIdx.x >> 1, nchunks = gridDim.x >> 1;
+    const int dir = ndir == 2 ? (blockIdx.x & 1) : 0;
+    const int chunk = ndir == 2 ? (blockIdx.x >> 1) : blockIdx.x, nchunks = ndir == 2 ? (gridDim.x >> 1) : gridDim.x;
     const int64_t P = (int64_t)n * L;
     const int64_t nblk = (P + GW_PAIRS - 1) / GW_PAIRS;
     const int64_t b0 = nblk * chunk / nchunks, b1 = nblk * (chunk + 1) / nchunks;
@@ -484,7 +446,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_wgrad_kernel(const double* __
             double* dst = ring + (int64_t)s * GW_PAIRS * GW_ROW + lane * GW_ROW;
             const int64_t i = p / L;
             const int l = (int)(p - i * L);
-            g_bulk_g2s(g_smem_u32(dst), dgi + (p * 2 + dir) * G3, G3 * 8, bars + 8 * s);
+            g_bulk_g2s(g_smem_u32(dst), dgi + (p * dgi_dirs + (dgi_dirs == 2 ? dir : 0)) * G3, G3 * 8, bars + 8 * s);
             g_bulk_g2s(g_smem_u32(dst + G3), gates + (p * 2 + dir) * (4 * GH), GH * 8, bars + 8 * s);
             const bool first = dir ? (l == L - 1) : (l == 0);          // first step of the direction: h_prev = h0
             const double* hp = first ? h0 + ((int64_t)dir * n + i) * GH : out + (dir ? p + 1 : p - 1) * (2 * GH) + dir * GH;
@@ -531,10 +493,10 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_wgrad_kernel(const double* __
 
 // dwhh [2][180][60], dbhh [2][180] = sum over chunks of part (fixed order: deterministic)
 __global__ void __launch_bounds__(256) gru_wgrad_reduce_kernel(const double* __restrict__ part, int nchunks,
-                                                               double* __restrict__ dwhh, double* __restrict__ dbhh)
+                                                               double* __restrict__ dwhh, double* __restrict__ dbhh, int ndir)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // over [2][180][61]
-    if (idx >= 2 * G3 * (GH + 1)) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // over [ndir][180][61]
+    if (idx >= ndir * G3 * (GH + 1)) return;
     const int j = idx % (GH + 1), c = (idx / (GH + 1)) % G3, dir = idx / ((GH + 1) * G3);
     double s = 0.0;
     for (int k = 0; k < nchunks; ++k) s += part[(((int64_t)k * 2 + dir) * (GW_MT * 8) + c) * 64 + j];
@@ -548,7 +510,7 @@ __global__ void __launch_bounds__(256) gru_wgrad_reduce_kernel(const double* __r
 DRP_API int drp_gru_hidden_size(void) { return GH; }
 
 // rows per CTA = 8 MT: the largest of 32 / 16 / 8 for which one wave of CTAs (2 directions) still covers the batch
-static int gru_pick_mt(int n)
+static int gru_pick_mt(int n, int ndir = 2)
 {
     static int n_sm = 0;
     if (!n_sm) {
@@ -561,8 +523,8 @@ static int gru_pick_mt(int n)
         const int r = atoi(e);
         if (r == 8 || r == 16 || r == 32) return r / 8;
     }
-    if (2 * ((n + 7) / 8) <= n_sm) return 1;
-    if (2 * ((n + 15) / 16) <= n_sm) return 2;
+    if (ndir * ((n + 7) / 8) <= n_sm) return 1;
+    if (ndir * ((n + 15) / 16) <= n_sm) return 2;
     return 4;
 }
 
@@ -582,7 +544,7 @@ static void gru_fwd_launch(const double* gi, const double* v, const double* whh,
 
 template <int MT>
 static void gru_bwd_launch(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
-                           int n, int L, double* dgi, double* dh0, cudaStream_t st)
+                           int n, int L, double* dgi, double* dh0, int ndir, int dgi_dirs, cudaStream_t st)
 {
     constexpr int smem = gb_smem(8 * MT);
     static bool attr_done = false;
@@ -590,8 +552,9 @@ static void gru_bwd_launch(const double* dout, const double* out, const double* 
         cudaFuncSetAttribute(gru_bwd_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
-    DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * GH, st);
-    gru_bwd_kernel<MT><<<dim3((n + 8 * MT - 1) / (8 * MT), 2), GTHREADS, smem, st>>>(dout, out, gates, whh, h0, n, L, dgi, dh0);
+    DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * ndir * G3 * GH, st);
+    gru_bwd_kernel<MT><<<dim3((n + 8 * MT - 1) / (8 * MT), ndir), GTHREADS, smem, st>>>(dout, out, gates, whh, h0, n, L, dgi, dh0,
+                                                                                    dgi_dirs);
 }
 
 DRP_API int drp_gru_fwd_f64(const double* gi, const double* whh, const double* bhh, const double* h0, int n, int L, int H,
@@ -627,20 +590,35 @@ DRP_API int drp_gru_fwd_uv_f64(const double* U, const double* V, const double* w
     return drp_launch_status();
 }
 
-DRP_API int drp_gru_bwd_f64(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
-                            int n, int L, int H, double* dgi, double* dh0, void* stream)
+static int gru_bwd_dispatch(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
+                            int n, int L, int H, double* dgi, double* dh0, int ndir, int dgi_dirs, void* stream)
 {
     if (!dout || !out || !gates || !whh || !h0) return -1;
     if (n <= 0 || L <= 0) return -6;
     if (H != GH) return -8;
     if (!dgi) return -9;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (gru_pick_mt(n)) {
-        case 1: gru_bwd_launch<1>(dout, out, gates, whh, h0, n, L, dgi, dh0, st); break;
-        case 2: gru_bwd_launch<2>(dout, out, gates, whh, h0, n, L, dgi, dh0, st); break;
-        default: gru_bwd_launch<4>(dout, out, gates, whh, h0, n, L, dgi, dh0, st); break;
+    switch (gru_pick_mt(n, ndir)) {
+        case 1: gru_bwd_launch<1>(dout, out, gates, whh, h0, n, L, dgi, dh0, ndir, dgi_dirs, st); break;
+        case 2: gru_bwd_launch<2>(dout, out, gates, whh, h0, n, L, dgi, dh0, ndir, dgi_dirs, st); break;
+        default: gru_bwd_launch<4>(dout, out, gates, whh, h0, n, L, dgi, dh0, ndir, dgi_dirs, st); break;
     }
     return drp_launch_status();
+}
+
+DRP_API int drp_gru_bwd_f64(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
+                            int n, int L, int H, double* dgi, double* dh0, void* stream)
+{
+    return gru_bwd_dispatch(dout, out, gates, whh, h0, n, L, H, dgi, dh0, 2, 2, stream);
+}
+
+// Forward direction only (direction 0): dgi0 [n,L,3H] compact, dh0 [n,H] (first direction's slice of a [2,n,H] buffer is
+// fine).  Used when the loss only sees the hidden state at the last position (the encoder, S/models_utils.py:57): the
+// reverse direction then needs a single cell step, which the caller does with dense ops.
+DRP_API int drp_gru_bwd_dir0_f64(const double* dout, const double* out, const double* gates, const double* whh,
+                                 const double* h0, int n, int L, int H, double* dgi0, double* dh0, void* stream)
+{
+    return gru_bwd_dispatch(dout, out, gates, whh, h0, n, L, H, dgi0, dh0, 1, 1, stream);
 }
 
 // Workspace (doubles) of drp_gru_wgrad_f64.
@@ -653,8 +631,8 @@ DRP_API int64_t drp_gru_wgrad_workspace_elems(void)
 }
 
 // dwhh [2,3H,H], dbhh [2,3H] from dgi [n,L,2,3H] (drp_gru_bwd_f64), the saved gates, the hidden states and h0.
-DRP_API int drp_gru_wgrad_f64(const double* dgi, const double* gates, const double* out, const double* h0, int n, int L,
-                              int H, double* dwhh, double* dbhh, double* ws, int64_t ws_elems, void* stream)
+static int gru_wgrad_dispatch(const double* dgi, const double* gates, const double* out, const double* h0, int n, int L,
+                              int H, double* dwhh, double* dbhh, double* ws, int64_t ws_elems, int ndir, void* stream)
 {
     if (!dgi || !gates || !out || !h0) return -1;
     if (n <= 0 || L <= 0) return -5;
@@ -671,16 +649,29 @@ DRP_API int drp_gru_wgrad_f64(const double* dgi, const double* gates, const doub
         attr_done = true;
     }
     const int64_t nblk = ((int64_t)n * L + GW_PAIRS - 1) / GW_PAIRS;
-    int nchunks = n_sm / 2 > 0 ? n_sm / 2 : 1;
+    int nchunks = n_sm / ndir > 0 ? n_sm / ndir : 1;
     if (nchunks > nblk) nchunks = (int)nblk;
     if (!ws || ws_elems < (int64_t)nchunks * 2 * (GW_MT * 8) * 64) return -10;
     {
-        DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * (GH + 1), st);
-        gru_wgrad_kernel<<<2 * nchunks, GTHREADS, GW_SMEM, st>>>(dgi, gates, out, h0, n, L, ws);
+        DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * ndir * G3 * (GH + 1), st);
+        gru_wgrad_kernel<<<ndir * nchunks, GTHREADS, GW_SMEM, st>>>(dgi, gates, out, h0, n, L, ws, ndir, ndir);
     }
     {
-        DRP_LAUNCH(DRP_K_REDUCE, (double)nchunks * 2 * G3 * (GH + 1) * 8.0, st);
-        gru_wgrad_reduce_kernel<<<(2 * G3 * (GH + 1) + 255) / 256, 256, 0, st>>>(ws, nchunks, dwhh, dbhh);
+        DRP_LAUNCH(DRP_K_REDUCE, (double)nchunks * ndir * G3 * (GH + 1) * 8.0, st);
+        gru_wgrad_reduce_kernel<<<(ndir * G3 * (GH + 1) + 255) / 256, 256, 0, st>>>(ws, nchunks, dwhh, dbhh, ndir);
     }
     return drp_launch_status();
+}
+
+DRP_API int drp_gru_wgrad_f64(const double* dgi, const double* gates, const double* out, const double* h0, int n, int L,
+                              int H, double* dwhh, double* dbhh, double* ws, int64_t ws_elems, void* stream)
+{
+    return gru_wgrad_dispatch(dgi, gates, out, h0, n, L, H, dwhh, dbhh, ws, ws_elems, 2, stream);
+}
+
+// Direction 0 only: dgi0 [n,L,3H] compact -> dwhh[0], dbhh[0] (the direction-1 slices of the outputs are not written).
+DRP_API int drp_gru_wgrad_dir0_f64(const double* dgi0, const double* gates, const double* out, const double* h0, int n, int L,
+                                   int H, double* dwhh, double* dbhh, double* ws, int64_t ws_elems, void* stream)
+{
+    return gru_wgrad_dispatch(dgi0, gates, out, h0, n, L, H, dwhh, dbhh, ws, ws_elems, 1, stream);
 }

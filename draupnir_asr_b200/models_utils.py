@@ -29,10 +29,12 @@ class RNNEncoder(nn.Module):
                           bidirectional=True, num_layers=self.num_layers, dropout=0.0)
 
     def forward(self, input, hidden):
-        rnn_hidden_states, rnn_final_bidirectional = ops.gru_module_forward(self.rnn, input, hidden)
+        # only the hidden state at the LAST position reaches the loss (S/models_utils.py:57); the full sequence of hidden
+        # states is returned for the caller's dictionary but carries no gradient
+        rnn_all, last, rnn_final_bidirectional = ops.gru_encoder_last(self.rnn, input, hidden)
         H = self.gru_hidden_dim
-        rnn_hidden_states = rnn_hidden_states[:, :, :H] + rnn_hidden_states[:, :, H:]
-        rnn_final_hidden_state = self.fc1(rnn_hidden_states[:, -1])
+        rnn_hidden_states = rnn_all[:, :, :H] + rnn_all[:, :, H:]
+        rnn_final_hidden_state = self.fc1(last[:, :H] + last[:, H:])
         z_loc = self.linear_means(rnn_final_hidden_state)
         z_scale = self.softplus(self.linear_std(rnn_final_hidden_state))
         return {"z_loc": z_loc, "z_scale": z_scale, "rnn_final_bidirectional": rnn_final_bidirectional,

@@ -412,6 +412,85 @@ def gru_bidirectional_uv(U: torch.Tensor, V: torch.Tensor, weight_hh, bias_hh, h
     return _GRUBidirUV.apply(U, V, weight_hh, bias_hh, h0)
 
 
+class _GRUEncoderLast(torch.autograd.Function):
+    """Bidirectional GRU over `x [n,L,I]` whose only DIFFERENTIABLE output is the hidden state at the last position
+    (`out[:, -1]`, what `RNNEncoder.forward` feeds to `fc1`, S/models_utils.py:57); the full `out [n,L,2H]` is returned
+    too, without gradient.  Back-propagation then needs the forward direction only (the reverse direction reaches
+    position L-1 after ONE cell step, done here with dense ops), with 16 instead of 32 sequences per CTA."""
+
+    @staticmethod
+    def forward(ctx, x, wih, bih, whh, bhh, h0):
+        x, wih, bih, whh, bhh, h0 = (_req(v, k).contiguous() for v, k in ((x, "input"), (wih, "weight_ih"), (bih, "bias_ih"),
+                                                                          (whh, "weight_hh"), (bhh, "bias_hh"), (h0, "h0")))
+        n, L, I = x.shape
+        H = whh.shape[-1]
+        gi = torch.addmm(bih.reshape(-1), x.reshape(n * L, I), wih.reshape(6 * H, I).t())        # [n*L, 2*3H]
+        want = any(ctx.needs_input_grad)
+        out = torch.empty((n, L, 2 * H), dtype=torch.float64, device=x.device)
+        gates = torch.empty((n, L, 2, 4, H), dtype=torch.float64, device=x.device) if want else None
+        _rc(lib.drp_gru_fwd_f64(_p(gi), _p(whh), _p(bhh), _p(h0), n, L, H, _p(out), _p(gates), _stream()), "drp_gru_fwd_f64")
+        del gi
+        if want:
+            ctx.save_for_backward(x, wih, whh, h0, out, gates)
+        ctx.mark_non_differentiable(out)
+        return out, out[:, -1].clone()
+
+    @staticmethod
+    def backward(ctx, _dout_ignored, dlast):
+        x, wih, whh, h0, out, gates = ctx.saved_tensors
+        n, L, I = x.shape
+        H = whh.shape[-1]
+        dev = x.device
+        # ---- forward direction: full BPTT, gradient enters at the last position only
+        dout = torch.zeros((n, L, 2 * H), dtype=torch.float64, device=dev)
+        dout[:, -1, :H] = dlast[:, :H]
+        dgi0 = torch.empty((n, L, 3 * H), dtype=torch.float64, device=dev)
+        dh0 = torch.empty_like(h0)
+        _rc(lib.drp_gru_bwd_dir0_f64(_p(dout), _p(out), _p(gates), _p(whh), _p(h0), n, L, H, _p(dgi0), _p(dh0), _stream()),
+            "drp_gru_bwd_dir0_f64")
+        del dout
+        dwhh = torch.empty_like(whh)
+        dbhh = torch.empty((2, 3 * H), dtype=torch.float64, device=dev)
+        wse = lib.drp_gru_wgrad_workspace_elems()
+        ws = torch.empty(wse, dtype=torch.float64, device=dev)
+        _rc(lib.drp_gru_wgrad_dir0_f64(_p(dgi0), _p(gates), _p(out), _p(h0), n, L, H, _p(dwhh), _p(dbhh), _p(ws), wse, _stream()),
+            "drp_gru_wgrad_dir0_f64")
+        # ---- reverse direction: position L-1 is its FIRST step (h_prev = h0[1])
+        g1 = gates[:, L - 1, 1]                                  # [n, 4, H]: r, z, n, q
+        r, z, nn, q = g1[:, 0], g1[:, 1], g1[:, 2], g1[:, 3]
+        d = dlast[:, H:]
+        dn = d * (1.0 - z) * (1.0 - nn * nn)
+        dz = d * (h0[1] - nn) * z * (1.0 - z)
+        dr = dn * q * r * (1.0 - r)
+        dgi1 = torch.cat((dr, dz, dn), dim=1)                    # [n, 3H] at position L-1
+        dgh1 = torch.cat((dr, dz, dn * r), dim=1)
+        dwhh[1] = dgh1.t() @ h0[1]
+        dbhh[1] = dgh1.sum(0)
+        dh0[1] = d * z + dgh1 @ whh[1]
+        # ---- input projection
+        dgi0f = dgi0.reshape(n * L, 3 * H)
+        xf = x.reshape(n * L, I)
+        dwih = torch.stack((dgi0f.t() @ xf, dgi1.t() @ x[:, L - 1]))
+        dbih = torch.stack((dgi0f.sum(0), dgi1.sum(0)))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = (dgi0f @ wih[0]).reshape(n, L, I)
+            dx[:, L - 1] += dgi1 @ wih[1]
+        return dx, dwih, dbih, dwhh, dbhh, dh0
+
+
+def gru_encoder_last(rnn: torch.nn.GRU, x: torch.Tensor, h0: torch.Tensor):
+    """`rnn(x, h0)` for the encoder: returns `(output_detached [n,L,2H], last [n,2H], h_n [2,n,H])` where only `last =
+    output[:, -1]` carries gradient (see `_GRUEncoderLast`)."""
+    H = rnn.hidden_size
+    if H != GRU_HIDDEN or not x.is_cuda:
+        out, hn = rnn(x, h0)
+        return out, out[:, -1], hn
+    wih, whh, bih, bhh = gru_stacked_params(rnn)
+    out, last = _GRUEncoderLast.apply(x, wih, bih, whh, bhh, h0)
+    return out, last, torch.stack((out[:, -1, :H], out[:, 0, H:]))
+
+
 def gru_bidirectional(gi: torch.Tensor, weight_hh: torch.Tensor, bias_hh: torch.Tensor, h0: torch.Tensor) -> torch.Tensor:
     """Hidden states `[n, L, 2H]` (torch's bidirectional layout) of a one-layer bidirectional GRU whose input
     projections `gi = W_ih x + b_ih` are given as `[n, L, 2, 3H]`; `weight_hh [2,3H,H]`, `bias_hh [2,3H]`, `h0 [2,n,H]`

@@ -108,6 +108,12 @@ int drp_gru_fwd_uv_f64(const double* U, const double* V, const double* whh, cons
 int drp_gru_bwd_f64(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
                     int n, int L, int H, double* dgi, double* dh0, void* stream);
 
+/* Forward direction only: dgi0 [n,L,3H] compact, dh0[0 .. n*H) written.  For callers whose loss only sees the hidden
+ * state at the last position (RNNEncoder.forward, S/models_utils.py:57): the reverse direction is then one cell step.  */
+int drp_gru_bwd_dir0_f64(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
+                         int n, int L, int H, double* dgi0, double* dh0, void* stream);
+int drp_gru_wgrad_dir0_f64(const double* dgi0, const double* gates, const double* out, const double* h0, int n, int L, int H,
+                           double* dwhh, double* dbhh, double* ws, int64_t ws_elems, void* stream);
 /* dwhh [2,3H,H] = sum_p dgh[p]^T h_prev[p], dbhh [2,3H] = sum_p dgh[p] (autograd of nn.GRU's weight_hh / bias_hh);
  * ws: drp_gru_wgrad_workspace_elems() doubles.                                                                   */
 int64_t drp_gru_wgrad_workspace_elems(void);

@@ -72,6 +72,31 @@ __global__ void __launch_bounds__(256) tput(double* out, int iters)
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// ---- do DMMA and DFMA share execution resources?  warps with (warp & 1) == sel_dmma run DMMAs, the others DFMAs
+template <int MODE>   // 0: all warps DMMA, 1: all warps DFMA, 2: even warps DMMA + odd warps DFMA
+__global__ void __launch_bounds__(256) mix(double* out, int iters)
+{
+    const int warp = threadIdx.x >> 5;
+    const bool do_dmma = MODE == 0 || (MODE == 2 && (warp & 1) == 0);
+    double acc[8][2], f[16];
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
+    for (int i = 0; i < 16; ++i) f[i] = 1.0 + i * 1e-3;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 0.999999;
+    if (do_dmma) {
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dmma884(acc[i][0], acc[i][1], a, b);
+    } else {
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fma(f[i], b, a);
+    }
+    double s = 0;
+    for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1];
+    for (int i = 0; i < 16; ++i) s += f[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main()
 {
     double hA[256], hB[128], hC[128], ref[128];
@@ -109,6 +134,22 @@ int main()
         const double per = mode == 0 ? 16.0 * 512 : (mode == 1 ? 8.0 * 4096 : 8.0 * 1024);
         const double flops = per * iters * (double)sms * 4 * 8;
         printf("%s: %.3f ms, %.2f TFLOP/s\n", mode == 0 ? "m8n8k4  " : (mode == 1 ? "m16n8k16" : "m16n8k4 "), ms, flops / ms / 1e9);
+    }
+    for (int mode = 0; mode < 3; ++mode) {
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(e0);
+            if (mode == 0) mix<0><<<sms * 4, 256>>>(out, iters);
+            if (mode == 1) mix<1><<<sms * 4, 256>>>(out, iters);
+            if (mode == 2) mix<2><<<sms * 4, 256>>>(out, iters);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+        }
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        // per warp-iteration: DMMA warps 8 x 512 flop, DFMA warps 16 x 64 flop
+        const double warps = (double)sms * 4 * 8;
+        const double dmma_fl = (mode == 1 ? 0.0 : (mode == 0 ? 1.0 : 0.5)) * warps * iters * 8.0 * 512;
+        const double dfma_fl = (mode == 0 ? 0.0 : (mode == 1 ? 1.0 : 0.5)) * warps * iters * 16.0 * 64;
+        printf("mix mode %d (%s): %.3f ms, DMMA %.2f TFLOP/s, DFMA %.2f TFLOP/s\n", mode,
+               mode == 0 ? "all DMMA" : (mode == 1 ? "all DFMA" : "half DMMA / half DFMA"), ms, dmma_fl / ms / 1e9, dfma_fl / ms / 1e9);
     }
     cudaError_t e = cudaGetLastError();
     printf("status: %s\n", cudaGetErrorString(e));

@@ -64,3 +64,30 @@ def test_no_grad_path_and_structured_decoder(cuda, monkeypatch, rows):
     # library nn.GRU (cuDNN) on the same device agrees as well
     ref, _ = dec.rnn(x, hidden)
     assert float((dec.linear_probs(dec.fc1(ref)) - a).abs().max()) < 1e-10
+
+
+@pytest.mark.parametrize("n,L,I", [(3, 1, 21), (37, 23, 21), (150, 40, 21)])
+def test_encoder_last_position_path(cuda, n, L, I):
+    """`gru_encoder_last`: same hidden states as nn.GRU, and for a loss that only sees the last position the gradients of
+    the input, h0 and every GRU parameter equal torch's (forward direction: full BPTT; reverse direction: one step)."""
+    from draupnir_asr_b200 import ops
+    torch.manual_seed(n + L)
+    rnn = torch.nn.GRU(input_size=I, hidden_size=60, batch_first=True, bidirectional=True, num_layers=1).double()
+    x = torch.randn(n, L, I, dtype=torch.float64, requires_grad=True)
+    h0 = torch.randn(2, n, 60, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(n, 120, dtype=torch.float64)
+    out_ref, hn_ref = rnn(x, h0)
+    (out_ref[:, -1] * w).sum().backward()
+    rnn_g = torch.nn.GRU(input_size=I, hidden_size=60, batch_first=True, bidirectional=True, num_layers=1).double().to(cuda)
+    rnn_g.load_state_dict(rnn.state_dict())
+    xg = x.detach().to(cuda).requires_grad_(True)
+    hg = h0.detach().to(cuda).requires_grad_(True)
+    out, last, hn = ops.gru_encoder_last(rnn_g, xg, hg)
+    assert not out.requires_grad
+    (last * w.to(cuda)).sum().backward()
+    pairs = [("out", out_ref.detach(), out.cpu()), ("hn", hn_ref.detach(), hn.detach().cpu()), ("x", x.grad, xg.grad.cpu()),
+             ("h0", h0.grad, hg.grad.cpu())]
+    pairs += [(k, p.grad, dict(rnn_g.named_parameters())[k].grad.cpu()) for k, p in rnn.named_parameters()]
+    for k, a, b in pairs:
+        err = float((a - b).abs().max() / a.abs().max().clamp_min(1e-30))
+        assert err < 1e-11, (k, err)
