@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) cat_fwd_kernel(const double* __restrict__
         double m = row[0];
         for (int a = 1; a < A; ++a) m = fmax(m, row[a]);
         double e = 0.0;
-        for (int a = 0; a < A; ++a) e += exp(row[a] - m);
+        for (int a = 0; a < A; ++a) e += drp_exp(row[a] - m);
         const double lse = m + log(e);
         const int x = (int)obs[r0 + threadIdx.x];
         ll = row[x] - lse;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) cat_bwd_kernel(const double* __restrict__
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = idx / A;
         const int a = (int)(idx - r * A);
-        const double p = exp(s[idx] - lse[r]);
+        const double p = drp_exp(s[idx] - lse[r]);
         ds[idx] = gv * (((int)obs[r] == a ? 1.0 : 0.0) - p);
     }
 }

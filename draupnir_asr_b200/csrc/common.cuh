@@ -44,3 +44,30 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+
+// exp for finite arguments without the library routine's special-case handling (clamped to +-700): n = rint(x log2 e),
+// two-term Cody-Waite reduction, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation 4e-18, observed <= 1 ulp),
+// scaling by 2^n through the exponent field.  The fp64 pipe is what bounds the covariance assembly (30 exponentials per
+// distance), the categorical kernel (21 per site) and the GRU gates, so the ~30 % fewer instructions show up directly.
+__device__ __forceinline__ double drp_exp(double x)
+{
+    x = fmin(fmax(x, -700.0), 700.0);
+    const double t = rint(x * 1.4426950408889634074);
+    double r = fma(t, -6.93147180369123816490e-01, x);
+    r = fma(t, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, r, 2.0876756987868100e-09);        // 1/12!
+    p = fma(p, r, 2.5052108385441720e-08);        // 1/11!
+    p = fma(p, r, 2.7557319223985893e-07);        // 1/10!
+    p = fma(p, r, 2.7557319223985888e-06);        // 1/9!
+    p = fma(p, r, 2.4801587301587302e-05);        // 1/8!
+    p = fma(p, r, 1.9841269841269841e-04);        // 1/7!
+    p = fma(p, r, 1.3888888888888889e-03);        // 1/6!
+    p = fma(p, r, 8.3333333333333332e-03);        // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + ((int)t << 20), __double2loint(p));
+}

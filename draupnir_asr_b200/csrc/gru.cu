@@ -68,34 +68,9 @@ __device__ __forceinline__ void g_bulk_g2s(uint32_t dst, const void* src, uint32
                  : "memory");
 }
 
-// exp for the gate non-linearities: arguments are pre-activations (clamped to +-700, never NaN-producing), so the
-// library routine's special-case handling is dropped: n = rint(x log2 e), two-term Cody-Waite reduction, degree-13
-// Taylor polynomial on |r| <= ln2/2 (truncation 4e-18), scaling by 2^n through the exponent field.
-__device__ __forceinline__ double gate_exp(double x)
-{
-    x = fmin(fmax(x, -700.0), 700.0);
-    const double t = rint(x * 1.4426950408889634074);
-    double r = fma(t, -6.93147180369123816490e-01, x);
-    r = fma(t, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;            // 1/13!
-    p = fma(p, r, 2.0876756987868100e-09);        // 1/12!
-    p = fma(p, r, 2.5052108385441720e-08);        // 1/11!
-    p = fma(p, r, 2.7557319223985893e-07);        // 1/10!
-    p = fma(p, r, 2.7557319223985888e-06);        // 1/9!
-    p = fma(p, r, 2.4801587301587302e-05);        // 1/8!
-    p = fma(p, r, 1.9841269841269841e-04);        // 1/7!
-    p = fma(p, r, 1.3888888888888889e-03);        // 1/6!
-    p = fma(p, r, 8.3333333333333332e-03);        // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    return __hiloint2double(__double2hiint(p) + ((int)t << 20), __double2loint(p));
-}
-__device__ __forceinline__ double sigmoid_f64(double x) { return __drcp_rn(1.0 + gate_exp(-x)); }
+__device__ __forceinline__ double sigmoid_f64(double x) { return __drcp_rn(1.0 + drp_exp(-x)); }
 // tanh(x) = 1 - 2 / (1 + e^{2x}): absolute error ~1e-16 (what the recurrence needs), saturates correctly at +-1
-__device__ __forceinline__ double tanh_f64(double x) { return fma(-2.0, __drcp_rn(1.0 + gate_exp(2.0 * x)), 1.0); }
+__device__ __forceinline__ double tanh_f64(double x) { return fma(-2.0, __drcp_rn(1.0 + drp_exp(2.0 * x)), 1.0); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Forward.  grid (ceil(n/ROWS), 2 directions), 256 threads; ROWS = 8 MT sequences per CTA (MT = 4, 2 or 1 chosen by

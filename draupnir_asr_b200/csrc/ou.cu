@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) ou_cov_fwd_kernel(const double* __restric
     double* out = K + (int64_t)r * n + c;
     const int64_t bs = (int64_t)n * n;
     for (int zz = 0; zz < z; ++zz) {
-        double v = hp[zz] * exp(d * hp[2 * z + zz]);
+        double v = hp[zz] * drp_exp(d * hp[2 * z + zz]);
         if (r == c) v += hp[z + zz];
         out[zz * bs] = v;
     }
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) ou_cov_bwd_kernel(const double* __restric
     double sE = 0.0, sED = 0.0;
     for (int c = threadIdx.x; c < n; c += blockDim.x) {
         const double d = drow[c];
-        const double t = g[c] * exp(d * nil);
+        const double t = g[c] * drp_exp(d * nil);
         sE += t;
         sED += t * d;
     }
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) ou_assemble_kernel(const double* __restri
     const double d = D[(int64_t)a * ldd + b];
     const bool diag = (pr == pc);
     for (int zz = 0; zz < z; ++zz) {
-        double v = hp[zz] * exp(d * hp[2 * z + zz]);
+        double v = hp[zz] * drp_exp(d * hp[2 * z + zz]);
         if (diag) v += hp[z + zz];
         out[zz * bs] = v;
     }
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) ou_grad_kernel(const double* __restrict__
         const double g = 0.5 * (ar * ac + krow[c]);          // krow = -Kinv
         const double d = drow[c];
         const double w = (c == r) ? 1.0 : 2.0;
-        const double t = w * g * exp(d * nil);
+        const double t = w * g * drp_exp(d * nil);
         sE += t;
         sED += t * d;
         if (c == r) gd = g;

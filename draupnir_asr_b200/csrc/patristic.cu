@@ -161,16 +161,24 @@ struct ChainEntry {
 
 constexpr int CHAIN_SMEM = 1024;   // ancestors held in shared memory; deeper chains spill to the global workspace
 
-// One CTA per requested row node.
+// One CTA per requested row node.  The ancestors a_0 = i, a_1, ..., root of the row node are laid out in shared memory; the
+// LCA of (i, j) is the deepest a_k whose subtree (the preorder interval [pre, pre + size)) contains j.
+//   TABLE = true : a lookup table over PREORDER positions (uint16 chain index per position, 2 N bytes of shared memory)
+//                  is filled once per row from the nested intervals - position p in subtree(a_k) \ subtree(a_{k-1}) gets
+//                  k - so every column costs two shared-memory reads instead of a binary search; this is what makes
+//                  the kernel HBM-bound instead of instruction-bound.
+//   TABLE = false: binary search over the chain per column (trees too large for the table, or chains deeper than 65535).
+template <bool TABLE>
 __global__ void __launch_bounds__(256) lca_patristic_kernel(const int32_t* __restrict__ parent, const int32_t* __restrict__ depth,
                                                             const double* __restrict__ root_dist, const int32_t* __restrict__ pre,
                                                             const int32_t* __restrict__ size, const int32_t* __restrict__ rows,
-                                                            const int32_t* __restrict__ cols, int nc,
+                                                            const int32_t* __restrict__ cols, int nc, int n_nodes,
                                                             int32_t* __restrict__ lca_out, double* __restrict__ dist_out,
                                                             double* __restrict__ clad_out, ChainEntry* __restrict__ spill,
                                                             int spill_stride)
 {
     __shared__ ChainEntry chain_s[CHAIN_SMEM];
+    extern __shared__ uint16_t table[];            // [n_nodes] chain index by preorder position (TABLE only)
     const int i = rows ? rows[blockIdx.x] : blockIdx.x;
     const int len = depth[i] + 1;
     ChainEntry* chain = len <= CHAIN_SMEM ? chain_s : spill + (int64_t)blockIdx.x * spill_stride;
@@ -190,26 +198,48 @@ __global__ void __launch_bounds__(256) lca_patristic_kernel(const int32_t* __res
     }
     __syncthreads();
     if (len > CHAIN_SMEM) __threadfence_block();
+    if (TABLE) {
+        int plo = 0, phi = 0;                      // interval of the previous (deeper) ancestor; empty for k = 0
+        for (int k = 0; k < len; ++k) {
+            const int lo = chain[k].lo, hi = chain[k].hi;
+            const int first = k == 0 ? hi : plo;   // k = 0: the whole interval [lo, hi)
+            for (int p = lo + threadIdx.x; p < first; p += blockDim.x) table[p] = (uint16_t)k;
+            if (k > 0)
+                for (int p = phi + threadIdx.x; p < hi; p += blockDim.x) table[p] = (uint16_t)k;
+            plo = lo;
+            phi = hi;
+        }
+        __syncthreads();
+    }
     const double ri = root_dist[i];
     const int di = depth[i];
     const int64_t obase = (int64_t)blockIdx.x * nc;
     for (int b = threadIdx.x; b < nc; b += blockDim.x) {
         const int j = cols ? cols[b] : b;
         const int p = pre[j];
-        // smallest k with lo_k <= p < hi_k (intervals are nested, the root's always matches)
-        int lo = 0, hi = len - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            const ChainEntry e = chain[mid];
-            if (e.lo <= p && p < e.hi) hi = mid;
-            else lo = mid + 1;
+        int k;
+        if (TABLE) {
+            k = table[p];
+        } else {
+            // smallest k with lo_k <= p < hi_k (intervals are nested, the root's always matches)
+            int lo = 0, hi = len - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const ChainEntry e = chain[mid];
+                if (e.lo <= p && p < e.hi) hi = mid;
+                else lo = mid + 1;
+            }
+            k = lo;
         }
-        const ChainEntry e = chain[lo];
+        const ChainEntry e = chain[k];
         if (lca_out) lca_out[obase + b] = e.id;
         if (dist_out) dist_out[obase + b] = (ri - e.rd) + (root_dist[j] - e.rd);
         if (clad_out) clad_out[obase + b] = (double)(di + depth[j] - 2 * e.depth);
     }
+    (void)n_nodes;
 }
+
+constexpr int TABLE_MAX_NODES = 80000;             // 2 bytes per node of dynamic shared memory
 
 }  // namespace
 
@@ -248,8 +278,20 @@ DRP_API int drp_lca_patristic_f64(const int32_t* parent, const int32_t* depth, c
     if (ws_bytes < drp_lca_workspace_bytes(nr, max_depth) || (ws_bytes > 0 && !ws)) return -16;
     {
         DRP_LAUNCH(DRP_K_PATRISTIC, ((double)nr * nc * ((dist_out ? 8.0 : 0.0) + (clad_out ? 8.0 : 0.0) + (lca_out ? 4.0 : 0.0))), st);
-        lca_patristic_kernel<<<nr, 256, 0, (cudaStream_t)stream>>>(parent, depth, root_dist, pre, size, rows, cols, nc, lca_out,
-                                                                dist_out, clad_out, (ChainEntry*)ws, max_depth + 1);
+        if (n_nodes <= TABLE_MAX_NODES && max_depth < 65535) {
+            const size_t sm = (size_t)n_nodes * sizeof(uint16_t);
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaFuncSetAttribute(lca_patristic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TABLE_MAX_NODES * (int)sizeof(uint16_t));
+                attr_done = true;
+            }
+            lca_patristic_kernel<true><<<nr, 256, sm, st>>>(parent, depth, root_dist, pre, size, rows, cols, nc, n_nodes, lca_out,
+                                                            dist_out, clad_out, (ChainEntry*)ws, max_depth + 1);
+        } else {
+            lca_patristic_kernel<false><<<nr, 256, 0, st>>>(parent, depth, root_dist, pre, size, rows, cols, nc, n_nodes, lca_out,
+                                                            dist_out, clad_out, (ChainEntry*)ws, max_depth + 1);
+        }
     }
     return drp_launch_status();
 }
