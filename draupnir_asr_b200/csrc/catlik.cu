@@ -25,9 +25,24 @@ __global__ void __launch_bounds__(256) cat_fwd_kernel(const double* __restrict__
     const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_CTA;
     const int nrow = (int)min((int64_t)ROWS_PER_CTA, rows - r0);
     const double* src = s + r0 * A;
-    for (int idx = threadIdx.x; idx < nrow * A; idx += blockDim.x) {
-        const int r = idx / A, a = idx - r * A;
-        tile[r * lda + a] = src[idx];
+    // flat, fully coalesced copy of the CTA's rows; eight loads per thread are issued before the first store so that the
+    // copy is bound by bandwidth instead of by the latency of one load per iteration
+    const int total = nrow * A;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 8 * 256) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = i0 + u * 256;
+            v[u] = idx < total ? src[idx] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = i0 + u * 256;
+            if (idx < total) {
+                const int r = idx / A, a = idx - r * A;
+                tile[r * lda + a] = v[u];
+            }
+        }
     }
     __syncthreads();
     double ll = 0.0;
@@ -63,11 +78,26 @@ __global__ void __launch_bounds__(256) cat_bwd_kernel(const double* __restrict__
 {
     const int64_t total = rows * A;
     const double gv = g[0];
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = idx / A;
-        const int a = (int)(idx - r * A);
-        const double p = drp_exp(s[idx] - lse[r]);
-        ds[idx] = gv * (((int)obs[r] == a ? 1.0 : 0.0) - p);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+        double sv[4], lv[4];
+        int ov[4], av[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {              // four independent element loads in flight per thread
+            const int64_t idx = i0 + u * stride;
+            if (idx < total) {
+                const int64_t r = idx / A;
+                av[u] = (int)(idx - r * A);
+                sv[u] = s[idx];
+                lv[u] = lse[r];
+                ov[u] = (int)obs[r];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t idx = i0 + u * stride;
+            if (idx < total) ds[idx] = gv * ((ov[u] == av[u] ? 1.0 : 0.0) - drp_exp(sv[u] - lv[u]));
+        }
     }
 }
 

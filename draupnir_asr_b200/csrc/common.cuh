@@ -45,29 +45,35 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                  : "d"(a), "d"(b));
 }
 
-// exp for finite arguments without the library routine's special-case handling (clamped to +-700): n = rint(x log2 e),
-// two-term Cody-Waite reduction, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation 4e-18, observed <= 1 ulp),
-// scaling by 2^n through the exponent field.  The fp64 pipe is what bounds the covariance assembly (30 exponentials per
-// distance), the categorical kernel (21 per site) and the GRU gates, so the ~30 % fewer instructions show up directly.
+// exp for finite arguments without the library routine's special-case handling (clamped to +-700):
+// x = (32 m + j) ln2/32 + r with |r| <= ln2/64, exp(x) = 2^m * 2^(j/32) * exp(r); 2^(j/32) from a 32-entry table (L1-resident),
+// exp(r) - 1 by a degree-6 polynomial (truncation 1e-18), two-term Cody-Waite reduction; observed error <= 1 ulp.  About
+// half the fp64 instructions of the library exp: the fp64 pipe is what bounds the covariance assembly (30 exponentials
+// per distance), the categorical kernel (21 per site) and the GRU gates.
+__device__ const double DRP_EXP2_TAB[32] = {
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237,
+    1.0905077326652577, 1.1143867425958924, 1.1387886347566916, 1.1637248587775775,
+    1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
+    1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,
+    1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228,
+    1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965,
+    1.681792830507429, 1.718619298122478, 1.7562521603732995, 1.7947090750031072,
+    1.8340080864093424, 1.8741676341103, 1.9152065613971474, 1.9571441241754002};
+
 __device__ __forceinline__ double drp_exp(double x)
 {
     x = fmin(fmax(x, -700.0), 700.0);
-    const double t = rint(x * 1.4426950408889634074);
-    double r = fma(t, -6.93147180369123816490e-01, x);
-    r = fma(t, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;            // 1/13!
-    p = fma(p, r, 2.0876756987868100e-09);        // 1/12!
-    p = fma(p, r, 2.5052108385441720e-08);        // 1/11!
-    p = fma(p, r, 2.7557319223985893e-07);        // 1/10!
-    p = fma(p, r, 2.7557319223985888e-06);        // 1/9!
-    p = fma(p, r, 2.4801587301587302e-05);        // 1/8!
-    p = fma(p, r, 1.9841269841269841e-04);        // 1/7!
-    p = fma(p, r, 1.3888888888888889e-03);        // 1/6!
-    p = fma(p, r, 8.3333333333333332e-03);        // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    return __hiloint2double(__double2hiint(p) + ((int)t << 20), __double2loint(p));
+    const double t = rint(x * 46.166241308446828384);          // 32 / ln 2
+    double r = fma(t, -0.021660849219188094, x);               // ln2/32, leading 27 bits (t * hi is exact)
+    r = fma(t, -1.733101967801894e-10, r);                     // ln2/32, remainder
+    double q = 1.3888888888888889e-03;                         // 1/720
+    q = fma(q, r, 8.3333333333333332e-03);
+    q = fma(q, r, 4.1666666666666664e-02);
+    q = fma(q, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    const int n = (int)t;
+    const double T = __ldg(DRP_EXP2_TAB + (n & 31));
+    const double v = fma(T, q * r, T);
+    return __hiloint2double(__double2hiint(v) + ((n >> 5) << 20), __double2loint(v));
 }

@@ -161,85 +161,132 @@ struct ChainEntry {
 
 constexpr int CHAIN_SMEM = 1024;   // ancestors held in shared memory; deeper chains spill to the global workspace
 
-// One CTA per requested row node.  The ancestors a_0 = i, a_1, ..., root of the row node are laid out in shared memory; the
+// RPC requested row nodes per CTA.  The ancestors a_0 = i, a_1, ..., root of a row node are laid out in shared memory; the
 // LCA of (i, j) is the deepest a_k whose subtree (the preorder interval [pre, pre + size)) contains j.
-//   TABLE = true : a lookup table over PREORDER positions (uint16 chain index per position, 2 N bytes of shared memory)
-//                  is filled once per row from the nested intervals - position p in subtree(a_k) \ subtree(a_{k-1}) gets
-//                  k - so every column costs two shared-memory reads instead of a binary search; this is what makes
-//                  the kernel HBM-bound instead of instruction-bound.
-//   TABLE = false: binary search over the chain per column (trees too large for the table, or chains deeper than 65535).
-template <bool TABLE>
-__global__ void __launch_bounds__(256) lca_patristic_kernel(const int32_t* __restrict__ parent, const int32_t* __restrict__ depth,
+//   TABLE = true : a lookup table over PREORDER positions (uint16 chain index per position, 2 N bytes of shared memory
+//                  per row) is filled once per row from the nested intervals - position p in subtree(a_k) \
+//                  subtree(a_{k-1}) gets k - so a column costs two shared-memory reads instead of a binary search, and
+//                  the per-column operands (pre[j], root_dist[j], depth[j]) are fetched once for the RPC rows of the CTA.
+//   TABLE = false: one row per CTA, binary search over the chain per column (trees too large for the table, or chains
+//                  deeper than 65535 / longer than the shared-memory chain).
+template <bool TABLE, int RPC, int NT>
+__global__ void __launch_bounds__(NT) lca_patristic_kernel(const int32_t* __restrict__ parent, const int32_t* __restrict__ depth,
                                                             const double* __restrict__ root_dist, const int32_t* __restrict__ pre,
                                                             const int32_t* __restrict__ size, const int32_t* __restrict__ rows,
-                                                            const int32_t* __restrict__ cols, int nc, int n_nodes,
+                                                            const int32_t* __restrict__ cols, int nr, int nc, int n_nodes,
                                                             int32_t* __restrict__ lca_out, double* __restrict__ dist_out,
                                                             double* __restrict__ clad_out, ChainEntry* __restrict__ spill,
                                                             int spill_stride)
 {
+    constexpr int CHAIN_PER_ROW = CHAIN_SMEM / RPC;
     __shared__ ChainEntry chain_s[CHAIN_SMEM];
-    extern __shared__ uint16_t table[];            // [n_nodes] chain index by preorder position (TABLE only)
-    const int i = rows ? rows[blockIdx.x] : blockIdx.x;
-    const int len = depth[i] + 1;
-    ChainEntry* chain = len <= CHAIN_SMEM ? chain_s : spill + (int64_t)blockIdx.x * spill_stride;
-    // ancestor k of i: walk is sequential, but only `len` steps; lane 0 does it, everyone else waits.
-    if (threadIdx.x == 0) {
-        int a = i;
-        for (int k = 0; k < len; ++k) {
-            ChainEntry e;
-            e.lo = pre[a];
-            e.hi = e.lo + size[a];
-            e.id = a;
-            e.depth = depth[a];
-            e.rd = root_dist[a];
-            chain[k] = e;
-            a = parent[a];
+    extern __shared__ uint16_t table[];            // [RPC][n_nodes] chain index by preorder position (TABLE only)
+    int irow[RPC], pi[RPC], di0[RPC];
+    double ri[RPC];
+    ChainEntry* chain[RPC];
+#pragma unroll
+    for (int q = 0; q < RPC; ++q) {
+        const int rix = min((int)blockIdx.x * RPC + q, nr - 1);            // tail CTA: repeat the last row (same values)
+        irow[q] = rows ? rows[rix] : rix;
+        pi[q] = pre[irow[q]];
+        di0[q] = depth[irow[q]];
+        ri[q] = root_dist[irow[q]];
+        chain[q] = (TABLE || di0[q] < CHAIN_PER_ROW) ? chain_s + q * CHAIN_PER_ROW
+                                                     : spill + (int64_t)(blockIdx.x * RPC + q) * spill_stride;
+    }
+    // ancestor k of i = the node of depth depth[i] - k whose preorder interval contains pre[i]: found by a parallel
+    // containment test over all nodes (coalesced) instead of a dependent parent[] walk by one lane (len x DRAM latency)
+    // (four nodes per thread and iteration, all loads issued before the first use: the kernel is bound by load latency)
+    for (int a0 = threadIdx.x; a0 < n_nodes; a0 += 4 * NT) {
+        int lo4[4], hi4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int a = a0 + u * NT;
+            lo4[u] = a < n_nodes ? pre[a] : 0x7fffffff;
+            hi4[u] = a < n_nodes ? size[a] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int a = a0 + u * NT;
+            const int lo = lo4[u], hi = lo + hi4[u];
+#pragma unroll
+            for (int q = 0; q < RPC; ++q) {
+                if (lo <= pi[q] && pi[q] < hi) {
+                    ChainEntry e;
+                    e.lo = lo;
+                    e.hi = hi;
+                    e.id = a;
+                    e.depth = depth[a];
+                    e.rd = root_dist[a];
+                    chain[q][di0[q] - e.depth] = e;
+                }
+            }
         }
     }
     __syncthreads();
-    if (len > CHAIN_SMEM) __threadfence_block();
+    if (!TABLE) __threadfence_block();
     if (TABLE) {
-        int plo = 0, phi = 0;                      // interval of the previous (deeper) ancestor; empty for k = 0
-        for (int k = 0; k < len; ++k) {
-            const int lo = chain[k].lo, hi = chain[k].hi;
-            const int first = k == 0 ? hi : plo;   // k = 0: the whole interval [lo, hi)
-            for (int p = lo + threadIdx.x; p < first; p += blockDim.x) table[p] = (uint16_t)k;
-            if (k > 0)
-                for (int p = phi + threadIdx.x; p < hi; p += blockDim.x) table[p] = (uint16_t)k;
-            plo = lo;
-            phi = hi;
+#pragma unroll
+        for (int q = 0; q < RPC; ++q) {
+            uint16_t* tb = table + (int64_t)q * n_nodes;
+            int plo = 0, phi = 0;                  // interval of the previous (deeper) ancestor; empty for k = 0
+            for (int k = 0; k <= di0[q]; ++k) {
+                const int lo = chain[q][k].lo, hi = chain[q][k].hi;
+                const int first = k == 0 ? hi : plo;   // k = 0: the whole interval [lo, hi)
+                for (int p = lo + threadIdx.x; p < first; p += blockDim.x) tb[p] = (uint16_t)k;
+                if (k > 0)
+                    for (int p = phi + threadIdx.x; p < hi; p += blockDim.x) tb[p] = (uint16_t)k;
+                plo = lo;
+                phi = hi;
+            }
         }
         __syncthreads();
     }
-    const double ri = root_dist[i];
-    const int di = depth[i];
-    const int64_t obase = (int64_t)blockIdx.x * nc;
-    for (int b = threadIdx.x; b < nc; b += blockDim.x) {
-        const int j = cols ? cols[b] : b;
-        const int p = pre[j];
-        int k;
-        if (TABLE) {
-            k = table[p];
-        } else {
-            // smallest k with lo_k <= p < hi_k (intervals are nested, the root's always matches)
-            int lo = 0, hi = len - 1;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                const ChainEntry e = chain[mid];
-                if (e.lo <= p && p < e.hi) hi = mid;
-                else lo = mid + 1;
-            }
-            k = lo;
+    for (int b0 = threadIdx.x; b0 < nc; b0 += 4 * NT) {
+        int p4[4], dj4[4];
+        double rj4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {              // all loads of four columns in flight before the first use
+            const int b = b0 + u * NT;
+            const int j = b < nc ? (cols ? cols[b] : b) : 0;
+            p4[u] = pre[j];
+            rj4[u] = root_dist[j];
+            dj4[u] = clad_out ? depth[j] : 0;
         }
-        const ChainEntry e = chain[k];
-        if (lca_out) lca_out[obase + b] = e.id;
-        if (dist_out) dist_out[obase + b] = (ri - e.rd) + (root_dist[j] - e.rd);
-        if (clad_out) clad_out[obase + b] = (double)(di + depth[j] - 2 * e.depth);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int b = b0 + u * NT;
+            if (b >= nc) break;
+            const int p = p4[u];
+#pragma unroll
+            for (int q = 0; q < RPC; ++q) {
+                const int rix = (int)blockIdx.x * RPC + q;
+                if (rix >= nr) break;
+                int k;
+                if (TABLE) {
+                    k = table[(int64_t)q * n_nodes + p];
+                } else {
+                    // smallest k with lo_k <= p < hi_k (intervals are nested, the root's always matches)
+                    int lo = 0, hi = di0[q];
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const ChainEntry e = chain[q][mid];
+                        if (e.lo <= p && p < e.hi) hi = mid;
+                        else lo = mid + 1;
+                    }
+                    k = lo;
+                }
+                const ChainEntry e = chain[q][k];
+                const int64_t o = (int64_t)rix * nc + b;
+                if (lca_out) lca_out[o] = e.id;
+                if (dist_out) dist_out[o] = (ri[q] - e.rd) + (rj4[u] - e.rd);
+                if (clad_out) clad_out[o] = (double)(di0[q] + dj4[u] - 2 * e.depth);
+            }
+        }
     }
-    (void)n_nodes;
 }
 
-constexpr int TABLE_MAX_NODES = 80000;             // 2 bytes per node of dynamic shared memory
+constexpr int TABLE_SMEM_MAX = 160 * 1024;         // dynamic shared memory for the preorder tables (2 bytes per node and row)
 
 }  // namespace
 
@@ -278,19 +325,27 @@ DRP_API int drp_lca_patristic_f64(const int32_t* parent, const int32_t* depth, c
     if (ws_bytes < drp_lca_workspace_bytes(nr, max_depth) || (ws_bytes > 0 && !ws)) return -16;
     {
         DRP_LAUNCH(DRP_K_PATRISTIC, ((double)nr * nc * ((dist_out ? 8.0 : 0.0) + (clad_out ? 8.0 : 0.0) + (lca_out ? 4.0 : 0.0))), st);
-        if (n_nodes <= TABLE_MAX_NODES && max_depth < 65535) {
-            const size_t sm = (size_t)n_nodes * sizeof(uint16_t);
-            static bool attr_done = false;
-            if (!attr_done) {
-                cudaFuncSetAttribute(lca_patristic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     TABLE_MAX_NODES * (int)sizeof(uint16_t));
-                attr_done = true;
-            }
-            lca_patristic_kernel<true><<<nr, 256, sm, st>>>(parent, depth, root_dist, pre, size, rows, cols, nc, n_nodes, lca_out,
-                                                            dist_out, clad_out, (ChainEntry*)ws, max_depth + 1);
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(lca_patristic_kernel<true, 2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_SMEM_MAX);
+            cudaFuncSetAttribute(lca_patristic_kernel<true, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_SMEM_MAX);
+            attr_done = true;
+        }
+        const size_t row_bytes = (size_t)n_nodes * sizeof(uint16_t);
+        // two rows per CTA of 512 threads: the per-column operands and the ancestor scan (both L2 traffic, which is what
+        // bounds this kernel) are shared by the two rows at the same number of resident threads per SM
+        if (max_depth < CHAIN_SMEM / 2 && 2 * row_bytes <= 80 * 1024 && nr >= 2) {
+            lca_patristic_kernel<true, 2, 512><<<(nr + 1) / 2, 512, 2 * row_bytes, st>>>(parent, depth, root_dist, pre, size, rows,
+                                                                                      cols, nr, nc, n_nodes, lca_out, dist_out,
+                                                                                      clad_out, (ChainEntry*)ws, max_depth + 1);
+        } else if (max_depth < CHAIN_SMEM && row_bytes <= (size_t)TABLE_SMEM_MAX) {
+            lca_patristic_kernel<true, 1, 256><<<nr, 256, row_bytes, st>>>(parent, depth, root_dist, pre, size, rows, cols, nr, nc,
+                                                                           n_nodes, lca_out, dist_out, clad_out, (ChainEntry*)ws,
+                                                                           max_depth + 1);
         } else {
-            lca_patristic_kernel<false><<<nr, 256, 0, st>>>(parent, depth, root_dist, pre, size, rows, cols, nc, n_nodes, lca_out,
-                                                            dist_out, clad_out, (ChainEntry*)ws, max_depth + 1);
+            lca_patristic_kernel<false, 1, 256><<<nr, 256, 0, st>>>(parent, depth, root_dist, pre, size, rows, cols, nr, nc,
+                                                                    n_nodes, lca_out, dist_out, clad_out, (ChainEntry*)ws,
+                                                                    max_depth + 1);
         }
     }
     return drp_launch_status();

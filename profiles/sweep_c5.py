@@ -94,6 +94,20 @@ def main():
         ms = timed(lambda: ops.tree_distances(parent, branch, want_lca=True), flush)
         row["patristic_lca_ms"] = ms
         row["patristic_lca_gbs"] = N * N * 12 / (ms * 1e-3) / 1e9
+        # the two kernels on their own (library instrumentation: CUDA events around each launch)
+        import ctypes
+        from draupnir_asr_b200._lib import lib
+        ops.tree_distances(parent, branch)
+        lib.drp_timing_enable(1)
+        for _ in range(5):
+            flush.zero_()
+            ops.tree_distances(parent, branch)
+        NK = lib.drp_timing_classes()
+        kms, kln, kwk = (ctypes.c_double * NK)(), (ctypes.c_int64 * NK)(), (ctypes.c_double * NK)()
+        lib.drp_timing_read(kms, kln, kwk)
+        lib.drp_timing_enable(0)
+        row["patristic_kernels_ms_per_build"] = kms[6] / 5          # tree_prepare + lca kernel
+        row["patristic_kernels_gbs"] = N * N * 8 / (kms[6] / 5 * 1e-3) / 1e9
         # ---- OU covariance [z, n, n] over the leaves
         leaves = torch.from_numpy(t.leaves).to(dev)
         D = ops.tree_distances(parent, branch, rows=leaves, cols=leaves)[0]
