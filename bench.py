@@ -220,8 +220,10 @@ def run_ours(args, w, rank, world, local_rank):
     clocks = sampler.stop()
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    h2d = torch.tensor([float(run.host_bytes_per_step(host))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)                     # max over ranks
+        dist.all_reduce(h2d, op=dist.ReduceOp.SUM)                   # bytes copied by all ranks together
     ms, ms_e2e = float(t[0]), float(t[1])
     if rank != 0:
         if world > 1:
@@ -280,7 +282,7 @@ def run_ours(args, w, rank, world, local_rank):
                        "guide": w["guide"], "z_dim": Z_DIM, "gru_hidden_dim": 60, "l2": "flushed between timed iterations",
                        "parallelism": "single GPU" if world == 1 else f"z-sharded OU prior + leaf-sharded decoder over {world} GPUs"},
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": run.host_bytes_per_step(host),
+            "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d[0]),
                     "d2h_bytes_per_step": 8 + 4 * Z_DIM, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "kernel_classes": per_class}
     emit(line)

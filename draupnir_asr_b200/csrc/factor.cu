@@ -38,59 +38,81 @@ static_assert(PR == 2 * NB, "trsm staging assumes two rows per pass");
 
 // ---------------------------------------------------------------------------------------------------------------
 // potf2: factor the nb x nb diagonal block at (c0, c0).  One CTA of 256 threads per matrix; thread (ty, tx) keeps the
-// 4x4 block (rows 4ty.., columns 4tx..) in registers.  Right-looking, one column per step: the owners of the column
-// publish it through shared memory, everybody applies the rank-1 update to its block.  Entries right of the diagonal
-// collect garbage that is never read back nor stored.  Compact code (16 x 4 unrolled steps): the fully unrolled
-// thread-per-row variant was instruction-fetch bound.
+// 4x4 block (rows 4ty.., columns 4tx..) in registers, tid = 16 tx + ty so that the 16 owners of a 4-column panel are
+// one half-warp.  Per panel: the owners factor the 64x4 panel among themselves with warp shuffles (pivot and the three
+// panel-row broadcasts come from the lane that owns the diagonal block), publish it to shared memory, and after ONE
+// barrier every thread applies the rank-4 update to its block.  Entries right of the diagonal collect garbage that is
+// never read back nor stored.  (A fully unrolled thread-per-row variant was instruction-fetch bound, a column-at-a-time
+// variant paid two barriers per column.)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb,
                                                     int32_t* __restrict__ info)
 {
-    __shared__ double colv[NB];
+    __shared__ double Lp[NB][4];                   // the current panel of L
+    __shared__ int sbad;
     double* A = Mb + (int64_t)blockIdx.x * bs + (int64_t)c0 * ld + c0;
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int tid = threadIdx.x, tx = tid >> 4, ty = tid & 15, lane = tid & 31;
+    if (tid == 0) sbad = 0;
     double a[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int i = 4 * ty + r, j = 4 * tx + k;
-            // rows / columns beyond nb: identity, so the 64-step elimination is a no-op there
+            // rows / columns beyond nb: identity, so the elimination is a no-op there
             a[r][k] = (i < nb && j <= i) ? A[(int64_t)i * ld + j] : (i == j ? 1.0 : 0.0);
         }
-    int bad = 0;
+    __syncthreads();
     for (int cb = 0; cb < NB / 4; ++cb) {
+        if (tx == cb) {                                            // one half-warp: lanes (cb & 1) * 16 + ty
+            const unsigned mask = (cb & 1) ? 0xffff0000u : 0x0000ffffu;
+            const int lane_d = (lane & 16) + cb;                   // owner of the diagonal block (ty == cb)
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c = 4 * cb + cc;
-            if (tx == cb) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) colv[4 * ty + r] = a[r][cc];
-            }
-            __syncthreads();
-            const double piv = colv[c];
-            if (!(piv > 0.0) && bad == 0) bad = c + 1;
-            const double rd = rsqrt(piv);
-            double lr[4], lc[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) lr[r] = colv[4 * ty + r] * rd;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) lc[k] = colv[4 * tx + k] * rd;
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (4 * tx + k > c) a[r][k] = fma(-lr[r], lc[k], a[r][k]);
-            if (tx == cb) {
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c = 4 * cb + cc;
+                const double piv = __shfl_sync(mask, a[cc][cc], lane_d);
+                if (ty == 0 && !(piv > 0.0) && sbad == 0) sbad = c + 1;
+                const double rd = rsqrt(piv);
+                double lv[4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const int i = 4 * ty + r;
-                    if (i == c) a[r][cc] = piv * rd;
-                    else if (i > c) a[r][cc] = lr[r];
+                    lv[r] = i > c ? a[r][cc] * rd : (i == c ? piv * rd : 0.0);
+                    if (i >= c) a[r][cc] = lv[r];
+                }
+#pragma unroll
+                for (int k = cc + 1; k < 4; ++k) {                 // remaining columns of the panel
+                    const double lck = __shfl_sync(mask, lv[k], lane_d);       // L[4 cb + k][c]
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) a[r][k] = fma(-lv[r], lck, a[r][k]);
                 }
             }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) Lp[4 * ty + r][k] = (4 * ty + r >= 4 * cb + k) ? a[r][k] : 0.0;
         }
+        __syncthreads();
+        if (tx > cb) {                                             // rank-4 update of the trailing blocks
+            double lr[4][4], lc[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    lr[r][q] = Lp[4 * ty + r][q];
+                    lc[r][q] = Lp[4 * tx + r][q];
+                }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    double v = a[r][k];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v = fma(-lr[r][q], lc[k][q], v);
+                    a[r][k] = v;
+                }
+        }
+        __syncthreads();
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -99,7 +121,7 @@ __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ Mb, int
             const int i = 4 * ty + r, j = 4 * tx + k;
             if (i < nb && j <= i) A[(int64_t)i * ld + j] = a[r][k];
         }
-    if (bad && bad <= nb && tid == 0 && info) atomicCAS(info + blockIdx.x, 0, c0 + bad);
+    if (tid == 0 && sbad && sbad <= nb && info) atomicCAS(info + blockIdx.x, 0, c0 + sbad);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

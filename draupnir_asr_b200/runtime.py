@@ -76,16 +76,32 @@ class Run(SimpleNamespace):
         host = {"dataset": pin(self.problem.dataset_train), "patristic": pin(self.problem.patristic_matrix_train)}
         if self.select_guide == "variational":
             host["blosum"] = pin(self.problem.dataset_train_blosum)
-        self._staging = {k: torch.empty_like(v, device=self.device) for k, v in host.items()}
+        self._staging = {k: v.to(self.device) for k, v in host.items()}       # rows outside a rank's block stay valid
         return host
 
+    def _leaf_rows(self):
+        """Rows of the per-leaf inputs this rank reads: all of them on one GPU, its leaf block when the run is sharded
+        (the model and the guide slice `family_data` / `data_blosum` to that block, so the other rows are never touched)."""
+        shard = getattr(self.Draupnir, "shard", None)
+        return (0, self.problem.n_leaves) if shard is None else (shard.leaf_lo, shard.leaf_hi)
+
     def host_bytes_per_step(self, host) -> int:
-        return int(sum(v.numel() * v.element_size() for v in host.values()))
+        """Bytes this rank copies host -> device per step."""
+        lo, hi = self._leaf_rows()
+        total = 0
+        for k, v in host.items():
+            rows = v.shape[0] if k == "patristic" else hi - lo
+            total += rows * (v.numel() // v.shape[0]) * v.element_size()
+        return int(total)
 
     def step_from_host(self, host) -> float:
         """H2D of the step inputs (pinned, async, same stream) -> svi.step -> loss back to the host as a float."""
+        lo, hi = self._leaf_rows()
         for k, v in host.items():
-            self._staging[k].copy_(v, non_blocking=True)
+            if k == "patristic":
+                self._staging[k].copy_(v, non_blocking=True)
+            else:
+                self._staging[k][lo:hi].copy_(v[lo:hi], non_blocking=True)
         st = self._staging
         return self.svi.step(st["dataset"], st["patristic"], None, st.get("blosum"), None, None)
 

@@ -72,12 +72,45 @@ __global__ void __launch_bounds__(256) tput(double* out, int iters)
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-// ---- do DMMA and DFMA share execution resources?  warps with (warp & 1) == sel_dmma run DMMAs, the others DFMAs
-template <int MODE>   // 0: all warps DMMA, 1: all warps DFMA, 2: even warps DMMA + odd warps DFMA
+// ---- legacy int8 mma.sync (IMMA) throughput, alone and next to fp64 FMAs (does it run beside the fp64 pipe?)
+__device__ __forceinline__ void imma16832(int (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <int MODE>   // 0: all warps IMMA, 2: warps 0-3 IMMA + warps 4-7 DFMA
+__global__ void __launch_bounds__(256) imix(double* out, int iters)
+{
+    const int warp = threadIdx.x >> 5;
+    const bool do_imma = MODE == 0 || (warp >> 2) == 0;
+    int acc[8][4];
+    double f[16];
+    for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+    for (int i = 0; i < 16; ++i) f[i] = 1.0 + i * 1e-3;
+    unsigned a[4] = {0x01020304u + threadIdx.x, 0x05060708u, 0x090a0b0cu, 0x0d0e0f10u}, b[2] = {0x01010101u, 0x02020202u};
+    const double fa = 1.0 + threadIdx.x * 1e-9, fb = 0.999999;
+    if (do_imma) {
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) imma16832(acc[i], a, b);
+    } else {
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fma(f[i], fb, fa);
+    }
+    double s = 0;
+    for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) s += acc[i][j];
+    for (int i = 0; i < 16; ++i) s += f[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---- do DMMA and DFMA share execution resources?  warps 0-3 run DMMAs, warps 4-7 DFMAs (every SM sub-partition hosts one warp of each kind)
+template <int MODE>   // 0: all warps DMMA, 1: all warps DFMA, 2: warps 0-3 DMMA + warps 4-7 DFMA
 __global__ void __launch_bounds__(256) mix(double* out, int iters)
 {
     const int warp = threadIdx.x >> 5;
-    const bool do_dmma = MODE == 0 || (MODE == 2 && (warp & 1) == 0);
+    const bool do_dmma = MODE == 0 || (MODE == 2 && (warp >> 2) == 0);   // warps w and w+4 share a sub-partition: one of each kind
     double acc[8][2], f[16];
     for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
     for (int i = 0; i < 16; ++i) f[i] = 1.0 + i * 1e-3;
@@ -150,6 +183,21 @@ int main()
         const double dfma_fl = (mode == 0 ? 0.0 : (mode == 1 ? 1.0 : 0.5)) * warps * iters * 16.0 * 64;
         printf("mix mode %d (%s): %.3f ms, DMMA %.2f TFLOP/s, DFMA %.2f TFLOP/s\n", mode,
                mode == 0 ? "all DMMA" : (mode == 1 ? "all DFMA" : "half DMMA / half DFMA"), ms, dmma_fl / ms / 1e9, dfma_fl / ms / 1e9);
+    }
+    for (int mode = 0; mode < 3; mode += 2) {
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(e0);
+            if (mode == 0) imix<0><<<sms * 4, 256>>>(out, iters);
+            if (mode == 2) imix<2><<<sms * 4, 256>>>(out, iters);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+        }
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        const double warps = (double)sms * 4 * 8;
+        const double imma_ops = (mode == 0 ? 1.0 : 0.5) * warps * iters * 8.0 * (16 * 8 * 32 * 2);
+        const double dfma_fl = (mode == 0 ? 0.0 : 0.5) * warps * iters * 16.0 * 64;
+        printf("imma mode %d (%s): %.3f ms, IMMA m16n8k32 %.1f TOP/s (%.0f MAC/clk/SM at 1.965 GHz), DFMA %.2f TFLOP/s\n", mode,
+               mode == 0 ? "all IMMA" : "half IMMA / half DFMA", ms, imma_ops / ms / 1e9,
+               imma_ops / 2 / (ms * 1e-3) / sms / 1.965e9, dfma_fl / ms / 1e9);
     }
     cudaError_t e = cudaGetLastError();
     printf("status: %s\n", cudaGetErrorString(e));
