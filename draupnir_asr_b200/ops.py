@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -412,6 +413,49 @@ def gru_bidirectional_uv(U: torch.Tensor, V: torch.Tensor, weight_hh, bias_hh, h
     return _GRUBidirUV.apply(U, V, weight_hh, bias_hh, h0)
 
 
+_GRAM_OFF = os.environ.get("DRP_GRAM", "1") == "0"      # A/B switch for measurements
+
+
+def gram_tn(A: torch.Tensor, B: torch.Tensor):
+    """`(A.t() @ B, A.sum(0))` for tall-skinny fp64 `A [K,M]`, `B [K,N]` (K huge, M, N <= 192): the weight / bias gradient
+    shapes of the dense layers around the recurrences, as one split-K kernel instead of a cuBLAS "tn" GEMM + a reduction."""
+    _req(A, "A"), _req(B, "B")
+    K, M = A.shape
+    N = B.shape[1]
+    tiles = ((M + 7) // 8) * ((N + 8) // 8)
+    if (_GRAM_OFF or not A.is_contiguous() or not B.is_contiguous() or A.data_ptr() % 16 or B.data_ptr() % 16 or M > 192 or N > 192
+            or tiles > 96 or 3 * 32 * (M + N) * 8 + 64 > 200 * 1024 or B.shape[0] != K):
+        return A.t() @ B, A.sum(0)
+    C = torch.empty((M, N), dtype=torch.float64, device=A.device)
+    cs = torch.empty(M, dtype=torch.float64, device=A.device)
+    wse = lib.drp_gram_workspace_elems(M, N)
+    ws = torch.empty(wse, dtype=torch.float64, device=A.device)
+    _rc(lib.drp_gram_tn_f64(_p(A), _p(B), K, M, N, _p(C), _p(cs), _p(ws), wse, _stream()), "drp_gram_tn_f64")
+    return C, cs
+
+
+class _AffineTall(torch.autograd.Function):
+    """`x @ W.t() + b` for `x [K,F]` with K in the millions and a small output width; the weight and bias gradients use
+    `gram_tn` (autograd's addmm backward runs them as a cuBLAS tn GEMM without split-K plus a separate reduction)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        ctx.save_for_backward(x, W)
+        return torch.addmm(b, x, W.t())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = dy.contiguous()
+        dW, db = gram_tn(dy, x)
+        dx = dy @ W if ctx.needs_input_grad[0] else None
+        return dx, dW, db
+
+
+def affine_tall(x: torch.Tensor, W: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    return _AffineTall.apply(x, W, b)
+
+
 class _GRUEncoderLast(torch.autograd.Function):
     """Bidirectional GRU over `x [n,L,I]` whose only DIFFERENTIABLE output is the hidden state at the last position
     (`out[:, -1]`, what `RNNEncoder.forward` feeds to `fc1`, S/models_utils.py:57); the full `out [n,L,2H]` is returned
@@ -470,8 +514,9 @@ class _GRUEncoderLast(torch.autograd.Function):
         # ---- input projection
         dgi0f = dgi0.reshape(n * L, 3 * H)
         xf = x.reshape(n * L, I)
-        dwih = torch.stack((dgi0f.t() @ xf, dgi1.t() @ x[:, L - 1]))
-        dbih = torch.stack((dgi0f.sum(0), dgi1.sum(0)))
+        dwih0, dbih0 = gram_tn(dgi0f, xf)
+        dwih = torch.stack((dwih0, dgi1.t() @ x[:, L - 1]))
+        dbih = torch.stack((dbih0, dgi1.sum(0)))
         dx = None
         if ctx.needs_input_grad[0]:
             dx = (dgi0f @ wih[0]).reshape(n, L, I)

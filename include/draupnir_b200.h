@@ -120,6 +120,12 @@ int64_t drp_gru_wgrad_workspace_elems(void);
 int drp_gru_wgrad_f64(const double* dgi, const double* gates, const double* out, const double* h0, int n, int L, int H,
                       double* dwhh, double* dbhh, double* ws, int64_t ws_elems, void* stream);
 
+/* ---- weight / bias gradients of the dense layers around the recurrences (autograd of nn.Linear: S/models_utils.py:54-65,
+ *      93-99):  C [M,N] = A^T B, colsum [M] = sum_k A[k][:] (nullable) for A [K,M], B [K,N], M, N <= 192, K arbitrary ------ */
+int64_t drp_gram_workspace_elems(int M, int N);
+int drp_gram_tn_f64(const double* A, const double* B, int64_t K, int M, int N, double* C, double* colsum, double* ws,
+                    int64_t ws_elems, void* stream);
+
 /* ---- K10  Categorical(logits).log_prob(obs).sum(): S/models.py:352 (+ LogSoftmax S/models_utils.py:98) --------- */
 int64_t drp_cat_loglik_partials(int64_t rows);
 int drp_cat_loglik_fwd_f64(const double* scores, const void* obs, int obs_is_f64, int64_t rows, int A, double* out,

@@ -91,3 +91,16 @@ def test_encoder_last_position_path(cuda, n, L, I):
     for k, a, b in pairs:
         err = float((a - b).abs().max() / a.abs().max().clamp_min(1e-30))
         assert err < 1e-11, (k, err)
+
+
+@pytest.mark.parametrize("K,M,N", [(1, 1, 1), (31, 21, 120), (32, 21, 120), (1000, 21, 120), (4099, 180, 21), (70000, 21, 120),
+                                   (513, 64, 64)])
+def test_gram_tn(cuda, K, M, N):
+    from draupnir_asr_b200 import ops
+    g = torch.Generator().manual_seed(K + M)
+    A = torch.randn(K, M, generator=g, dtype=torch.float64)
+    B = torch.randn(K, N, generator=g, dtype=torch.float64)
+    C, cs = ops.gram_tn(A.to(cuda), B.to(cuda))
+    C_ref, cs_ref = A.t() @ B, A.sum(0)
+    assert float((C.cpu() - C_ref).abs().max() / C_ref.abs().max().clamp_min(1e-30)) < 1e-12
+    assert float((cs.cpu() - cs_ref).abs().max() / cs_ref.abs().max().clamp_min(1e-30)) < 1e-12
