@@ -79,6 +79,16 @@ class ClockSampler:
             log("clock sampler unavailable:", e)
             self.proc = None
 
+    def wait_first_sample(self, timeout_s: float = 5.0):
+        t0 = time.time()
+        while self.proc is not None and time.time() - t0 < timeout_s:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.05)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
@@ -210,13 +220,15 @@ def run_ours(args, w, rank, world, local_rank):
         log(f"[rank {rank}] per-step ms: " + " ".join(f"{v:.2f}" for v in per))
         return sum(per)
 
+    # the sampler starts BEFORE the warm-up: nvidia-smi's start-up (NVML attaching to every GPU of the box) stalls the
+    # launches of a running context for 50-150 ms, which must not land inside a timed step; its 200 ms polling does not
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         loss = run.step()
     log(f"[rank {rank}] warm-up done, -ELBO {loss:.4f}")
-
-    sampler = ClockSampler(local_rank)
+    sampler.wait_first_sample()
     barrier()
-    sampler.start()
     lib.drp_timing_enable(1)
     l0 = lib.drp_launch_count()
     ms = timed(run.step, args.steps)
@@ -227,6 +239,8 @@ def run_ours(args, w, rank, world, local_rank):
     kwk = (ctypes.c_double * NK)()
     lib.drp_timing_read(kms, kln, kwk)
     lib.drp_timing_enable(0)
+    for _ in range(max(args.warmup, 3)):                                # the host-fed path has its own warm-up (copy stream, events)
+        run.step_from_host(host)
     barrier()
     ms_e2e = timed(lambda: run.step_from_host(host), args.steps)
     barrier()

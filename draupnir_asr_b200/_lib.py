@@ -40,6 +40,7 @@ SIGNATURES = {
     "drp_ou_conditional_f64": (_i32, [_p, _i64, _p, _i32, _i32, _p, _p, _p, _p, _i32, _f64, _p, _p, _p, _p, _p]),
     "drp_gru_hidden_size": (_i32, []),
     "drp_gru_fwd_f64": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "drp_gru_fwd_dir0_f64": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "drp_gru_fwd_uv_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "drp_gru_bwd_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "drp_gru_bwd_dir0_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),

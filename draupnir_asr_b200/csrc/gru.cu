@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
                                                               const double* __restrict__ whh,
                                                               const double* __restrict__ bhh, const double* __restrict__ h0,
                                                               int n, int L, double* __restrict__ out,
-                                                              double* __restrict__ gates)
+                                                              double* __restrict__ gates, int gi_dirs)
 {
     constexpr int GROWS = 8 * MT;
     constexpr int GF_STAGE_BYTES = GROWS * G3 * 8;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
         __syncwarp();
         if (lane < nrows)
             g_bulk_g2s(g_smem_u32(ring + (int64_t)s * GROWS * G3 + lane * G3),
-                       gi + (((int64_t)(row0 + lane) * L + l) * 2 + dir) * G3, G3 * 8, bars + 8 * s);
+                       gi + (((int64_t)(row0 + lane) * L + l) * gi_dirs + (gi_dirs == 2 ? dir : 0)) * G3, G3 * 8, bars + 8 * s);
     };
     if (warp == 0)
         for (int t = 0; t < min(GF_STAGES - 1, L); ++t) issue(t);
@@ -505,7 +505,7 @@ static int gru_pick_mt(int n, int ndir = 2)
 
 template <bool UV, int MT>
 static void gru_fwd_launch(const double* gi, const double* v, const double* whh, const double* bhh, const double* h0, int n,
-                           int L, double* out, double* gates, cudaStream_t st)
+                           int L, double* out, double* gates, cudaStream_t st, int ndir = 2)
 {
     constexpr int smem = gf_smem(8 * MT, UV);
     static bool attr_done = false;
@@ -513,8 +513,9 @@ static void gru_fwd_launch(const double* gi, const double* v, const double* whh,
         cudaFuncSetAttribute(gru_fwd_kernel<UV, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
-    DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * 2.0 * G3 * GH, st);
-    gru_fwd_kernel<UV, MT><<<dim3((n + 8 * MT - 1) / (8 * MT), 2), GTHREADS, smem, st>>>(gi, v, whh, bhh, h0, n, L, out, gates);
+    DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * ndir * G3 * GH, st);
+    gru_fwd_kernel<UV, MT><<<dim3((n + 8 * MT - 1) / (8 * MT), ndir), GTHREADS, smem, st>>>(gi, v, whh, bhh, h0, n, L, out, gates,
+                                                                                        ndir);
 }
 
 template <int MT>
@@ -544,6 +545,24 @@ DRP_API int drp_gru_fwd_f64(const double* gi, const double* whh, const double* b
         case 1: gru_fwd_launch<false, 1>(gi, nullptr, whh, bhh, h0, n, L, out, gates, st); break;
         case 2: gru_fwd_launch<false, 2>(gi, nullptr, whh, bhh, h0, n, L, out, gates, st); break;
         default: gru_fwd_launch<false, 4>(gi, nullptr, whh, bhh, h0, n, L, out, gates, st); break;
+    }
+    return drp_launch_status();
+}
+
+// Forward direction only: gi0 [n, L, 3H]; `out [n,L,2H]` / `gates [n,L,2,4,H]` keep the two-direction layout and only
+// their direction-0 halves are written (the encoder's loss path, see ops._GRUEncoderLast).
+DRP_API int drp_gru_fwd_dir0_f64(const double* gi0, const double* whh, const double* bhh, const double* h0, int n, int L,
+                                 int H, double* out, double* gates, void* stream)
+{
+    if (!gi0 || !whh || !bhh || !h0) return -1;
+    if (n <= 0 || L <= 0) return -5;
+    if (H != GH) return -7;
+    if (!out) return -8;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (gru_pick_mt(n, 1)) {
+        case 1: gru_fwd_launch<false, 1>(gi0, nullptr, whh, bhh, h0, n, L, out, gates, st, 1); break;
+        case 2: gru_fwd_launch<false, 2>(gi0, nullptr, whh, bhh, h0, n, L, out, gates, st, 1); break;
+        default: gru_fwd_launch<false, 4>(gi0, nullptr, whh, bhh, h0, n, L, out, gates, st, 1); break;
     }
     return drp_launch_status();
 }

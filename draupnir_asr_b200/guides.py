@@ -8,6 +8,7 @@ import torch.nn as nn
 
 from .backend import pyro, dist, USING_REAL_PYRO
 from .models_utils import EmbedComplexEncoder, RNNEncoder
+from .utils import DeferredDict
 
 if USING_REAL_PYRO:  # pragma: no cover
     from pyro.contrib.easyguide import EasyGuide
@@ -68,7 +69,8 @@ class DRAUPNIRGUIDES(EasyGuide):
         if shard is not None:        # one all-gather of [z_loc | z_scale] rebuilds the [n, z] posterior parameters
             z = out["z_loc"].shape[1]
             both = shard.gather_leaf_rows(torch.cat((out["z_loc"], out["z_scale"]), dim=1))
-            out = dict(out, z_loc=both[:, :z], z_scale=both[:, z:])
+            out = DeferredDict({k: out.raw(k) for k in out})
+            out["z_loc"], out["z_scale"] = both[:, :z], both[:, z:]
         return out, n
 
     def _latent_site(self, out):
@@ -81,10 +83,12 @@ class DRAUPNIRGUIDES(EasyGuide):
 
     @staticmethod
     def _result(alpha, sigma_n, sigma_f, lambd, latent_z, out):
-        return {"alpha": alpha, "sigma_n": sigma_n, "sigma_f": sigma_f, "lambd": lambd, "z_loc": out["z_loc"],
-                "z_scale": out["z_scale"], "latent_z": latent_z,
-                "rnn_final_bidirectional": out["rnn_final_bidirectional"],
-                "rnn_final_hidden_state": out["rnn_final_hidden_state"], "rnn_hidden_states": out["rnn_hidden_states"]}
+        # same ten keys in the same order as S/guides.py:123-133; the encoder's full hidden-state entries stay deferred
+        return DeferredDict({"alpha": alpha, "sigma_n": sigma_n, "sigma_f": sigma_f, "lambd": lambd, "z_loc": out["z_loc"],
+                             "z_scale": out["z_scale"], "latent_z": latent_z,
+                             "rnn_final_bidirectional": out.raw("rnn_final_bidirectional"),
+                             "rnn_final_hidden_state": out["rnn_final_hidden_state"],
+                             "rnn_hidden_states": out.raw("rnn_hidden_states")})
 
     def guide_noplating(self, family_data, patristic_matrix_sorted, cladistic_matrix, data_blosum, batch_blosum=None,
                         map_estimates=None):

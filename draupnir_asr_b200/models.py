@@ -79,6 +79,7 @@ class DRAUPNIRModelClass(nn.Module):
         self.h_0_MODEL = nn.Parameter(torch.randn(self.gru_hidden_dim, dtype=torch.float64), requires_grad=False)
         self._one = None
         self._pos_cache = {}
+        self._cond_cache = None
         self.shard = None          # zshard.ShardContext when the run is spread over several GPUs
         for name in ("blosum_weighted", "dataset_train_blosum", "internal_nodes", "leaves_nodes", "aa_frequencies",
                      "blosum", "blosum_max"):
@@ -175,14 +176,38 @@ class DRAUPNIRModelClass(nn.Module):
         return ops.ou_conditional(patristic_matrix[1:, 1:], leaf_pos, int_pos, sigma_f.detach(), sigma_n.detach(),
                                   lambd.detach(), xb.detach(), jitter=jitter, want_cov=want_cov)
 
+    def _conditional_factor(self, map_estimates, patristic_matrix):
+        """Conditional mean `[z,ni]` and Cholesky factor `[z,ni,ni]` of the conditional covariance (+1e-6 on every
+        entry as S/models.py:193), kept for as long as the SAME estimate tensors come back: the reference's marginal
+        sampling loop (S/main.py:1337-1350) calls `sample(..., use_test=True)` once per draw with unchanged
+        `map_estimates` and re-derives both every time.  The key holds the tensors themselves (identity + version
+        counter), so a recycled allocation can never alias a stale entry."""
+        keys = tuple(map_estimates[k] for k in ("sigma_f", "sigma_n", "lambd", "latent_z")) + (patristic_matrix,)
+        stamp = tuple(int(t._version) for t in keys)
+        hit = self._cond_cache
+        if hit is not None and len(hit[0]) == len(keys) and all(a is b for a, b in zip(hit[0], keys)) and hit[1] == stamp:
+            return hit[2], hit[3]
+        mean, cov = self._conditional(map_estimates, patristic_matrix, self.internal_nodes, self.n_internal, 0.0, 1e-6, True)
+        tril = ops.potrf(cov)
+        del cov
+        self._cond_cache = (keys, stamp, mean, tril)
+        return mean, tril
+
     def conditional_sampling(self, map_estimates, patristic_matrix):
         """One draw of the internal nodes given the leaves (S/models.py:149-196; Bishop B.49-50).  The reference adds
         1e-6 to every entry of the conditional covariance (:193); so does this."""
+        return self.conditional_sampling_many(map_estimates, patristic_matrix, 1)[0]
+
+    def conditional_sampling_many(self, map_estimates, patristic_matrix, n_samples: int):
+        """`n_samples` independent draws `[S, ni, z]` of the internal nodes given the leaves from ONE factorisation:
+        `mean + L eps` as a single batched product (replaces S x `conditional_sampling`)."""
         assert patristic_matrix[1:, 1:].shape == (self.n_all, self.n_all), \
             "Remember to use the entire/full patristic matrix for conditional sampling!"
-        mean, cov = self._conditional(map_estimates, patristic_matrix, self.internal_nodes, self.n_internal, 0.0, 1e-6, True)
-        latent_space = dist.MultivariateNormal(mean, cov).to_event(1).sample().T
-        assert latent_space.shape == (self.n_internal, self.z_dim)
+        mean, tril = self._conditional_factor(map_estimates, patristic_matrix)
+        eps = torch.randn((self.z_dim, self.n_internal, int(n_samples)), dtype=mean.dtype, device=mean.device)
+        draws = mean.unsqueeze(-1) + torch.bmm(tril, eps)                       # [z, ni, S]
+        latent_space = draws.permute(2, 1, 0).contiguous()
+        assert latent_space.shape == (int(n_samples), self.n_internal, self.z_dim)
         return latent_space
 
     def conditional_samplingMAP(self, map_estimates, patristic_matrix):
@@ -286,3 +311,23 @@ class DRAUPNIRModel_classic(DRAUPNIRModelClass):
         return SamplingOutput(aa_sequences=aa_sequences.detach(), latent_space=latent_space.detach(),
                               logits=logits.detach(), phis=None, psis=None, mean_phi=None, mean_psi=None, kappa_phi=None,
                               kappa_psi=None)
+
+    @torch.no_grad()
+    def sample_marginal(self, map_estimates, n_samples, patristic_matrix, nodes_per_call: int = 8192):
+        """The marginal ancestral samples of S/main.py:1334-1350 in one call: `n_samples` draws of the internal nodes'
+        latent vectors from one conditional factorisation, each decoded and followed by one categorical draw — what
+        the reference obtains from `n_samples` x `sample(map_estimates, 1, ..., use_test=True)`.  Returns a
+        `SamplingOutput` with `aa_sequences [S, ni, L]`, `latent_space [S, ni, z]`, `logits [S, ni, L, A]`; the decoder
+        runs over all draws as one batch of sequences (`nodes_per_call` bounds the rows per launch)."""
+        S = int(n_samples)
+        latent = self.conditional_sampling_many(map_estimates, patristic_matrix, S)          # [S, ni, z]
+        flat = latent.reshape(S * self.n_internal, self.z_dim)
+        blosum = self.embed(self.blosum_weighted)
+        logits = torch.empty((flat.shape[0], self.align_seq_len, self.aa_probs), dtype=flat.dtype, device=flat.device)
+        for lo in range(0, flat.shape[0], nodes_per_call):
+            hi = min(lo + nodes_per_call, flat.shape[0])
+            logits[lo:hi] = self.decoder.forward_structured(flat[lo:hi], blosum, hidden=self._hidden(hi - lo))
+        aa = dist.Categorical(logits=logits).sample()
+        return SamplingOutput(aa_sequences=aa.reshape(S, self.n_internal, self.align_seq_len),
+                              latent_space=latent, logits=logits.reshape(S, self.n_internal, self.align_seq_len, self.aa_probs),
+                              phis=None, psis=None, mean_phi=None, mean_psi=None, kappa_phi=None, kappa_psi=None)

@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .utils import Deferred, DeferredDict
 
 
 class RNNEncoder(nn.Module):
@@ -29,16 +30,18 @@ class RNNEncoder(nn.Module):
                           bidirectional=True, num_layers=self.num_layers, dropout=0.0)
 
     def forward(self, input, hidden):
-        # only the hidden state at the LAST position reaches the loss (S/models_utils.py:57); the full sequence of hidden
-        # states is returned for the caller's dictionary but carries no gradient
-        rnn_all, last, rnn_final_bidirectional = ops.gru_encoder_last(self.rnn, input, hidden)
+        # only the hidden state at the LAST position reaches the loss (S/models_utils.py:57): that is all that is computed
+        # here; the full sequence of hidden states and h_n (needing the whole reverse pass) are dictionary entries that
+        # are evaluated when somebody reads them (utils.DeferredDict) — svi.step never does
+        last, full = ops.gru_encoder_last(self.rnn, input, hidden)
         H = self.gru_hidden_dim
-        rnn_hidden_states = rnn_all[:, :, :H] + rnn_all[:, :, H:]
         rnn_final_hidden_state = self.fc1(last[:, :H] + last[:, H:])
         z_loc = self.linear_means(rnn_final_hidden_state)
         z_scale = self.softplus(self.linear_std(rnn_final_hidden_state))
-        return {"z_loc": z_loc, "z_scale": z_scale, "rnn_final_bidirectional": rnn_final_bidirectional,
-                "rnn_hidden_states": rnn_hidden_states, "rnn_final_hidden_state": rnn_final_hidden_state}
+        return DeferredDict({"z_loc": z_loc, "z_scale": z_scale,
+                             "rnn_final_bidirectional": Deferred(lambda: full.value()[1]),
+                             "rnn_hidden_states": Deferred(lambda: full.value()[0][:, :, :H] + full.value()[0][:, :, H:]),
+                             "rnn_final_hidden_state": rnn_final_hidden_state})
 
 
 class RNNDecoder_Tiling(nn.Module):
@@ -103,7 +106,15 @@ class EmbedComplex(nn.Module):
         self.fc2 = nn.Linear(self.embedding_dim, self.aa_probs)
 
     def forward(self, input):
-        return self.softmax(self.fc2(self.fc1(input)))
+        # fc2(fc1(x)) has no non-linearity in between (S/models_utils.py:235-236): applied as ONE [A -> A] affine map
+        # (W2 W1, W2 b1 + b2) — the encoder's copy runs on n*L rows, where this saves the [n*L, embedding_dim]
+        # intermediate and two thirds of the flops; autograd still delivers the gradients of fc1 / fc2 themselves
+        if not input.is_cuda:
+            return self.softmax(self.fc2(self.fc1(input)))
+        W = self.fc2.weight @ self.fc1.weight
+        b = torch.addmv(self.fc2.bias, self.fc2.weight, self.fc1.bias)
+        A = input.shape[-1]
+        return self.softmax(ops.affine_tall(input.reshape(-1, A), W, b).reshape(input.shape[:-1] + (W.shape[0],)))
 
 
 class EmbedComplexEncoder(EmbedComplex):

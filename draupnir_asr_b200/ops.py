@@ -457,10 +457,10 @@ def affine_tall(x: torch.Tensor, W: torch.Tensor, b: torch.Tensor) -> torch.Tens
 
 
 class _GRUEncoderLast(torch.autograd.Function):
-    """Bidirectional GRU over `x [n,L,I]` whose only DIFFERENTIABLE output is the hidden state at the last position
-    (`out[:, -1]`, what `RNNEncoder.forward` feeds to `fc1`, S/models_utils.py:57); the full `out [n,L,2H]` is returned
-    too, without gradient.  Back-propagation then needs the forward direction only (the reverse direction reaches
-    position L-1 after ONE cell step, done here with dense ops), with 16 instead of 32 sequences per CTA."""
+    """Hidden state at the LAST position, `output[:, -1]` `[n, 2H]`, of a bidirectional GRU over `x [n,L,I]` — all that
+    `RNNEncoder.forward` feeds to `fc1` (S/models_utils.py:57).  The forward direction runs the recurrence kernel for
+    direction 0 alone (16 instead of 32 sequences per CTA at 2,000 leaves, half the input projection); the reverse
+    direction reaches position L-1 after ONE cell step from `h0[1]`, done with dense ops.  Back-propagation likewise."""
 
     @staticmethod
     def forward(ctx, x, wih, bih, whh, bhh, h0):
@@ -468,23 +468,32 @@ class _GRUEncoderLast(torch.autograd.Function):
                                                                           (whh, "weight_hh"), (bhh, "bias_hh"), (h0, "h0")))
         n, L, I = x.shape
         H = whh.shape[-1]
-        gi = torch.addmm(bih.reshape(-1), x.reshape(n * L, I), wih.reshape(6 * H, I).t())        # [n*L, 2*3H]
+        gi0 = torch.addmm(bih[0], x.reshape(n * L, I), wih[0].t())                                # [n*L, 3H]
         want = any(ctx.needs_input_grad)
-        out = torch.empty((n, L, 2 * H), dtype=torch.float64, device=x.device)
+        out = torch.empty((n, L, 2 * H), dtype=torch.float64, device=x.device)       # direction-0 half is written
         gates = torch.empty((n, L, 2, 4, H), dtype=torch.float64, device=x.device) if want else None
-        _rc(lib.drp_gru_fwd_f64(_p(gi), _p(whh), _p(bhh), _p(h0), n, L, H, _p(out), _p(gates), _stream()), "drp_gru_fwd_f64")
-        del gi
+        _rc(lib.drp_gru_fwd_dir0_f64(_p(gi0), _p(whh), _p(bhh), _p(h0), n, L, H, _p(out), _p(gates), _stream()),
+            "drp_gru_fwd_dir0_f64")
+        del gi0
+        # reverse direction: position L-1 is its first step (h_prev = h0[1])
+        gi1 = torch.addmm(bih[1], x[:, L - 1], wih[1].t())
+        gh1 = torch.addmm(bhh[1], h0[1], whh[1].t())
+        r = torch.sigmoid(gi1[:, :H] + gh1[:, :H])
+        z = torch.sigmoid(gi1[:, H:2 * H] + gh1[:, H:2 * H])
+        q = gh1[:, 2 * H:]
+        nn = torch.tanh(gi1[:, 2 * H:] + r * q)
+        h1 = (1.0 - z) * nn + z * h0[1]
         if want:
-            ctx.save_for_backward(x, wih, whh, h0, out, gates)
-        ctx.mark_non_differentiable(out)
-        return out, out[:, -1].clone()
+            ctx.save_for_backward(x, wih, whh, h0, out, gates, torch.stack((r, z, nn, q), dim=1))
+        return torch.cat((out[:, L - 1, :H], h1), dim=1)
 
     @staticmethod
-    def backward(ctx, _dout_ignored, dlast):
-        x, wih, whh, h0, out, gates = ctx.saved_tensors
+    def backward(ctx, dlast):
+        x, wih, whh, h0, out, gates, g1 = ctx.saved_tensors
         n, L, I = x.shape
         H = whh.shape[-1]
         dev = x.device
+        dlast = dlast.contiguous()
         # ---- forward direction: full BPTT, gradient enters at the last position only
         dout = torch.zeros((n, L, 2 * H), dtype=torch.float64, device=dev)
         dout[:, -1, :H] = dlast[:, :H]
@@ -499,8 +508,7 @@ class _GRUEncoderLast(torch.autograd.Function):
         ws = torch.empty(wse, dtype=torch.float64, device=dev)
         _rc(lib.drp_gru_wgrad_dir0_f64(_p(dgi0), _p(gates), _p(out), _p(h0), n, L, H, _p(dwhh), _p(dbhh), _p(ws), wse, _stream()),
             "drp_gru_wgrad_dir0_f64")
-        # ---- reverse direction: position L-1 is its FIRST step (h_prev = h0[1])
-        g1 = gates[:, L - 1, 1]                                  # [n, 4, H]: r, z, n, q
+        # ---- reverse direction: its single relevant cell step
         r, z, nn, q = g1[:, 0], g1[:, 1], g1[:, 2], g1[:, 3]
         d = dlast[:, H:]
         dn = d * (1.0 - z) * (1.0 - nn * nn)
@@ -525,15 +533,28 @@ class _GRUEncoderLast(torch.autograd.Function):
 
 
 def gru_encoder_last(rnn: torch.nn.GRU, x: torch.Tensor, h0: torch.Tensor):
-    """`rnn(x, h0)` for the encoder: returns `(output_detached [n,L,2H], last [n,2H], h_n [2,n,H])` where only `last =
-    output[:, -1]` carries gradient (see `_GRUEncoderLast`)."""
+    """The encoder's use of `rnn(x, h0)`: returns `(last, full)` where `last = output[:, -1]` `[n,2H]` carries the
+    gradient (see `_GRUEncoderLast`) and `full` is a `utils.Deferred` whose `.value()` is `(output [n,L,2H], h_n [2,n,H])`
+    without gradient — the complete bidirectional pass, run only if somebody asks, on the weights as they were at THIS
+    call (`gru_stacked_params` copies them)."""
+    from .utils import Deferred
     H = rnn.hidden_size
     if H != GRU_HIDDEN or not x.is_cuda:
         out, hn = rnn(x, h0)
-        return out, out[:, -1], hn
+        return out[:, -1], Deferred(lambda: (out.detach(), hn.detach()))
     wih, whh, bih, bhh = gru_stacked_params(rnn)
-    out, last = _GRUEncoderLast.apply(x, wih, bih, whh, bhh, h0)
-    return out, last, torch.stack((out[:, -1, :H], out[:, 0, H:]))
+    last = _GRUEncoderLast.apply(x, wih, bih, whh, bhh, h0)
+    snap = tuple(t.detach() for t in (x, wih, bih, whh, bhh, h0))
+
+    def run_full():
+        xs, wih_s, bih_s, whh_s, bhh_s, h0_s = snap
+        n, L, I = xs.shape
+        with torch.no_grad():
+            gi = torch.addmm(bih_s.reshape(-1), xs.reshape(n * L, I), wih_s.reshape(6 * H, I).t()).reshape(n, L, 2, 3 * H)
+            out = gru_bidirectional(gi, whh_s, bhh_s, h0_s)
+        return out, torch.stack((out[:, -1, :H], out[:, 0, H:]))
+
+    return last, Deferred(run_full)
 
 
 def gru_bidirectional(gi: torch.Tensor, weight_hh: torch.Tensor, bias_hh: torch.Tensor, h0: torch.Tensor) -> torch.Tensor:

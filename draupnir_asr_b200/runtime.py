@@ -95,15 +95,43 @@ class Run(SimpleNamespace):
         return int(total)
 
     def step_from_host(self, host) -> float:
-        """H2D of the step inputs (pinned, async, same stream) -> svi.step -> loss back to the host as a float."""
+        """H2D of the step inputs (pinned, asynchronous) -> svi.step -> loss back to the host as a float.
+
+        The copies run on a side stream in the order the step consumes them: the guide only needs the BLOSUM-encoded data
+        set, so the patristic matrix and the data set travel while the encoder computes; the model waits for them (a
+        stream-wait injected in front of `Draupnir.model`, no host synchronisation)."""
         lo, hi = self._leaf_rows()
-        for k, v in host.items():
-            if k == "patristic":
-                self._staging[k].copy_(v, non_blocking=True)
-            else:
-                self._staging[k][lo:hi].copy_(v[lo:hi], non_blocking=True)
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._ev_guide, self._ev_model = torch.cuda.Event(), torch.cuda.Event()
+            self._pending = None
+            real_model = self.svi.model
+
+            def model_after_inputs(*a, **k):
+                if self._pending is not None:
+                    torch.cuda.current_stream().wait_event(self._pending)
+                    self._pending = None
+                return real_model(*a, **k)
+
+            self.svi.model = model_after_inputs
+        cs = self._copy_stream
+        cs.wait_stream(main)                       # the previous step has finished reading the staging buffers
+        with torch.cuda.stream(cs):
+            if "blosum" in host:
+                self._staging["blosum"][lo:hi].copy_(host["blosum"][lo:hi], non_blocking=True)
+            self._ev_guide.record(cs)
+            self._staging["patristic"].copy_(host["patristic"], non_blocking=True)
+            self._staging["dataset"][lo:hi].copy_(host["dataset"][lo:hi], non_blocking=True)
+            self._ev_model.record(cs)
+        main.wait_event(self._ev_guide)
+        self._pending = self._ev_model
         st = self._staging
-        return self.svi.step(st["dataset"], st["patristic"], None, st.get("blosum"), None, None)
+        loss = self.svi.step(st["dataset"], st["patristic"], None, st.get("blosum"), None, None)
+        if self._pending is not None:              # a guide-less path never entered the wrapped model: do not leak the wait
+            main.wait_event(self._pending)
+            self._pending = None
+        return loss
 
 
 def build_run(problem: SyntheticProblem, select_guide: str, device="cuda", init: Optional[Dict[str, torch.Tensor]] = None,

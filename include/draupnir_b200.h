@@ -100,6 +100,10 @@ int drp_ou_conditional_f64(const double* D, int64_t ldd, const int32_t* idx, int
 int drp_gru_hidden_size(void);
 int drp_gru_fwd_f64(const double* gi, const double* whh, const double* bhh, const double* h0, int n, int L, int H,
                     double* out, double* gates, void* stream);
+/* Forward direction only: gi0 [n,L,3H] compact; out / gates keep the two-direction layout and only their direction-0
+ * halves are written (the encoder's loss path only needs output[:, -1]: S/models_utils.py:57).                    */
+int drp_gru_fwd_dir0_f64(const double* gi0, const double* whh, const double* bhh, const double* h0, int n, int L, int H,
+                         double* out, double* gates, void* stream);
 /* Same with gi[i][l] = U[i] + V[l], U [n,2,3H], V [L,2,3H]: the decoder's tiled input [latent_i ; blosum_l]
  * (S/models.py:339-342) is never materialised.                                                                     */
 int drp_gru_fwd_uv_f64(const double* U, const double* V, const double* whh, const double* bhh, const double* h0, int n,

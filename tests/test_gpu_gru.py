@@ -82,15 +82,48 @@ def test_encoder_last_position_path(cuda, n, L, I):
     rnn_g.load_state_dict(rnn.state_dict())
     xg = x.detach().to(cuda).requires_grad_(True)
     hg = h0.detach().to(cuda).requires_grad_(True)
-    out, last, hn = ops.gru_encoder_last(rnn_g, xg, hg)
-    assert not out.requires_grad
+    last, full = ops.gru_encoder_last(rnn_g, xg, hg)
     (last * w.to(cuda)).sum().backward()
-    pairs = [("out", out_ref.detach(), out.cpu()), ("hn", hn_ref.detach(), hn.detach().cpu()), ("x", x.grad, xg.grad.cpu()),
-             ("h0", h0.grad, hg.grad.cpu())]
-    pairs += [(k, p.grad, dict(rnn_g.named_parameters())[k].grad.cpu()) for k, p in rnn.named_parameters()]
+    grads = {k: p.grad.clone() for k, p in rnn_g.named_parameters()}
+    # the deferred complete pass uses the weights of the call, even if they are updated before somebody looks
+    with torch.no_grad():
+        for p in rnn_g.parameters():
+            p.add_(0.25)
+    out, hn = full.value()
+    assert not out.requires_grad and full.value()[0] is out
+    pairs = [("last", out_ref[:, -1].detach(), last.detach().cpu()), ("out", out_ref.detach(), out.cpu()),
+             ("hn", hn_ref.detach(), hn.cpu()), ("x", x.grad, xg.grad.cpu()), ("h0", h0.grad, hg.grad.cpu())]
+    pairs += [(k, p.grad, grads[k].cpu()) for k, p in rnn.named_parameters()]
     for k, a, b in pairs:
         err = float((a - b).abs().max() / a.abs().max().clamp_min(1e-30))
         assert err < 1e-11, (k, err)
+
+
+def test_encoder_dictionary_entries_are_deferred_and_exact(cuda):
+    """RNNEncoder.forward (S/models_utils.py:52-65): z_loc / z_scale / rnn_final_hidden_state are computed; the entries
+    that need the complete bidirectional pass are evaluated on first access and equal nn.GRU's."""
+    import pickle
+    from draupnir_asr_b200.models_utils import RNNEncoder
+    from draupnir_asr_b200.utils import Deferred, DeferredDict
+    torch.manual_seed(4)
+    n, L = 21, 17
+    enc = RNNEncoder(L, 21, n, 60, 30, 21, 0, 1, None).double().to(cuda)
+    x = torch.randn(n, L, 21, dtype=torch.float64, device=cuda)
+    h0 = torch.randn(2, n, 60, dtype=torch.float64, device=cuda)
+    out = enc(x, h0)
+    assert isinstance(out, DeferredDict) and list(out) == ["z_loc", "z_scale", "rnn_final_bidirectional", "rnn_hidden_states",
+                                                          "rnn_final_hidden_state"]
+    assert isinstance(out.raw("rnn_hidden_states"), Deferred) and isinstance(out.raw("rnn_final_bidirectional"), Deferred)
+    states_ref, hn_ref = enc.rnn(x, h0)
+    last_ref = enc.fc1(states_ref[:, -1, :60] + states_ref[:, -1, 60:])
+    assert float((out["rnn_final_hidden_state"] - last_ref).abs().max()) < 1e-11
+    assert float((out["z_loc"] - enc.linear_means(last_ref)).abs().max()) < 1e-11
+    assert float((out["z_scale"] - enc.softplus(enc.linear_std(last_ref))).abs().max()) < 1e-11
+    assert float((out["rnn_hidden_states"] - (states_ref[:, :, :60] + states_ref[:, :, 60:])).abs().max()) < 1e-11
+    assert not isinstance(out.raw("rnn_hidden_states"), Deferred)
+    back = pickle.loads(pickle.dumps(out))
+    assert type(back) is dict and float((back["rnn_final_bidirectional"] - hn_ref).abs().max()) < 1e-11
+    assert all(torch.is_tensor(v) for v in out.values())
 
 
 @pytest.mark.parametrize("K,M,N", [(1, 1, 1), (31, 21, 120), (32, 21, 120), (1000, 21, 120), (4099, 180, 21), (70000, 21, 120),

@@ -120,6 +120,50 @@ def test_ancestral_argmax_matches_oracle(cuda, n, L):
     assert out_s.aa_sequences.shape == (3, problem.n_internal, L) and torch.isfinite(out_s.latent_space).all()
 
 
+@pytest.mark.parametrize("n,L", [(19, 225), (90, 60)])
+def test_marginal_samples_share_one_factorisation(cuda, n, L, monkeypatch):
+    """S draws from one conditional factorisation equal the oracle's S separate draws on the same
+    standard-normal numbers, and repeated `sample(..., use_test=True)` calls re-use the cached factor."""
+    from draupnir_asr_b200 import ops
+    problem, run, ref = _pair(n, L, "delta_map", cuda)
+    map_est = {k: v.detach() for k, v in run.guide(*run.step_args()).items()}
+    vals = {k: v.detach() for k, v in ref.constrained().items()}
+    calls = []
+    real = ops.ou_conditional
+    monkeypatch.setattr(ops, "ou_conditional", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    S_draws, ni = 4, problem.n_internal
+    torch.manual_seed(11)
+    out = run.Draupnir.sample_marginal(map_est, S_draws, run.patristic_matrix_full)
+    torch.manual_seed(11)
+    eps = torch.randn((30, ni, S_draws), dtype=torch.float64, device=cuda).cpu()
+    assert out.latent_space.shape == (S_draws, ni, 30) and out.aa_sequences.shape == (S_draws, ni, L)
+    assert out.logits.shape == (S_draws, ni, L, 21)
+    for s in range(S_draws):
+        want = O.conditional_sampling(vals, problem.patristic_matrix_full, problem.internal_nodes, eps[:, :, s])
+        assert torch.allclose(out.latent_space[s].cpu(), want, rtol=1e-7, atol=1e-8)
+        want_logits = O.sample(ref.nets, want, problem.blosum_weighted, use_argmax=True).logits
+        assert torch.allclose(out.logits[s].cpu(), want_logits, rtol=1e-6, atol=1e-7)
+    assert int(out.aa_sequences.min()) >= 0 and int(out.aa_sequences.max()) <= 20
+    # the per-draw loop of S/main.py:1337-1350: same estimates -> the factorisation is computed once in total
+    for _ in range(3):
+        one = run.Draupnir.sample(map_est, 1, None, run.patristic_matrix_full, None, use_argmax=False, use_test=True)
+        assert one.latent_space.shape == (ni, 30)
+    assert len(calls) == 1
+    # new estimates (even with equal values) invalidate it; an in-place update does too
+    map_est2 = {k: v.clone() for k, v in map_est.items()}
+    run.Draupnir.sample(map_est2, 1, None, run.patristic_matrix_full, None, use_argmax=False, use_test=True)
+    assert len(calls) == 2
+    map_est2["latent_z"].mul_(1.5)
+    torch.manual_seed(3)
+    got = run.Draupnir.conditional_sampling(map_est2, run.patristic_matrix_full)
+    assert len(calls) == 3
+    torch.manual_seed(3)
+    e1 = torch.randn((30, ni, 1), dtype=torch.float64, device=cuda).cpu()[:, :, 0]
+    vals2 = dict(vals, latent_z=vals["latent_z"] * 1.5)
+    assert torch.allclose(got.cpu(), O.conditional_sampling(vals2, problem.patristic_matrix_full, problem.internal_nodes, e1),
+                          rtol=1e-7, atol=1e-8)
+
+
 def test_model_refuses_cpu_device():
     from draupnir_asr_b200 import runtime
     problem = S.make_problem(5, 7)

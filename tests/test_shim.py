@@ -109,3 +109,26 @@ def test_install_as_pyro_makes_reference_imports_work():
     from pyro.infer import SVI as S2, Trace_ELBO as T2  # noqa: F401
     from pyro.contrib.easyguide import EasyGuide  # noqa: F401
     assert hasattr(p2, "sample") and hasattr(d2, "HalfNormal")
+
+
+def test_deferred_dict_behaves_like_a_dict_of_values():
+    """utils.DeferredDict (the variational guide's return value, S/guides.py:123-133): deferred entries are evaluated once,
+    on first access through any of the reading paths, and the dictionary pickles as a plain dict."""
+    import pickle
+    from draupnir_asr_b200.utils import Deferred, DeferredDict
+    calls = []
+
+    def make():
+        return DeferredDict({"a": 1, "b": Deferred(lambda: (calls.append(1), 7)[1]), "c": 3})
+
+    d = make()
+    assert list(d) == ["a", "b", "c"] and len(d) == 3 and "b" in d and calls == []
+    handed_on = DeferredDict({k: d.raw(k) for k in d})
+    assert calls == [] and handed_on["b"] == 7 and d["b"] == 7 and calls == [1]          # shared, evaluated once
+    assert d.get("b") == 7 and d.get("x", 9) == 9
+    for read in (lambda m: dict(m), lambda m: {**m}, lambda m: dict(m.items()), lambda m: dict(zip(m, m.values())),
+                 lambda m: pickle.loads(pickle.dumps(m)), lambda m: m.copy().materialize(), lambda m: {"b": m.pop("b"), **m}):
+        got = read(make())
+        assert got == {"a": 1, "b": 7, "c": 3}, got
+        assert not any(isinstance(v, Deferred) for v in dict.values(got))
+    assert type(pickle.loads(pickle.dumps(make()))) is dict
