@@ -68,9 +68,22 @@ __device__ __forceinline__ void g_bulk_g2s(uint32_t dst, const void* src, uint32
                  : "memory");
 }
 
-__device__ __forceinline__ double sigmoid_f64(double x) { return __drcp_rn(1.0 + drp_exp(-x)); }
+// 1 / x for x in [1, 1e304] (the denominators 1 + e^y below): MUFU.RCP64H seed (~2^-19) + two Newton steps, <= 1 ulp.
+// Branch-free on purpose: __drcp_rn carries a slow-path CALL that keeps the compiler from interleaving the gate
+// arithmetic of a thread's 2 MT independent elements, which made the gate phase a serial latency chain
+// (profiles/r01/trace_gru_v1.txt: 8.8 k of the 15.5 k cycles of a 32-row step).
+__device__ __forceinline__ double gru_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double sigmoid_f64(double x) { return gru_rcp(1.0 + drp_exp(-x)); }
 // tanh(x) = 1 - 2 / (1 + e^{2x}): absolute error ~1e-16 (what the recurrence needs), saturates correctly at +-1
-__device__ __forceinline__ double tanh_f64(double x) { return fma(-2.0, __drcp_rn(1.0 + drp_exp(2.0 * x)), 1.0); }
+__device__ __forceinline__ double tanh_f64(double x) { return fma(-2.0, gru_rcp(1.0 + drp_exp(2.0 * x)), 1.0); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Forward.  grid (ceil(n/ROWS), 2 directions), 256 threads; ROWS = 8 MT sequences per CTA (MT = 4, 2 or 1 chosen by
@@ -80,6 +93,21 @@ __device__ __forceinline__ double tanh_f64(double x) { return fma(-2.0, __drcp_r
 //   out   [n, L, 120]      hidden states (forward direction in [:60], backward in [60:], torch layout)
 //   gates [n, L, 2, 4, 60] r, z, n, (W_hn h + b_hn) for the backward pass; nullable
 // ---------------------------------------------------------------------------------------------------------------
+#ifdef DRP_GRU_TRACE
+// profiling build only (profiles/trace_gru.py): clock64 at the phase boundaries of the forward step, CTA (0,0), warps 0 and 7
+__device__ long long g_gru_trace[8 * 64 * 2];
+#define GRU_TRACE(slot)                                                                                   \
+    do {                                                                                                  \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 7) && t >= 200 && t < 264) \
+            g_gru_trace[((warp ? 1 : 0) * 64 + (t - 200)) * 8 + (slot)] = clock64();                     \
+    } while (0)
+extern "C" __attribute__((visibility("default"))) int drp_gru_trace_read(long long* host)
+{
+    return (int)cudaMemcpyFromSymbol(host, g_gru_trace, sizeof(g_gru_trace));
+}
+#else
+#define GRU_TRACE(slot) do { } while (0)
+#endif
 constexpr int GF_STAGES = 3;
 __host__ __device__ constexpr int gf_smem(int rows, bool uv)        // h double buffer + gi ring + barriers (+ the CTA's U rows)
 {
@@ -155,20 +183,25 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
             }
             return;
         }
-        if (lane == 0) g_mbar_expect_tx(bars + 8 * s, (uint32_t)nrows * G3 * 8);
-        __syncwarp();
-        if (lane < nrows)
-            g_bulk_g2s(g_smem_u32(ring + (int64_t)s * GROWS * G3 + lane * G3),
-                       gi + (((int64_t)(row0 + lane) * L + l) * gi_dirs + (gi_dirs == 2 ? dir : 0)) * G3, G3 * 8, bars + 8 * s);
+        // every warp issues the copies of MT rows (a bulk-copy issue costs ~60 cycles; 32 of them on one warp put that warp
+        // 1.9 k cycles behind the others at every step); the single arrival that carries the byte count is warp 0's, so
+        // the phase cannot complete before it, whatever the order in which the copies land
+        if (warp == 0 && lane == 0) g_mbar_expect_tx(bars + 8 * s, (uint32_t)nrows * G3 * 8);
+        const int rr = warp * MT + lane;
+        if (lane < MT && rr < nrows)
+            g_bulk_g2s(g_smem_u32(ring + (int64_t)s * GROWS * G3 + rr * G3),
+                       gi + (((int64_t)(row0 + rr) * L + l) * gi_dirs + (gi_dirs == 2 ? dir : 0)) * G3, G3 * 8, bars + 8 * s);
     };
-    if (warp == 0)
+    if (!UV || warp == 0)
         for (int t = 0; t < min(GF_STAGES - 1, L); ++t) issue(t);
 
     for (int t = 0; t < L; ++t) {
         const int l = dir ? L - 1 - t : t;
         const double* hc = hbuf + (t & 1) * GROWS * GHS;
         double* hn = hbuf + ((t + 1) & 1) * GROWS * GHS;
-        if (warp == 0 && t + GF_STAGES - 1 < L) issue(t + GF_STAGES - 1);   // its stage was drained in step t-1
+        GRU_TRACE(0);
+        if ((!UV || warp == 0) && t + GF_STAGES - 1 < L) issue(t + GF_STAGES - 1);   // its stage was drained in step t-1
+        GRU_TRACE(1);
         double acc[3][MT][2];
 #pragma unroll
         for (int g = 0; g < 3; ++g)
@@ -185,7 +218,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
                 for (int mt = 0; mt < MT; ++mt) dmma_8x8x4(acc[g][mt][0], acc[g][mt][1], a[mt], B[g][ks]);
         }
         const int s = t % GF_STAGES;
+        GRU_TRACE(2);
         g_mbar_wait(bars + 8 * s, (uint32_t)(t / GF_STAGES) & 1u);
+        GRU_TRACE(3);
         const double* gs = ring + (int64_t)s * GROWS * G3;
         if (jok) {
 #pragma unroll
@@ -233,7 +268,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
                 }
             }
         }
+        GRU_TRACE(4);
         __syncthreads();      // h of step t complete in hn; ring stage s and hc free for reuse
+        GRU_TRACE(5);
     }
 }
 
@@ -286,17 +323,22 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
         const int t = L - 1 - tb;
         const int l = dir ? L - 1 - t : t;
         const int lp = dir ? l + 1 : l - 1;       // position of h_prev (outside [0,L): h0)
-        if (lane == 0) g_mbar_expect_tx(bars + 8 * s, (uint32_t)nrows * GB_ROW_BYTES);
-        __syncwarp();
-        if (lane < nrows) {
-            const int64_t row = row0 + lane;
-            double* dst = ring + (int64_t)s * GROWS * RS + lane * RS;
-            g_bulk_g2s(g_smem_u32(dst), gates + ((row * L + l) * 2 + dir) * (4 * GH), 4 * GH * 8, bars + 8 * s);
-            const double* hp = t == 0 ? h0 + ((int64_t)dir * n + row) * GH : out + (row * L + lp) * (2 * GH) + dir * GH;
-            g_bulk_g2s(g_smem_u32(dst + 4 * GH), hp, GH * 8, bars + 8 * s);
+        // all warps issue (2 MT copies each, one per lane): 64 bulk-copy issues on one warp cost it ~3.8 k cycles per step.
+        // Warp 0's arrival carries the byte count, so the phase cannot complete early whatever the landing order.
+        if (warp == 0 && lane == 0) g_mbar_expect_tx(bars + 8 * s, (uint32_t)nrows * GB_ROW_BYTES);
+        const int rr = warp * MT + (lane >> 1);
+        if (lane < 2 * MT && rr < nrows) {
+            const int64_t row = row0 + rr;
+            double* dst = ring + (int64_t)s * GROWS * RS + rr * RS;
+            if (lane & 1) {
+                const double* hp = t == 0 ? h0 + ((int64_t)dir * n + row) * GH : out + (row * L + lp) * (2 * GH) + dir * GH;
+                g_bulk_g2s(g_smem_u32(dst + 4 * GH), hp, GH * 8, bars + 8 * s);
+            } else {
+                g_bulk_g2s(g_smem_u32(dst), gates + ((row * L + l) * 2 + dir) * (4 * GH), 4 * GH * 8, bars + 8 * s);
+            }
         }
     };
-    if (warp == 0) issue(0);
+    issue(0);
     double dh[MT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) dh[mt][0] = dh[mt][1] = 0.0;
@@ -304,7 +346,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
     for (int tb = 0; tb < L; ++tb) {
         const int t = L - 1 - tb;
         const int l = dir ? L - 1 - t : t;
-        if (warp == 0 && tb + 1 < L) issue(tb + 1);      // the other stage was drained before the last barrier
+        if (tb + 1 < L) issue(tb + 1);                   // the other stage was drained before the last barrier
         double2 dO[MT];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
@@ -411,32 +453,36 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_wgrad_kernel(const double* __
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int64_t blk) {      // warp 0, one pair per lane
+    auto issue = [&](int64_t blk) {      // every warp: 4 pairs, one copy per lane (96 issues on one warp stalled it ~5.7 k cycles)
         const int s = (int)((blk - b0) % GW_STAGES);
-        const int64_t p = blk * GW_PAIRS + lane;
         const int valid = (int)min((int64_t)GW_PAIRS, P - blk * GW_PAIRS);
-        if (lane == 0) g_mbar_expect_tx(bars + 8 * s, (uint32_t)valid * GW_ROW * 8);
-        __syncwarp();
-        if (lane < valid) {
-            double* dst = ring + (int64_t)s * GW_PAIRS * GW_ROW + lane * GW_ROW;
-            const int64_t i = p / L;
-            const int l = (int)(p - i * L);
-            g_bulk_g2s(g_smem_u32(dst), dgi + (p * dgi_dirs + (dgi_dirs == 2 ? dir : 0)) * G3, G3 * 8, bars + 8 * s);
-            g_bulk_g2s(g_smem_u32(dst + G3), gates + (p * 2 + dir) * (4 * GH), GH * 8, bars + 8 * s);
-            const bool first = dir ? (l == L - 1) : (l == 0);          // first step of the direction: h_prev = h0
-            const double* hp = first ? h0 + ((int64_t)dir * n + i) * GH : out + (dir ? p + 1 : p - 1) * (2 * GH) + dir * GH;
-            g_bulk_g2s(g_smem_u32(dst + G3 + GH), hp, GH * 8, bars + 8 * s);
+        if (warp == 0 && lane == 0) g_mbar_expect_tx(bars + 8 * s, (uint32_t)valid * GW_ROW * 8);
+        const int pr = warp * (GW_PAIRS / 8) + lane / 3, which = lane % 3;      // 4 pairs per warp, 3 copies per pair
+        if (lane < 3 * (GW_PAIRS / 8) && pr < valid) {
+            const int64_t p = blk * GW_PAIRS + pr;
+            double* dst = ring + (int64_t)s * GW_PAIRS * GW_ROW + pr * GW_ROW;
+            if (which == 0) {
+                g_bulk_g2s(g_smem_u32(dst), dgi + (p * dgi_dirs + (dgi_dirs == 2 ? dir : 0)) * G3, G3 * 8, bars + 8 * s);
+            } else if (which == 1) {
+                g_bulk_g2s(g_smem_u32(dst + G3), gates + (p * 2 + dir) * (4 * GH), GH * 8, bars + 8 * s);
+            } else {
+                const int64_t i = p / L;
+                const int l = (int)(p - i * L);
+                const bool first = dir ? (l == L - 1) : (l == 0);      // first step of the direction: h_prev = h0
+                const double* hp = first ? h0 + ((int64_t)dir * n + i) * GH : out + (dir ? p + 1 : p - 1) * (2 * GH) + dir * GH;
+                g_bulk_g2s(g_smem_u32(dst + G3 + GH), hp, GH * 8, bars + 8 * s);
+            }
         }
     };
     double acc[GW_MT][2];
 #pragma unroll
     for (int mt = 0; mt < GW_MT; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
-    if (warp == 0 && b0 < b1) issue(b0);
+    if (b0 < b1) issue(b0);
     const int jb = warp * 8 + gid;                 // column of h_prev (60: ones -> bias gradient; 61..63: zero)
     for (int64_t blk = b0; blk < b1; ++blk) {
         const int it = (int)(blk - b0);
         const int s = it % GW_STAGES;
-        if (warp == 0 && blk + 1 < b1) issue(blk + 1);
+        if (blk + 1 < b1) issue(blk + 1);
         g_mbar_wait(bars + 8 * s, (uint32_t)(it / GW_STAGES) & 1u);
         double* st = ring + (int64_t)s * GW_PAIRS * GW_ROW;
         const int valid = (int)min((int64_t)GW_PAIRS, P - blk * GW_PAIRS);
