@@ -60,7 +60,67 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and clock-event (throttle) reasons DURING the timed region — the quantities of the nvidia-smi line in
+    B200_PROFILING.md (clocks.sm, clocks.max.sm, clocks_event_reasons.*), read through NVML in a background thread every
+    100 ms.  An `nvidia-smi -lms` child process was used first: its queries stalled the launches of the running context
+    for 60-160 ms once in a while (single 95-190 ms steps among 30 ms ones); the in-process NVML calls do not."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.thread, self.stop_flag = gpu_index, None, False
+        self.sm, self.mx, self.reasons, self.error = [], [], set(), None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
+
+    def _loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.mx.append(float(mx))
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for name, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+            pynvml.nvmlShutdown()
+        except Exception as e:  # pragma: no cover
+            self.error = e
+
+    def start(self):
+        import threading
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def wait_first_sample(self, timeout_s: float = 5.0):
+        t0 = time.time()
+        while not self.sm and self.error is None and time.time() - t0 < timeout_s:
+            time.sleep(0.02)
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvml"}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=5)
+        if self.error is not None:
+            log("clock sampler unavailable:", self.error)
+        if self.sm:
+            sm = sorted(self.sm)
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(self.mx), reasons=sorted(self.reasons), samples=len(sm))
+        return out
+
+
+class SmiClockSampler:
+    """Fallback when NVML cannot be loaded in-process: an `nvidia-smi -lms 200` child (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -119,6 +179,16 @@ class ClockSampler:
             sm.sort()
             out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
         return out
+
+
+def make_clock_sampler(gpu_index: int):
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        return ClockSampler(gpu_index)
+    except Exception as e:
+        log("NVML not usable in-process (", e, "): falling back to an nvidia-smi child")
+        return SmiClockSampler(gpu_index)
 
 
 def oracle_steps_per_sec(w, budget_s: float, max_steps: int, warmup: int):
@@ -220,16 +290,19 @@ def run_ours(args, w, rank, world, local_rank):
         log(f"[rank {rank}] per-step ms: " + " ".join(f"{v:.2f}" for v in per))
         return sum(per)
 
-    # the sampler starts BEFORE the warm-up: nvidia-smi's start-up (NVML attaching to every GPU of the box) stalls the
-    # launches of a running context for 50-150 ms, which must not land inside a timed step; its 200 ms polling does not
-    sampler = ClockSampler(local_rank)
+    # the sampler starts BEFORE the warm-up: NVML's start-up (attaching to every GPU of the box) can stall the launches
+    # of a running context for tens of ms, which must not land inside a timed step; its polling does not
+    sampler = make_clock_sampler(local_rank)
     sampler.start()
     for _ in range(max(args.warmup, 3)):
+        lw = lib.drp_launch_count()
         loss = run.step()
-    log(f"[rank {rank}] warm-up done, -ELBO {loss:.4f}")
+        launches_warm = lib.drp_launch_count() - lw
+    log(f"[rank {rank}] warm-up done, -ELBO {loss:.4f}; {launches_warm} launches of this library per step")
     sampler.wait_first_sample()
     barrier()
-    lib.drp_timing_enable(1)
+    torch.cuda.synchronize()
+    lib.drp_timing_enable(int(launches_warm * (args.steps + 1)) + 64)   # events for the whole timed region, created now
     l0 = lib.drp_launch_count()
     ms = timed(run.step, args.steps)
     launches = lib.drp_launch_count() - l0

@@ -13,6 +13,19 @@ struct Span { cudaEvent_t a, b; };
 std::vector<Span> g_spans[DRP_K_CLASSES];
 double g_work[DRP_K_CLASSES];
 cudaEvent_t g_pending[DRP_K_CLASSES];
+std::vector<cudaEvent_t> g_free;      // recycled events: creating them inside a timed region stalls the driver now and then
+
+cudaEvent_t take_event()
+{
+    cudaEvent_t e;
+    if (!g_free.empty()) {
+        e = g_free.back();
+        g_free.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
 }  // namespace
 
 void drp_instr_begin(int k, double work, cudaStream_t st)
@@ -21,8 +34,7 @@ void drp_instr_begin(int k, double work, cudaStream_t st)
     if (!g_timing.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lk(g_mu);
     g_work[k] += work;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
+    cudaEvent_t e = take_event();
     cudaEventRecord(e, st);
     g_pending[k] = e;
 }
@@ -31,8 +43,7 @@ void drp_instr_end(int k, cudaStream_t st)
 {
     if (!g_timing.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lk(g_mu);
-    cudaEvent_t e;
-    cudaEventCreate(&e);
+    cudaEvent_t e = take_event();
     cudaEventRecord(e, st);
     g_spans[k].push_back({g_pending[k], e});
 }
@@ -50,14 +61,23 @@ DRP_API int64_t drp_launch_count(void)
     return (int64_t)s;
 }
 
-// Enable (1) / disable (0) CUDA-event timing of every launch; enabling clears previous records.
+// Enable (on >= 1) / disable (0) CUDA-event timing of every launch; enabling clears previous records.  `on` > 1 also
+// pre-creates events for that many launches, so that no event is created inside the caller's timed region (the driver
+// grows its event pool in steps that cost ~100 ms once every ~1000 events).
 DRP_API int drp_timing_enable(int on)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     for (int k = 0; k < DRP_K_CLASSES; ++k) {
-        for (auto& s : g_spans[k]) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+        for (auto& s : g_spans[k]) { g_free.push_back(s.a); g_free.push_back(s.b); }
         g_spans[k].clear();
         g_work[k] = 0.0;
+    }
+    if (on > 1) {
+        while ((long long)g_free.size() < 2ll * on) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) break;
+            g_free.push_back(e);
+        }
     }
     g_timing.store(on ? 1 : 0);
     return 0;

@@ -63,7 +63,11 @@ __device__ const double DRP_EXP2_TAB[32] = {
 __device__ __forceinline__ double drp_exp(double x)
 {
     x = fmin(fmax(x, -700.0), 700.0);
-    const double t = rint(x * 46.166241308446828384);          // 32 / ln 2
+    // t = rint(x * 32/ln2) and n = (int)t through the 1.5 * 2^52 shift: two fp64-pipe operations instead of FRND.F64 +
+    // F2I.F64, which run on the XU pipe at a small fraction of the fp64 rate (the GRU gate phase was XU-bound on them)
+    const double sh = fma(x, 46.166241308446828384, 6755399441055744.0);
+    const int n = __double2loint(sh);
+    const double t = sh - 6755399441055744.0;
     double r = fma(t, -0.021660849219188094, x);               // ln2/32, leading 27 bits (t * hi is exact)
     r = fma(t, -1.733101967801894e-10, r);                     // ln2/32, remainder
     double q = 1.3888888888888889e-03;                         // 1/720
@@ -72,7 +76,6 @@ __device__ __forceinline__ double drp_exp(double x)
     q = fma(q, r, 1.6666666666666666e-01);
     q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
-    const int n = (int)t;
     const double T = __ldg(DRP_EXP2_TAB + (n & 31));
     const double v = fma(T, q * r, T);
     return __hiloint2double(__double2hiint(v) + ((n >> 5) << 20), __double2loint(v));

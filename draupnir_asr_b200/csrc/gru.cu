@@ -85,6 +85,47 @@ __device__ __forceinline__ double sigmoid_f64(double x) { return gru_rcp(1.0 + d
 // tanh(x) = 1 - 2 / (1 + e^{2x}): absolute error ~1e-16 (what the recurrence needs), saturates correctly at +-1
 __device__ __forceinline__ double tanh_f64(double x) { return fma(-2.0, gru_rcp(1.0 + drp_exp(2.0 * x)), 1.0); }
 
+// Lean variants for the second-generation forward kernel: about half the instructions of the pair above (the gate phase is
+// bound by instruction issue and dependent-issue latency, not by the fp64 pipe).  Both work on a = min(|x|, 704) — two
+// integer instructions on the high word instead of a two-sided fp64 clamp — evaluate e^{-a} in (0, 1] (no overflow case,
+// denominators in (1, 2]) with the exponent table in shared memory, and restore the sign at the end.
+__device__ __forceinline__ double gru_abs_clamped(double x)
+{
+    return __hiloint2double(min(__double2hiint(x) & 0x7fffffff, 0x40860000), __double2loint(x));
+}
+__device__ __forceinline__ double gru_copysign_pos(double m, double x)      // m >= 0
+{
+    return __hiloint2double(__double2hiint(m) | (__double2hiint(x) & 0x80000000), __double2loint(m));
+}
+__device__ __forceinline__ double gru_expm(double a, const double* __restrict__ tab)     // e^{-a}, 0 <= a <= 1408
+{
+    const double sh = fma(a, -46.166241308446828384, 6755399441055744.0);   // rint(-a 32/ln2) by the 1.5 * 2^52 shift
+    const int n = max(__double2loint(sh), -32000);                          // 2^-1000: far below 1 ulp of the results
+    const double t = sh - 6755399441055744.0;
+    double r = fma(t, -0.021660849219188094, -a);
+    r = fma(t, -1.733101967801894e-10, r);
+    double q = 1.3888888888888889e-03;
+    q = fma(q, r, 8.3333333333333332e-03);
+    q = fma(q, r, 4.1666666666666664e-02);
+    q = fma(q, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    const double T = tab[n & 31];
+    const double v = fma(T, q * r, T);
+    return __hiloint2double(__double2hiint(v) + ((n >> 5) << 20), __double2loint(v));
+}
+__device__ __forceinline__ double gru_sigmoid(double x, const double* __restrict__ tab)
+{
+    const double y = gru_rcp(1.0 + gru_expm(gru_abs_clamped(x), tab));      // sigma(|x|) in [1/2, 1)
+    return 0.5 + gru_copysign_pos(y - 0.5, x);
+}
+__device__ __forceinline__ double gru_tanh(double x, const double* __restrict__ tab)
+{
+    const double a = gru_abs_clamped(x);
+    const double y = gru_rcp(1.0 + gru_expm(a + a, tab));
+    return gru_copysign_pos(fma(2.0, y, -1.0), x);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Forward.  grid (ceil(n/ROWS), 2 directions), 256 threads; ROWS = 8 MT sequences per CTA (MT = 4, 2 or 1 chosen by
 // the host so that one wave of CTAs covers the batch: the recurrence is latency-bound, fewer rows = shorter steps).
@@ -94,19 +135,25 @@ __device__ __forceinline__ double tanh_f64(double x) { return fma(-2.0, gru_rcp(
 //   gates [n, L, 2, 4, 60] r, z, n, (W_hn h + b_hn) for the backward pass; nullable
 // ---------------------------------------------------------------------------------------------------------------
 #ifdef DRP_GRU_TRACE
-// profiling build only (profiles/trace_gru.py): clock64 at the phase boundaries of the forward step, CTA (0,0), warps 0 and 7
+// profiling build only (profiles/trace_gru.py): clock64 at the phase boundaries of the forward step, CTA (0,0), warps 0 and 8 (7 in 256-thread CTAs)
 __device__ long long g_gru_trace[8 * 64 * 2];
 #define GRU_TRACE(slot)                                                                                   \
     do {                                                                                                  \
-        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 7) && t >= 200 && t < 264) \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == (blockDim.x > 256 ? 8 : 7)) && t >= 200 && t < 264) \
             g_gru_trace[((warp ? 1 : 0) * 64 + (t - 200)) * 8 + (slot)] = clock64();                     \
     } while (0)
 extern "C" __attribute__((visibility("default"))) int drp_gru_trace_read(long long* host)
 {
     return (int)cudaMemcpyFromSymbol(host, g_gru_trace, sizeof(g_gru_trace));
 }
+#define GRU_TRACE_B(slot)                                                                                 \
+    do {                                                                                                  \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 7) && tb >= 200 && tb < 264) \
+            g_gru_trace[((warp ? 1 : 0) * 64 + (tb - 200)) * 8 + (slot)] = clock64();                    \
+    } while (0)
 #else
 #define GRU_TRACE(slot) do { } while (0)
+#define GRU_TRACE_B(slot) do { } while (0)
 #endif
 constexpr int GF_STAGES = 3;
 __host__ __device__ constexpr int gf_smem(int rows, bool uv)        // h double buffer + gi ring + barriers (+ the CTA's U rows)
@@ -275,6 +322,225 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Forward, second generation: W_hh lives in SHARED memory (k-major, row stride 184: conflict-free B-fragment loads) instead
+// of 90 registers per thread, which (a) lets 16 warps share a CTA (warp = hidden-unit group x row half) so that the
+// latency-bound gate arithmetic has twice the warps to hide behind, and (b) leaves the compiler the registers to
+// interleave the independent elements of a thread (profiles/r01/trace_gru_v2.txt: at 32 rows the gate phase took 6.5-7.1 k
+// of the 13.7 k cycles of a step although its fp64 work is ~2 k cycles).  Same arguments and layouts as gru_fwd_kernel.
+//   WS = 2: 512 threads, each warp owns MT/2 row tiles;  WS = 1: 256 threads (8-row CTAs).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GWS = 180;      // row stride of W^T in shared memory: 180 mod 16 == 4, so the 16 lanes of a half-warp (gid 0-3 x tig 0-3,
+                              // address tig * GWS + gid) hit 16 distinct 8-byte banks
+constexpr int GRS = 184;      // row stride of the gi / U rows: 16-byte accesses at r * GRS + 2 tig want GRS / 2 == 4 (mod 8)
+constexpr int GF2_STAGES = 2;
+__host__ __device__ constexpr int gf2_smem(int rows, bool uv)
+{
+    // h double buffer | W^T | per-half rings (UV: 2 halves x stages x one V row, + the CTA's U rows) | barriers
+    return 2 * rows * GHS * 8 + (GH * GWS + 8) * 8 + (uv ? (2 * GF2_STAGES * GRS * 8 + rows * GRS * 8) : GF2_STAGES * rows * GRS * 8) +
+           64 + 256;                                   // + the 32-entry 2^{j/32} table of the exponential
+}
+__device__ __forceinline__ void g_named_barrier(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void g_named_arrive(int id, int nthreads)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// The two row halves of a 512-thread CTA (warps 0-7 / 8-15) never exchange data: each has its own ring, mbarriers and named
+// barrier.  They take turns on the recurrent product (token passed through named barriers 3/4), so that one half's gate
+// arithmetic (latency/issue-bound, fp64 pipe ~1/3 busy) runs under the other half's product (fp64 pipe saturated by DMMA).
+// Left alone the halves fall back into lockstep (the trailing half gets the whole pipe and catches up), hence the token.
+template <bool UV, int MT, int WS>
+__global__ void __launch_bounds__(256 * WS, 1) gru_fwd2_kernel(const double* __restrict__ gi, const double* __restrict__ vrow,
+                                                               const double* __restrict__ whh,
+                                                               const double* __restrict__ bhh, const double* __restrict__ h0,
+                                                               int n, int L, double* __restrict__ out,
+                                                               double* __restrict__ gates, int gi_dirs, int stagger_ns)
+{
+    constexpr int NT = 256 * WS;
+    constexpr int GROWS = 8 * MT;
+    constexpr int MTW = MT / WS;                                      // row tiles per warp
+    constexpr int HROWS = 8 * MTW;                                    // rows per half
+    constexpr int STAGE_ROWS = UV ? 1 : HROWS;
+    static_assert(MT % WS == 0, "row tiles must split evenly over the warp halves");
+    extern __shared__ __align__(16) uint8_t gsm[];
+    double* hbuf = reinterpret_cast<double*>(gsm);                                   // [2][rows][68]
+    double* wt = hbuf + 2 * GROWS * GHS;                                              // [60][184]: wt[k][c] = W_hh[c][k]
+    double* ring0 = wt + GH * GWS + 8;                                                // [half][stage][rows/half or 1][184]
+    double* ubuf = ring0 + WS * GF2_STAGES * STAGE_ROWS * GRS + (UV && WS == 1 ? GF2_STAGES * GRS : 0);   // [rows][184] (UV only)
+    double* etab = reinterpret_cast<double*>(gsm + gf2_smem(GROWS, UV) - 256);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    const int wg = warp & 7, wr = warp >> 3;                                          // hidden-unit group, row half
+    double* ring = ring0 + wr * GF2_STAGES * STAGE_ROWS * GRS;
+    const uint32_t bars = g_smem_u32(gsm + gf2_smem(GROWS, UV) - 320) + wr * GF2_STAGES * 8;
+    const int dir = blockIdx.y;
+    const int row0 = blockIdx.x * GROWS;
+    const int nrows = min(GROWS, n - row0);
+    const int hrow0 = wr * HROWS;                                                     // first CTA row of this half
+    const int nrows_h = max(0, min(HROWS, nrows - hrow0));
+    const int j0 = wg * 8 + 2 * tig;              // this thread's hidden units j0, j0+1 (as C-fragment columns)
+    const bool jok = j0 < GH;
+    const int jb = wg * 8 + gid;                  // hidden unit whose W_hh row this lane feeds as B-fragment
+    const double* W = whh + (int64_t)dir * G3 * GH;
+
+    for (int idx = tid; idx < GH * GWS + 8; idx += NT) {     // (+8: the unused lanes of hidden group 7 read up to 3 past the end)
+        const int k = idx / GWS, c = idx - k * GWS;
+        wt[idx] = k < GH ? W[(int64_t)c * GH + k] : 0.0;
+    }
+    if (tid < 32) etab[tid] = DRP_EXP2_TAB[tid];
+    double bh[3][2];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        bh[g][0] = jok ? bhh[dir * G3 + g * GH + j0] : 0.0;
+        bh[g][1] = jok ? bhh[dir * G3 + g * GH + j0 + 1] : 0.0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < WS * GF2_STAGES; ++s) g_mbar_init(g_smem_u32(gsm + gf2_smem(GROWS, UV) - 320) + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int idx = tid; idx < GROWS * GH; idx += NT) {
+        const int r = idx / GH, j = idx - r * GH;
+        hbuf[r * GHS + j] = r < nrows ? h0[((int64_t)dir * n + row0 + r) * GH + j] : 0.0;
+    }
+    if (UV) {
+        for (int idx = tid; idx < GROWS * G3; idx += NT) {
+            const int r = idx / G3, c = idx - r * G3;
+            ubuf[r * GRS + c] = r < nrows ? gi[((int64_t)(row0 + r) * 2 + dir) * G3 + c] : 0.0;
+        }
+    }
+    __syncthreads();
+    double hold[MTW][2];
+#pragma unroll
+    for (int mt = 0; mt < MTW; ++mt) {
+        const int r = hrow0 + 8 * mt + gid;
+        hold[mt][0] = jok ? hbuf[r * GHS + j0] : 0.0;
+        hold[mt][1] = jok ? hbuf[r * GHS + j0 + 1] : 0.0;
+    }
+    auto issue = [&](int t) {      // stream the gi rows (UV: the V row) of step t into this half's ring stage
+        const int s = t % GF2_STAGES;
+        const int l = dir ? L - 1 - t : t;
+        if (UV) {
+            if (wg == 0 && lane == 0) {
+                g_mbar_expect_tx(bars + 8 * s, G3 * 8);
+                g_bulk_g2s(g_smem_u32(ring + s * GRS), vrow + ((int64_t)l * 2 + dir) * G3, G3 * 8, bars + 8 * s);
+            }
+            return;
+        }
+        // the half's first warp carries the byte count, so the phase cannot complete before it whatever the landing order
+        if (wg == 0 && lane == 0) g_mbar_expect_tx(bars + 8 * s, (uint32_t)nrows_h * G3 * 8);
+        const int rr = wg * MTW + lane;                                 // MTW copies per warp (an issue costs ~60 cycles)
+        if (lane < MTW && rr < nrows_h)
+            g_bulk_g2s(g_smem_u32(ring + (int64_t)s * HROWS * GRS + rr * GRS),
+                       gi + (((int64_t)(row0 + hrow0 + rr) * L + l) * gi_dirs + (gi_dirs == 2 ? dir : 0)) * G3, G3 * 8,
+                       bars + 8 * s);
+    };
+    issue(0);
+    const bool handoff = WS == 2 && stagger_ns != 0;
+
+    for (int t = 0; t < L; ++t) {
+        const int l = dir ? L - 1 - t : t;
+        const double* hc = hbuf + (t & 1) * GROWS * GHS;
+        double* hn = hbuf + ((t + 1) & 1) * GROWS * GHS;
+        GRU_TRACE(0);
+        if (t + 1 < L) issue(t + 1);               // the other stage was drained before the barrier that ended step t-1
+        if (handoff && (wr == 1 || t > 0)) g_named_barrier(3 + wr, 512);   // the other half has finished its product
+        GRU_TRACE(1);
+        double acc[3][MTW][2];
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt) acc[g][mt][0] = bh[g][0], acc[g][mt][1] = bh[g][1];
+#pragma unroll
+        for (int ks = 0; ks < 15; ++ks) {
+            double a[MTW], b[3];
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt) a[mt] = hc[(hrow0 + 8 * mt + gid) * GHS + 4 * ks + tig];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) b[g] = wt[(4 * ks + tig) * GWS + g * GH + jb];
+#pragma unroll
+            for (int g = 0; g < 3; ++g)
+#pragma unroll
+                for (int mt = 0; mt < MTW; ++mt) dmma_8x8x4(acc[g][mt][0], acc[g][mt][1], a[mt], b[g]);
+        }
+        if (handoff && (wr == 0 || t + 1 < L)) g_named_arrive(3 + (wr ^ 1), 512);   // the product token goes to the other half
+        const int s = t % GF2_STAGES;
+        GRU_TRACE(2);
+        g_mbar_wait(bars + 8 * s, (uint32_t)(t / GF2_STAGES) & 1u);
+        GRU_TRACE(3);
+        const double* gs = ring + (int64_t)s * STAGE_ROWS * GRS;
+        if (jok) {
+            double xr[MTW][2], xz[MTW][2], xn[MTW][2];
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt) {
+                const int r = 8 * mt + gid;                              // row within the half
+                double2 ar, az, an;
+                if (UV) {
+                    const double* up = ubuf + (hrow0 + r) * GRS;
+                    const double2 ur = *reinterpret_cast<const double2*>(up + j0);
+                    const double2 uz = *reinterpret_cast<const double2*>(up + GH + j0);
+                    const double2 un = *reinterpret_cast<const double2*>(up + 2 * GH + j0);
+                    const double2 vr = *reinterpret_cast<const double2*>(gs + j0);
+                    const double2 vz = *reinterpret_cast<const double2*>(gs + GH + j0);
+                    const double2 vn = *reinterpret_cast<const double2*>(gs + 2 * GH + j0);
+                    ar = make_double2(ur.x + vr.x, ur.y + vr.y);
+                    az = make_double2(uz.x + vz.x, uz.y + vz.y);
+                    an = make_double2(un.x + vn.x, un.y + vn.y);
+                } else {
+                    ar = *reinterpret_cast<const double2*>(gs + r * GRS + j0);
+                    az = *reinterpret_cast<const double2*>(gs + r * GRS + GH + j0);
+                    an = *reinterpret_cast<const double2*>(gs + r * GRS + 2 * GH + j0);
+                }
+                xr[mt][0] = ar.x, xr[mt][1] = ar.y, xz[mt][0] = az.x, xz[mt][1] = az.y, xn[mt][0] = an.x, xn[mt][1] = an.y;
+            }
+            double hv[MTW][2], rv[MTW][2], zv[MTW][2], nv[MTW][2], qv[MTW][2];
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    qv[mt][e] = acc[2][mt][e];                           // the accumulators started from b_hh
+                    xr[mt][e] += acc[0][mt][e];
+                    xz[mt][e] += acc[1][mt][e];
+                    rv[mt][e] = gru_sigmoid(xr[mt][e], etab);
+                    zv[mt][e] = gru_sigmoid(xz[mt][e], etab);
+                }
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double gn = fma(rv[mt][e], qv[mt][e], xn[mt][e]);
+                    nv[mt][e] = gru_tanh(gn, etab);
+                    hv[mt][e] = fma(zv[mt][e], hold[mt][e] - nv[mt][e], nv[mt][e]);
+                    // the integer clamp of the lean gate functions hides a NaN pre-activation: hand it on to h (0 * finite = 0)
+                    hv[mt][e] = fma(0.0, (xr[mt][e] + xz[mt][e]) + gn, hv[mt][e]);
+                    hold[mt][e] = hv[mt][e];
+                }
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt) {
+                const int r = hrow0 + 8 * mt + gid;
+                *reinterpret_cast<double2*>(hn + r * GHS + j0) = make_double2(hv[mt][0], hv[mt][1]);
+                if (r < nrows) {
+                    const int64_t site = (int64_t)(row0 + r) * L + l;
+                    *reinterpret_cast<double2*>(out + site * (2 * GH) + dir * GH + j0) = make_double2(hv[mt][0], hv[mt][1]);
+                    if (gates) {
+                        double* gp = gates + (site * 2 + dir) * (4 * GH) + j0;
+                        *reinterpret_cast<double2*>(gp) = make_double2(rv[mt][0], rv[mt][1]);
+                        *reinterpret_cast<double2*>(gp + GH) = make_double2(zv[mt][0], zv[mt][1]);
+                        *reinterpret_cast<double2*>(gp + 2 * GH) = make_double2(nv[mt][0], nv[mt][1]);
+                        *reinterpret_cast<double2*>(gp + 3 * GH) = make_double2(qv[mt][0], qv[mt][1]);
+                    }
+                }
+            }
+        }
+        GRU_TRACE(4);
+        g_named_barrier(1 + wr, 256);      // this half: h of step t complete in hn; its ring stage s and hc rows free for reuse
+        GRU_TRACE(5);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Backward through time.  Steps run in the reverse of the forward order of the direction.
 //   dout  [n, L, 120]  gradient w.r.t. the hidden states   out / gates / h0 / whh as in the forward kernel
 //   dgi   [n, L, 2, 180]  gradient w.r.t. gi (r, z, n pre-activations); dgh = dgi with the n-part multiplied by r
@@ -282,7 +548,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_fwd_kernel(const double* __re
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int GB_STAGES = 2;
 constexpr int GB_ROW_BYTES = (4 * GH + GH) * 8;                                   // saved gates + h_prev = 2400
-__host__ __device__ constexpr int gb_smem(int rows) { return rows * GDS * 8 + GB_STAGES * rows * GB_ROW_BYTES + 64; }
+constexpr int GB_ROW_STRIDE = 312;     // doubles between ring rows: 16-byte accesses at r * stride + 2 tig want stride / 2 == 4 (mod 8)
+__host__ __device__ constexpr int gb_smem(int rows) { return rows * GDS * 8 + GB_STAGES * rows * GB_ROW_STRIDE * 8 + 64; }
 
 template <int MT>
 __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __restrict__ dout, const double* __restrict__ out,
@@ -292,7 +559,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
                                                               int dgi_dirs)
 {
     constexpr int GROWS = 8 * MT;
-    constexpr int GB_STAGE_BYTES = GROWS * GB_ROW_BYTES;
+    constexpr int GB_STAGE_BYTES = GROWS * GB_ROW_STRIDE * 8;
     extern __shared__ __align__(16) uint8_t gsm[];
     double* dgh = reinterpret_cast<double*>(gsm);                                    // [32][180]
     double* ring = reinterpret_cast<double*>(gsm + GROWS * GDS * 8);                  // [stages][32][300]
@@ -305,7 +572,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
     const bool jok = j0 < GH;
     const int jb = warp * 8 + gid;
     const double* W = whh + (int64_t)dir * G3 * GH;
-    constexpr int RS = GB_ROW_BYTES / 8;          // 300 doubles per ring row: [r | z | n | q | h_prev]
+    constexpr int RS = GB_ROW_STRIDE;             // ring row: [r | z | n | q | h_prev] = 300 doubles, padded to 312
 
     double B[45];                                 // B[k][n] = W_hh[c = 4 ks + tig][j = jb]
 #pragma unroll
@@ -342,20 +609,41 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
     double dh[MT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) dh[mt][0] = dh[mt][1] = 0.0;
+    double2 dOn[MT];
+    {
+        const int l0 = dir ? 0 : L - 1;            // position of backward step 0
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int r = 8 * mt + gid;
+            dOn[mt] = (jok && r < nrows) ? *reinterpret_cast<const double2*>(dout + ((int64_t)(row0 + r) * L + l0) * (2 * GH) + dir * GH + j0)
+                                         : make_double2(0.0, 0.0);
+        }
+    }
 
     for (int tb = 0; tb < L; ++tb) {
         const int t = L - 1 - tb;
         const int l = dir ? L - 1 - t : t;
+        GRU_TRACE_B(0);
         if (tb + 1 < L) issue(tb + 1);                   // the other stage was drained before the last barrier
+        GRU_TRACE_B(1);
+        // dout of the NEXT step is requested now and consumed a whole step later: a global load issued and used inside the
+        // same step exposed ~1.5 k cycles of DRAM latency in front of the gate arithmetic (profiles/r01/trace_gru_v4.txt)
         double2 dO[MT];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            const int r = 8 * mt + gid;
-            dO[mt] = (jok && r < nrows) ? *reinterpret_cast<const double2*>(dout + ((int64_t)(row0 + r) * L + l) * (2 * GH) + dir * GH + j0)
-                                        : make_double2(0.0, 0.0);
+        for (int mt = 0; mt < MT; ++mt) dO[mt] = dOn[mt];
+        if (tb + 1 < L) {
+            const int ln = dir ? l + 1 : l - 1;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int r = 8 * mt + gid;
+                dOn[mt] = (jok && r < nrows) ? *reinterpret_cast<const double2*>(dout + ((int64_t)(row0 + r) * L + ln) * (2 * GH) + dir * GH + j0)
+                                             : make_double2(0.0, 0.0);
+            }
         }
         const int s = tb % GB_STAGES;
+        GRU_TRACE_B(2);
         g_mbar_wait(bars + 8 * s, (uint32_t)(tb / GB_STAGES) & 1u);
+        GRU_TRACE_B(3);
         const double* gs = ring + (int64_t)s * GROWS * RS;
         if (jok) {
 #pragma unroll
@@ -389,7 +677,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
                 }
             }
         }
+        GRU_TRACE_B(4);
         __syncthreads();                           // dgh of this step complete; ring stage s drained
+        GRU_TRACE_B(5);
         double acc[MT][2];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
@@ -406,7 +696,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
             dh[mt][0] += acc[mt][0];
             dh[mt][1] += acc[mt][1];
         }
+        GRU_TRACE_B(6);
         __syncthreads();                           // everyone done reading dgh before the next step overwrites it
+        GRU_TRACE_B(7);
     }
     if (dh0 && jok) {
 #pragma unroll
@@ -549,10 +841,45 @@ static int gru_pick_mt(int n, int ndir = 2)
     return 4;
 }
 
+static int gru_fwd_generation()
+{
+    static int gen = 0;
+    if (!gen) {
+        const char* e = getenv("DRP_GRU_FWD");
+        gen = (e && atoi(e) == 1) ? 1 : 2;
+    }
+    return gen;
+}
+
+template <bool UV, int MT>
+static void gru_fwd2_launch(const double* gi, const double* v, const double* whh, const double* bhh, const double* h0, int n,
+                            int L, double* out, double* gates, cudaStream_t st, int ndir)
+{
+    constexpr int WS = MT >= 2 ? 2 : 1;
+    constexpr int smem = gf2_smem(8 * MT, UV);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gru_fwd2_kernel<UV, MT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_done = true;
+    }
+    DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * ndir * G3 * GH, st);
+    static int stagger = -1;
+    if (stagger < 0) {
+        const char* e = getenv("DRP_GRU_HANDOFF");
+        stagger = e ? atoi(e) : 0;                 // 0: the halves run free (they fall into lockstep: measured best); else: product token
+    }
+    gru_fwd2_kernel<UV, MT, WS><<<dim3((n + 8 * MT - 1) / (8 * MT), ndir), 256 * WS, smem, st>>>(gi, v, whh, bhh, h0, n, L, out,
+                                                                                              gates, ndir, stagger);
+}
+
 template <bool UV, int MT>
 static void gru_fwd_launch(const double* gi, const double* v, const double* whh, const double* bhh, const double* h0, int n,
                            int L, double* out, double* gates, cudaStream_t st, int ndir = 2)
 {
+    if (gru_fwd_generation() == 2) {
+        gru_fwd2_launch<UV, MT>(gi, v, whh, bhh, h0, n, L, out, gates, st, ndir);
+        return;
+    }
     constexpr int smem = gf_smem(8 * MT, UV);
     static bool attr_done = false;
     if (!attr_done) {

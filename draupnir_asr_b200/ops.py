@@ -15,6 +15,21 @@ from ._lib import lib
 
 _DEFERRED: Optional[List[Tuple[torch.Tensor, str]]] = None
 
+# The OU prior (a chain of ~150 mostly narrow kernels: 64-wide panel factorisations, solves, slicing) and the GRU
+# recurrences (one CTA per SM on 126 of 148 SMs, latency-bound) are independent until the loss is summed: the prior's
+# log-density is evaluated on a side stream so that the two fill each other's idle SMs.  DRP_PRIOR_STREAM=0 disables.
+PRIOR_STREAM_ENABLED = os.environ.get("DRP_PRIOR_STREAM", "1") != "0"
+_SIDE_STREAMS = {}
+
+
+def side_stream(device) -> "torch.cuda.Stream":
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return st
+
 
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())

@@ -38,10 +38,29 @@ class TorchDistributionMixin:
         return self.rsample(sample_shape) if self.has_rsample else self.sample(sample_shape)
 
 
+class AsyncTerm:
+    """A summed log-density being evaluated on a side stream.  `join()` makes the current stream wait for it and returns
+    the scalar tensor; until then nothing on the current stream may touch `value`."""
+    __slots__ = ("value", "stream")
+
+    def __init__(self, value, stream):
+        self.value, self.stream = value, stream
+
+    def join(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self.stream)
+        self.value.record_stream(cur)
+        return self.value
+
+
 class Independent(td.Independent, TorchDistributionMixin):
     def log_prob_sum(self, value):
         f = getattr(self.base_dist, "log_prob_sum", None)
         return f(value) if f is not None else self.log_prob(value).sum()
+
+    def log_prob_sum_async(self, value, scale=1.0):
+        f = getattr(self.base_dist, "log_prob_sum_async", None)
+        return f(value, scale) if f is not None else None
 
 
 class HalfNormal(td.HalfNormal, TorchDistributionMixin):
@@ -209,6 +228,20 @@ class OUProcessPrior(td.Distribution, TorchDistributionMixin):
             return ops.ou_prior_logp(self.patristic, self.sigma_f[lo:hi], self.sigma_n[lo:hi], self.lambd[lo:hi],
                                      value[lo:hi])
         return ops.ou_prior_logp(self.patristic, self.sigma_f, self.sigma_n, self.lambd, value)
+
+    def log_prob_sum_async(self, value, scale=1.0):
+        """Summed log-density evaluated on the side stream (`ops.side_stream`): forked from the current stream here,
+        joined by whoever needs the number (`AsyncTerm.join`).  None when the side stream is switched off."""
+        from .. import ops
+        if not ops.PRIOR_STREAM_ENABLED or not value.is_cuda:
+            return None
+        side = ops.side_stream(value.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            lp = self.log_prob(value).sum()
+            if scale != 1.0:
+                lp = lp * scale
+        return AsyncTerm(lp, side)
 
     def rsample(self, sample_shape=torch.Size()):
         from .. import ops

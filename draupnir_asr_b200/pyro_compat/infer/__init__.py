@@ -25,13 +25,18 @@ class Trace_ELBO:
         if num_particles != 1:
             raise NotImplementedError("num_particles > 1 is not used by the reference path")
         self.num_particles = num_particles
+        # called after the guide and the model have run and before any site is scored (the observations are first read
+        # by the likelihood kernel there): lets a host-fed step keep copying the data set while the networks compute
+        self.pre_score_hook = None
 
     def _traces(self, model, guide, args, kwargs):
         guide_trace = poutine.trace(guide).get_trace(*args, **kwargs)
-        model_trace = poutine.trace(poutine.replay(model, trace=guide_trace)).get_trace(*args, **kwargs)
+        model_trace = poutine.trace(poutine.replay(model, trace=guide_trace), async_log_prob=True).get_trace(*args, **kwargs)
         for name, site in guide_trace.sample_sites():
             if not getattr(site["fn"], "has_rsample", False):
                 raise NotImplementedError(f"guide site {name!r} is not reparameterised")
+        if self.pre_score_hook is not None:
+            self.pre_score_hook()
         return model_trace, guide_trace
 
     def differentiable_loss(self, model, guide, *args, **kwargs):
@@ -44,9 +49,25 @@ class Trace_ELBO:
             return float(self.differentiable_loss(model, guide, *args, **kwargs))
 
     def loss_and_grads(self, model, guide, *args, **kwargs):
-        loss = self.differentiable_loss(model, guide, *args, **kwargs)
-        if isinstance(loss, torch.Tensor) and loss.requires_grad:
-            loss.backward()
+        model_trace, guide_trace = self._traces(model, guide, args, kwargs)
+        self.last_traces = (model_trace, guide_trace)
+        model_lp, pending = model_trace.split_log_prob()
+        loss = -(model_lp - guide_trace.log_prob_sum())
+        if not pending:
+            if isinstance(loss, torch.Tensor) and loss.requires_grad:
+                loss.backward()
+            return loss
+        # terms still running on a side stream are separate roots of ONE backward call: autograd runs every node on the
+        # stream of its forward op, so the recurrences' back-propagation (this stream) does not wait for the OU prior
+        terms = [site["log_prob_async"].value for site in pending]
+        roots = [loss] + terms
+        grads = [torch.ones_like(loss)] + [-torch.ones_like(loss)] * len(terms)
+        keep = [(r, g) for r, g in zip(roots, grads) if isinstance(r, torch.Tensor) and r.requires_grad]
+        if keep:
+            torch.autograd.backward([r for r, _ in keep], [g for _, g in keep])
+        for site in pending:
+            site["log_prob_sum"] = site["log_prob_async"].join()
+            loss = loss - site["log_prob_sum"].detach()
         return loss
 
     def __repr__(self):

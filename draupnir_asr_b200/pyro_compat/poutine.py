@@ -57,8 +57,12 @@ class Trace:
     def param_sites(self):
         return [(k, v) for k, v in self.nodes.items() if v["type"] == "param"]
 
-    def compute_log_prob(self):
+    def compute_log_prob(self, join_async: bool = True):
         for _, site in self.sample_sites():
+            if "log_prob_sum" not in site and "log_prob_async" in site:
+                if join_async:
+                    site["log_prob_sum"] = site["log_prob_async"].join()
+                continue
             if "log_prob_sum" not in site:
                 fused = getattr(site["fn"], "log_prob_sum", None) if site["mask"] is None else None
                 if fused is not None:
@@ -79,11 +83,25 @@ class Trace:
             total = total + site["log_prob_sum"]
         return total
 
+    def split_log_prob(self):
+        """(sum of the site terms evaluated on the current stream, [AsyncTerm, ...] still running on a side stream)."""
+        self.compute_log_prob(join_async=False)
+        total, pending = 0.0, []
+        for _, site in self.sample_sites():
+            if "log_prob_sum" in site:
+                total = total + site["log_prob_sum"]
+            else:
+                pending.append(site)
+        return total, pending
+
 
 class trace(Messenger):
-    def __init__(self, fn=None, param_only: bool = False):
+    def __init__(self, fn=None, param_only: bool = False, async_log_prob: bool = False):
         super().__init__(fn)
         self.param_only = param_only
+        # async_log_prob: sites whose distribution offers `log_prob_sum_async` start scoring on a side stream the
+        # moment the site is recorded (the OU prior overlaps with the decoder that way)
+        self.async_log_prob = async_log_prob
         self.trace = Trace()
 
     def __enter__(self):
@@ -94,7 +112,13 @@ class trace(Messenger):
         if self.param_only and msg["type"] != "param":
             return
         if msg["type"] in ("sample", "param"):
-            self.trace.add_node(msg["name"], dict(msg))
+            site = dict(msg)
+            self.trace.add_node(msg["name"], site)
+            if self.async_log_prob and msg["type"] == "sample" and msg["mask"] is None:
+                start = getattr(msg["fn"], "log_prob_sum_async", None)
+                term = start(msg["value"], msg["scale"]) if start is not None else None
+                if term is not None:
+                    site["log_prob_async"] = term
 
     def get_trace(self, *args, **kwargs) -> Trace:
         self(*args, **kwargs)

@@ -97,24 +97,32 @@ class Run(SimpleNamespace):
     def step_from_host(self, host) -> float:
         """H2D of the step inputs (pinned, asynchronous) -> svi.step -> loss back to the host as a float.
 
-        The copies run on a side stream in the order the step consumes them: the guide only needs the BLOSUM-encoded data
-        set, so the patristic matrix and the data set travel while the encoder computes; the model waits for them (a
-        stream-wait injected in front of `Draupnir.model`, no host synchronisation)."""
+        The copies run on a side stream in the order the step consumes them, and every consumer waits for its own input
+        only (stream-waits, no host synchronisation): the guide needs the BLOSUM-encoded data set; the model's prior the
+        patristic matrix; the data set itself is first read when the likelihood is scored, after both networks ran."""
         lo, hi = self._leaf_rows()
         main = torch.cuda.current_stream()
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._ev_guide, self._ev_model = torch.cuda.Event(), torch.cuda.Event()
-            self._pending = None
+            self._ev_guide, self._ev_model, self._ev_score = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            self._pending = []
             real_model = self.svi.model
 
+            def wait_for(upto):
+                while self._pending and self._pending[0][0] <= upto:
+                    torch.cuda.current_stream().wait_event(self._pending.pop(0)[1])
+
             def model_after_inputs(*a, **k):
-                if self._pending is not None:
-                    torch.cuda.current_stream().wait_event(self._pending)
-                    self._pending = None
+                wait_for(1)
                 return real_model(*a, **k)
 
+            self._wait_for = wait_for
             self.svi.model = model_after_inputs
+            if hasattr(self.svi.loss, "pre_score_hook"):
+                self.svi.loss.pre_score_hook = lambda: wait_for(2)
+                self._score_level = 2
+            else:                                   # an ELBO without the hook (real Pyro): the model waits for everything
+                self._score_level = 1
         cs = self._copy_stream
         cs.wait_stream(main)                       # the previous step has finished reading the staging buffers
         with torch.cuda.stream(cs):
@@ -122,15 +130,14 @@ class Run(SimpleNamespace):
                 self._staging["blosum"][lo:hi].copy_(host["blosum"][lo:hi], non_blocking=True)
             self._ev_guide.record(cs)
             self._staging["patristic"].copy_(host["patristic"], non_blocking=True)
-            self._staging["dataset"][lo:hi].copy_(host["dataset"][lo:hi], non_blocking=True)
             self._ev_model.record(cs)
+            self._staging["dataset"][lo:hi].copy_(host["dataset"][lo:hi], non_blocking=True)
+            self._ev_score.record(cs)
         main.wait_event(self._ev_guide)
-        self._pending = self._ev_model
+        self._pending = [(1, self._ev_model), (self._score_level, self._ev_score)]
         st = self._staging
         loss = self.svi.step(st["dataset"], st["patristic"], None, st.get("blosum"), None, None)
-        if self._pending is not None:              # a guide-less path never entered the wrapped model: do not leak the wait
-            main.wait_event(self._pending)
-            self._pending = None
+        self._wait_for(2)                          # nothing may be left waiting when the step returns
         return loss
 
 

@@ -33,8 +33,10 @@ int drp_abi_version(void);
 int64_t drp_launch_count(void);
 /* CUDA-event timing of every launch, by kernel class: 0 syrk (fp64 mma.sync), 1 trsm, 2 potf2 (work = flops),
  * 3 assembly, 4 reductions, 5 categorical, 6 patristic (work = bytes), 7 other, 8 syrk on the int8 tcgen05 pipe
- * (work = fp64-equivalent flops), 9 int8 slicing (work = bytes), 10 GRU recurrence (work = flops).  enable(1) clears earlier records; read()
- * synchronises the device and fills three arrays of drp_timing_classes() entries (HOST pointers).                  */
+ * (work = fp64-equivalent flops), 9 int8 slicing (work = bytes), 10 GRU recurrence (work = flops).  enable(on >= 1) clears
+ * earlier records (on > 1 additionally pre-creates the events for `on` launches, keeping event creation out of the
+ * caller's timed region); read() synchronises the device and fills three arrays of drp_timing_classes() entries (HOST
+ * pointers).                                                                                                        */
 int drp_timing_classes(void);
 int drp_timing_enable(int on);
 int drp_timing_read(double* ms, int64_t* launches, double* work);

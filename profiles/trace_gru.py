@@ -45,7 +45,28 @@ assert lib.drp_gru_trace_read(buf) == 0
 t = np.frombuffer(buf, dtype=np.int64).reshape(2, 64, 8)
 print(f"# gru_fwd n={n} L={L}: {a.elapsed_time(b):.3f} ms = {a.elapsed_time(b) * 1e6 / L:.0f} ns/step; rows/CTA = {os.environ.get('DRP_GRU_ROWS', 'auto')}")
 print("# cycles per phase (mean over steps 200..263): issue | product | (to wait) | wait gi | gates+stores | barrier | step total")
-for w, name in ((0, "warp 0"), (1, "warp 7")):
+for w, name in ((0, "warp 0"), (1, "warp 8/7")):
     d = np.diff(t[w, :, :6], axis=1).astype(np.float64)            # [64, 5]
     step = np.diff(t[w, :, 0]).astype(np.float64)
     print(name, " ".join(f"{v:8.0f}" for v in d.mean(0)), f"| step {step.mean():8.0f} (min {step.min():.0f} max {step.max():.0f})")
+print("# start of step 230: second traced warp minus warp 0 =", int(t[1, 30, 0] - t[0, 30, 0]), "cycles")
+# ---- backward kernel (both directions), same buffer
+dout = torch.randn(n, L, 2 * H, dtype=torch.float64, device=dev, generator=g)
+dgi = torch.empty(n, L, 2, 3 * H, dtype=torch.float64, device=dev)
+dh0 = torch.empty(2, n, H, dtype=torch.float64, device=dev)
+st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+for _ in range(2):
+    rc = lib.drp_gru_bwd_f64(P(dout), P(outb), P(gates), P(whh), P(h0), n, L, H, P(dgi), P(dh0), st)
+    assert rc == 0, rc
+a.record()
+lib.drp_gru_bwd_f64(P(dout), P(outb), P(gates), P(whh), P(h0), n, L, H, P(dgi), P(dh0), st)
+b.record()
+torch.cuda.synchronize()
+assert lib.drp_gru_trace_read(buf) == 0
+t = np.frombuffer(buf, dtype=np.int64).reshape(2, 64, 8)
+print(f"# gru_bwd n={n} L={L}: {a.elapsed_time(b):.3f} ms = {a.elapsed_time(b) * 1e6 / L:.0f} ns/step")
+print("# cycles per phase: issue | dout loads issued | wait ring | gates+stores | barrier 1 | product | barrier 2 | step total")
+for w, name in ((0, "warp 0"), (1, "warp 7")):
+    d = np.diff(t[w, :, :8], axis=1).astype(np.float64)
+    step = np.diff(t[w, :, 0]).astype(np.float64)
+    print(name, " ".join(f"{v:8.0f}" for v in d.mean(0)), f"| step {step.mean():8.0f}")
