@@ -44,6 +44,9 @@ SIGNATURES = {
     "drp_gru_fwd_uv_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "drp_gru_bwd_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "drp_gru_bwd_dir0_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "drp_gru_bwd_last_dir0_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "drp_gru_input_sums_blocks": (_i32, [_i32]),
+    "drp_gru_input_sums_f64": (_i32, [_p, _i32, _i32, _i32, _p, _p, _p]),
     "drp_gru_wgrad_dir0_f64": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),
     "drp_gru_wgrad_workspace_elems": (_i64, []),
     "drp_gru_wgrad_f64": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),

@@ -151,9 +151,15 @@ extern "C" __attribute__((visibility("default"))) int drp_gru_trace_read(long lo
         if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 7) && tb >= 200 && tb < 264) \
             g_gru_trace[((warp ? 1 : 0) * 64 + (tb - 200)) * 8 + (slot)] = clock64();                    \
     } while (0)
+#define GRU_TRACE_W(slot)                                                                                 \
+    do {                                                                                                  \
+        if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7) && it >= 200 && it < 264)            \
+            g_gru_trace[((warp ? 1 : 0) * 64 + (it - 200)) * 8 + (slot)] = clock64();                    \
+    } while (0)
 #else
 #define GRU_TRACE(slot) do { } while (0)
 #define GRU_TRACE_B(slot) do { } while (0)
+#define GRU_TRACE_W(slot) do { } while (0)
 #endif
 constexpr int GF_STAGES = 3;
 __host__ __device__ constexpr int gf_smem(int rows, bool uv)        // h double buffer + gi ring + barriers (+ the CTA's U rows)
@@ -556,8 +562,10 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
                                                               const double* __restrict__ gates, const double* __restrict__ whh,
                                                               const double* __restrict__ h0, int n, int L,
                                                               double* __restrict__ dgi, double* __restrict__ dh0,
-                                                              int dgi_dirs)
+                                                              int dgi_dirs, int dout_last)
 {
+    // dout_last != 0: `dout` is [n, 120] and holds the gradient of the hidden state at the LAST position only (every
+    // other position's gradient is zero): the encoder's case, which spares a zero-filled [n, L, 120] tensor
     constexpr int GROWS = 8 * MT;
     constexpr int GB_STAGE_BYTES = GROWS * GB_ROW_STRIDE * 8;
     extern __shared__ __align__(16) uint8_t gsm[];
@@ -615,8 +623,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             const int r = 8 * mt + gid;
-            dOn[mt] = (jok && r < nrows) ? *reinterpret_cast<const double2*>(dout + ((int64_t)(row0 + r) * L + l0) * (2 * GH) + dir * GH + j0)
-                                         : make_double2(0.0, 0.0);
+            const double* src = dout_last ? dout + (int64_t)(row0 + r) * (2 * GH) + dir * GH + j0
+                                          : dout + ((int64_t)(row0 + r) * L + l0) * (2 * GH) + dir * GH + j0;
+            dOn[mt] = (jok && r < nrows && !(dout_last && l0 != L - 1)) ? *reinterpret_cast<const double2*>(src) : make_double2(0.0, 0.0);
         }
     }
 
@@ -636,8 +645,14 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int r = 8 * mt + gid;
-                dOn[mt] = (jok && r < nrows) ? *reinterpret_cast<const double2*>(dout + ((int64_t)(row0 + r) * L + ln) * (2 * GH) + dir * GH + j0)
-                                             : make_double2(0.0, 0.0);
+                if (dout_last) {
+                    const bool hit = jok && r < nrows && ln == L - 1;
+                    dOn[mt] = hit ? *reinterpret_cast<const double2*>(dout + (int64_t)(row0 + r) * (2 * GH) + dir * GH + j0)
+                                  : make_double2(0.0, 0.0);
+                } else {
+                    dOn[mt] = (jok && r < nrows) ? *reinterpret_cast<const double2*>(dout + ((int64_t)(row0 + r) * L + ln) * (2 * GH) + dir * GH + j0)
+                                                 : make_double2(0.0, 0.0);
+                }
             }
         }
         const int s = tb % GB_STAGES;
@@ -725,14 +740,24 @@ constexpr int GW_STAGES = 2;
 constexpr int GW_SMEM = GW_STAGES * GW_STAGE_BYTES + 64;
 constexpr int GW_MT = 23;                                      // 184 = 23 m-tiles cover the 180 gate columns
 
-__global__ void __launch_bounds__(GTHREADS, 1) gru_wgrad_kernel(const double* __restrict__ dgi, const double* __restrict__ gates,
-                                                                const double* __restrict__ out, const double* __restrict__ h0,
-                                                                int n, int L, double* __restrict__ part, int ndir,
-                                                                int dgi_dirs)
+constexpr int GW_THREADS = GTHREADS + 64;      // 8 consumer warps (one 8-column group of [h_prev | 1] each) + 2 producer warps
+__device__ __forceinline__ void g_mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Warps 8 and 9 only issue the bulk copies (96 per 32-pair stage, ~60 cycles of issue each: on the consumer warps they
+// cost 1.4 k of the 8.9 k cycles of a stage, profiles/r01/trace_gru_v6.txt); the consumers never leave the DMMA loop:
+// full[s] (transaction barrier) says the stage has landed, empty[s] (one arrival per consumer warp) that it may be refilled.
+__global__ void __launch_bounds__(GW_THREADS, 1) gru_wgrad_kernel(const double* __restrict__ dgi, const double* __restrict__ gates,
+                                                                  const double* __restrict__ out, const double* __restrict__ h0,
+                                                                  int n, int L, double* __restrict__ part, int ndir,
+                                                                  int dgi_dirs)
 {
     extern __shared__ __align__(16) uint8_t gsm[];
     double* ring = reinterpret_cast<double*>(gsm);
-    const uint32_t bars = g_smem_u32(gsm + GW_STAGES * GW_STAGE_BYTES);
+    const uint32_t full = g_smem_u32(gsm + GW_STAGES * GW_STAGE_BYTES);
+    const uint32_t empty = full + 8 * GW_STAGES;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
     const int dir = ndir == 2 ? (blockIdx.x & 1) : 0;
     const int chunk = ndir == 2 ? (blockIdx.x >> 1) : blockIdx.x, nchunks = ndir == 2 ? (gridDim.x >> 1) : gridDim.x;
@@ -740,48 +765,65 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_wgrad_kernel(const double* __
     const int64_t nblk = (P + GW_PAIRS - 1) / GW_PAIRS;
     const int64_t b0 = nblk * chunk / nchunks, b1 = nblk * (chunk + 1) / nchunks;
     if (tid == 0) {
-        for (int s = 0; s < GW_STAGES; ++s) g_mbar_init(bars + 8 * s, 1);
+        for (int s = 0; s < GW_STAGES; ++s) {
+            g_mbar_init(full + 8 * s, 1);
+            g_mbar_init(empty + 8 * s, 8);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int64_t blk) {      // every warp: 4 pairs, one copy per lane (96 issues on one warp stalled it ~5.7 k cycles)
-        const int s = (int)((blk - b0) % GW_STAGES);
-        const int valid = (int)min((int64_t)GW_PAIRS, P - blk * GW_PAIRS);
-        if (warp == 0 && lane == 0) g_mbar_expect_tx(bars + 8 * s, (uint32_t)valid * GW_ROW * 8);
-        const int pr = warp * (GW_PAIRS / 8) + lane / 3, which = lane % 3;      // 4 pairs per warp, 3 copies per pair
-        if (lane < 3 * (GW_PAIRS / 8) && pr < valid) {
-            const int64_t p = blk * GW_PAIRS + pr;
-            double* dst = ring + (int64_t)s * GW_PAIRS * GW_ROW + pr * GW_ROW;
-            if (which == 0) {
-                g_bulk_g2s(g_smem_u32(dst), dgi + (p * dgi_dirs + (dgi_dirs == 2 ? dir : 0)) * G3, G3 * 8, bars + 8 * s);
-            } else if (which == 1) {
-                g_bulk_g2s(g_smem_u32(dst + G3), gates + (p * 2 + dir) * (4 * GH), GH * 8, bars + 8 * s);
-            } else {
-                const int64_t i = p / L;
-                const int l = (int)(p - i * L);
-                const bool first = dir ? (l == L - 1) : (l == 0);      // first step of the direction: h_prev = h0
-                const double* hp = first ? h0 + ((int64_t)dir * n + i) * GH : out + (dir ? p + 1 : p - 1) * (2 * GH) + dir * GH;
-                g_bulk_g2s(g_smem_u32(dst + G3 + GH), hp, GH * 8, bars + 8 * s);
+    if (warp >= 8) {
+        // ---------------- producers: 48 of the 96 copies of a stage each
+        const int pw = warp - 8;
+        for (int64_t blk = b0; blk < b1; ++blk) {
+            const int it = (int)(blk - b0);
+            const int s = it % GW_STAGES;
+            if (it >= GW_STAGES) g_mbar_wait(empty + 8 * s, (uint32_t)(it / GW_STAGES - 1) & 1u);
+            const int valid = (int)min((int64_t)GW_PAIRS, P - blk * GW_PAIRS);
+            // the first producer's arrival carries the byte count, so the phase cannot complete before it
+            if (pw == 0 && lane == 0) g_mbar_expect_tx(full + 8 * s, (uint32_t)valid * GW_ROW * 8);
+#pragma unroll
+            for (int rep = 0; rep < 2; ++rep) {
+                const int task = pw * 48 + rep * 32 + lane;              // 0..95 = pair * 3 + which
+                if (rep == 1 && lane >= 16) break;
+                const int pr = task / 3, which = task - 3 * pr;
+                if (pr >= valid) continue;
+                const int64_t p = blk * GW_PAIRS + pr;
+                double* dst = ring + (int64_t)s * GW_PAIRS * GW_ROW + pr * GW_ROW;
+                if (which == 0) {
+                    g_bulk_g2s(g_smem_u32(dst), dgi + (p * dgi_dirs + (dgi_dirs == 2 ? dir : 0)) * G3, G3 * 8, full + 8 * s);
+                } else if (which == 1) {
+                    g_bulk_g2s(g_smem_u32(dst + G3), gates + (p * 2 + dir) * (4 * GH), GH * 8, full + 8 * s);
+                } else {
+                    const int64_t i = p / L;
+                    const int l = (int)(p - i * L);
+                    const bool first = dir ? (l == L - 1) : (l == 0);  // first step of the direction: h_prev = h0
+                    const double* hp = first ? h0 + ((int64_t)dir * n + i) * GH : out + (dir ? p + 1 : p - 1) * (2 * GH) + dir * GH;
+                    g_bulk_g2s(g_smem_u32(dst + G3 + GH), hp, GH * 8, full + 8 * s);
+                }
             }
         }
-    };
+        return;
+    }
+    // ---------------- consumers
     double acc[GW_MT][2];
 #pragma unroll
     for (int mt = 0; mt < GW_MT; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
-    if (b0 < b1) issue(b0);
     const int jb = warp * 8 + gid;                 // column of h_prev (60: ones -> bias gradient; 61..63: zero)
     for (int64_t blk = b0; blk < b1; ++blk) {
         const int it = (int)(blk - b0);
         const int s = it % GW_STAGES;
-        if (blk + 1 < b1) issue(blk + 1);
-        g_mbar_wait(bars + 8 * s, (uint32_t)(it / GW_STAGES) & 1u);
+        GRU_TRACE_W(0);
+        g_mbar_wait(full + 8 * s, (uint32_t)(it / GW_STAGES) & 1u);
+        GRU_TRACE_W(1);
         double* st = ring + (int64_t)s * GW_PAIRS * GW_ROW;
         const int valid = (int)min((int64_t)GW_PAIRS, P - blk * GW_PAIRS);
         if (valid < GW_PAIRS) {                    // ragged last block: rows that were not loaded must not contribute
             for (int idx = tid; idx < (GW_PAIRS - valid) * GW_ROW; idx += GTHREADS) st[valid * GW_ROW + idx] = 0.0;
-            __syncthreads();
+            g_named_barrier(1, GTHREADS);
         }
+        GRU_TRACE_W(2);
 #pragma unroll 2
         for (int ks = 0; ks < GW_PAIRS / 4; ++ks) {
             const double* row = st + (4 * ks + tig) * GW_ROW;
@@ -794,7 +836,10 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_wgrad_kernel(const double* __
                 dmma_8x8x4(acc[mt][0], acc[mt][1], a, b);
             }
         }
-        __syncthreads();                           // stage s drained before it is refilled
+        GRU_TRACE_W(3);
+        __syncwarp();
+        if (lane == 0) g_mbar_arrive(empty + 8 * s);   // this warp is done with stage s
+        GRU_TRACE_W(4);
     }
     double* dst = part + ((int64_t)chunk * 2 + dir) * (GW_MT * 8) * 64;
 #pragma unroll
@@ -893,7 +938,7 @@ static void gru_fwd_launch(const double* gi, const double* v, const double* whh,
 
 template <int MT>
 static void gru_bwd_launch(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
-                           int n, int L, double* dgi, double* dh0, int ndir, int dgi_dirs, cudaStream_t st)
+                           int n, int L, double* dgi, double* dh0, int ndir, int dgi_dirs, cudaStream_t st, int dout_last = 0)
 {
     constexpr int smem = gb_smem(8 * MT);
     static bool attr_done = false;
@@ -903,7 +948,7 @@ static void gru_bwd_launch(const double* dout, const double* out, const double* 
     }
     DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * ndir * G3 * GH, st);
     gru_bwd_kernel<MT><<<dim3((n + 8 * MT - 1) / (8 * MT), ndir), GTHREADS, smem, st>>>(dout, out, gates, whh, h0, n, L, dgi, dh0,
-                                                                                    dgi_dirs);
+                                                                                    dgi_dirs, dout_last);
 }
 
 DRP_API int drp_gru_fwd_f64(const double* gi, const double* whh, const double* bhh, const double* h0, int n, int L, int H,
@@ -958,7 +1003,7 @@ DRP_API int drp_gru_fwd_uv_f64(const double* U, const double* V, const double* w
 }
 
 static int gru_bwd_dispatch(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
-                            int n, int L, int H, double* dgi, double* dh0, int ndir, int dgi_dirs, void* stream)
+                            int n, int L, int H, double* dgi, double* dh0, int ndir, int dgi_dirs, void* stream, int dout_last = 0)
 {
     if (!dout || !out || !gates || !whh || !h0) return -1;
     if (n <= 0 || L <= 0) return -6;
@@ -966,9 +1011,9 @@ static int gru_bwd_dispatch(const double* dout, const double* out, const double*
     if (!dgi) return -9;
     cudaStream_t st = (cudaStream_t)stream;
     switch (gru_pick_mt(n, ndir)) {
-        case 1: gru_bwd_launch<1>(dout, out, gates, whh, h0, n, L, dgi, dh0, ndir, dgi_dirs, st); break;
-        case 2: gru_bwd_launch<2>(dout, out, gates, whh, h0, n, L, dgi, dh0, ndir, dgi_dirs, st); break;
-        default: gru_bwd_launch<4>(dout, out, gates, whh, h0, n, L, dgi, dh0, ndir, dgi_dirs, st); break;
+        case 1: gru_bwd_launch<1>(dout, out, gates, whh, h0, n, L, dgi, dh0, ndir, dgi_dirs, st, dout_last); break;
+        case 2: gru_bwd_launch<2>(dout, out, gates, whh, h0, n, L, dgi, dh0, ndir, dgi_dirs, st, dout_last); break;
+        default: gru_bwd_launch<4>(dout, out, gates, whh, h0, n, L, dgi, dh0, ndir, dgi_dirs, st, dout_last); break;
     }
     return drp_launch_status();
 }
@@ -986,6 +1031,76 @@ DRP_API int drp_gru_bwd_dir0_f64(const double* dout, const double* out, const do
                                  const double* h0, int n, int L, int H, double* dgi0, double* dh0, void* stream)
 {
     return gru_bwd_dispatch(dout, out, gates, whh, h0, n, L, H, dgi0, dh0, 1, 1, stream);
+}
+
+// Same with the gradient given at the last position only: dlast [n, 2H] (its direction-0 half is read); the gradient of
+// every other hidden state is zero.
+DRP_API int drp_gru_bwd_last_dir0_f64(const double* dlast, const double* out, const double* gates, const double* whh,
+                                      const double* h0, int n, int L, int H, double* dgi0, double* dh0, void* stream)
+{
+    return gru_bwd_dispatch(dlast, out, gates, whh, h0, n, L, H, dgi0, dh0, 1, 1, stream, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sums of dgi [n, L, C] over the positions (-> dU [n, C]) and, per block of rows, over the rows (-> dVpart [nblk, L, C]):
+// the gradients of the decoder's broadcast input terms U[i] + V[l], in ONE pass over dgi (two torch reductions read the
+// 2.9 GB tensor twice).  C even, C / 2 <= 256 threads; the caller adds the nblk partial dV blocks.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GS_ROWS = 16;                                      // rows per CTA at most
+__global__ void __launch_bounds__(256) gru_input_sums_kernel(const double* __restrict__ dgi, int n, int L, int C, int rows_per_blk,
+                                                             double* __restrict__ dU, double* __restrict__ dVpart)
+{
+    const int c2 = threadIdx.x;
+    if (2 * c2 >= C) return;
+    const int r0 = blockIdx.x * rows_per_blk;
+    const int nr = min(rows_per_blk, n - r0);
+    double2 du[GS_ROWS];
+#pragma unroll
+    for (int r = 0; r < GS_ROWS; ++r) du[r] = make_double2(0.0, 0.0);
+    const double2* base = reinterpret_cast<const double2*>(dgi) + (int64_t)r0 * L * (C / 2) + c2;
+    double2* dv = reinterpret_cast<double2*>(dVpart) + (int64_t)blockIdx.x * L * (C / 2) + c2;
+    for (int l = 0; l < L; ++l) {
+        double2 v[GS_ROWS];
+#pragma unroll
+        for (int r = 0; r < GS_ROWS; ++r)
+            v[r] = r < nr ? __ldcs(base + ((int64_t)r * L + l) * (C / 2)) : make_double2(0.0, 0.0);
+        double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int r = 0; r < GS_ROWS; ++r) {
+            du[r].x += v[r].x, du[r].y += v[r].y;
+            s.x += v[r].x, s.y += v[r].y;
+        }
+        dv[(int64_t)l * (C / 2)] = s;
+    }
+#pragma unroll
+    for (int r = 0; r < GS_ROWS; ++r)
+        if (r < nr) reinterpret_cast<double2*>(dU)[(int64_t)(r0 + r) * (C / 2) + c2] = du[r];
+}
+
+// Number of row blocks (= leading dimension of dVpart) drp_gru_input_sums_f64 uses for n rows.
+DRP_API int drp_gru_input_sums_blocks(int n)
+{
+    if (n <= 0) return 0;
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    int rows = (n + n_sm - 1) / n_sm;
+    if (rows > GS_ROWS) rows = GS_ROWS;
+    return (n + rows - 1) / rows;
+}
+
+DRP_API int drp_gru_input_sums_f64(const double* dgi, int n, int L, int C, double* dU, double* dVpart, void* stream)
+{
+    if (!dgi) return -1;
+    if (n <= 0 || L <= 0) return -2;
+    if (C <= 0 || (C & 1) || C / 2 > 256) return -4;
+    if (!dU || !dVpart) return -5;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = drp_gru_input_sums_blocks(n);
+    const int rows = (n + nblk - 1) / nblk;
+    DRP_LAUNCH(DRP_K_REDUCE, (double)n * L * C * 8.0 + (double)nblk * L * C * 8.0, st);
+    gru_input_sums_kernel<<<nblk, 256, 0, st>>>(dgi, n, L, C, rows, dU, dVpart);
+    return drp_launch_status();
 }
 
 // Workspace (doubles) of drp_gru_wgrad_f64.
@@ -1021,7 +1136,7 @@ static int gru_wgrad_dispatch(const double* dgi, const double* gates, const doub
     if (!ws || ws_elems < (int64_t)nchunks * 2 * (GW_MT * 8) * 64) return -10;
     {
         DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * ndir * G3 * (GH + 1), st);
-        gru_wgrad_kernel<<<ndir * nchunks, GTHREADS, GW_SMEM, st>>>(dgi, gates, out, h0, n, L, ws, ndir, ndir);
+        gru_wgrad_kernel<<<ndir * nchunks, GW_THREADS, GW_SMEM, st>>>(dgi, gates, out, h0, n, L, ws, ndir, ndir);
     }
     {
         DRP_LAUNCH(DRP_K_REDUCE, (double)nchunks * ndir * G3 * (GH + 1) * 8.0, st);

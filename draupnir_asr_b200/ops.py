@@ -417,8 +417,17 @@ class _GRUBidirUV(torch.autograd.Function):
     def backward(ctx, dout):
         dgi, dwhh, dbhh, dh0 = _gru_backward_common(ctx.saved_tensors, dout, ctx.needs_input_grad[2] or ctx.needs_input_grad[3],
                                                     ctx.needs_input_grad[4])
-        dU = dgi.sum(1).reshape(ctx.shapes[0]) if ctx.needs_input_grad[0] else None
-        dV = dgi.sum(0).reshape(ctx.shapes[1]) if ctx.needs_input_grad[1] else None
+        dU = dV = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            # both sums in one pass over dgi (2.9 GB at 2,000 leaves x 500 sites)
+            n, L = dgi.shape[0], dgi.shape[1]
+            C = dgi.numel() // (n * L)
+            nblk = lib.drp_gru_input_sums_blocks(n)
+            dU = torch.empty((n, C), dtype=torch.float64, device=dgi.device)
+            dVp = torch.empty((nblk, L, C), dtype=torch.float64, device=dgi.device)
+            _rc(lib.drp_gru_input_sums_f64(_p(dgi), n, L, C, _p(dU), _p(dVp), _stream()), "drp_gru_input_sums_f64")
+            dU = dU.reshape(ctx.shapes[0])
+            dV = dVp.sum(0).reshape(ctx.shapes[1])
         return dU, dV, dwhh, dbhh, dh0
 
 
@@ -510,13 +519,10 @@ class _GRUEncoderLast(torch.autograd.Function):
         dev = x.device
         dlast = dlast.contiguous()
         # ---- forward direction: full BPTT, gradient enters at the last position only
-        dout = torch.zeros((n, L, 2 * H), dtype=torch.float64, device=dev)
-        dout[:, -1, :H] = dlast[:, :H]
         dgi0 = torch.empty((n, L, 3 * H), dtype=torch.float64, device=dev)
         dh0 = torch.empty_like(h0)
-        _rc(lib.drp_gru_bwd_dir0_f64(_p(dout), _p(out), _p(gates), _p(whh), _p(h0), n, L, H, _p(dgi0), _p(dh0), _stream()),
-            "drp_gru_bwd_dir0_f64")
-        del dout
+        _rc(lib.drp_gru_bwd_last_dir0_f64(_p(dlast), _p(out), _p(gates), _p(whh), _p(h0), n, L, H, _p(dgi0), _p(dh0), _stream()),
+            "drp_gru_bwd_last_dir0_f64")
         dwhh = torch.empty_like(whh)
         dbhh = torch.empty((2, 3 * H), dtype=torch.float64, device=dev)
         wse = lib.drp_gru_wgrad_workspace_elems()

@@ -118,6 +118,15 @@ int drp_gru_bwd_f64(const double* dout, const double* out, const double* gates, 
  * state at the last position (RNNEncoder.forward, S/models_utils.py:57): the reverse direction is then one cell step.  */
 int drp_gru_bwd_dir0_f64(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
                          int n, int L, int H, double* dgi0, double* dh0, void* stream);
+/* Same when the gradient enters at the last position only: dlast [n,2H] (direction-0 half read); spares the caller a
+ * zero-filled [n,L,2H] tensor (RNNEncoder.forward, S/models_utils.py:57).                                             */
+int drp_gru_bwd_last_dir0_f64(const double* dlast, const double* out, const double* gates, const double* whh,
+                              const double* h0, int n, int L, int H, double* dgi0, double* dh0, void* stream);
+/* Gradients of the decoder's broadcast input terms gi[i][l] = U[i] + V[l] (drp_gru_fwd_uv_f64) in one pass over
+ * dgi [n,L,C]: dU [n,C] = sum over l; dVpart [drp_gru_input_sums_blocks(n), L, C] = per-row-block sums over i, which the
+ * caller adds up.  C even, C <= 512.                                                                                  */
+int drp_gru_input_sums_blocks(int n);
+int drp_gru_input_sums_f64(const double* dgi, int n, int L, int C, double* dU, double* dVpart, void* stream);
 int drp_gru_wgrad_dir0_f64(const double* dgi0, const double* gates, const double* out, const double* h0, int n, int L, int H,
                            double* dwhh, double* dbhh, double* ws, int64_t ws_elems, void* stream);
 /* dwhh [2,3H,H] = sum_p dgh[p]^T h_prev[p], dbhh [2,3H] = sum_p dgh[p] (autograd of nn.GRU's weight_hh / bias_hh);

@@ -70,3 +70,24 @@ for w, name in ((0, "warp 0"), (1, "warp 7")):
     d = np.diff(t[w, :, :8], axis=1).astype(np.float64)
     step = np.diff(t[w, :, 0]).astype(np.float64)
     print(name, " ".join(f"{v:8.0f}" for v in d.mean(0)), f"| step {step.mean():8.0f}")
+# ---- weight-gradient kernel (both directions)
+dwhh = torch.empty_like(whh)
+dbhh = torch.empty(2, 3 * H, dtype=torch.float64, device=dev)
+lib.drp_gru_wgrad_workspace_elems.restype = ctypes.c_int64
+wse = lib.drp_gru_wgrad_workspace_elems()
+ws = torch.empty(wse, dtype=torch.float64, device=dev)
+for _ in range(2):
+    rc = lib.drp_gru_wgrad_f64(P(dgi), P(gates), P(outb), P(h0), n, L, H, P(dwhh), P(dbhh), P(ws), ctypes.c_int64(wse), st)
+    assert rc == 0, rc
+a.record()
+lib.drp_gru_wgrad_f64(P(dgi), P(gates), P(outb), P(h0), n, L, H, P(dwhh), P(dbhh), P(ws), ctypes.c_int64(wse), st)
+b.record()
+torch.cuda.synchronize()
+assert lib.drp_gru_trace_read(buf) == 0
+t = np.frombuffer(buf, dtype=np.int64).reshape(2, 64, 8)
+print(f"# gru_wgrad n={n} L={L}: {a.elapsed_time(b):.3f} ms")
+print("# cycles per 32-pair stage: issue | wait ring | product | barrier | stage total")
+for w, name in ((0, "warp 0"), (1, "warp 7")):
+    d = np.diff(t[w, :, :5], axis=1).astype(np.float64)
+    step = np.diff(t[w, :, 0]).astype(np.float64)
+    print(name, " ".join(f"{v:8.0f}" for v in d.mean(0)), f"| stage {step.mean():8.0f}")

@@ -137,3 +137,20 @@ def test_gram_tn(cuda, K, M, N):
     C_ref, cs_ref = A.t() @ B, A.sum(0)
     assert float((C.cpu() - C_ref).abs().max() / C_ref.abs().max().clamp_min(1e-30)) < 1e-12
     assert float((cs.cpu() - cs_ref).abs().max() / cs_ref.abs().max().clamp_min(1e-30)) < 1e-12
+
+
+@pytest.mark.parametrize("n,L,C", [(1, 1, 360), (37, 5, 360), (300, 17, 360), (2500, 3, 24)])
+def test_input_sums_one_pass(cuda, n, L, C):
+    """drp_gru_input_sums_f64: dU = dgi.sum(1), dV = sum of the row-block partials = dgi.sum(0)."""
+    from draupnir_asr_b200.ops import _p, _rc, _stream
+    from draupnir_asr_b200._lib import lib
+    g = torch.Generator().manual_seed(n + L)
+    dgi = torch.randn(n, L, C, generator=g, dtype=torch.float64)
+    d = dgi.to(cuda)
+    nblk = lib.drp_gru_input_sums_blocks(n)
+    assert 1 <= nblk <= n
+    dU = torch.empty(n, C, dtype=torch.float64, device=cuda)
+    dVp = torch.full((nblk, L, C), float("nan"), dtype=torch.float64, device=cuda)
+    _rc(lib.drp_gru_input_sums_f64(_p(d), n, L, C, _p(dU), _p(dVp), _stream()), "drp_gru_input_sums_f64")
+    assert torch.allclose(dU.cpu(), dgi.sum(1), rtol=1e-13, atol=1e-12)
+    assert torch.allclose(dVp.sum(0).cpu(), dgi.sum(0), rtol=1e-13, atol=1e-12)
