@@ -52,6 +52,7 @@ SIGNATURES = {
     "drp_gru_wgrad_f64": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),
     "drp_gram_workspace_elems": (_i64, [_i32, _i32]),
     "drp_gram_tn_f64": (_i32, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _i64, _p]),
+    "drp_tall_gemm_f64": (_i32, [_p, _p, _p, _i64, _i32, _i32, _p, _p]),
     "drp_cat_loglik_partials": (_i64, [_i64]),
     "drp_cat_loglik_fwd_f64": (_i32, [_p, _p, _i32, _i64, _i32, _p, _p, _p, _p]),
     "drp_cat_loglik_bwd_f64": (_i32, [_p, _p, _i32, _p, _p, _i64, _i32, _p, _p]),

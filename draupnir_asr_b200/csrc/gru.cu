@@ -1244,6 +1244,140 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tn_kernel(const double* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tall-skinny dense layer  Y [M, N] = X [M, K] W^T + bias  for M in the millions and K, N <= 192: the input projection of
+// the encoder GRU (K 21 -> N 180), the collapsed fc2.fc1 maps, the decoder head (120 -> 21) and their input gradients
+// (dY W).  cuBLAS runs these fp64 shapes at 10-25 % of what the memory traffic allows (cutlass_80 d884 tiles sized for
+// square problems).  Here W^T stays in shared memory and every WARP is its own pipeline: it owns a contiguous range of
+// 8-row tiles of X, streams them through a private TMA-bulk ring (the 8 rows of a tile are contiguous: one copy, issued
+// by the warp's lane 0), turns a tile into all N outputs with fp64 mma.sync (accumulators start from the bias) and
+// stores them; no CTA-wide barrier in the loop, so one warp's stores overlap the others' arithmetic.  HBM-bound by
+// construction: X read once, Y written once.
+//   Wt [K, N] row-major (= W^T), bias [N] nullable.  NT = number of 8-column output tiles (3, 15 or 23).
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int tg_ns(int nt) { return nt * 8 + 4; }             // W^T row stride: == 12 (mod 16), conflict-free
+__host__ __device__ constexpr int tg_wbytes(int K, int nt) { return ((K + 3) / 4 * 4) * tg_ns(nt) * 8; }
+__host__ __device__ constexpr int tg_obytes(int nt, int mtw) { return 8 * 8 * mtw * (nt * 8) * 8; }   // 8 warps x one output tile
+__host__ __device__ constexpr int tg_stages(int K, int nt, int mtw)   // ring stages per warp that fit next to W^T and the output tiles
+{
+    const int room = (227 * 1024 - 1024 - tg_wbytes(K, nt) - tg_obytes(nt, mtw)) / (8 * 8 * mtw * K * 8);
+    return room > 4 ? 4 : room;
+}
+__host__ __device__ constexpr int tg_smem(int K, int nt, int mtw)
+{
+    return tg_wbytes(K, nt) + tg_obytes(nt, mtw) + tg_stages(K, nt, mtw) * 8 * 8 * mtw * K * 8 + 1024;
+}
+
+// MTW = 8-row tiles per warp iteration: the B fragments (W^T from shared memory, one 8-byte load per DMMA) are shared by
+// the MTW row tiles, which halves the shared-memory traffic that otherwise rivals the DMMA time (138 loads per 138 DMMAs).
+template <int NT, int MTW>
+__global__ void __launch_bounds__(GTHREADS, 1) tall_gemm_kernel(const double* __restrict__ X, const double* __restrict__ Wt,
+                                                                const double* __restrict__ bias, int64_t M, int K, int N,
+                                                                double* __restrict__ Y)
+{
+    constexpr int NS = tg_ns(NT), TR = 8 * MTW;                                       // rows per warp iteration
+    extern __shared__ __align__(16) uint8_t gsm[];
+    const int Kp = (K + 3) / 4 * 4, stages = tg_stages(K, NT, MTW);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    double* wsm = reinterpret_cast<double*>(gsm);                                    // [Kp][NS]
+    double* osm = wsm + Kp * NS + warp * TR * (NT * 8);                               // this warp's output tile [TR][N] (dense)
+    double* ring = wsm + Kp * NS + 8 * TR * (NT * 8) + (int64_t)warp * stages * TR * K;   // this warp's [stages][TR][K]
+    const uint32_t bars = g_smem_u32(gsm + tg_smem(K, NT, MTW) - 1024) + warp * 4 * 8;  // this warp's barriers
+    for (int idx = tid; idx < Kp * NS; idx += GTHREADS) {
+        const int k = idx / NS, c = idx - k * NS;
+        wsm[idx] = (k < K && c < N) ? Wt[(int64_t)k * N + c] : 0.0;
+    }
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) g_mbar_init(bars + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();                                             // W^T in place (the only CTA-wide barrier)
+    const int64_t ntiles = (M + TR - 1) / TR;
+    const int64_t gw = (int64_t)blockIdx.x * 8 + warp, nw = (int64_t)gridDim.x * 8;
+    const int64_t t0 = ntiles * gw / nw, t1 = ntiles * (gw + 1) / nw;
+    const uint32_t tile_bytes = (uint32_t)TR * K * 8, out_bytes = (uint32_t)TR * N * 8;
+    auto issue = [&](int64_t tile) {                             // lane 0: the rows of a tile are one contiguous copy
+        if (M - tile * TR < TR) return;                          // ragged last tile: plain loads below
+        const int s = (int)((tile - t0) % stages);
+        g_mbar_expect_tx(bars + 8 * s, tile_bytes);
+        g_bulk_g2s(g_smem_u32(ring + (int64_t)s * TR * K), X + tile * TR * K, tile_bytes, bars + 8 * s);
+    };
+    if (lane == 0)
+        for (int64_t tile = t0; tile < min(t1, t0 + stages - 1); ++tile) issue(tile);
+    const bool vec = (N & 1) == 0;                               // 16-byte shared-memory stores need an even row length
+    for (int64_t tile = t0; tile < t1; ++tile) {
+        const int it = (int)(tile - t0);
+        const int s = it % stages;
+        if (tile + stages - 1 < t1) {                            // refill the stage this warp drained in the last iteration
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(tile + stages - 1);
+            }
+        }
+        double* xs = ring + (int64_t)s * TR * K;
+        const int valid = (int)min((int64_t)TR, M - tile * TR);
+        if (valid == TR) {
+            g_mbar_wait(bars + 8 * s, (uint32_t)(it / stages) & 1u);
+        } else {
+            const double* gx = X + tile * TR * K;
+            for (int idx = lane; idx < TR * K; idx += 32) xs[idx] = idx < valid * K ? gx[idx] : 0.0;
+            __syncwarp();
+        }
+        double acc[MTW][NT][2];
+#pragma unroll
+        for (int mt = 0; mt < MTW; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        for (int ks = 0; ks < Kp / 4; ++ks) {
+            const int k = 4 * ks + tig;
+            double a[MTW];
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt) a[mt] = k < K ? xs[(8 * mt + gid) * K + k] : 0.0;
+            const double* wr = wsm + k * NS + gid;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double b = wr[8 * nt];
+#pragma unroll
+                for (int mt = 0; mt < MTW; ++mt) dmma_8x8x4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b);
+            }
+        }
+        // the output rows of a tile are contiguous in Y: staged densely in shared memory and written by ONE bulk store (the
+        // accumulator fragments would otherwise leave as 64-byte pieces of 8 different rows per instruction)
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile has left osm
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int c = 8 * nt + 2 * tig;
+            const double b0v = (bias && c < N) ? __ldg(bias + c) : 0.0, b1v = (bias && c + 1 < N) ? __ldg(bias + c + 1) : 0.0;
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt) {
+                double* orow = osm + (8 * mt + gid) * N;
+                if (vec) {
+                    if (c < N) *reinterpret_cast<double2*>(orow + c) = make_double2(acc[mt][nt][0] + b0v, acc[mt][nt][1] + b1v);
+                } else {
+                    if (c < N) orow[c] = acc[mt][nt][0] + b0v;
+                    if (c + 1 < N) orow[c + 1] = acc[mt][nt][1] + b1v;
+                }
+            }
+        }
+        __syncwarp();
+        if (valid == TR) {
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(Y + tile * TR * N),
+                             "r"(g_smem_u32(osm)), "r"(out_bytes)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            for (int idx = lane; idx < valid * N; idx += 32) Y[tile * TR * N + idx] = osm[idx];
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");            // stores complete before the CTA exits
+}
+
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ part, int nparts, int M, int N,
                                                           double* __restrict__ C, double* __restrict__ colsum)
 {
@@ -1297,6 +1431,52 @@ DRP_API int drp_gram_tn_f64(const double* A, const double* B, int64_t K, int M, 
     {
         DRP_LAUNCH(DRP_K_REDUCE, (double)grid * M * (N + 1) * 8.0, st);
         gram_reduce_kernel<<<(M * (N + 1) + 255) / 256, 256, 0, st>>>(ws, grid, M, N, C, colsum);
+    }
+    return drp_launch_status();
+}
+
+template <int NT, int MTW>
+static void tall_gemm_launch(const double* X, const double* Wt, const double* bias, int64_t M, int K, int N, double* Y,
+                             int n_sm, cudaStream_t st)
+{
+    const int smem = tg_smem(K, NT, MTW);
+    cudaFuncSetAttribute(tall_gemm_kernel<NT, MTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int64_t ntiles = (M + 8 * MTW - 1) / (8 * MTW);
+    const int64_t want = (ntiles + 7) / 8;                        // at least one tile per warp
+    const int grid = (int)(want < n_sm ? want : n_sm);
+    DRP_LAUNCH(DRP_K_OTHER, (double)M * (K + N) * 8.0, st);
+    tall_gemm_kernel<NT, MTW><<<grid, GTHREADS, smem, st>>>(X, Wt, bias, M, K, N, Y);
+}
+
+// Y [M,N] = X [M,K] Wt + bias for row-major contiguous fp64 X, Wt [K,N] (the transposed weight), bias [N] (nullable).
+// K <= 192, N <= 184.  Returns 1 (nothing launched) when W^T and the ring do not fit in shared memory (large K and N).
+DRP_API int drp_tall_gemm_f64(const double* X, const double* Wt, const double* bias, int64_t M, int K, int N, double* Y,
+                              void* stream)
+{
+    if (!X || !Wt) return -1;
+    if (M <= 0) return -4;
+    if (K <= 0 || K > 192) return -5;
+    if (N <= 0 || N > 184) return -6;
+    if (!Y) return -7;
+    if ((reinterpret_cast<uintptr_t>(X) & 15) != 0 || (reinterpret_cast<uintptr_t>(Y) & 15) != 0) return -1;
+    const int nt = N <= 24 ? 3 : (N <= 120 ? 15 : 23);
+    const int mtw = tg_stages(K, nt, 2) >= 2 ? 2 : 1;             // two row tiles per warp share the B fragments when shared memory allows
+    if (tg_stages(K, nt, mtw) < 1) return 1;                      // declined: W^T + ring do not fit
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mtw == 2) {
+        if (nt == 3) tall_gemm_launch<3, 2>(X, Wt, bias, M, K, N, Y, n_sm, st);
+        else if (nt == 15) tall_gemm_launch<15, 2>(X, Wt, bias, M, K, N, Y, n_sm, st);
+        else tall_gemm_launch<23, 2>(X, Wt, bias, M, K, N, Y, n_sm, st);
+    } else {
+        if (nt == 3) tall_gemm_launch<3, 1>(X, Wt, bias, M, K, N, Y, n_sm, st);
+        else if (nt == 15) tall_gemm_launch<15, 1>(X, Wt, bias, M, K, N, Y, n_sm, st);
+        else tall_gemm_launch<23, 1>(X, Wt, bias, M, K, N, Y, n_sm, st);
     }
     return drp_launch_status();
 }

@@ -458,21 +458,46 @@ def gram_tn(A: torch.Tensor, B: torch.Tensor):
     return C, cs
 
 
+_TALL_OFF = os.environ.get("DRP_TALL_GEMM", "1") == "0"      # A/B switch for measurements
+
+
+def tall_gemm(x: torch.Tensor, Wt: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`x @ Wt + bias` for row-major `x [M,K]`, `Wt [K,N]` (M huge, K <= 192, N <= 184) as one HBM-bound kernel; shapes
+    outside that range (or DRP_TALL_GEMM=0) go to cuBLAS."""
+    _req(x, "x"), _req(Wt, "Wt")
+    M, K = x.shape
+    N = Wt.shape[1]
+    if _TALL_OFF or K > 192 or N > 184 or M == 0:
+        return torch.addmm(bias, x, Wt) if bias is not None else x @ Wt
+    x, Wt = x.contiguous(), Wt.contiguous()
+    b = None if bias is None else _req(bias, "bias").contiguous()
+    y = torch.empty((M, N), dtype=torch.float64, device=x.device)
+    rc = lib.drp_tall_gemm_f64(_p(x), _p(Wt), _p(b), M, K, N, _p(y), _stream())
+    if rc == 1:                                   # declined (W^T + ring exceed shared memory): library GEMM
+        return torch.addmm(bias, x, Wt) if bias is not None else x @ Wt
+    _rc(rc, "drp_tall_gemm_f64")
+    return y
+
+
 class _AffineTall(torch.autograd.Function):
-    """`x @ W.t() + b` for `x [K,F]` with K in the millions and a small output width; the weight and bias gradients use
-    `gram_tn` (autograd's addmm backward runs them as a cuBLAS tn GEMM without split-K plus a separate reduction)."""
+    """`x @ W.t() + b` for `x [M,K]` with M in the millions and small K, N: forward and input gradient through
+    `tall_gemm` (one read, one write), weight and bias gradients through `gram_tn` (split-K) — cuBLAS runs these fp64
+    shapes far below what their memory traffic allows."""
 
     @staticmethod
     def forward(ctx, x, W, b):
         ctx.save_for_backward(x, W)
-        return torch.addmm(b, x, W.t())
+        return tall_gemm(x, W.t().contiguous(), b)
 
     @staticmethod
     def backward(ctx, dy):
         x, W = ctx.saved_tensors
         dy = dy.contiguous()
-        dW, db = gram_tn(dy, x)
-        dx = dy @ W if ctx.needs_input_grad[0] else None
+        dW = db = dx = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dW, db = gram_tn(dy, x)
+        if ctx.needs_input_grad[0]:
+            dx = tall_gemm(dy, W)
         return dx, dW, db
 
 
@@ -492,7 +517,7 @@ class _GRUEncoderLast(torch.autograd.Function):
                                                                           (whh, "weight_hh"), (bhh, "bias_hh"), (h0, "h0")))
         n, L, I = x.shape
         H = whh.shape[-1]
-        gi0 = torch.addmm(bih[0], x.reshape(n * L, I), wih[0].t())                                # [n*L, 3H]
+        gi0 = tall_gemm(x.reshape(n * L, I), wih[0].t().contiguous(), bih[0])                      # [n*L, 3H]
         want = any(ctx.needs_input_grad)
         out = torch.empty((n, L, 2 * H), dtype=torch.float64, device=x.device)       # direction-0 half is written
         gates = torch.empty((n, L, 2, 4, H), dtype=torch.float64, device=x.device) if want else None
@@ -548,7 +573,7 @@ class _GRUEncoderLast(torch.autograd.Function):
         dbih = torch.stack((dbih0, dgi1.sum(0)))
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = (dgi0f @ wih[0]).reshape(n, L, I)
+            dx = tall_gemm(dgi0f, wih[0]).reshape(n, L, I)
             dx[:, L - 1] += dgi1 @ wih[1]
         return dx, dwih, dbih, dwhh, dbhh, dh0
 

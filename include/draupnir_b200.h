@@ -141,6 +141,14 @@ int64_t drp_gram_workspace_elems(int M, int N);
 int drp_gram_tn_f64(const double* A, const double* B, int64_t K, int M, int N, double* C, double* colsum, double* ws,
                     int64_t ws_elems, void* stream);
 
+/* ---- nn.Linear on n*L rows (EmbedComplex.fc1/fc2 S/models_utils.py:232-236, RNNDecoder_Tiling.fc1/linear_probs :97-98,
+ *          the GRU input projection W_ih x + b_ih of RNNEncoder :54) and its input gradient --------------------------- */
+/* Y [M,N] = X [M,K] Wt + bias: X row-major contiguous (16-byte aligned), Wt [K,N] = the TRANSPOSED weight, bias [N]
+ * nullable.  M huge, K <= 192, N <= 184.  One read of X, one write of Y.  Returns 1 without launching when W^T and
+ * the ring of X blocks exceed shared memory (K and N both large).                                                    */
+int drp_tall_gemm_f64(const double* X, const double* Wt, const double* bias, int64_t M, int K, int N, double* Y,
+                      void* stream);
+
 /* ---- K10  Categorical(logits).log_prob(obs).sum(): S/models.py:352 (+ LogSoftmax S/models_utils.py:98) --------- */
 int64_t drp_cat_loglik_partials(int64_t rows);
 int drp_cat_loglik_fwd_f64(const double* scores, const void* obs, int obs_is_f64, int64_t rows, int A, double* out,

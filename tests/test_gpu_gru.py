@@ -154,3 +154,27 @@ def test_input_sums_one_pass(cuda, n, L, C):
     _rc(lib.drp_gru_input_sums_f64(_p(d), n, L, C, _p(dU), _p(dVp), _stream()), "drp_gru_input_sums_f64")
     assert torch.allclose(dU.cpu(), dgi.sum(1), rtol=1e-13, atol=1e-12)
     assert torch.allclose(dVp.sum(0).cpu(), dgi.sum(0), rtol=1e-13, atol=1e-12)
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 21, 180), (63, 21, 180), (64, 21, 21), (1000, 120, 21), (4099, 180, 21), (130, 21, 120),
+                                   (70001, 21, 180), (20000, 120, 21), (257, 192, 184), (300, 4, 8)])
+def test_tall_gemm(cuda, M, K, N):
+    """drp_tall_gemm_f64 (the dense layers on n*L rows) against torch, with and without bias; and through `affine_tall`
+    the gradients of input, weight and bias."""
+    from draupnir_asr_b200 import ops
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, K, generator=g, dtype=torch.float64)
+    W = torch.randn(N, K, generator=g, dtype=torch.float64)
+    b = torch.randn(N, generator=g, dtype=torch.float64)
+    xg, Wg, bg = x.to(cuda), W.to(cuda), b.to(cuda)
+    ref = x @ W.t() + b
+    scale = float(ref.abs().max())
+    assert float((ops.tall_gemm(xg, Wg.t().contiguous(), bg).cpu() - ref).abs().max()) < 1e-12 * scale
+    assert float((ops.tall_gemm(xg, Wg.t().contiguous()).cpu() - x @ W.t()).abs().max()) < 1e-12 * scale
+    xr, Wr, br = (t.clone().requires_grad_(True) for t in (x, W, b))
+    w = torch.randn(M, N, generator=g, dtype=torch.float64)
+    ((xr @ Wr.t() + br) * w).sum().backward()
+    xq, Wq, bq = (t.clone().requires_grad_(True) for t in (xg, Wg, bg))
+    (ops.affine_tall(xq, Wq, bq) * w.to(cuda)).sum().backward()
+    for a, c in ((xr.grad, xq.grad), (Wr.grad, Wq.grad), (br.grad, bq.grad)):
+        assert float((a - c.cpu()).abs().max() / a.abs().max().clamp_min(1e-30)) < 1e-12
