@@ -46,9 +46,9 @@ template <int S, int KBN>
 struct OzCfg {
     static constexpr int NA = S * KBN;                                   // resident A tiles per strip
     static constexpr int A_BYTES = NA * OZ_A_TILE;
-    static constexpr int NST_RAW = (OZ_SMEM_MAX - 1024 - 256 - A_BYTES) / OZ_B_TILE;
+    static constexpr int NST_RAW = (OZ_SMEM_MAX - 1024 - 320 - A_BYTES) / OZ_B_TILE;
     static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;                // B ring stages
-    static constexpr int SMEM = 1024 + A_BYTES + NST * OZ_B_TILE + 256;
+    static constexpr int SMEM = 1024 + A_BYTES + NST * OZ_B_TILE + 320;
     static constexpr int TMEM_COLS = (S * OZ_TN <= 64) ? 64 : (S * OZ_TN <= 128) ? 128 : (S * OZ_TN <= 256) ? 256 : 512;
     static_assert(NST >= 2, "A strip does not leave room for the B ring");
     static_assert(S * OZ_TN <= 512, "too many accumulators for TMEM");
@@ -64,6 +64,7 @@ struct OzParams {
     int nTi, nTj, units_per_z, total_units;
     int K;                     // real contraction length (columns of the panel); the k-blocks are zero-padded
     long long* trace;          // optional event trace of CTA 0 (debug; nullptr in production)
+    int* counter;              // next work unit (zeroed by the slicing kernel that precedes every update)
 };
 
 // ------------------------------------------------ PTX wrappers ---------------------------------------------------
@@ -220,8 +221,9 @@ __device__ __forceinline__ void oz_decode(const OzParams& p, int u, int& zz, int
 template <int S>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ Mb, int64_t ld, int64_t bs, int k0, int Kcols, int KBN,
                                                        int rb, int c1, int R, int Rpad, uint8_t* __restrict__ sl,
-                                                       int64_t sl_bs, int32_t* __restrict__ scl)
+                                                       int64_t sl_bs, int32_t* __restrict__ scl, int* __restrict__ counter)
 {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *counter = 0;      // work-unit counter of the update that follows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rr = blockIdx.x * 8 + warp;
     const int zz = blockIdx.y;
@@ -284,8 +286,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
     // mbarriers: A strip full/empty, accumulators drained, accumulator d complete (one per anti-diagonal), B ring
     const uint32_t bar_a_full = bars, bar_a_empty = bars + 8, bar_acc_empty = bars + 16, bar_acc_full = bars + 24;
     const uint32_t bar_b_full = bars + 24 + 8 * OZ_MAXS, bar_b_empty = bar_b_full + 8 * NST;
+    // work units are handed out dynamically (atomic counter): the producer publishes each unit id in a 4-slot queue
+    // (bar_unit[slot] = "slot written"); the pipeline depth keeps every role within 2 units of the producer
+    const uint32_t bar_unit = bar_b_empty + 8 * NST;
+    volatile int* unit_q = reinterpret_cast<volatile int*>(gen + Cfg::A_BYTES + NST * OZ_B_TILE + 24 + 8 * OZ_MAXS + 16 * NST + 32);
     volatile uint32_t* tmem_slot =
-        reinterpret_cast<volatile uint32_t*>(gen + Cfg::A_BYTES + NST * OZ_B_TILE + 24 + 8 * OZ_MAXS + 16 * NST);
+        reinterpret_cast<volatile uint32_t*>(gen + Cfg::A_BYTES + NST * OZ_B_TILE + 24 + 8 * OZ_MAXS + 16 * NST + 48);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -297,6 +303,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
             mbar_init(bar_b_full + 8 * s, 1);
             mbar_init(bar_b_empty + 8 * s, 1);
         }
+        for (int j = 0; j < 4; ++j) mbar_init(bar_unit + 8 * j, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -311,7 +318,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
         if (lane == 0) {
             uint32_t a_phase = 0, b_phase = 0;
             int st = 0;
-            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            for (int i = 0;; ++i) {
+                int u = atomicAdd(p.counter, 1);
+                if (u >= p.total_units) u = -1;
+                unit_q[i & 3] = u;
+                mbar_arrive(bar_unit + 8 * (i & 3));
+                if (u < 0) break;
                 int zz, ti, tj0, ntj;
                 oz_decode(p, u, zz, ti, tj0, ntj);
                 const uint8_t* src = p.sl + (int64_t)zz * p.sl_bs;
@@ -347,7 +359,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
         uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
         int st = 0;
         const bool full_k = p.K == KBN * OZ_ROWB;      // no ragged last k-block
-        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        for (int i = 0;; ++i) {
+            mbar_wait(bar_unit + 8 * (i & 3), (uint32_t)(i >> 2) & 1u);
+            const int u = unit_q[i & 3];
+            if (u < 0) break;
             int zz, ti, tj0, ntj;
             oz_decode(p, u, zz, ti, tj0, ntj);
             mbar_wait(bar_a_full, a_phase);
@@ -409,7 +424,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
         const int tr = lane >> 2, tc = 2 * (lane & 3);
         const bool vec_ok = ((p.ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.M) & 15) == 0) && ((p.bs & 1) == 0);
         uint32_t acc_phase = 0;
-        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        for (int i = 0;; ++i) {
+            mbar_wait(bar_unit + 8 * (i & 3), (uint32_t)(i >> 2) & 1u);
+            const int u = unit_q[i & 3];
+            if (u < 0) break;
             int zz, ti, tj0, ntj;
             oz_decode(p, u, zz, ti, tj0, ntj);
             const int32_t* sc = p.scl + (int64_t)zz * p.Rpad;
@@ -527,7 +545,7 @@ int oz_launch(const OzParams& p, int z, int k0, int Kcols, cudaStream_t st, doub
         DRP_LAUNCH(DRP_K_SLICE, (double)z * p.Rpad * KBN * 128 * (8.0 + S), st);
         oz_slice_kernel<S><<<dim3((p.Rpad + 7) / 8, z), 256, 0, st>>>(p.M, p.ld, p.bs, k0, Kcols, KBN, p.rb, p.c1, p.R, p.Rpad,
                                                                      const_cast<uint8_t*>(p.sl), p.sl_bs,
-                                                                     const_cast<int32_t*>(p.scl));
+                                                                     const_cast<int32_t*>(p.scl), p.counter);
     }
     {
         DRP_LAUNCH(DRP_K_SYRK_TC, flops, st);
@@ -547,7 +565,7 @@ DRP_API void drp_ozaki_set_trace(void* buf) { g_oz_trace = (long long*)buf; }
 int64_t drp_ozaki_workspace_bytes(int R_full, int z)
 {
     const int64_t Rpad = (((int64_t)R_full + 127) / 128 + 1) * 128;
-    return (int64_t)z * Rpad * (12 * OZ_ROWB + 8) + 1024;
+    return (int64_t)z * Rpad * (12 * OZ_ROWB + 8) + 2048;
 }
 
 int drp_ozaki_slices()
@@ -587,11 +605,12 @@ int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     p.nTj = (cmax - p.rb + OZ_TN - 1) / OZ_TN;
     p.Rpad = p.nTi * OZ_TM;
     p.sl_bs = (int64_t)S * KBN * p.Rpad * OZ_ROWB;
-    const int64_t need = (int64_t)z * p.sl_bs + (int64_t)z * p.Rpad * 8 + 1024;
+    const int64_t need = (int64_t)z * p.sl_bs + (int64_t)z * p.Rpad * 8 + 2048;
     if (need > ws_bytes) return 1;
     uint8_t* w = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
     p.sl = w;
     p.scl = reinterpret_cast<const int32_t*>(w + (int64_t)z * p.sl_bs);
+    p.counter = reinterpret_cast<int*>(w + (int64_t)z * p.sl_bs + (int64_t)z * p.Rpad * 8);
     int upz = 0;
     for (int ti = 0; ti < p.nTi; ++ti) {
         const int tot = 2 * ti + 2 < p.nTj ? 2 * ti + 2 : p.nTj;
