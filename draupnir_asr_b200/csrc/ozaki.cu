@@ -35,7 +35,7 @@ constexpr int OZ_TN = 64;                        // tile cols  (UMMA N)
 constexpr int OZ_ROWB = 128;                     // bytes (= int8 K elements) per swizzled row of a k-block
 constexpr int OZ_A_TILE = OZ_TM * OZ_ROWB;       // 16 KB
 constexpr int OZ_B_TILE = OZ_TN * OZ_ROWB;       // 8 KB
-constexpr int OZ_CHUNK = 16;                     // column tiles per work unit (A strip reloaded per unit)
+constexpr int OZ_CHUNK = 8;                      // column tiles per work unit (A strip reloaded per unit)
 constexpr int OZ_EPI_WARPS = 16;                 // 4 TMEM lane quadrants x 4 column quarters of the 128x64 tile
 constexpr int OZ_THREADS = (2 + OZ_EPI_WARPS) * 32;
 constexpr int OZ_SMEM_MAX = 232448;              // 227 KB
