@@ -64,7 +64,19 @@ class Independent(td.Independent, TorchDistributionMixin):
 
 
 class HalfNormal(td.HalfNormal, TorchDistributionMixin):
-    pass
+    """torch's constructor builds `Normal(0, scale)`: the Python 0 becomes a CPU tensor that is copied to the device from
+    pageable memory, and such a copy stalls the launch thread until everything queued on the stream has run (four of them
+    per model evaluation).  Same distribution, location created on the device."""
+
+    def __init__(self, scale, validate_args=None):
+        if isinstance(scale, torch.Tensor):
+            base_dist = td.Normal(torch.zeros_like(scale), scale, validate_args=False)
+            td.TransformedDistribution.__init__(self, base_dist, td.transforms.AbsTransform(), validate_args=validate_args)
+        else:
+            super().__init__(scale, validate_args=validate_args)
+
+    def expand(self, batch_shape, _instance=None):
+        return HalfNormal(self.base_dist.scale.expand(torch.Size(batch_shape)), validate_args=False)
 
 
 class Normal(td.Normal, TorchDistributionMixin):

@@ -33,7 +33,7 @@ def test_argument_validation_without_a_gpu():
     assert lib.drp_cat_loglik_fwd_f64(None, None, 1, 10, 21, None, None, None, None) == -1
     assert lib.drp_ou_workspace_ld(19, 19) == 40 and lib.drp_ou_workspace_ld(2000, 2000) == 4008
     assert lib.drp_ou_workspace_elems(19, 0, 30) == 30 * 20 * 24 + (lib.drp_factor_workspace_bytes(20, 30) + 7) // 8
-    assert lib.drp_factor_workspace_bytes(2000, 30) == 30 * 2176 * (12 * 128 + 8) + 1024
+    assert lib.drp_factor_workspace_bytes(2000, 30) == 30 * 2176 * (12 * 128 + 8) + 2048
     assert lib.drp_timing_classes() == 11
     assert lib.drp_gru_hidden_size() == 60
     assert lib.drp_gru_fwd_f64(None, None, None, None, 4, 4, 60, None, None, None) == -1
