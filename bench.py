@@ -62,7 +62,7 @@ def measured_peaks():
 class ClockSampler:
     """SM clock and clock-event (throttle) reasons DURING the timed region — the quantities of the nvidia-smi line in
     B200_PROFILING.md (clocks.sm, clocks.max.sm, clocks_event_reasons.*), read through NVML in a background thread every
-    100 ms.  An `nvidia-smi -lms` child process was used first: its queries stalled the launches of the running context
+    250 ms.  An `nvidia-smi -lms` child process was used first: its queries stalled the launches of the running context
     for 60-160 ms once in a while (single 95-190 ms steps among 30 ms ones); the in-process NVML calls do not."""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
@@ -91,7 +91,7 @@ class ClockSampler:
                 for name, bit in self.REASONS:
                     if mask & bit:
                         self.reasons.add(name)
-                time.sleep(0.1)
+                time.sleep(0.25)
             pynvml.nvmlShutdown()
         except Exception as e:  # pragma: no cover
             self.error = e
