@@ -62,8 +62,8 @@ DRP_API int64_t drp_launch_count(void)
 }
 
 // Enable (on >= 1) / disable (0) CUDA-event timing of every launch; enabling clears previous records.  `on` > 1 also
-// pre-creates events for that many launches, so that no event is created inside the caller's timed region (the driver
-// grows its event pool in steps that cost ~100 ms once every ~1000 events).
+// pre-creates (and pre-records) events for that many launches, so that the driver grows neither its event pool nor its
+// timestamp pool inside the caller's timed region (either costs ~100 ms once every ~1000 events).
 DRP_API int drp_timing_enable(int on)
 {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -77,6 +77,15 @@ DRP_API int drp_timing_enable(int on)
             cudaEvent_t e;
             if (cudaEventCreate(&e) != cudaSuccess) break;
             g_free.push_back(e);
+        }
+        // ... and records every event once: the driver attaches the timestamp storage of an event at its first record and
+        // grows that pool in steps too (single 100-190 ms steps were seen when the 1024th / 2048th record of a run fell
+        // into the timed region)
+        cudaStream_t tmp;
+        if (cudaStreamCreateWithFlags(&tmp, cudaStreamNonBlocking) == cudaSuccess) {
+            for (cudaEvent_t e : g_free) cudaEventRecord(e, tmp);
+            cudaStreamSynchronize(tmp);
+            cudaStreamDestroy(tmp);
         }
     }
     g_timing.store(on ? 1 : 0);
