@@ -245,8 +245,8 @@ class OUProcessPrior(td.Distribution, TorchDistributionMixin):
         """Summed log-density evaluated on the side stream (`ops.side_stream`): forked from the current stream here,
         joined by whoever needs the number (`AsyncTerm.join`).  None when the side stream is switched off."""
         from .. import ops
-        if not ops.PRIOR_STREAM_ENABLED or not value.is_cuda:
-            return None
+        if not ops.PRIOR_STREAM_ENABLED or not value.is_cuda or value.shape[-1] < 400:
+            return None                      # small trees: the prior is a few short kernels, forking costs more than it hides
         side = ops.side_stream(value.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
