@@ -164,6 +164,26 @@ def test_marginal_samples_share_one_factorisation(cuda, n, L, monkeypatch):
                           rtol=1e-7, atol=1e-8)
 
 
+@pytest.mark.parametrize("guide", ["delta_map", "variational"])
+def test_host_fed_step_equals_resident_step(cuda, guide):
+    """`Run.step_from_host` (pinned host inputs copied on a side stream every step, each consumer waiting for its own
+    input; the number bench.py reports as e2e) walks the same trajectory as `Run.step` on device-resident inputs; 450
+    leaves so that the prior runs on its side stream as well."""
+    n, L = 450, 30
+    torch.manual_seed(0)
+    problem, run_a, _ = _pair(n, L, guide, cuda)
+    torch.manual_seed(0)
+    _, run_b, _ = _pair(n, L, guide, cuda)
+    host = run_b.make_host_inputs()
+    eps = torch.randn(30, n, dtype=torch.float64, generator=torch.Generator().manual_seed(7))
+    for _ in range(3):
+        with _FixedNoise(eps):
+            la = run_a.step()
+        with _FixedNoise(eps):
+            lb = run_b.step_from_host(host)
+        assert abs(la - lb) <= 1e-10 * abs(la), (la, lb)
+
+
 def test_model_refuses_cpu_device():
     from draupnir_asr_b200 import runtime
     problem = S.make_problem(5, 7)
