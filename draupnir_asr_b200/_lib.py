@@ -34,6 +34,9 @@ SIGNATURES = {
     "drp_ou_workspace_ld": (_i64, [_i32, _i32]),
     "drp_ou_workspace_elems": (_i64, [_i32, _i32, _i32]),
     "drp_ou_prior_f64": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "drp_ou_prior_factor_f64": (_i32, [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p]),
+    "drp_ou_prior_apply_workspace_elems": (_i64, [_i32, _i32]),
+    "drp_ou_prior_apply_f64": (_i32, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "drp_mvn_logprob_f64": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "drp_mvn_grad_cov_f64": (_i32, [_p, _i32, _i32, _p, _p, _p]),
     "drp_potri_batched_f64": (_i32, [_p, _i32, _i32, _p, _p, _p, _p]),

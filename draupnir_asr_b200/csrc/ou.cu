@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) ou_assemble_kernel(const double* __restri
     const int pr = r < n ? r : (r == n ? -1 : r - 1);
     const int pc = c < n ? c : (c == n ? -1 : c - 1);
     if (pr < 0 || pc < 0) {                       // right-hand-side row, or the (unused) column n
-        for (int zz = 0; zz < z; ++zz) out[zz * bs] = (pr < 0 && c < n) ? x[(int64_t)zz * n + c] : 0.0;
+        for (int zz = 0; zz < z; ++zz) out[zz * bs] = (x && pr < 0 && c < n) ? x[(int64_t)zz * n + c] : 0.0;
         return;
     }
     if (identity && r > n) {                      // [ I | 0 ] block
@@ -163,6 +163,77 @@ __global__ void alpha_extract_kernel(const double* __restrict__ M, int64_t ld, i
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cnt) out[(int64_t)blockIdx.y * cnt + i] = -M[(int64_t)blockIdx.y * bs + (int64_t)(n + 1 + i) * ld + n];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Second phase of the two-phase prior: the factorisation (L, -K^-1: everything that costs time) depends on the
+// hyper-parameters only and can start before the latent vector x exists; once x is there, alpha = K^-1 x is a symmetric
+// matrix-vector product with the lower-stored -K^-1 block.  One CTA per 64 x 64 tile (I >= J): y_I += T x_J and, off the
+// diagonal, y_J += T^T x_I.  Every (row block, other block) pair is produced exactly once -> ypart [z][nb][n], summed in
+// a fixed order afterwards (deterministic, no atomics).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SYMV_TB = 64;
+__global__ void __launch_bounds__(128) ou_symv_tile_kernel(const double* __restrict__ M, int64_t ld, int64_t bs, int n,
+                                                           const double* __restrict__ x, int nb, double* __restrict__ ypart)
+{
+    __shared__ double T[SYMV_TB][SYMV_TB + 1];
+    __shared__ double xi[SYMV_TB], xj[SYMV_TB];
+    const int zz = blockIdx.y;
+    int I = 0, t = blockIdx.x;                     // tile index -> (I, J), J <= I
+    while (t > I) {
+        t -= I + 1;
+        ++I;
+    }
+    const int J = t;
+    const double* A = M + (int64_t)zz * bs + (int64_t)(n + 1 + I * SYMV_TB) * ld + n + 1 + J * SYMV_TB;
+    const int ri = min(SYMV_TB, n - I * SYMV_TB), cj = min(SYMV_TB, n - J * SYMV_TB);
+    for (int idx = threadIdx.x; idx < SYMV_TB * SYMV_TB; idx += blockDim.x) {
+        const int r = idx / SYMV_TB, c = idx - r * SYMV_TB;
+        const bool in = r < ri && c < cj && (I != J || c <= r);
+        T[r][c] = in ? A[(int64_t)r * ld + c] : 0.0;
+    }
+    if (threadIdx.x < SYMV_TB) {
+        const int k = threadIdx.x;
+        xi[k] = k < ri ? x[(int64_t)zz * n + I * SYMV_TB + k] : 0.0;
+        xj[k] = k < cj ? x[(int64_t)zz * n + J * SYMV_TB + k] : 0.0;
+    }
+    __syncthreads();
+    const int k = threadIdx.x & (SYMV_TB - 1);
+    if (threadIdx.x < SYMV_TB) {                   // rows of block I
+        double s = 0.0;
+        if (I == J) {
+            for (int c = 0; c < SYMV_TB; ++c) s += (c <= k ? T[k][c] : T[c][k]) * xj[c];
+        } else {
+            for (int c = 0; c < SYMV_TB; ++c) s += T[k][c] * xj[c];
+        }
+        if (k < ri) ypart[((int64_t)zz * nb + J) * n + I * SYMV_TB + k] = s;
+    } else if (I != J) {                           // rows of block J: transposed tile
+        double s = 0.0;
+        for (int r = 0; r < SYMV_TB; ++r) s += T[r][k] * xi[r];
+        if (k < cj) ypart[((int64_t)zz * nb + I) * n + J * SYMV_TB + k] = s;
+    }
+}
+
+// alpha_i = -sum_q ypart[q][i] (the block holds -K^-1); written to alpha[z][n] and, in the layout the gradient kernels read,
+// to M[n+1+i][n] = -alpha_i and M[n][n] = -x^T alpha.
+__global__ void __launch_bounds__(256) ou_symv_finish_kernel(double* __restrict__ M, int64_t ld, int64_t bs, int n,
+                                                             const double* __restrict__ x, int nb, const double* __restrict__ ypart,
+                                                             double* __restrict__ alpha)
+{
+    __shared__ double red[32];
+    const int zz = blockIdx.x;
+    double* A = M + (int64_t)zz * bs;
+    double maha = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < nb; ++q) s += ypart[((int64_t)zz * nb + q) * n + i];
+        const double a = -s;
+        if (alpha) alpha[(int64_t)zz * n + i] = a;
+        A[(int64_t)(n + 1 + i) * ld + n] = -a;
+        maha += a * x[(int64_t)zz * n + i];
+    }
+    maha = block_sum(maha, red);
+    if (threadIdx.x == 0) A[(int64_t)n * ld + n] = -maha;
 }
 
 // K5: hyper-parameter gradient sums.  With G = 1/2 (alpha alpha^T - K^-1) = dlogp/dK:
@@ -323,6 +394,73 @@ DRP_API int drp_ou_prior_f64(const double* D, int64_t ldd, int n, const double* 
             DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 24.0), st);
             reduce3_kernel<<<z, 256, 0, st>>>(part, n, gsum);
         }
+    }
+    return drp_launch_status();
+}
+
+// Two-phase form of drp_ou_prior_f64 (want_grad = 1 layout).  Phase 1 needs the hyper-parameters only: assembly +
+// factorisation, leaving L and -K^-1 in M.  Phase 2 needs the latent vectors: alpha = K^-1 x, log-densities and the
+// hyper-parameter gradient sums.  Same results as the one-call form up to rounding (alpha through the explicit inverse).
+DRP_API int drp_ou_prior_factor_f64(const double* D, int64_t ldd, int n, const double* sf, const double* sn, const double* lam,
+                                    int z, double* M, int32_t* info, void* stream)
+{
+    if (!D) return -1;
+    if (n <= 0 || ldd < n) return -3;
+    if (!sf || !sn || !lam) return -4;
+    if (z <= 0) return -7;
+    if (!M) return -8;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = n + 1 + n;
+    const int64_t ld = drp_ou_workspace_ld(n, n), bs = (int64_t)R * ld;
+    dim3 g((R + 255) / 256, R);
+    {
+        DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)z * R * (R + 1) * 4.0), st);
+        ou_assemble_kernel<<<g, 256, 3 * z * sizeof(double), st>>>(D, ldd, nullptr, n, n, 1, sf, sn, lam, nullptr, z, M, ld, bs);
+    }
+    int rc = drp_factor_run(M, ld, bs, z, n, R, n + 1, R, info, M + ou_matrix_elems(n, n, z), drp_ozaki_workspace_bytes(R, z), st);
+    if (rc) return rc;
+    return drp_launch_status();
+}
+
+// Doubles of scratch (ypart) drp_ou_prior_apply_f64 needs.
+DRP_API int64_t drp_ou_prior_apply_workspace_elems(int n, int z)
+{
+    const int64_t nb = (n + SYMV_TB - 1) / SYMV_TB;
+    return (int64_t)z * nb * n;
+}
+
+DRP_API int drp_ou_prior_apply_f64(const double* D, int64_t ldd, int n, const double* lam, const double* x, int z, double* M,
+                                   double* logp, double* alpha, double* gsum, double* part, double* ypart, void* stream)
+{
+    if (!D) return -1;
+    if (n <= 0 || ldd < n) return -3;
+    if (!lam || !x) return -4;
+    if (z <= 0) return -6;
+    if (!M) return -7;
+    if (!logp || !alpha || !gsum || !part || !ypart) return -8;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = n + 1 + n;
+    const int64_t ld = drp_ou_workspace_ld(n, n), bs = (int64_t)R * ld;
+    const int nb = (n + SYMV_TB - 1) / SYMV_TB;
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * n * 4.0), st);
+        ou_symv_tile_kernel<<<dim3(nb * (nb + 1) / 2, z), 128, 0, st>>>(M, ld, bs, n, x, nb, ypart);
+    }
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * nb * n * 8.0), st);
+        ou_symv_finish_kernel<<<z, 256, 0, st>>>(M, ld, bs, n, x, nb, ypart, alpha);
+    }
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 8.0), st);
+        mvn_finish_kernel<<<z, 256, 0, st>>>(M, ld, bs, n, logp);
+    }
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * n * 4.0 + (double)n * n * 4.0), st);
+        ou_grad_kernel<<<dim3(n, z), 256, 0, st>>>(M, ld, bs, n, D, ldd, lam, part);
+    }
+    {
+        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 24.0), st);
+        reduce3_kernel<<<z, 256, 0, st>>>(part, n, gsum);
     }
     return drp_launch_status();
 }

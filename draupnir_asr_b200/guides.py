@@ -58,6 +58,9 @@ class DRAUPNIRGUIDES(EasyGuide):
         return self.guide_noplating(family_data, patristic_matrix, cladistic_matrix, data_blosum, batch_blosum=None)
 
     def _encode(self, data_blosum):
+        hook = self.__dict__.get("_before_encode")      # a host-fed step waits for the BLOSUM-encoded data set only here
+        if hook is not None:
+            hook()
         shard = getattr(self.draupnir, "shard", None)
         n = data_blosum.shape[0]
         if shard is not None:        # encoder is data-parallel over contiguous blocks of leaves
@@ -112,6 +115,8 @@ class DRAUPNIRGUIDES(EasyGuide):
             sigma_n = pyro.sample("sigma_n", dist.Delta(self.sigma_n).to_event(1))
             sigma_f = pyro.sample("sigma_f", dist.Delta(self.sigma_f).to_event(1))
             lambd = pyro.sample("lambd", dist.Delta(self.lambd).to_event(1))
+            # the model's OU covariances depend on these three values only: their factorisation starts now
+            self.draupnir.prefetch_prior(patristic_matrix_sorted, sigma_f, sigma_n, lambd)
             out, n = self._encode(data_blosum)
             latent_z = self._latent_site(out)
             assert latent_z.shape == (self.draupnir.z_dim, n)

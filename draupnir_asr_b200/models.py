@@ -80,6 +80,8 @@ class DRAUPNIRModelClass(nn.Module):
         self._one = None
         self._pos_cache = {}
         self._cond_cache = None
+        self._prefetched = None
+        self._hyper_sites = ()
         self.shard = None          # zshard.ShardContext when the run is spread over several GPUs
         for name in ("blosum_weighted", "dataset_train_blosum", "internal_nodes", "leaves_nodes", "aa_frequencies",
                      "blosum", "blosum_max"):
@@ -116,11 +118,32 @@ class DRAUPNIRModelClass(nn.Module):
 
     def _hyper_prior_sites(self, eps: float):
         alpha = pyro.sample("alpha", dist.HalfNormal(self._one).expand_by([3, ]).to_event(1)) + eps
-        sigma_f = pyro.sample("sigma_f", dist.HalfNormal(alpha[0]).expand_by([self.z_dim, ]).to_event(1)) + eps
-        sigma_n = pyro.sample("sigma_n", dist.HalfNormal(alpha[1]).expand_by([self.z_dim, ]).to_event(1)) + eps
-        lambd = pyro.sample("lambd", dist.HalfNormal(alpha[2]).expand_by([self.z_dim, ]).to_event(1)) + eps
-        return (squeeze_tensor(1, alpha), squeeze_tensor(1, sigma_f), squeeze_tensor(1, sigma_n),
-                squeeze_tensor(1, lambd))
+        sf_site = pyro.sample("sigma_f", dist.HalfNormal(alpha[0]).expand_by([self.z_dim, ]).to_event(1))
+        sn_site = pyro.sample("sigma_n", dist.HalfNormal(alpha[1]).expand_by([self.z_dim, ]).to_event(1))
+        lam_site = pyro.sample("lambd", dist.HalfNormal(alpha[2]).expand_by([self.z_dim, ]).to_event(1))
+        self._hyper_sites = (sf_site, sn_site, lam_site)         # what a prefetched factorisation is matched against
+        return (squeeze_tensor(1, alpha), squeeze_tensor(1, sf_site + eps), squeeze_tensor(1, sn_site + eps),
+                squeeze_tensor(1, lam_site + eps))
+
+    def prefetch_prior(self, patristic_matrix_sorted, sigma_f, sigma_n, lambd):
+        """Called by the guide as soon as ITS values of the three kernel hyper-parameters exist (under `Trace_ELBO` the
+        model's sites are replayed from them): starts assembling and factoring the OU covariances on the side stream, so
+        that the part of the prior that costs time runs while the encoder, and in a host-fed step the copy of the
+        BLOSUM-encoded data set, are still under way.  `gp_prior` picks the factorisation up if, and only if, it is handed
+        the very same tensors; otherwise it is dropped unused."""
+        self._prefetched = None
+        n = patristic_matrix_sorted.shape[0] - 1
+        if not (ops.PRIOR_STREAM_ENABLED and ops.in_elbo_scope() and patristic_matrix_sorted.is_cuda and n >= 400
+                and torch.is_grad_enabled()):
+            return
+        sf, sn, lam = (squeeze_tensor(1, t + 1e-6) for t in (sigma_f, sigma_n, lambd))
+        if self.shard is not None:
+            lo, hi = self.shard.z_lo, self.shard.z_hi
+            if hi <= lo:
+                return
+            sf, sn, lam = sf[lo:hi], sn[lo:hi], lam[lo:hi]
+        self._prefetched = ops.ou_prior_factor(patristic_matrix_sorted[1:, 1:], sf, sn, lam, key=(sigma_f, sigma_n, lambd),
+                                               stream=ops.side_stream(patristic_matrix_sorted.device))
 
     def gp_prior(self, patristic_matrix_sorted):
         """Ornstein-Uhlenbeck process prior over the latent space (S/models.py:85-121).  Returns `[n, z]`."""
@@ -130,8 +153,11 @@ class DRAUPNIRModelClass(nn.Module):
         assert patristic_matrix.shape == (n_expected, n_expected), \
             f"Expected shape {(self.z_dim, n_expected, n_expected)}, got {(self.z_dim,) + tuple(patristic_matrix.shape)}"
         z_slice = None if self.shard is None else (self.shard.z_lo, self.shard.z_hi)
+        factor, self._prefetched = self._prefetched, None
+        if factor is not None and not factor.matches(patristic_matrix, self._hyper_sites):
+            factor = None
         latent_space = pyro.sample("latent_z", dist.OUProcessPrior(patristic_matrix, sigma_f, sigma_n, lambd,
-                                                                   z_slice=z_slice).to_event(1))  # [z, n]
+                                                                   z_slice=z_slice, factor=factor).to_event(1))  # [z, n]
         return latent_space.T
 
     def gp_prior_batched(self, patristic_matrix_sorted):

@@ -194,9 +194,95 @@ class _OUPrior(torch.autograd.Function):
         return None, d_sf, d_sn, d_lam, d_x
 
 
-def ou_prior_logp(patristic: torch.Tensor, sigma_f, sigma_n, lambd, latent_z) -> torch.Tensor:
+_ELBO_DEPTH = 0
+
+
+@contextlib.contextmanager
+def elbo_scope():
+    """Marks an ELBO evaluation (guide followed by model): only there is it worth starting the prior's factorisation
+    from the guide — a stand-alone `guide(...)` call (S/main.py:1097) must not launch one."""
+    global _ELBO_DEPTH
+    _ELBO_DEPTH += 1
+    try:
+        yield
+    finally:
+        _ELBO_DEPTH -= 1
+
+
+def in_elbo_scope() -> bool:
+    return _ELBO_DEPTH > 0
+
+
+class PriorFactor:
+    """Phase 1 of the two-phase OU prior: the factored workspace of `K(sigma_f, sigma_n, lambd)` (L and -K^-1), enqueued on
+    `stream`.  `key` are the objects it was derived from: a consumer presents the same ones (`matches`) or does not get it."""
+    __slots__ = ("D", "ldd", "key", "M", "info", "stream", "n", "z", "used")
+
+    def matches(self, D, key) -> bool:
+        Dv, ldd = _matrix_view(D, "patristic_matrix")
+        return (not self.used and Dv.data_ptr() == self.D.data_ptr() and ldd == self.ldd and Dv.shape[0] == self.n
+                and len(key) == len(self.key) and all(a is b for a, b in zip(key, self.key)))
+
+
+def ou_prior_factor(patristic: torch.Tensor, sigma_f, sigma_n, lambd, key=(), stream=None) -> PriorFactor:
+    """Assemble and factor the OU covariances of all latent dimensions (everything of the prior that costs time) before the
+    latent vectors exist; `ou_prior_logp(..., factor=...)` completes the log-density and its gradients.  Runs on `stream`
+    (default: the current one) after that stream has waited for the current one."""
+    Dv, ldd = _matrix_view(patristic, "patristic_matrix")
+    f = PriorFactor()
+    f.D, f.ldd, f.key, f.used = Dv, ldd, tuple(key), False
+    sf, sn, lam = (_req(v.detach(), k).contiguous() for v, k in ((sigma_f, "sigma_f"), (sigma_n, "sigma_n"), (lambd, "lambd")))
+    f.n, f.z = Dv.shape[0], sf.shape[0]
+    cur = torch.cuda.current_stream()
+    f.stream = cur if stream is None else stream
+    if f.stream != cur:
+        f.stream.wait_stream(cur)
+    with torch.cuda.stream(f.stream):
+        f.M = torch.empty(lib.drp_ou_workspace_elems(f.n, f.n, f.z), dtype=torch.float64, device=sf.device)
+        f.info = torch.empty(f.z, dtype=torch.int32, device=sf.device)
+        _rc(lib.drp_ou_prior_factor_f64(_p(Dv), ldd, f.n, _p(sf), _p(sn), _p(lam), f.z, _p(f.M), _p(f.info), _stream()),
+            "drp_ou_prior_factor_f64")
+    return f
+
+
+class _OUPriorFromFactor(torch.autograd.Function):
+    """log N(x_z; 0, K_z) and its gradients from a `PriorFactor` (must run on the factor's stream)."""
+
+    @staticmethod
+    def forward(ctx, sf, sn, lam, x, factor):
+        sf, sn, lam, x = (_req(v, k).contiguous() for v, k in ((sf, "sigma_f"), (sn, "sigma_n"), (lam, "lambd"), (x, "latent_z")))
+        z, n = x.shape
+        if (n, z) != (factor.n, factor.z):
+            raise RuntimeError(f"ou_prior_logp: latent_z {tuple(x.shape)} does not fit the factor ({factor.z}, {factor.n})")
+        dev = x.device
+        logp = torch.empty(z, dtype=torch.float64, device=dev)
+        alpha = torch.empty((z, n), dtype=torch.float64, device=dev)
+        gsum = torch.empty((z, 3), dtype=torch.float64, device=dev)
+        part = torch.empty((z, n, 3), dtype=torch.float64, device=dev)
+        yp = torch.empty(lib.drp_ou_prior_apply_workspace_elems(n, z), dtype=torch.float64, device=dev)
+        _rc(lib.drp_ou_prior_apply_f64(_p(factor.D), factor.ldd, n, _p(lam), _p(x), z, _p(factor.M), _p(logp), _p(alpha), _p(gsum),
+                                       _p(part), _p(yp), _stream()), "drp_ou_prior_apply_f64")
+        factor.used = True
+        factor.M = None                           # the workspace goes back to the allocator (stream-ordered)
+        _info_done(factor.info, "linalg.cholesky")
+        ctx.save_for_backward(sf, sn, lam, alpha, gsum)
+        return logp
+
+    @staticmethod
+    def backward(ctx, g):
+        sf, sn, lam, alpha, gsum = ctx.saved_tensors
+        d_sf = g * 2.0 * sf * gsum[:, 0]
+        d_sn = g * 2.0 * sn * gsum[:, 2]
+        d_lam = g * sf * sf * gsum[:, 1] / (lam * lam)
+        d_x = -g[:, None] * alpha
+        return d_sf, d_sn, d_lam, d_x, None
+
+
+def ou_prior_logp(patristic: torch.Tensor, sigma_f, sigma_n, lambd, latent_z, factor: Optional[PriorFactor] = None) -> torch.Tensor:
     """`[z]` log-densities of the zero-mean OU process prior at `latent_z [z,n]` (S/models.py:100-118), with
     analytic gradients w.r.t. sigma_f, sigma_n, lambd and latent_z.  The covariance is never materialised."""
+    if factor is not None:
+        return _OUPriorFromFactor.apply(sigma_f, sigma_n, lambd, latent_z, factor)
     return _OUPrior.apply(patristic, sigma_f, sigma_n, lambd, latent_z)
 
 

@@ -215,8 +215,11 @@ class OUProcessPrior(td.Distribution, TorchDistributionMixin):
     arg_constraints = {}
     support = constraints.real_vector
 
-    def __init__(self, patristic, sigma_f, sigma_n, lambd, z_slice=None, validate_args=None):
+    def __init__(self, patristic, sigma_f, sigma_n, lambd, z_slice=None, factor=None, validate_args=None):
         self.patristic, self.sigma_f, self.sigma_n, self.lambd = patristic, sigma_f, sigma_n, lambd
+        # factor: an `ops.PriorFactor` of exactly these covariances already being computed (started from the guide); the
+        # log-density then only adds the part that needs the value
+        self.factor = factor
         # z_slice = (lo, hi): this process owns only these latent dimensions (multi-GPU z-sharding); log_prob then
         # returns the densities of the slice alone, the other ranks contribute theirs
         self.z_slice = z_slice
@@ -231,15 +234,29 @@ class OUProcessPrior(td.Distribution, TorchDistributionMixin):
     def mean(self):
         return torch.zeros(self.batch_shape + self.event_shape, dtype=self.sigma_f.dtype, device=self.sigma_f.device)
 
-    def log_prob(self, value):
+    def _log_prob_here(self, value, factor=None):
         from .. import ops
         if self.z_slice is not None:
             lo, hi = self.z_slice
             if hi <= lo:
                 return value.new_zeros(0)
             return ops.ou_prior_logp(self.patristic, self.sigma_f[lo:hi], self.sigma_n[lo:hi], self.lambd[lo:hi],
-                                     value[lo:hi])
-        return ops.ou_prior_logp(self.patristic, self.sigma_f, self.sigma_n, self.lambd, value)
+                                     value[lo:hi], factor=factor)
+        return ops.ou_prior_logp(self.patristic, self.sigma_f, self.sigma_n, self.lambd, value, factor=factor)
+
+    def log_prob(self, value):
+        f, self.factor = self.factor, None
+        if f is None or f.used:
+            return self._log_prob_here(value)
+        cur = torch.cuda.current_stream()
+        if f.stream == cur:
+            return self._log_prob_here(value, f)
+        f.stream.wait_stream(cur)                     # the value (and whatever else the caller produced) is ready
+        with torch.cuda.stream(f.stream):
+            lp = self._log_prob_here(value, f)
+        cur.wait_stream(f.stream)
+        lp.record_stream(cur)
+        return lp
 
     def log_prob_sum_async(self, value, scale=1.0):
         """Summed log-density evaluated on the side stream (`ops.side_stream`): forked from the current stream here,
@@ -250,7 +267,7 @@ class OUProcessPrior(td.Distribution, TorchDistributionMixin):
         side = ops.side_stream(value.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            lp = self.log_prob(value).sum()
+            lp = self.log_prob(value).sum()           # a factor started from the guide lives on this same stream
             if scale != 1.0:
                 lp = lp * scale
         return AsyncTerm(lp, side)

@@ -30,8 +30,10 @@ class Trace_ELBO:
         self.pre_score_hook = None
 
     def _traces(self, model, guide, args, kwargs):
-        guide_trace = poutine.trace(guide).get_trace(*args, **kwargs)
-        model_trace = poutine.trace(poutine.replay(model, trace=guide_trace), async_log_prob=True).get_trace(*args, **kwargs)
+        from ... import ops
+        with ops.elbo_scope():
+            guide_trace = poutine.trace(guide).get_trace(*args, **kwargs)
+            model_trace = poutine.trace(poutine.replay(model, trace=guide_trace), async_log_prob=True).get_trace(*args, **kwargs)
         for name, site in guide_trace.sample_sites():
             if not getattr(site["fn"], "has_rsample", False):
                 raise NotImplementedError(f"guide site {name!r} is not reparameterised")

@@ -97,44 +97,52 @@ class Run(SimpleNamespace):
     def step_from_host(self, host) -> float:
         """H2D of the step inputs (pinned, asynchronous) -> svi.step -> loss back to the host as a float.
 
-        The copies run on a side stream in the order the step consumes them, and every consumer waits for its own input
-        only (stream-waits, no host synchronisation): the guide needs the BLOSUM-encoded data set; the model's prior the
-        patristic matrix; the data set itself is first read when the likelihood is scored, after both networks ran."""
+        The copies run on a copy stream in the order the step consumes them, and every consumer waits for its own input
+        only (stream-waits, no host synchronisation): the patristic matrix first — the guide hands it to the prior's
+        factorisation before anything else happens; the BLOSUM-encoded data set is awaited in front of the encoder; the
+        data set itself when the likelihood is scored, after both networks ran."""
         lo, hi = self._leaf_rows()
         main = torch.cuda.current_stream()
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._ev_guide, self._ev_model, self._ev_score = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            self._events = [torch.cuda.Event() for _ in range(3)]      # 0 patristic, 1 blosum, 2 data set
             self._pending = []
-            real_model = self.svi.model
+            real_model, real_guide = self.svi.model, self.svi.guide
 
             def wait_for(upto):
                 while self._pending and self._pending[0][0] <= upto:
                     torch.cuda.current_stream().wait_event(self._pending.pop(0)[1])
 
+            def guide_after_inputs(*a, **k):
+                wait_for(self._guide_level)
+                return real_guide(*a, **k)
+
             def model_after_inputs(*a, **k):
-                wait_for(1)
+                wait_for(self._model_level)
                 return real_model(*a, **k)
 
             self._wait_for = wait_for
-            self.svi.model = model_after_inputs
+            self.svi.model, self.svi.guide = model_after_inputs, guide_after_inputs
+            hooked_guide = hasattr(self.guide, "_encode")              # DRAUPNIRGUIDES: waits for the BLOSUM copy itself
+            if hooked_guide:
+                self.guide.__dict__["_before_encode"] = lambda: wait_for(1)
+            self._guide_level = 0 if hooked_guide else 1
             if hasattr(self.svi.loss, "pre_score_hook"):
                 self.svi.loss.pre_score_hook = lambda: wait_for(2)
-                self._score_level = 2
+                self._model_level = 1
             else:                                   # an ELBO without the hook (real Pyro): the model waits for everything
-                self._score_level = 1
+                self._model_level = 2
         cs = self._copy_stream
         cs.wait_stream(main)                       # the previous step has finished reading the staging buffers
         with torch.cuda.stream(cs):
+            self._staging["patristic"].copy_(host["patristic"], non_blocking=True)
+            self._events[0].record(cs)
             if "blosum" in host:
                 self._staging["blosum"][lo:hi].copy_(host["blosum"][lo:hi], non_blocking=True)
-            self._ev_guide.record(cs)
-            self._staging["patristic"].copy_(host["patristic"], non_blocking=True)
-            self._ev_model.record(cs)
+            self._events[1].record(cs)
             self._staging["dataset"][lo:hi].copy_(host["dataset"][lo:hi], non_blocking=True)
-            self._ev_score.record(cs)
-        main.wait_event(self._ev_guide)
-        self._pending = [(1, self._ev_model), (self._score_level, self._ev_score)]
+            self._events[2].record(cs)
+        self._pending = [(k, e) for k, e in enumerate(self._events)]
         st = self._staging
         loss = self.svi.step(st["dataset"], st["patristic"], None, st.get("blosum"), None, None)
         self._wait_for(2)                          # nothing may be left waiting when the step returns

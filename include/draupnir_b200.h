@@ -82,6 +82,16 @@ int drp_ou_prior_f64(const double* D, int64_t ldd, int n, const double* sf, cons
                      const double* x, int z, int want_grad, double* logp, double* alpha, double* gsum, double* M,
                      double* part, int32_t* info, void* stream);
 
+/* The same in two phases (want_grad = 1 layout, M of drp_ou_workspace_elems(n, n, z) doubles): the factorisation needs
+ * only the hyper-parameters (S/models.py:90-92,101-105) and may be enqueued before the latent vectors exist (they come
+ * out of the guide's encoder, S/guides.py:116-120); the second call needs x (S/models.py:118) and costs one symmetric
+ * matrix-vector product per latent dimension.  ypart: drp_ou_prior_apply_workspace_elems(n, z) doubles.             */
+int drp_ou_prior_factor_f64(const double* D, int64_t ldd, int n, const double* sf, const double* sn, const double* lam,
+                            int z, double* M, int32_t* info, void* stream);
+int64_t drp_ou_prior_apply_workspace_elems(int n, int z);
+int drp_ou_prior_apply_f64(const double* D, int64_t ldd, int n, const double* lam, const double* x, int z, double* M,
+                           double* logp, double* alpha, double* gsum, double* part, double* ypart, void* stream);
+
 /* ---- K4/K5  MultivariateNormal(0, K).log_prob(x) for an explicit covariance batch ------------------------------ */
 int drp_mvn_logprob_f64(const double* K, const double* x, int n, int z, int want_grad, double* logp, double* alpha,
                         double* M, int32_t* info, void* stream);

@@ -127,6 +127,35 @@ def test_ou_prior_logp_and_gradients(cuda, n, z):
     assert rel(lp2.cpu(), lp_ref.detach()) < 1e-11
 
 
+@pytest.mark.parametrize("n,z", [(5, 3), (64, 2), (130, 4), (450, 3)])
+def test_ou_prior_two_phase(cuda, n, z):
+    """Factor first (hyper-parameters only, possibly on another stream), complete with the latent vectors later: same
+    log-densities and gradients as the oracle, and a factor is handed out only for the tensors it was made from."""
+    from draupnir_asr_b200 import ops
+    D, sf, sn, lam, x = _spd_problem(n, z, seed=n + 2)
+    ps = [v.clone().requires_grad_(True) for v in (sf, sn, lam, x)]
+    K = O.ou_covariance(D, *ps[:3])
+    lp_ref = torch.distributions.MultivariateNormal(torch.zeros(1, n, dtype=torch.float64), K).log_prob(ps[3])
+    w = torch.linspace(0.5, 1.5, z, dtype=torch.float64)
+    (lp_ref * w).sum().backward()
+    Dg = D.to(cuda)
+    pg = [v.clone().to(cuda).requires_grad_(True) for v in (sf, sn, lam, x)]
+    side = torch.cuda.Stream()
+    f = ops.ou_prior_factor(Dg, *pg[:3], key=tuple(pg[:3]), stream=side)
+    assert f.matches(Dg, tuple(pg[:3])) and not f.matches(Dg, (pg[0], pg[1], pg[2].clone()))
+    cur = torch.cuda.current_stream()
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        lp = ops.ou_prior_logp(Dg, *pg, factor=f)
+    cur.wait_stream(side)
+    assert f.used and not f.matches(Dg, tuple(pg[:3]))
+    assert rel(lp.detach().cpu(), lp_ref.detach()) < 1e-10
+    (lp * w.to(cuda)).sum().backward()
+    torch.cuda.synchronize()
+    for a, b, name in zip(pg, ps, ("sigma_f", "sigma_n", "lambd", "latent_z")):
+        assert rel(a.grad.cpu(), b.grad) < 1e-7, name
+
+
 def test_mvn_logprob_explicit_cov(cuda):
     from draupnir_asr_b200 import ops
     n, z = 90, 4
