@@ -300,9 +300,9 @@ def run_ours(args, w, rank, world, local_rank):
         launches_warm = lib.drp_launch_count() - lw
     log(f"[rank {rank}] warm-up done, -ELBO {loss:.4f}; {launches_warm} launches of this library per step")
     sampler.wait_first_sample()
-    barrier()
     torch.cuda.synchronize()
     lib.drp_timing_enable(int(launches_warm * (args.steps + 1)) + 64)   # events for the whole timed region, created now
+    barrier()                                                          # ranks leave the (rank-dependent) set-up together
     l0 = lib.drp_launch_count()
     ms = timed(run.step, args.steps)
     launches = lib.drp_launch_count() - l0
