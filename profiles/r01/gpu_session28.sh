@@ -6,6 +6,6 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; ech
 tail -8 gpurun_out/t_all.log
 grep -q "rc=0" gpurun_out/t_all.log || exit 0
 timeout 300 python profiles/trace_patristic.py > gpurun_out/trace_patristic.txt 2>&1
-timeout 900 python profiles/sweep_c5.py > gpurun_out/sweep_c5.json 2> gpurun_out/sweep_c5.err
+timeout 900 python tests/sweep_c5.py > gpurun_out/sweep_c5.json 2> gpurun_out/sweep_c5.err
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err
 ls -la gpurun_out

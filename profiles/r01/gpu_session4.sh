@@ -8,5 +8,5 @@ grep -q "rc=0" gpurun_out/t_ozaki.log || exit 0
 for s in 5 6; do
   DRP_OZAKI_SLICES=$s timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4_s$s.json 2> gpurun_out/bench_c4_s$s.err
 done
-timeout 900 python profiles/sweep_c5.py > gpurun_out/sweep_c5.json 2> gpurun_out/sweep_c5.err
+timeout 900 python tests/sweep_c5.py > gpurun_out/sweep_c5.json 2> gpurun_out/sweep_c5.err
 ls -la gpurun_out

@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """C5 of BASELINE.json: patristic-matrix + OU-covariance build sweep, 100-8,000 leaves, on one B200.
 
+Test infrastructure (it checks against and times `oracle/`, which only tests/, smoke() and bench.py's CPU legs may use);
+a script, not collected by pytest.
+
 For each size: (a) LCA indices bit-exact against the scalar C oracle (all pairs up to 2,000 leaves, a seeded random
 256 x 256 rows x cols subset above), distances rtol 1e-12; (b) device time (CUDA events, median of 7 after 3 warm-ups,
 L2 flushed between repetitions) of the all-node patristic build and of the [30, n, n] OU covariance assembly, reported
 as algorithmic GB/s against the measured HBM peak; (c) the host-CPU time of the same builds with the oracle
 (parent-walk C port / torch restatement of OUKernel_Fast) on a bounded sample.
 
-    python profiles/sweep_c5.py > gpurun_out/sweep_c5.json
+    python tests/sweep_c5.py > gpurun_out/sweep_c5.json
 """
 from __future__ import annotations
 
