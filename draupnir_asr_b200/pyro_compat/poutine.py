@@ -42,6 +42,7 @@ class Trace:
 
     def __init__(self):
         self.nodes = OrderedDict()
+        self.return_value = None
 
     def add_node(self, name, site):
         # sample sites are keyed by their name, param sites by "name@param": a PyroParam and a sample site may
@@ -121,7 +122,7 @@ class trace(Messenger):
                     site["log_prob_async"] = term
 
     def get_trace(self, *args, **kwargs) -> Trace:
-        self(*args, **kwargs)
+        self.trace.return_value = self(*args, **kwargs)       # Pyro records it as the `_RETURN` node
         return self.trace
 
 

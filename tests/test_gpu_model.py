@@ -184,6 +184,47 @@ def test_host_fed_step_equals_resident_step(cuda, guide):
         assert abs(la - lb) <= 1e-10 * abs(la), (la, lb)
 
 
+@pytest.mark.parametrize("guide", ["delta_map", "variational"])
+def test_slim_epoch_loop(cuda, guide, tmp_path):
+    """epochs.run_epochs: same loss trajectory as bare `svi.step` calls, the reference's per-epoch
+    statistics and checkpoints without a second guide forward."""
+    from draupnir_asr_b200 import epochs
+    from draupnir_asr_b200.utils import Deferred
+    n, L = 25, 18
+    torch.manual_seed(0)
+    problem, run_a, _ = _pair(n, L, guide, cuda)
+    torch.manual_seed(0)
+    _, run_b, _ = _pair(n, L, guide, cuda)
+    eps = torch.randn(30, n, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    with _FixedNoise(eps):
+        want = [run_a.step() for _ in range(4)]
+        out = epochs.run_epochs(run_b.svi, run_b.Draupnir, run_b.guide, run_b.step_args(), run_b.patristic_matrix_full, 4,
+                                results_dir=str(tmp_path), stats_every=2, check_point_epoch=3)
+    assert out["train_loss"] == pytest.approx(want, rel=1e-12)
+    assert out["stats_epochs"] == [0, 2] and len(out["average_pid"]) == 2 and all(0.0 <= p <= 100.0 for p in out["average_pid"])
+    ent = out["entropies"]
+    assert ent.shape == (n, L + 1) and torch.equal(ent[:, 0], problem.dataset_train[:, 0, 1].to(ent))
+    assert torch.isfinite(ent).all() and bool((ent[:, 1:] >= 0).all())
+    est = out["map_estimates"]
+    assert {"alpha", "sigma_f", "sigma_n", "lambd", "latent_z"} <= set(est)
+    if guide == "variational":                      # the encoder's complete pass was never run
+        assert isinstance(dict.__getitem__(est, "rnn_hidden_states"), Deferred)
+    ck = tmp_path / "Draupnir_Checkpoints"
+    assert (ck / "Model_state_dict.p").exists() and (ck / "Optimizer_state.p").exists()
+    state = torch.load(ck / "Model_state_dict.p")
+    assert set(state) == set(run_b.Draupnir.state_dict())
+    # the helpers against their definitions (S/main.py:527-539, S/models_utils.py:409-427)
+    data = problem.dataset_train.to(cuda)
+    pred = data[:, 2:, 0].clone()
+    pred[:, 0] += 1
+    pid, std = epochs.calculate_percent_id(data, pred, L)
+    assert pid == pytest.approx(100.0 * (L - 1) / L) and std == pytest.approx(0.0, abs=1e-9)
+    logits = torch.randn(n, L, 21, dtype=torch.float64, device=cuda)
+    p = torch.exp(logits) / (1 + torch.exp(logits))
+    ref = -(p * p.log()).sum(2)
+    assert torch.allclose(epochs.compute_sites_entropies(logits, data[:, 0, 1])[:, 1:], ref, rtol=1e-12)
+
+
 def test_model_refuses_cpu_device():
     from draupnir_asr_b200 import runtime
     problem = S.make_problem(5, 7)
