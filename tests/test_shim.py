@@ -132,3 +132,42 @@ def test_deferred_dict_behaves_like_a_dict_of_values():
         assert got == {"a": 1, "b": 7, "c": 3}, got
         assert not any(isinstance(v, Deferred) for v in dict.values(got))
     assert type(pickle.loads(pickle.dumps(make()))) is dict
+
+
+def test_guide_return_value_is_recorded_and_epoch_helpers():
+    """The guide trace keeps the guide's return value (Pyro's `_RETURN` node): `epochs.run_epochs` takes `map_estimates`
+    from the step it just ran instead of a second guide forward.  Plus the two statistics helpers on plain tensors."""
+    from draupnir_asr_b200 import epochs
+    from draupnir_asr_b200.backend import dist, pyro
+    from draupnir_asr_b200.pyro_compat.infer import SVI, Trace_ELBO
+    from draupnir_asr_b200.pyro_compat.optim import ClippedAdam
+    pyro.clear_param_store()
+
+    def model(x):
+        z = pyro.sample("z", dist.Normal(torch.zeros(3, dtype=torch.float64), 1.0).to_event(1))
+        pyro.sample("x", dist.Normal(z, 1.0).to_event(1), obs=x)
+
+    def guide(x):
+        loc = pyro.param("loc", torch.zeros(3, dtype=torch.float64))
+        return {"latent": pyro.sample("z", dist.Normal(loc, 0.5).to_event(1))}
+
+    svi = SVI(model, guide, ClippedAdam({"lr": 1e-2}), Trace_ELBO())
+    x = torch.ones(3, dtype=torch.float64)
+    svi.step(x)
+    guide_trace = svi.loss.last_traces[1]
+    assert guide_trace.return_value["latent"] is guide_trace.nodes["z"]["value"]
+    assert epochs._guide_return(svi, guide, (x,)) is guide_trace.return_value
+    n, L = 4, 6
+    data = torch.zeros(n, L + 2, 30, dtype=torch.float64)
+    data[:, 2:, 0] = torch.randint(0, 21, (n, L)).double()
+    data[:, 0, 1] = torch.arange(n)
+    pred = data[:, 2:, 0].clone()
+    pred[:2, 0] += 1                                        # two sequences with one wrong site
+    pid, std = epochs.calculate_percent_id(data, pred, L)
+    per_seq = torch.tensor([100.0 * (L - 1) / L] * 2 + [100.0] * 2, dtype=torch.float64)
+    assert pid == pytest.approx(float(per_seq.mean())) and std == pytest.approx(float(per_seq.std()))
+    logits = torch.randn(n, L, 21, dtype=torch.float64)
+    p = torch.exp(logits) / (1 + torch.exp(logits))
+    ent = epochs.compute_sites_entropies(logits, data[:, 0, 1])
+    assert ent.shape == (n, L + 1) and torch.equal(ent[:, 0], data[:, 0, 1])
+    assert torch.allclose(ent[:, 1:], -(p * p.log()).sum(2), rtol=1e-12)
