@@ -3,8 +3,9 @@
 The reference's loop (S/main.py:1089-1128; S/ = /root/reference/draupnir/src/draupnir/) does, EVERY epoch: a second guide
 forward to obtain `map_estimates` (:1097), one `svi.step` (:1100), an argmax decode of all leaves (:1113-1120: one more
 decoder forward), two checkpoint writes (:1121-1122), and the per-site entropies / percent identity of the decoded leaves
-(:1124-1128, the latter on the CPU).  Measured on this implementation (`profiles/epoch_extras.py`) these extras cost as
-much as the step itself or more, so the loop below keeps their RESULTS and drops their repetition:
+(:1124-1128, the latter on the CPU).  Measured on this implementation (`profiles/epoch_extras.py`,
+`profiles/r01/epoch_extras.txt`) these extras cost 0.4-0.55 of a step before any disk I/O (C4: 6.2 ms second guide call +
+3.1 ms decode + 1.8 ms serialisation against a 23.3 ms step), so the loop below keeps their RESULTS and drops their repetition:
 
 * `map_estimates` are the guide's return value of the step that was just taken (`Trace_ELBO.last_traces`: no second guide
   forward; the entries that need the encoder's complete pass stay deferred until somebody reads them);
