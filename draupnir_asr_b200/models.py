@@ -224,13 +224,16 @@ class DRAUPNIRModelClass(nn.Module):
         1e-6 to every entry of the conditional covariance (:193); so does this."""
         return self.conditional_sampling_many(map_estimates, patristic_matrix, 1)[0]
 
-    def conditional_sampling_many(self, map_estimates, patristic_matrix, n_samples: int):
+    def conditional_sampling_many(self, map_estimates, patristic_matrix, n_samples: int, eps=None):
         """`n_samples` independent draws `[S, ni, z]` of the internal nodes given the leaves from ONE factorisation:
-        `mean + L eps` as a single batched product (replaces S x `conditional_sampling`)."""
+        `mean + L eps` as a single batched product (replaces S x `conditional_sampling`).  `eps`
+        (`[z, ni, S]` standard-normal numbers) can be supplied to reproduce a draw."""
         assert patristic_matrix[1:, 1:].shape == (self.n_all, self.n_all), \
             "Remember to use the entire/full patristic matrix for conditional sampling!"
         mean, tril = self._conditional_factor(map_estimates, patristic_matrix)
-        eps = torch.randn((self.z_dim, self.n_internal, int(n_samples)), dtype=mean.dtype, device=mean.device)
+        if eps is None:
+            eps = torch.randn((self.z_dim, self.n_internal, int(n_samples)), dtype=mean.dtype, device=mean.device)
+        assert eps.shape == (self.z_dim, self.n_internal, int(n_samples))
         draws = mean.unsqueeze(-1) + torch.bmm(tril, eps)                       # [z, ni, S]
         latent_space = draws.permute(2, 1, 0).contiguous()
         assert latent_space.shape == (int(n_samples), self.n_internal, self.z_dim)

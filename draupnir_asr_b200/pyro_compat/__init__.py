@@ -208,4 +208,9 @@ def install_as_pyro(force: bool = False) -> bool:
     sys.modules["pyro"] = me
     for sub in ("poutine", "distributions", "optim", "nn", "infer", "infer.autoguide", "contrib", "contrib.easyguide"):
         sys.modules[f"pyro.{sub}"] = sys.modules[f"{__name__}.{sub}"]
+    import types
+    td_mod = types.ModuleType("pyro.distributions.torch_distribution")      # S/models_utils.py:18 imports it by path
+    td_mod.TorchDistribution = distributions.TorchDistribution
+    td_mod.TorchDistributionMixin = distributions.TorchDistributionMixin
+    sys.modules["pyro.distributions.torch_distribution"] = td_mod
     return True

@@ -280,5 +280,12 @@ class OUProcessPrior(td.Distribution, TorchDistributionMixin):
         return (L * eps.unsqueeze(-2)).sum(-1)
 
 
+class TorchDistribution(td.Distribution, TorchDistributionMixin):
+    """Base class name reference code subclasses (`pyro.distributions.torch_distribution.TorchDistribution`,
+    S/models_utils.py:18,330)."""
+
+
+Distribution = TorchDistribution      # `dist.Distribution` appears in type annotations (S/models_utils.py:337)
+
 __all__ = ["HalfNormal", "Normal", "Delta", "MultivariateNormal", "Categorical", "Independent", "OUProcessPrior",
-           "TorchDistributionMixin", "constraints"]
+           "TorchDistributionMixin", "TorchDistribution", "constraints"]

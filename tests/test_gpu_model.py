@@ -230,3 +230,65 @@ def test_model_refuses_cpu_device():
     problem = S.make_problem(5, 7)
     with pytest.raises(RuntimeError, match="CUDA"):
         runtime.build_run(problem, "delta_map", device="cpu")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The CUDA path against vectors produced by the REFERENCE'S OWN code (tests/golden/ref_*.npz; generator:
+# tests/golden/make_reference_golden.py — the reference's models.py / guides.py / train.py executed on the CPU).
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case,n,L,guide,seed", [("ref_c1_delta_map", 19, 225, "delta_map", 0),
+                                                 ("ref_c1_variational", 19, 225, "variational", 0),
+                                                 ("ref_n48_delta_map", 48, 64, "delta_map", 3),
+                                                 ("ref_n48_variational", 48, 64, "variational", 3)])
+def test_cuda_path_reproduces_reference_vectors(cuda, case, n, L, guide, seed):
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{case}.npz"))
+    problem, run, _ = _pair(n, L, guide, cuda, seed=seed)
+    eps = torch.from_numpy(g["eps"])
+    # -ELBO (gate 1e-4 relative; achieved ~1e-12) and every site's log-prob sum
+    with _FixedNoise(eps):
+        loss = run.svi.loss.differentiable_loss(run.Draupnir.model, run.guide, *run.step_args())
+    mt, gt = run.svi.loss.last_traces
+    assert abs(float(loss) - float(g["loss0"])) / abs(float(g["loss0"])) <= 1e-10
+    for name, site in mt.sample_sites():
+        got, want = float(site["log_prob_sum"]), float(g[f"term_{name}"])
+        assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (name, got, want)
+    assert abs(float(gt.log_prob_sum()) - float(g["term_log_q"])) <= 1e-9 * max(1.0, abs(float(g["term_log_q"])))
+    # gradients (gate 1e-3 relative per parameter group)
+    loss.backward()
+    for k in ("alpha", "sigma_f", "sigma_n", "lambd") + (("latent_z",) if guide == "delta_map" else ()):
+        u = getattr(run.guide, f"{k}_unconstrained")
+        got, want = u.grad.detach().cpu().numpy().reshape(-1), g[f"grad_{k}"].reshape(-1)
+        assert np.linalg.norm(got - want) <= 1e-7 * max(np.linalg.norm(want), 1e-30), k
+        u.grad = None
+    groups = {"decoder": run.Draupnir.decoder, "embed": run.Draupnir.embed}
+    if guide == "variational":
+        groups.update(encoder=run.guide.encoder, embeddingencoder=run.guide.embeddingencoder)
+    for k, mod in groups.items():
+        got = float(torch.cat([p.grad.reshape(-1) for p in mod.parameters()]).norm())
+        assert abs(got - float(g[f"gradnorm_{k}"])) <= 1e-7 * float(g[f"gradnorm_{k}"]), k
+        for p in mod.parameters():
+            p.grad = None
+    # three epochs of the reference's training loop
+    for step in range(3):
+        with _FixedNoise(eps):
+            l = run.step()
+        assert abs(l - g["losses"][step]) / abs(g["losses"][step]) <= 1e-8, (step, l, g["losses"][step])
+    # the guide's dictionary, conditional mean, one conditional draw on the stored numbers, argmax sequences
+    with torch.no_grad(), _FixedNoise(eps):
+        map_est = run.guide(*run.step_args())
+    assert sorted(map_est.keys()) == list(g["guide_keys"])
+    map_est = {k: map_est[k].detach() for k in ("alpha", "sigma_f", "sigma_n", "lambd", "latent_z")}
+    assert np.allclose(map_est["latent_z"].cpu().numpy(), g["map_latent_z"], rtol=1e-7, atol=1e-9)
+    mean = run.Draupnir.conditional_samplingMAP(map_est, run.patristic_matrix_full)
+    assert np.allclose(mean.cpu().numpy(), g["cond_mean"], rtol=1e-7, atol=1e-9)
+    draws = run.Draupnir.conditional_sampling_many(map_est, run.patristic_matrix_full, 1,
+                                                   eps=torch.from_numpy(g["cond_eps"]).to(cuda)[:, :, None])
+    assert np.allclose(draws[0].cpu().numpy(), g["cond_draw"], rtol=1e-6, atol=1e-8)
+    out = run.Draupnir.sample(map_est, 1, None, run.patristic_matrix_full, None, use_argmax=True, use_test=False,
+                              use_test2=True)
+    assert (out.aa_sequences.cpu().numpy() == g["argmax_internal"]).mean() >= 0.999
+    assert abs(float(torch.logsumexp(out.logits[..., 0].reshape(-1), 0)) - float(g["logits_internal_lse0"])) <= 1e-8
+    out = run.Draupnir.sample(map_est, 1, None, run.patristic_matrix_full, None, use_argmax=True, use_test=False)
+    assert (out.aa_sequences.cpu().numpy() == g["argmax_leaves"]).mean() >= 0.999

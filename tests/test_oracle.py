@@ -1,4 +1,5 @@
-"""Pins the CPU oracle (parity is otherwise unpinned: the reference ships no golden vectors for this path).
+"""Cross-checks of the CPU oracle that need no reference (tests/test_reference_pin.py pins it to the reference's own
+code; the reference ships no golden vectors for this path).
 
 (i) closed forms on tiny trees, (ii) the precision-partition conditional (the reference's form) against an independent
 Schur-complement derivation, (iii) parent-walk LCA vs brute-force path sums vs the C port, on random / caterpillar /
