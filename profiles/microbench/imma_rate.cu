@@ -79,8 +79,8 @@ __device__ __forceinline__ uint32_t elect_one()
 // The whole warp walks the loop convergently and one elected lane issues (tcgen05.mma inside divergent single-thread
 // code is wrapped in an ELECT/branch loop that costs more than the MMA lasts - that version of this benchmark measured
 // 151 cycles per MMA for every shape: the issue path, not the tensor pipe).
-template <int KIND, int N, int NACC, int NA>
-__device__ long long run_cfg(uint32_t tmem, uint32_t sA, uint32_t sB, uint32_t bar, uint32_t& phase, int reps)
+template <int KIND, int N, int NACC, int NA, int CI>
+__device__ long long run_cfg(uint32_t tmem, uint32_t sA, uint32_t sB, uint32_t bar, uint32_t bar2, uint32_t& phase, int reps)
 {
     const uint32_t idesc = KIND == 2 ? idesc_bf16(N, 128) : idesc_i8(N, 128);
     const uint32_t a_tmem = tmem + 480;     // TS mode: A in the last 32 columns (8 columns per 32-byte k-step)
@@ -103,6 +103,9 @@ __device__ long long run_cfg(uint32_t tmem, uint32_t sA, uint32_t sB, uint32_t b
                         else mma_f16_ss(d, ad, bd, idesc, 1);
                     }
                 }
+                // CI > 0: a tcgen05.commit (to a barrier nobody waits on) after every CI MMAs, as the update kernel
+                // does once or twice per B block - does a commit cost tensor-pipe time?
+                if (CI > 0 && ((r + 4) % CI) == 0) commit(bar2);
             }
             __syncwarp();
             di = (di + 4) % NACC;
@@ -112,7 +115,7 @@ __device__ long long run_cfg(uint32_t tmem, uint32_t sA, uint32_t sB, uint32_t b
         __syncwarp();
         long long spins = 0;
         while (!mbar_try_wait(bar, phase)) {
-            if (++spins > 200000000ll) break;       // bounded: never hang the device
+            if (++spins > 5000000ll) break;         // bounded: never hang the device
         }
         phase ^= 1;
         const long long t1 = clock64();
@@ -122,9 +125,10 @@ __device__ long long run_cfg(uint32_t tmem, uint32_t sA, uint32_t sB, uint32_t b
 }
 
 #define CFG_LIST(X) \
-    X(0, 64, 1, 1) X(0, 64, 6, 1) X(0, 64, 6, 12) X(0, 128, 1, 1) X(0, 128, 3, 12) X(0, 256, 1, 1) X(0, 256, 2, 12) \
-    X(1, 64, 1, 1) X(1, 64, 6, 1) X(1, 128, 3, 1) X(1, 256, 1, 1) \
-    X(2, 64, 1, 1) X(2, 64, 6, 12) X(2, 128, 3, 12) X(2, 256, 2, 12)
+    X(0, 64, 1, 1, 0) X(0, 64, 6, 1, 0) X(0, 64, 6, 12, 0) X(0, 128, 1, 1, 0) X(0, 128, 3, 12, 0) X(0, 256, 1, 1, 0) X(0, 256, 2, 12, 0) \
+    X(1, 64, 1, 1, 0) X(1, 64, 6, 1, 0) X(1, 128, 3, 1, 0) X(1, 256, 1, 1, 0) \
+    X(2, 64, 1, 1, 0) X(2, 64, 6, 12, 0) X(2, 128, 3, 12, 0) X(2, 256, 2, 12, 0) \
+    X(0, 64, 6, 12, 4) X(0, 64, 6, 12, 8) X(0, 64, 6, 12, 24) X(0, 128, 3, 12, 4)
 
 __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long* out)
 {
@@ -134,11 +138,12 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long* out)
     uint8_t* gen = raw_smem + (base - raw);
     const uint32_t sA = base;                       // 12 x 16 KB
     const uint32_t sB = base + 12 * 16384;          // 32 KB (N = 256 rows x 128 B)
-    const uint32_t bar = sB + 32768;
+    const uint32_t bar = sB + 32768, bar2 = sB + 32768 + 8;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + 12 * 16384 + 32768 + 16);
     for (int i = threadIdx.x; i < (12 * 16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(gen)[i] = 0;
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -153,9 +158,9 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long* out)
     if (threadIdx.x < 32) {
         uint32_t phase = 0;
         int c = 0;
-#define RUN(K, N, NACC, NA)                                                         \
+#define RUN(K, N, NACC, NA, CI)                                                      \
     {                                                                               \
-        const long long t = run_cfg<K, N, NACC, NA>(tmem, sA, sB, bar, phase, reps); \
+        const long long t = run_cfg<K, N, NACC, NA, CI>(tmem, sA, sB, bar, bar2, phase, reps); \
         if (blockIdx.x == 0 && threadIdx.x == 0) out[c] = t;                        \
         ++c;                                                                        \
     }
@@ -169,14 +174,14 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long* out)
 int main(int argc, char** argv)
 {
     const int ctas = argc > 1 ? atoi(argv[1]) : 1;
-#define HOSTCFG(K, N, NACC, NA) {K, N, NACC, NA, 512},
+#define HOSTCFG(K, N, NACC, NA, CI) {K, N, NACC, NA, CI},
     const Cfg host[] = {CFG_LIST(HOSTCFG)};
     const int n = sizeof(host) / sizeof(host[0]);
     long long* dout;
     cudaMalloc(&dout, n * sizeof(long long));
     const int smem = 1024 + 12 * 16384 + 32768 + 64;
     cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    rate_kernel<<<ctas, 128, smem>>>(host[0].reps, dout);
+    rate_kernel<<<ctas, 128, smem>>>(528, dout);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         printf("error: %s\n", cudaGetErrorString(e));
@@ -185,10 +190,10 @@ int main(int argc, char** argv)
     long long res[64];
     cudaMemcpy(res, dout, n * sizeof(long long), cudaMemcpyDeviceToHost);
     const char* kinds[] = {"i8 SS (A,B in smem)", "i8 TS (A in TMEM) ", "bf16 SS            "};
-    printf("# %d CTA(s); M = 128; cycles per MMA (K = 32 bytes per row), best of 3 x %d back-to-back MMAs\n", ctas, host[0].reps);
-    printf("# kind                 N   accumulators  A tiles   cycles/MMA   math floor (128*N/256)\n");
+    printf("# %d CTA(s); M = 128; cycles per MMA (K = 32 bytes per row), best of 3 x %d back-to-back MMAs\n", ctas, 528);
+    printf("# kind                 N   accumulators  A tiles   cycles/MMA   math floor (128*N/256)   commit every\n");
     for (int c = 0; c < n; ++c)
-        printf("%s  %4d  %6d  %10d  %11.1f  %8d\n", kinds[host[c].kind], host[c].N, host[c].nacc, host[c].na,
-               (double)res[c] / host[c].reps, 128 * host[c].N / 256);
+        printf("%s  %4d  %6d  %10d  %11.1f  %8d  %12d\n", kinds[host[c].kind], host[c].N, host[c].nacc, host[c].na,
+               (double)res[c] / 528, 128 * host[c].N / 256, host[c].reps);
     return 0;
 }
