@@ -30,6 +30,7 @@ SIGNATURES = {
     "drp_factor_workspace_bytes": (_i64, [_i32, _i32]),
     "drp_potrf_batched_f64": (_i32, [_p, _i32, _i32, _i32, _p, _p, _i64, _p]),
     "drp_ozaki_set_trace": (None, [_p]),
+    "drp_ozaki_set_prof": (None, [_p]),
     "drp_syrk_update_f64": (_i32, [_p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),
     "drp_ou_workspace_ld": (_i64, [_i32, _i32]),
     "drp_ou_workspace_elems": (_i64, [_i32, _i32, _i32]),

@@ -64,6 +64,7 @@ struct OzParams {
     int nTi, nTj, units_per_z, total_units;
     int K;                     // real contraction length (columns of the panel); the k-blocks are zero-padded
     long long* trace;          // optional event trace of CTA 0 (debug; nullptr in production)
+    long long* prof;           // optional per-CTA wait-time sums [grid][16] (debug; nullptr in production)
     int* counter;              // next work unit (zeroed by the slicing kernel that precedes every update)
 };
 
@@ -102,6 +103,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) {
         if (((++spins) & 0xFFF) == 0 && clock64() - t0 > OZ_TIMEOUT_CYCLES) __trap();
     }
+}
+// mbar_wait that adds the cycles it blocked to `acc` (phase accounting of the roles; two clock reads per wait)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc)
+{
+    const long long t = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t;
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
@@ -318,6 +326,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
         if (lane == 0) {
             uint32_t a_phase = 0, b_phase = 0;
             int st = 0;
+            long long w_a = 0, w_b = 0;
+            const long long t_start = clock64();
             for (int i = 0;; ++i) {
                 int u = atomicAdd(p.counter, 1);
                 if (u >= p.total_units) u = -1;
@@ -327,7 +337,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                 int zz, ti, tj0, ntj;
                 oz_decode(p, u, zz, ti, tj0, ntj);
                 const uint8_t* src = p.sl + (int64_t)zz * p.sl_bs;
-                mbar_wait(bar_a_empty, a_phase ^ 1);
+                mbar_wait_t(bar_a_empty, a_phase ^ 1, w_a);
                 OZ_TRACE(100);
                 mbar_expect_tx(bar_a_full, Cfg::A_BYTES);
                 for (int a = 0; a < Cfg::NA; ++a)
@@ -337,7 +347,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                 for (int t = 0; t < ntj; ++t) {
                     const int64_t cc0 = (int64_t)(tj0 + t) * OZ_TN;
                     for (int b = 0; b < Cfg::NA; ++b) {
-                        mbar_wait(bar_b_empty + 8 * st, b_phase ^ 1);
+                        mbar_wait_t(bar_b_empty + 8 * st, b_phase ^ 1, w_b);
                         OZ_TRACE(200 + b);
                         mbar_expect_tx(bar_b_full + 8 * st, OZ_B_TILE);
                         bulk_g2s(sB + st * OZ_B_TILE, src + ((int64_t)b * p.Rpad + cc0) * OZ_ROWB, OZ_B_TILE,
@@ -349,6 +359,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                     }
                 }
             }
+            if (p.prof) {
+                long long* o = p.prof + 16 * blockIdx.x;
+                o[0] = clock64() - t_start;   // producer: total, waiting for the A strip to be released, for a free B stage
+                o[1] = w_a;
+                o[2] = w_b;
+            }
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -359,25 +375,28 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
         uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
         int st = 0;
         const bool full_k = p.K == KBN * OZ_ROWB;      // no ragged last k-block
+        long long w_unit = 0, w_a = 0, w_acc = 0, w_b = 0, n_tiles = 0;
+        const long long t_start = clock64();
         for (int i = 0;; ++i) {
-            mbar_wait(bar_unit + 8 * (i & 3), (uint32_t)(i >> 2) & 1u);
+            mbar_wait_t(bar_unit + 8 * (i & 3), (uint32_t)(i >> 2) & 1u, w_unit);
             const int u = unit_q[i & 3];
             if (u < 0) break;
             int zz, ti, tj0, ntj;
             oz_decode(p, u, zz, ti, tj0, ntj);
-            mbar_wait(bar_a_full, a_phase);
+            mbar_wait_t(bar_a_full, a_phase, w_a);
             a_phase ^= 1;
             tc_fence_after();
             if (lane == 0) OZ_TRACE(300);
             for (int t = 0; t < ntj; ++t) {
-                mbar_wait(bar_acc_empty, acc_phase ^ 1);
+                mbar_wait_t(bar_acc_empty, acc_phase ^ 1, w_acc);
+                ++n_tiles;
                 tc_fence_after();
                 if (lane == 0) OZ_TRACE(310);
 #pragma unroll
                 for (int ub = 0; ub < S; ++ub) {               // slice of B (columns of the update)
 #pragma unroll
                     for (int kb = 0; kb < KBN; ++kb) {
-                        mbar_wait(bar_b_full + 8 * st, b_phase);
+                        mbar_wait_t(bar_b_full + 8 * st, b_phase, w_b);
                         tc_fence_after();
                         if (lane == 0) OZ_TRACE(400 + ub * KBN + kb);
                         if (elect_one()) {
@@ -413,6 +432,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                 acc_phase ^= 1;
             }
         }
+        if (p.prof && lane == 0) {
+            long long* o = p.prof + 16 * blockIdx.x;
+            o[3] = clock64() - t_start;       // MMA issuer: total, waiting for a unit, the A strip, drained accumulators, a B block
+            o[4] = w_unit;
+            o[5] = w_a;
+            o[6] = w_acc;
+            o[7] = w_b;
+            o[8] = n_tiles;
+        }
     } else {
         // ============================ epilogue ================================
         // warp (q, h) owns rows 32q.. and columns 16h.. of the 128x64 tile; thread t holds, for row select i = 0..3,
@@ -424,8 +452,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
         const int tr = lane >> 2, tc = 2 * (lane & 3);
         const bool vec_ok = ((p.ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.M) & 15) == 0) && ((p.bs & 1) == 0);
         uint32_t acc_phase = 0;
+        long long w_unit = 0, w_acc = 0;
+        const long long t_start = clock64();
         for (int i = 0;; ++i) {
-            mbar_wait(bar_unit + 8 * (i & 3), (uint32_t)(i >> 2) & 1u);
+            mbar_wait_t(bar_unit + 8 * (i & 3), (uint32_t)(i >> 2) & 1u, w_unit);
             const int u = unit_q[i & 3];
             if (u < 0) break;
             int zz, ti, tj0, ntj;
@@ -439,6 +469,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
             double* const cbase = p.M + (int64_t)zz * p.bs + (int64_t)r0 * p.ld;
             const int64_t rstep = 8 * p.ld;
 #define OZ_CLIMIT(i) ((r0 + 8 * (i) >= p.c1 && r0 + 8 * (i) < p.R) ? min(r0 + 8 * (i) + 1, p.cmax) : 0)
+            // Interior fast path (warp-uniform): the warp's 32 rows x 16 columns lie entirely inside the updated region
+            // (most tiles off the diagonal) and every scale exponent is far from the fp64 limits, so the C update needs
+            // no per-element masks, no range checks and no divergence.  Per tile that removes ~40 % of the epilogue's
+            // instructions (compares, selects, branches), which - not the tensor pipe - is what a tile's time is made of.
+            const int rw0 = p.rb + ti * OZ_TM + q * 32;   // first row of this warp's window
+            const bool rows_in = vec_ok && rw0 >= p.c1 && rw0 + 31 < p.R;
+            const bool er_safe = (abs(er[0]) | abs(er[1]) | abs(er[2]) | abs(er[3])) < 256;
             for (int t = 0; t < ntj; ++t) {
                 const int cc0 = (tj0 + t) * OZ_TN + 16 * h + tc;      // local column of this thread's first pair
                 int ec[4];                                 // column exponents of this thread's two column pairs
@@ -447,19 +484,28 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                     ec[2 * k] = sc[cc0 + 8 * k];
                     ec[2 * k + 1] = sc[cc0 + 8 * k + 1];
                 }
+                const int cw0 = p.rb + (tj0 + t) * OZ_TN + 16 * h;     // first column of this warp's window
+                const bool geom = rows_in && cw0 >= p.c1 && cw0 + 15 < min(rw0 + 1, p.cmax);
                 // pull this thread's part of the C tile towards L2 while the tile's MMAs run
+                if (geom) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int col = p.rb + cc0 + 8 * k;
-                        if (col < OZ_CLIMIT(i)) prefetch_l2(cbase + i * rstep + col);
-                    }
+                        for (int k = 0; k < 2; ++k) prefetch_l2(cbase + i * rstep + (p.rb + cc0 + 8 * k));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const int col = p.rb + cc0 + 8 * k;
+                            if (col < OZ_CLIMIT(i)) prefetch_l2(cbase + i * rstep + col);
+                        }
+                }
                 double v[4][4];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * h);
 #pragma unroll
                 for (int d = 0; d < S; ++d) {                    // in the order the anti-diagonals complete
-                    mbar_wait(bar_acc_full + 8 * d, acc_phase);
+                    mbar_wait_t(bar_acc_full + 8 * d, acc_phase, w_acc);
                     tc_fence_after();
                     if (warp == 2 && lane == 0) OZ_TRACE(500 + d);
                     const double w = 1.0 / (double)(1ull << (8 * d));                 // 2^-8d
@@ -488,39 +534,65 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_acc_empty);       // accumulators may be overwritten by the next tile
                 if (warp == 2 && lane == 0) OZ_TRACE(600);
-                double2 c[4][2];
+                const bool ec_safe = (abs(ec[0]) | abs(ec[1]) | abs(ec[2]) | abs(ec[3])) < 256;
+                if (geom && __all_sync(0xffffffffu, er_safe && ec_safe)) {
+                    double2 c[4][2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int col = p.rb + cc0 + 8 * k;
-                        const int cl = OZ_CLIMIT(i);
-                        const double* crow = cbase + i * rstep;
-                        c[i][k] = make_double2(0.0, 0.0);
-                        if (vec_ok && col >= p.c1 && col + 1 < cl) {
-                            c[i][k] = *reinterpret_cast<const double2*>(crow + col);
-                        } else {
-                            if (col >= p.c1 && col < cl) c[i][k].x = crow[col];
-                            if (col + 1 >= p.c1 && col + 1 < cl) c[i][k].y = crow[col + 1];
+                        for (int k = 0; k < 2; ++k)
+                            c[i][k] = *reinterpret_cast<const double2*>(cbase + i * rstep + (p.rb + cc0 + 8 * k));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            // 2^(er + ec - 14): both exponents are below 256 in magnitude, no range check needed
+                            const double s0 = __hiloint2double((er[i] + ec[2 * k] - 14 + 1023) << 20, 0);
+                            const double s1 = __hiloint2double((er[i] + ec[2 * k + 1] - 14 + 1023) << 20, 0);
+                            *reinterpret_cast<double2*>(cbase + i * rstep + (p.rb + cc0 + 8 * k)) =
+                                make_double2(fma(-v[i][2 * k], s0, c[i][k].x), fma(-v[i][2 * k + 1], s1, c[i][k].y));
                         }
-                    }
+                } else {
+                    double2 c[4][2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int col = p.rb + cc0 + 8 * k;
-                        const int cl = OZ_CLIMIT(i);
-                        double* crow = cbase + i * rstep;
-                        const double w0 = c[i][k].x - v[i][2 * k] * oz_pow2(er[i] + ec[2 * k] - 14);
-                        const double w1 = c[i][k].y - v[i][2 * k + 1] * oz_pow2(er[i] + ec[2 * k + 1] - 14);
-                        if (vec_ok && col >= p.c1 && col + 1 < cl) {
-                            *reinterpret_cast<double2*>(crow + col) = make_double2(w0, w1);
-                        } else {
-                            if (col >= p.c1 && col < cl) crow[col] = w0;
-                            if (col + 1 >= p.c1 && col + 1 < cl) crow[col + 1] = w1;
+                        for (int k = 0; k < 2; ++k) {
+                            const int col = p.rb + cc0 + 8 * k;
+                            const int cl = OZ_CLIMIT(i);
+                            const double* crow = cbase + i * rstep;
+                            c[i][k] = make_double2(0.0, 0.0);
+                            if (vec_ok && col >= p.c1 && col + 1 < cl) {
+                                c[i][k] = *reinterpret_cast<const double2*>(crow + col);
+                            } else {
+                                if (col >= p.c1 && col < cl) c[i][k].x = crow[col];
+                                if (col + 1 >= p.c1 && col + 1 < cl) c[i][k].y = crow[col + 1];
+                            }
                         }
-                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const int col = p.rb + cc0 + 8 * k;
+                            const int cl = OZ_CLIMIT(i);
+                            double* crow = cbase + i * rstep;
+                            const double w0 = c[i][k].x - v[i][2 * k] * oz_pow2(er[i] + ec[2 * k] - 14);
+                            const double w1 = c[i][k].y - v[i][2 * k + 1] * oz_pow2(er[i] + ec[2 * k + 1] - 14);
+                            if (vec_ok && col >= p.c1 && col + 1 < cl) {
+                                *reinterpret_cast<double2*>(crow + col) = make_double2(w0, w1);
+                            } else {
+                                if (col >= p.c1 && col < cl) crow[col] = w0;
+                                if (col + 1 >= p.c1 && col + 1 < cl) crow[col + 1] = w1;
+                            }
+                        }
+                }
             }
+        }
+        if (p.prof && warp == 2 && lane == 0) {
+            long long* o = p.prof + 16 * blockIdx.x;
+            o[9] = clock64() - t_start;       // epilogue warp 2: total, waiting for a unit, for completed accumulators
+            o[10] = w_unit;
+            o[11] = w_acc;
         }
     }
     tc_fence_before();
@@ -558,6 +630,10 @@ int oz_launch(const OzParams& p, int z, int k0, int Kcols, cudaStream_t st, doub
 }  // namespace
 
 static long long* g_oz_trace = nullptr;
+static long long* g_oz_prof = nullptr;
+// Debug hook: device buffer of >= 16 * (number of SMs) int64; every CTA of the following updates stores the cycles its
+// producer / MMA issuer / epilogue warp 2 spent in total and blocked on each barrier (layout: see the kernel).
+DRP_API void drp_ozaki_set_prof(void* buf) { g_oz_prof = (long long*)buf; }
 // Debug hook: device buffer of >= 8002 int64 ([0] = event count) that CTA 0 of every following update appends to.
 DRP_API void drp_ozaki_set_trace(void* buf) { g_oz_trace = (long long*)buf; }
 
@@ -601,6 +677,7 @@ int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     p.cmax = cmax;
     p.K = K;
     p.trace = g_oz_trace;
+    p.prof = g_oz_prof;
     p.nTi = (R - p.rb + OZ_TM - 1) / OZ_TM;
     p.nTj = (cmax - p.rb + OZ_TN - 1) / OZ_TN;
     p.Rpad = p.nTi * OZ_TM;

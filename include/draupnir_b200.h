@@ -70,6 +70,9 @@ int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info
 /* Debug hook: device buffer of >= 8002 int64 ([0] = event count, then (event id, clock64) pairs) that CTA 0 of every
  * following tcgen05 update appends to; NULL switches tracing off (the default).                                     */
 void drp_ozaki_set_trace(void* buf);
+/* Debug hook: device buffer of >= 16 int64 per SM; every CTA of the following tcgen05 updates stores the cycles its
+ * producer, MMA issuer and first epilogue warp ran in total and blocked on each barrier; NULL (default) = off.       */
+void drp_ozaki_set_prof(void* buf);
 int drp_syrk_update_f64(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, int slices,
                         void* ws, int64_t ws_bytes, void* stream);
 
