@@ -84,7 +84,7 @@ def import_reference():
     if root not in sys.path:
         sys.path.insert(0, root)
     import draupnir_asr_b200.pyro_compat as compat
-    compat.install_as_pyro()
+    compat.install_as_pyro(force=True)       # always the shim: the fixtures must not depend on which pyro-ppl is installed
     for name in _STUB_ROOTS:
         try:                                     # only stand in for what is really missing
             importlib.import_module(name)
