@@ -333,6 +333,16 @@ def run_ours(args, w, rank, world, local_rank):
     peaks = measured_peaks()
     per_class = {KCLASS[k]: {"ms_per_step": kms[k] / args.steps, "launches_per_step": kln[k] / args.steps,
                              "work_per_step": kwk[k] / args.steps} for k in range(NK) if kln[k]}
+    # achieved rate of every class against the peak that bounds it (north star: tensor-pipe utilisation for the
+    # Cholesky / GEMM kernels, HBM GB/s for assembly and likelihood); with the prior on a side stream the classes overlap,
+    # so these per-class rates are lower bounds of what each kernel does alone (DRP_PRIOR_STREAM=0 gives the unshared ones)
+    for k in range(NK):
+        if kln[k] and kms[k] > 0:
+            flop = k in FLOP_CLASSES
+            rate = kwk[k] / (kms[k] * 1e-3) / (1e12 if flop else 1e9)
+            pk = peaks["tensor_sustained"] if flop else peaks["hbm"]
+            per_class[KCLASS[k]].update({"achieved": rate, "unit": "TFLOP/s" if flop else "GB/s", "frac_of_peak": rate / pk,
+                                         "bound": "tensor" if flop else "hbm"})
     dom = max(range(NK), key=lambda k: kms[k])
     tensor_bound = dom in FLOP_CLASSES
     avg_ms = kms[dom] / max(kln[dom], 1)
