@@ -402,9 +402,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                         if (elect_one()) {
                             const uint64_t bdesc = umma_desc(sB + st * OZ_B_TILE);
                             const int k4n = full_k ? 4 : min(4, (p.K - OZ_ROWB * kb + 31) >> 5);   // 32-column steps with data
-                            // k-step outer, A slice inner: consecutive MMAs accumulate into DIFFERENT TMEM tiles
-                            // (anti-diagonals d = ta + ub).  Back-to-back MMAs into the same accumulator serialise on
-                            // the accumulate latency (~90 cycles measured, vs 32 cycles of math for a 128x64x32 MMA).
+                            // k-step outer, A slice inner: consecutive MMAs accumulate into different TMEM tiles
+                            // (anti-diagonals d = ta + ub).  The order does not matter for the rate: 48-51 cycles per
+                            // 128x64x32 MMA either way in isolation (profiles/microbench/imma_rate.cu; the "accumulate
+                            // latency" an earlier comment quoted was the trace hook's own cost), and the A-slice-outer
+                            // order timed 0-2 % slower in the kernel (profiles/r01/oz_syrk_ab_variants.txt).
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4) {
                                 if (!full_k && k4 >= k4n) break;
