@@ -168,3 +168,54 @@ def test_reference_ou_kernel_and_squeeze():
     for shape, nd in [((30, 1, 1, 40), 2), ((3, 1), 1), ((30, 1), 1), ((1, 1, 5), 1), ((4, 5), 2), ((3,), 1)]:
         x = torch.zeros(shape)
         assert O.squeeze_tensor(nd, x).shape == ref.utils.squeeze_tensor(nd, x).shape, shape
+
+
+@needs_reference
+@pytest.mark.parametrize("n", [2, 9, 40])
+def test_reference_loader_reads_our_tree_files(tmp_path, n):
+    """Row a1 / f3 layout: the patristic / cladistic CSVs and the level-order file written by `tree_io` go through the
+    REFERENCE'S own loader steps (S/main.py:196-207 with pandas, then `symmetrize_and_clean`, `rename_axis`,
+    `pandas_to_numpy` of S/utils.py:931-979 and the `matrix_sort` of S/load_utils.py:452-458 restated inline because it is
+    a closure) and must give the header matrix `tree_io.load_distance_matrix` + `sort_by_node_id` produce — which is the
+    matrix the oracle builds from the tree.  (The builder of the distances themselves, ete3 / R ape, cannot run here.)"""
+    import pandas as pd
+    from draupnir_asr_b200 import tree_io as T
+    from oracle import patristic_oracle as P
+    import test_tree_io as TT
+    ref = H.import_reference()
+    text, st = TT._random_newick(n, seed=100 + n)
+    t = T.rename_tree_internal_nodes(T.read_newick(text))
+    order = t.file_order()
+    depth = TT._depth(t)
+    _, pat, cla = P.patristic_c(t.parent, t.branch, depth, order, order, want_cladistic=True)
+    base = os.path.join(tmp_path, "fam")
+    labels = [t.names[i] for i in order]
+    T._write_matrix_csv(base + "_patristic_distance_matrix.csv", labels, np.triu(pat))
+    T._write_matrix_csv(base + "_cladistic_distance_matrix.csv", labels, cla)
+    T.write_tree_levelorder_info(base + "_tree_levelorder_info.csv", t)
+    # --- the reference's steps, S/main.py:196-207 ---
+    patristic = pd.read_csv(base + "_patristic_distance_matrix.csv", low_memory=False, float_precision="round_trip")
+    patristic = patristic.rename(columns={'Unnamed: 0': 'rows'})
+    patristic.set_index('rows', inplace=True)
+    cladistic = pd.read_csv(base + "_cladistic_distance_matrix.csv", index_col="rows", low_memory=False)
+    info = pd.read_csv(base + "_tree_levelorder_info.csv", sep="\t", index_col=False, low_memory=False)
+    info["0"] = info["0"].astype(str)
+    info.drop('Unnamed: 0', inplace=True, axis=1)
+    names = np.asarray(info["0"].tolist())
+    assert names.tolist() == t.names
+    _, full, full_cla = P.patristic_c(t.parent, t.branch, depth, want_cladistic=True)
+    for frame, want, mine in ((patristic, full, base + "_patristic_distance_matrix.csv"),
+                              (cladistic, full_cla, base + "_cladistic_distance_matrix.csv")):
+        m = ref.utils.symmetrize_and_clean(frame, ancestral=True)
+        m = ref.utils.rename_axis(m, names, name_file="fam")
+        m = ref.utils.pandas_to_numpy(m)
+        m = torch.from_numpy(np.asarray(m, dtype=np.float64))
+        _, idx = torch.sort(m[:, 0])                                            # matrix_sort, S/load_utils.py:452-458
+        m = m[idx][:, idx].numpy()
+        got = T.sort_by_node_id(T.load_distance_matrix(mine, T.read_tree_levelorder_names(base + "_tree_levelorder_info.csv")))
+        assert np.array_equal(m, got)
+        assert np.isneginf(m[0, 0]) and np.array_equal(m[1:, 1:], want.astype(np.float64))
+    # the reference reads with pandas' default float parser (not round-trip exact): same matrix to a few ulp
+    default = pd.read_csv(base + "_patristic_distance_matrix.csv", low_memory=False).rename(columns={'Unnamed: 0': 'rows'})
+    default.set_index('rows', inplace=True)
+    assert np.allclose(default.to_numpy(dtype=np.float64), patristic.to_numpy(dtype=np.float64), rtol=1e-14, atol=0.0)
