@@ -12,7 +12,7 @@ from .backend import pyro
 from .guides import DRAUPNIRGUIDES
 from .models import DRAUPNIRModel_classic
 from .pyro_compat.infer import SVI, Trace_ELBO
-from .pyro_compat.infer.autoguide import AutoDelta, init_to_value
+from .pyro_compat.infer.autoguide import AutoDelta, AutoDiagonalNormal, AutoNormal, init_to_value
 from .pyro_compat.optim import ClippedAdam
 from .synthetic import SyntheticProblem
 
@@ -154,7 +154,7 @@ def build_run(problem: SyntheticProblem, select_guide: str, device="cuda", init:
               shard=None) -> Run:
     """Mirror of `draupnir_train`'s setup (S/main.py:991-1059): ModelLoad -> DRAUPNIRModel_classic -> guide
     (`AutoDelta` for delta_map, `DRAUPNIRGUIDES` otherwise) -> Trace_ELBO -> ClippedAdam -> SVI."""
-    assert select_guide in ("delta_map", "variational")
+    assert select_guide in ("delta_map", "variational", "normal", "diagonal_normal")          # S/main.py:511-524
     cfg = dict(DEFAULT_CONFIG, **(config or {}))
     pyro.clear_param_store()
     pyro.enable_validation(False)
@@ -167,6 +167,12 @@ def build_run(problem: SyntheticProblem, select_guide: str, device="cuda", init:
         if select_guide == "delta_map":
             values = None if init is None else {k: v.to(ml.device) for k, v in init.items()}
             guide = AutoDelta(Draupnir.model, init_loc_fn=init_to_value(values=values))
+        elif select_guide in ("normal", "diagonal_normal"):
+            cls = AutoNormal if select_guide == "normal" else AutoDiagonalNormal
+            if init is None:
+                guide = cls(Draupnir.model)
+            else:
+                guide = cls(Draupnir.model, init_loc_fn=init_to_value(values={k: v.to(ml.device) for k, v in init.items()}))
         else:
             guide = DRAUPNIRGUIDES(Draupnir.model, ml, Draupnir)
             if init is not None:

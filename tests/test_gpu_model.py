@@ -309,3 +309,35 @@ def test_full_size_losses_match_reference_code(cuda, name):
         with _FixedNoise(eps):
             got = run.step()
         assert abs(got - want) / abs(want) <= 1e-9, (name, step, got, want)
+
+
+@pytest.mark.parametrize("guide", ["normal", "diagonal_normal"])
+def test_mean_field_autoguides_on_the_cuda_model(cuda, guide):
+    """S/main.py:517-518: `AutoNormal` / `AutoDiagonalNormal` over the same model.  The model side of the ELBO at the
+    guide's draw equals the oracle's log-joint at the same values; gradients reach every guide parameter and network."""
+    from draupnir_asr_b200 import runtime
+    n, L = 40, 25
+    problem = S.make_problem(n, L, seed=1)
+    init = S.make_parameters(n, seed=1)
+    nets = O.Networks(variational=False, seed=1)
+    run = runtime.build_run(problem, guide, device=cuda, init=init)
+    runtime.load_networks(run, {"decoder": nets.decoder.state_dict(), "embed": nets.embed.state_dict(),
+                                "h_0_MODEL": nets.h_0_MODEL})
+    torch.manual_seed(21)
+    loss = run.svi.loss.differentiable_loss(run.Draupnir.model, run.guide, *run.step_args())
+    mt, gt = run.svi.loss.last_traces
+    vals = {k: gt.nodes[k]["value"].detach().cpu() for k in ("alpha", "sigma_f", "sigma_n", "lambd", "latent_z")}
+    assert vals["latent_z"].shape == (30, n) and bool((vals["sigma_f"] > 0).all())
+    log_p, terms, _ = O.model_log_joint(nets, vals, problem.dataset_train, problem.patristic_matrix_train,
+                                        problem.blosum_weighted, 30)
+    for name, site in mt.sample_sites():
+        got, want = float(site["log_prob_sum"]), float(terms[name])
+        assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (name, got, want)
+    log_q = float(gt.log_prob_sum())
+    assert abs(float(loss) - (-(float(log_p) - log_q))) <= 1e-9 * abs(float(log_p))
+    loss.backward()
+    for name, p in run.guide.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0, name
+    assert all(p.grad is not None for p in run.Draupnir.decoder.parameters())
+    losses = [run.step() for _ in range(3)]
+    assert all(l == l and abs(l) < 1e9 for l in losses)
