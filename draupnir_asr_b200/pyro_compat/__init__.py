@@ -2,7 +2,7 @@
 
 Only what S/models.py, S/guides.py, S/train.py and S/main.py:1021-1059 use is provided (S/ =
 /root/reference/draupnir/src/draupnir/): `sample`, `plate`, `module`, `param`, the param store, `poutine.trace/replay`,
-`distributions`, `infer.SVI/Trace_ELBO`, `infer.autoguide.AutoDelta`, `optim.ClippedAdam`, `nn.PyroParam/PyroModule`,
+`distributions`, `infer.SVI/Trace_ELBO`, `infer.autoguide.AutoDelta / AutoNormal / AutoDiagonalNormal`, `optim.ClippedAdam`, `nn.PyroParam/PyroModule`,
 `contrib.easyguide.EasyGuide`.  Semantics follow pyro-ppl 1.8/1.9 for these features: effect handlers
 as a messenger stack, size-less plates are no-ops, Delta guide sites score 0, positive parameters live in log space.
 
