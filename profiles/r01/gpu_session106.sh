@@ -1,0 +1,3 @@
+#!/bin/bash
+set -x
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
