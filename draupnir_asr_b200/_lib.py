@@ -9,9 +9,10 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdraupnir_b200.so")
+# DRP_LIB: another build of the same ABI (profiles/build_debug.sh: the library with the tcgen05 kernel's debug hooks)
+LIB_PATH = os.environ.get("DRP_LIB") or os.path.join(_HERE, "libdraupnir_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _i32, _i64, _f64, _p = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 
@@ -28,9 +29,8 @@ SIGNATURES = {
     "drp_ou_cov_fwd_f64": (_i32, [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p]),
     "drp_ou_cov_bwd_f64": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _p]),
     "drp_factor_workspace_bytes": (_i64, [_i32, _i32]),
-    "drp_potrf_batched_f64": (_i32, [_p, _i32, _i32, _i32, _p, _p, _i64, _p]),
-    "drp_ozaki_set_trace": (None, [_p]),
-    "drp_ozaki_set_prof": (None, [_p]),
+    "drp_ozaki_cond_limit_f64": (_f64, []),
+    "drp_potrf_batched_f64": (_i32, [_p, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),
     "drp_syrk_update_f64": (_i32, [_p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),
     "drp_ou_workspace_ld": (_i64, [_i32, _i32]),
     "drp_ou_workspace_elems": (_i64, [_i32, _i32, _i32]),
@@ -38,9 +38,9 @@ SIGNATURES = {
     "drp_ou_prior_factor_f64": (_i32, [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p]),
     "drp_ou_prior_apply_workspace_elems": (_i64, [_i32, _i32]),
     "drp_ou_prior_apply_f64": (_i32, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
-    "drp_mvn_logprob_f64": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "drp_mvn_logprob_f64": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "drp_mvn_grad_cov_f64": (_i32, [_p, _i32, _i32, _p, _p, _p]),
-    "drp_potri_batched_f64": (_i32, [_p, _i32, _i32, _p, _p, _p, _p]),
+    "drp_potri_batched_f64": (_i32, [_p, _i32, _i32, _p, _p, _p, _p, _p]),
     "drp_ou_conditional_f64": (_i32, [_p, _i64, _p, _i32, _i32, _p, _p, _p, _p, _i32, _f64, _p, _p, _p, _p, _p]),
     "drp_gru_hidden_size": (_i32, []),
     "drp_gru_fwd_f64": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
@@ -79,6 +79,9 @@ def _load() -> ctypes.CDLL:
         except AttributeError as e:
             raise DraupnirB200LibraryError(f"{LIB_PATH} does not export {name}; rebuild it") from e
         fn.restype, fn.argtypes = res, args
+    for name in ("drp_ozaki_set_trace", "drp_ozaki_set_prof"):      # only a -DDRP_DEBUG_HOOKS build has them
+        if hasattr(lib, name):
+            getattr(lib, name).restype, getattr(lib, name).argtypes = None, [_p]
     v = lib.drp_abi_version()
     if v != ABI_VERSION:
         raise DraupnirB200LibraryError(f"{LIB_PATH} has ABI {v}, this package expects {ABI_VERSION}; rebuild it")

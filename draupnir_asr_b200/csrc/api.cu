@@ -1,6 +1,7 @@
 // ABI bookkeeping + instrumentation for libdraupnir_b200.so (see include/draupnir_b200.h).
 #include "common.cuh"
 #include "instrument.cuh"
+#include "factor.cuh"
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -48,7 +49,18 @@ void drp_instr_end(int k, cudaStream_t st)
     g_spans[k].push_back({g_pending[k], e});
 }
 
-DRP_API int drp_abi_version(void) { return 3; }
+// cudaFuncSetAttribute (opt-in shared memory) is a per-device setting: the lazily applied attributes are tracked per
+// (kernel key, device), so a process that drives several GPUs configures each of them.
+bool drp_first_on_device(int key)
+{
+    static std::atomic<unsigned long long> seen[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return (seen[key & 63].fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+}
+
+DRP_API int drp_abi_version(void) { return 4; }
 
 // Number of kernel classes reported by drp_timing_read (length of its three arrays).
 DRP_API int drp_timing_classes(void) { return DRP_K_CLASSES; }

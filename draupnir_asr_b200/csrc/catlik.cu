@@ -10,6 +10,7 @@
 // casts with .long() inside log_prob) or as int64.
 #include "common.cuh"
 #include "instrument.cuh"
+#include "factor.cuh"
 
 namespace {
 
@@ -53,8 +54,10 @@ __global__ void __launch_bounds__(256) cat_fwd_kernel(const double* __restrict__
         double e = 0.0;
         for (int a = 0; a < A; ++a) e += drp_exp(row[a] - m);
         const double lse = m + log(e);
+        // an observation outside [0, A) (a code the alphabet does not have, a negative or NaN entry) poisons the sum with
+        // NaN instead of reading a neighbouring row: the reference's gather would trip a device assert there
         const int x = (int)obs[r0 + threadIdx.x];
-        ll = row[x] - lse;
+        ll = (x >= 0 && x < A) ? row[x] - lse : __longlong_as_double(0x7ff8000000000000LL);
         if (lse_out) lse_out[r0 + threadIdx.x] = lse;
     }
     ll = block_sum(ll, red);
@@ -96,7 +99,10 @@ __global__ void __launch_bounds__(256) cat_bwd_kernel(const double* __restrict__
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t idx = i0 + u * stride;
-            if (idx < total) ds[idx] = gv * ((ov[u] == av[u] ? 1.0 : 0.0) - drp_exp(sv[u] - lv[u]));
+            if (idx < total) {
+                const double d = gv * ((ov[u] == av[u] ? 1.0 : 0.0) - drp_exp(sv[u] - lv[u]));
+                ds[idx] = (ov[u] >= 0 && ov[u] < A) ? d : __longlong_as_double(0x7ff8000000000000LL);
+            }
         }
     }
 }
@@ -117,11 +123,9 @@ DRP_API int drp_cat_loglik_fwd_f64(const double* scores, const void* obs, int ob
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = (int)drp_cat_loglik_partials(rows);
     const size_t sm = (size_t)ROWS_PER_CTA * (A | 1) * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (drp_first_on_device(56)) {
         cudaFuncSetAttribute(cat_fwd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 65 * 8);
         cudaFuncSetAttribute(cat_fwd_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 65 * 8);
-        attr_done = true;
     }
     if (obs_is_f64) {
         DRP_LAUNCH(DRP_K_CATLIK, ((double)rows * (A * 8.0 + 16.0)), st);

@@ -199,65 +199,90 @@ __global__ void __launch_bounds__(PR) trsm_kernel(double* __restrict__ Mb, int64
 // 64x64 output tile per CTA, 4 warps (2x2) of 32x32, fp64 mma.sync m8n8k4, K consumed in chunks of 64.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) syrk_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int k0, int K, int c1,
-                                                   int R, int col_limit)
+                                                   int R, int col_limit, const int* __restrict__ zmap, int z)
 {
     const int tj = blockIdx.x, ti = blockIdx.y;
     if (tj > ti) return;
     extern __shared__ double sm[];
     double* As = sm;
     double* Bs = (ti == tj) ? As : sm + TS * SLD;
-    double* A = Mb + (int64_t)blockIdx.z * bs;
     const int tid = threadIdx.x;
     const int r0 = c1 + ti * TS, q0 = c1 + tj * TS;
     const int warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
-    double acc[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const double* ap = As + (wm * 32 + gid) * SLD + tig;
     const double* bp = Bs + (wn * 32 + gid) * SLD + tig;
-    for (int kc = 0; kc < K; kc += NB) {
-        const int kb = min(NB, K - kc);
-        if (kc) __syncthreads();
-        for (int idx = tid; idx < TS * NB; idx += 128) {
-            const int r = idx / NB, k = idx - r * NB;
-            As[r * SLD + k] = (r0 + r < R && k < kb) ? A[(int64_t)(r0 + r) * ld + k0 + kc + k] : 0.0;
-        }
-        if (ti != tj) {
+    // without a zmap: one matrix per blockIdx.z; with one: this CTA walks the matrices of the fp64 list (usually none)
+    const int nq = zmap ? zmap[1] : 1;
+    for (int q = 0; q < nq; ++q) {
+        double* A = Mb + (int64_t)(zmap ? zmap[2 + z + q] : (int)blockIdx.z) * bs;
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int kc = 0; kc < K; kc += NB) {
+            const int kb = min(NB, K - kc);
+            if (kc || q) __syncthreads();
             for (int idx = tid; idx < TS * NB; idx += 128) {
                 const int r = idx / NB, k = idx - r * NB;
-                Bs[r * SLD + k] = (q0 + r < R && k < kb) ? A[(int64_t)(q0 + r) * ld + k0 + kc + k] : 0.0;
+                As[r * SLD + k] = (r0 + r < R && k < kb) ? A[(int64_t)(r0 + r) * ld + k0 + kc + k] : 0.0;
+            }
+            if (ti != tj) {
+                for (int idx = tid; idx < TS * NB; idx += 128) {
+                    const int r = idx / NB, k = idx - r * NB;
+                    Bs[r * SLD + k] = (q0 + r < R && k < kb) ? A[(int64_t)(q0 + r) * ld + k0 + kc + k] : 0.0;
+                }
+            }
+            __syncthreads();
+            const int kmax = (kb + 3) & ~3;
+            for (int k = 0; k < kmax; k += 4) {
+                double a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = ap[i * 8 * SLD + k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = bp[j * 8 * SLD + k];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
         }
-        __syncthreads();
-        const int kmax = (kb + 3) & ~3;
-        for (int k = 0; k < kmax; k += 4) {
-            double a[4], b[4];
+        const int cmax = min(R, col_limit);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = ap[i * 8 * SLD + k];
+        for (int i = 0; i < 4; ++i) {
+            const int row = r0 + wm * 32 + i * 8 + gid;
+            if (row >= R) continue;
+            double* crow = A + (int64_t)row * ld;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = bp[j * 8 * SLD + k];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            for (int j = 0; j < 4; ++j) {
+                const int col = q0 + wn * 32 + j * 8 + 2 * tig;
+                if (col <= row && col < cmax) crow[col] -= acc[i][j][0];
+                if (col + 1 <= row && col + 1 < cmax) crow[col + 1] -= acc[i][j][1];
+            }
         }
     }
-    const int cmax = min(R, col_limit);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int row = r0 + wm * 32 + i * 8 + gid;
-        if (row >= R) continue;
-        double* crow = A + (int64_t)row * ld;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = q0 + wn * 32 + j * 8 + 2 * tig;
-            if (col <= row && col < cmax) crow[col] -= acc[i][j][0];
-            if (col + 1 <= row && col + 1 < cmax) crow[col + 1] -= acc[i][j][1];
+}
+
+// Precision gate (factor.cuh): one thread sorts the z matrices into the tensor-path list and the fp64 list.
+__global__ void gate_kernel(const double* __restrict__ cond, const double* __restrict__ sf, const double* __restrict__ sn,
+                            double nnorm, int z, double limit, int* __restrict__ zmap)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int nt = 0, nf = 0;
+    for (int i = 0; i < z; ++i) {
+        double c;
+        if (cond) {
+            c = cond[i];
+        } else {
+            const double f2 = sf[i] * sf[i], n2 = sn[i] * sn[i];
+            c = (nnorm * f2 + n2) / n2;
         }
+        if (c <= limit) zmap[2 + nt++] = i;          // NaN / inf bounds fail the comparison -> fp64
+        else zmap[2 + z + nf++] = i;
     }
+    zmap[0] = nt;
+    zmap[1] = nf;
 }
 
 }  // namespace
@@ -266,13 +291,10 @@ __global__ void __launch_bounds__(128) syrk_kernel(double* __restrict__ Mb, int6
 static const int TRSM_SMEM = (NB * NB + NB + PR * PLD) * (int)sizeof(double);
 static const int SYRK_SMEM = 2 * TS * SLD * (int)sizeof(double);
 
-void drp_dmma_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, cudaStream_t st)
+void drp_dmma_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, const int* zmap,
+                   cudaStream_t st)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM);
-        attr_done = true;
-    }
+    if (drp_first_on_device(0)) cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM);
     const int below = R - c1;
     const int cl = min(R, col_limit) - c1;
     if (below <= 0 || cl <= 0) return;
@@ -281,16 +303,18 @@ void drp_dmma_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     // algorithmic flops: 2*K per updated entry of the lower trapezoid rows [c1,R) x cols [c1,c1+cl)
     const double entries = (double)cl * (cl + 1) / 2.0 + (double)(below - cl) * cl;
     DRP_LAUNCH(DRP_K_SYRK, (double)z * entries * 2.0 * K, st);
-    syrk_kernel<<<dim3(Tc, T, z), 128, SYRK_SMEM, st>>>(M, ld, bs, k0, K, c1, R, col_limit);
+    syrk_kernel<<<dim3(Tc, T, zmap ? 1 : z), 128, SYRK_SMEM, st>>>(M, ld, bs, k0, K, c1, R, col_limit, zmap, z);
 }
 
 // Trailing update: int8 tcgen05 pipe when a workspace is given and the update is large, fp64 mma.sync otherwise.
 static int trailing_update(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, void* ws,
-                           int64_t ws_bytes, cudaStream_t st)
+                           int64_t ws_bytes, const int* zmap, cudaStream_t st)
 {
-    const int rc = drp_ozaki_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, drp_ozaki_slices(), ws, ws_bytes, st);
-    if (rc != 1) return rc;
-    drp_dmma_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, st);
+    const int rc = drp_ozaki_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, drp_ozaki_slices(), ws, ws_bytes, zmap, st);
+    if (rc > 1 || rc < 0) return rc;
+    // rc == 1: the shape does not qualify for the tensor path -> every matrix on the fp64 kernel;
+    // rc == 0: the matrices the precision gate kept off the tensor path (normally none: the CTAs find an empty list)
+    drp_dmma_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, rc == 1 ? nullptr : zmap, st);
     return 0;
 }
 
@@ -312,17 +336,22 @@ static int outer_block(int R_full, bool tensor_path)
 // (halves / quarters the read-modify-write traffic of the trailing matrix compared with K = NB, and gives the tensor
 // path a contraction length of 128-256).
 int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_full, int grow_base, int col_limit,
-                   int32_t* info, void* ws, int64_t ws_bytes, cudaStream_t st)
+                   int32_t* info, void* ws, int64_t ws_bytes, const DrpGate& gate, cudaStream_t st)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM);
-        attr_done = true;
-    }
+    if (drp_first_on_device(1)) cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM);
     if (info) cudaMemsetAsync(info, 0, sizeof(int32_t) * z, st);
-    const bool tensor_path = ws != nullptr && drp_ozaki_slices() != 0 && ws_bytes >= drp_ozaki_workspace_bytes(R_full, z);
+    const bool gated = gate.cond != nullptr || (gate.sf != nullptr && gate.sn != nullptr);
+    const bool tensor_path = gated && ws != nullptr && drp_ozaki_slices() != 0 && ws_bytes >= drp_ozaki_workspace_bytes(R_full, z)
+                             && R_full >= 384 + NB;                 // smaller matrices never reach a qualifying update
     const int NBO = outer_block(R_full, tensor_path);
     void* tws = tensor_path ? ws : nullptr;
+    int* zmap = nullptr;
+    if (tensor_path) {
+        ws_bytes -= drp_zmap_bytes(z);
+        zmap = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + ws_bytes);
+        DRP_LAUNCH(DRP_K_OTHER, 16.0 * z, st);
+        gate_kernel<<<1, 32, 0, st>>>(gate.cond, gate.sf, gate.sn, gate.nnorm, z, drp_ozaki_cond_limit(), zmap);
+    }
     for (int C0 = 0; C0 < nfactor; C0 += NBO) {
         const int W = min(NBO, nfactor - C0);
         const int C1 = C0 + W;
@@ -347,17 +376,17 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
                         trsm_kernel<<<g, PR, TRSM_SMEM, st>>>(M, ld, bs, c0, nb, R);
                     }
                     if (c1 < Q1) {                                                              // inside the sub-panel
-                        const int rc = trailing_update(M, ld, bs, z, c0, nb, c1, R, min(col_limit, Q1), tws, ws_bytes, st);
+                        const int rc = trailing_update(M, ld, bs, z, c0, nb, c1, R, min(col_limit, Q1), tws, ws_bytes, zmap, st);
                         if (rc) return rc;
                     }
                 }
             }
             if (Q1 < C1) {                                                                              // rest of the outer panel
-                const int rc = trailing_update(M, ld, bs, z, Q0, Q1 - Q0, Q1, R, min(col_limit, C1), tws, ws_bytes, st);
+                const int rc = trailing_update(M, ld, bs, z, Q0, Q1 - Q0, Q1, R, min(col_limit, C1), tws, ws_bytes, zmap, st);
                 if (rc) return rc;
             }
         }
-        const int rc = trailing_update(M, ld, bs, z, C0, W, C1, R, col_limit, tws, ws_bytes, st);          // rest of the matrix
+        const int rc = trailing_update(M, ld, bs, z, C0, W, C1, R, col_limit, tws, ws_bytes, zmap, st);          // rest of the matrix
         if (rc) return rc;
     }
     return drp_launch_status();
@@ -375,6 +404,7 @@ __global__ void zero_upper_kernel(double* __restrict__ A, int n, int64_t ld, int
 }  // namespace
 
 DRP_API int64_t drp_factor_workspace_bytes(int rows, int z) { return drp_ozaki_workspace_bytes(rows, z); }
+DRP_API double drp_ozaki_cond_limit_f64(void) { return drp_ozaki_cond_limit(); }
 
 // Test hook: one trailing update C[r][c] -= sum_{k in [k0,k0+K)} P[r][k] P[c][k] (rows [c1,R), cols [c1,min(R,col_limit)),
 // c <= r) with slices = 0: fp64 mma.sync kernel, 4..7: int8 tcgen05 kernel with that many slices.  Returns 1 if the
@@ -386,20 +416,21 @@ DRP_API int drp_syrk_update_f64(double* M, int64_t ld, int64_t bs, int z, int k0
     if (z <= 0 || K <= 0 || R <= c1) return -4;
     cudaStream_t st = (cudaStream_t)stream;
     if (slices == 0) {
-        drp_dmma_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, st);
+        drp_dmma_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, nullptr, st);
         return drp_launch_status();
     }
-    return drp_ozaki_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, slices, ws, ws_bytes, st);
+    return drp_ozaki_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, slices, ws, ws_bytes, nullptr, st);
 }
 
-DRP_API int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info, void* ws, int64_t ws_bytes,
-                                  void* stream)
+DRP_API int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info, const double* cond_bound, void* ws,
+                                  int64_t ws_bytes, void* stream)
 {
     if (!A) return -1;
     if (n <= 0) return -2;
     if (z <= 0) return -3;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = drp_factor_run(A, n, (int64_t)n * n, z, n, n, 0, n, info, ws, ws_bytes, st);
+    const DrpGate gate{cond_bound, nullptr, nullptr, 0.0};
+    int rc = drp_factor_run(A, n, (int64_t)n * n, z, n, n, 0, n, info, ws, ws_bytes, gate, st);
     if (rc) return rc;
     if (zero_upper) {
         dim3 g((n + 255) / 256, n, z);

@@ -20,6 +20,7 @@
 // writes dgi; the weight gradients are dense reductions over all (sequence, step) pairs and are left to one GEMM each.
 #include "common.cuh"
 #include "instrument.cuh"
+#include "factor.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -902,10 +903,8 @@ static void gru_fwd2_launch(const double* gi, const double* v, const double* whh
 {
     constexpr int WS = MT >= 2 ? 2 : 1;
     constexpr int smem = gf2_smem(8 * MT, UV);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (drp_first_on_device(32 + 8 * (int)UV + MT)) {
         cudaFuncSetAttribute(gru_fwd2_kernel<UV, MT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_done = true;
     }
     DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * ndir * G3 * GH, st);
     static int stagger = -1;
@@ -926,10 +925,8 @@ static void gru_fwd_launch(const double* gi, const double* v, const double* whh,
         return;
     }
     constexpr int smem = gf_smem(8 * MT, UV);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (drp_first_on_device(44 + 8 * (int)UV + MT)) {
         cudaFuncSetAttribute(gru_fwd_kernel<UV, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_done = true;
     }
     DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * ndir * G3 * GH, st);
     gru_fwd_kernel<UV, MT><<<dim3((n + 8 * MT - 1) / (8 * MT), ndir), GTHREADS, smem, st>>>(gi, v, whh, bhh, h0, n, L, out, gates,
@@ -941,10 +938,8 @@ static void gru_bwd_launch(const double* dout, const double* out, const double* 
                            int n, int L, double* dgi, double* dh0, int ndir, int dgi_dirs, cudaStream_t st, int dout_last = 0)
 {
     constexpr int smem = gb_smem(8 * MT);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (drp_first_on_device(24 + MT)) {
         cudaFuncSetAttribute(gru_bwd_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_done = true;
     }
     DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * ndir * G3 * GH, st);
     gru_bwd_kernel<MT><<<dim3((n + 8 * MT - 1) / (8 * MT), ndir), GTHREADS, smem, st>>>(dout, out, gates, whh, h0, n, L, dgi, dh0,
@@ -1121,14 +1116,12 @@ static int gru_wgrad_dispatch(const double* dgi, const double* gates, const doub
     if (H != GH) return -7;
     if (!dwhh || !dbhh) return -8;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_done = false;
     static int n_sm = 148;
-    if (!attr_done) {
+    if (drp_first_on_device(30)) {
         cudaFuncSetAttribute(gru_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GW_SMEM);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        attr_done = true;
     }
     const int64_t nblk = ((int64_t)n * L + GW_PAIRS - 1) / GW_PAIRS;
     int nchunks = n_sm / ndir > 0 ? n_sm / ndir : 1;
@@ -1412,8 +1405,8 @@ DRP_API int drp_gram_tn_f64(const double* A, const double* B, int64_t K, int M, 
     const int tiles = ((M + 7) / 8) * ((N + 1 + 7) / 8);
     if (tiles > 8 * GG_MAX_TILES) return -4;
     cudaStream_t st = (cudaStream_t)stream;
-    static int n_sm = 0;
-    if (!n_sm) {
+    static int n_sm = 148;
+    if (drp_first_on_device(57)) {
         int dev = 0;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;

@@ -375,7 +375,8 @@ DRP_API int drp_ou_prior_f64(const double* D, int64_t ldd, int n, const double* 
         DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)z * R * (R + 1) * 4.0), st);
         ou_assemble_kernel<<<g, 256, 3 * z * sizeof(double), st>>>(D, ldd, nullptr, n, n2, 1, sf, sn, lam, x, z, M, ld, bs);
     }
-    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, M + ou_matrix_elems(n, n2, z), drp_ozaki_workspace_bytes(R, z), st);
+    const DrpGate gate{nullptr, sf, sn, (double)n};
+    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, M + ou_matrix_elems(n, n2, z), drp_ozaki_workspace_bytes(R, z), gate, st);
     if (rc) return rc;
     {
         DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 8.0), st);
@@ -417,7 +418,8 @@ DRP_API int drp_ou_prior_factor_f64(const double* D, int64_t ldd, int n, const d
         DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)z * R * (R + 1) * 4.0), st);
         ou_assemble_kernel<<<g, 256, 3 * z * sizeof(double), st>>>(D, ldd, nullptr, n, n, 1, sf, sn, lam, nullptr, z, M, ld, bs);
     }
-    int rc = drp_factor_run(M, ld, bs, z, n, R, n + 1, R, info, M + ou_matrix_elems(n, n, z), drp_ozaki_workspace_bytes(R, z), st);
+    const DrpGate gate{nullptr, sf, sn, (double)n};
+    int rc = drp_factor_run(M, ld, bs, z, n, R, n + 1, R, info, M + ou_matrix_elems(n, n, z), drp_ozaki_workspace_bytes(R, z), gate, st);
     if (rc) return rc;
     return drp_launch_status();
 }
@@ -467,8 +469,10 @@ DRP_API int drp_ou_prior_apply_f64(const double* D, int64_t ldd, int n, const do
 
 // General batched MVN log-prob from an explicit covariance K [z,n,n] (zero mean handled by the caller: pass x - mu).
 // want_grad: alpha [z,n] and Kinv-based G are available afterwards through drp_mvn_grad_cov_f64 on the same M.
+// cond_bound (nullable, device [z]): upper bounds of cond_2(K_z); matrices within drp_ozaki_cond_limit take the
+// split-integer tensor-core update, all others (and all of them without a bound) the fp64 one.
 DRP_API int drp_mvn_logprob_f64(const double* K, const double* x, int n, int z, int want_grad, double* logp, double* alpha,
-                                double* M, int32_t* info, void* stream)
+                                double* M, int32_t* info, const double* cond_bound, void* stream)
 {
     if (!K || !x) return -1;
     if (n <= 0) return -3;
@@ -483,7 +487,8 @@ DRP_API int drp_mvn_logprob_f64(const double* K, const double* x, int n, int z, 
         DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)z * R * (R + 1) * 4.0 + (double)z * n * n * 4.0), st);
         cov_assemble_kernel<<<dim3((R + 255) / 256, R, z), 256, 0, st>>>(K, n, x, M, ld, bs);
     }
-    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, M + ou_matrix_elems(n, n2, z), drp_ozaki_workspace_bytes(R, z), st);
+    const DrpGate gate{cond_bound, nullptr, nullptr, 0.0};
+    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, M + ou_matrix_elems(n, n2, z), drp_ozaki_workspace_bytes(R, z), gate, st);
     if (rc) return rc;
     {
         DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 8.0), st);
@@ -513,7 +518,8 @@ DRP_API int drp_mvn_grad_cov_f64(const double* M, int n, int z, const double* gs
 }
 
 // K^-1 of z SPD matrices via the same elimination (potri equivalent); Kinv [z,n,n] full symmetric.
-DRP_API int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, double* M, int32_t* info, void* stream)
+DRP_API int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, double* M, int32_t* info,
+                                  const double* cond_bound, void* stream)
 {
     if (!K) return -1;
     if (n <= 0 || z <= 0) return -2;
@@ -526,7 +532,8 @@ DRP_API int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, d
         DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)z * R * (R + 1) * 4.0 + (double)z * n * n * 4.0), st);
         cov_assemble_kernel<<<dim3((R + 255) / 256, R, z), 256, 0, st>>>(K, n, Kinv, M, ld, bs);
     }
-    int rc = drp_factor_run(M, ld, bs, z, n, R, n + 1, R, info, M + ou_matrix_elems(n, n, z), drp_ozaki_workspace_bytes(R, z), st);
+    const DrpGate gate{cond_bound, nullptr, nullptr, 0.0};
+    int rc = drp_factor_run(M, ld, bs, z, n, R, n + 1, R, info, M + ou_matrix_elems(n, n, z), drp_ozaki_workspace_bytes(R, z), gate, st);
     if (rc) return rc;
     {
         DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * n * 12.0), st);
@@ -557,7 +564,8 @@ DRP_API int drp_ou_conditional_f64(const double* D, int64_t ldd, const int32_t* 
         ou_assemble_kernel<<<dim3((R + 255) / 256, R), 256, 3 * z * sizeof(double), st>>>(D, ldd, idx, n, ni, 0, sf, sn, lam,
                                                                                   x_leaf, z, M, ld, bs);
     }
-    int rc = drp_factor_run(M, ld, bs, z, n, R, 0, cov ? R : n + 1, info, M + ou_matrix_elems(n, ni, z), drp_ozaki_workspace_bytes(R, z), st);
+    const DrpGate gate{nullptr, sf, sn, (double)(n + ni)};
+    int rc = drp_factor_run(M, ld, bs, z, n, R, 0, cov ? R : n + 1, info, M + ou_matrix_elems(n, ni, z), drp_ozaki_workspace_bytes(R, z), gate, st);
     if (rc) return rc;
     {
         DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 16.0), st);

@@ -63,9 +63,10 @@ struct OzParams {
     int Rpad, rb, c1, R, cmax;
     int nTi, nTj, units_per_z, total_units;
     int K;                     // real contraction length (columns of the panel); the k-blocks are zero-padded
-    long long* trace;          // optional event trace of CTA 0 (debug; nullptr in production)
-    long long* prof;           // optional per-CTA wait-time sums [grid][16] (debug; nullptr in production)
+    long long* trace;          // event trace of CTA 0 (DRP_DEBUG_HOOKS builds only)
+    long long* prof;           // per-CTA wait-time sums [grid][16] (DRP_DEBUG_HOOKS builds only)
     int* counter;              // next work unit (zeroed by the slicing kernel that precedes every update)
+    const int* zmap;           // precision gate (factor.cuh): [0] matrices on this path, [2..] their indices; null = all z
 };
 
 // ------------------------------------------------ PTX wrappers ---------------------------------------------------
@@ -107,9 +108,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 // mbar_wait that adds the cycles it blocked to `acc` (phase accounting of the roles; two clock reads per wait)
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc)
 {
+#ifdef DRP_DEBUG_HOOKS
     const long long t = clock64();
     mbar_wait(bar, parity);
     acc += clock64() - t;
+#else
+    (void)acc;
+    mbar_wait(bar, parity);
+#endif
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
@@ -192,6 +198,9 @@ __device__ __forceinline__ double i32_to_f64(uint32_t a)
 }
 
 // debug trace: (event id, clock) pairs appended by single threads of CTA 0
+#ifndef DRP_DEBUG_HOOKS
+#define OZ_TRACE(id) do { } while (0)
+#else
 #define OZ_TRACE(id)                                                                   \
     do {                                                                               \
         if (p.trace && blockIdx.x == 0) {                                              \
@@ -202,12 +211,14 @@ __device__ __forceinline__ double i32_to_f64(uint32_t a)
             }                                                                          \
         }                                                                              \
     } while (0)
+#endif
 
 // work unit u -> (matrix, 128-row strip, first column tile, number of column tiles); strips longest first
 __device__ __forceinline__ void oz_decode(const OzParams& p, int u, int& zz, int& ti, int& tj0, int& ntj)
 {
     zz = u / p.units_per_z;
     int v = u - zz * p.units_per_z;
+    if (p.zmap) zz = p.zmap[2 + zz];
     tj0 = 0;
     ntj = 0;
     for (ti = p.nTi - 1; ti >= 0; --ti) {
@@ -229,12 +240,17 @@ __device__ __forceinline__ void oz_decode(const OzParams& p, int u, int& zz, int
 template <int S>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ Mb, int64_t ld, int64_t bs, int k0, int Kcols, int KBN,
                                                        int rb, int c1, int R, int Rpad, uint8_t* __restrict__ sl,
-                                                       int64_t sl_bs, int32_t* __restrict__ scl, int* __restrict__ counter)
+                                                       int64_t sl_bs, int32_t* __restrict__ scl, int* __restrict__ counter,
+                                                       const int* __restrict__ zmap)
 {
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *counter = 0;      // work-unit counter of the update that follows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rr = blockIdx.x * 8 + warp;
-    const int zz = blockIdx.y;
+    int zz = blockIdx.y;
+    if (zmap) {                                    // matrices the precision gate keeps on the fp64 path are not sliced
+        if (zz >= zmap[0]) return;
+        zz = zmap[2 + zz];
+    }
     if (rr >= Rpad) return;
     const int r = rb + rr;
     const bool live = (r >= c1 && r < R);
@@ -328,9 +344,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
             int st = 0;
             long long w_a = 0, w_b = 0;
             const long long t_start = clock64();
+            const int total_units = p.zmap ? p.zmap[0] * p.units_per_z : p.total_units;
             for (int i = 0;; ++i) {
                 int u = atomicAdd(p.counter, 1);
-                if (u >= p.total_units) u = -1;
+                if (u >= total_units) u = -1;
                 unit_q[i & 3] = u;
                 mbar_arrive(bar_unit + 8 * (i & 3));
                 if (u < 0) break;
@@ -359,12 +376,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                     }
                 }
             }
+#ifdef DRP_DEBUG_HOOKS
             if (p.prof) {
                 long long* o = p.prof + 16 * blockIdx.x;
                 o[0] = clock64() - t_start;   // producer: total, waiting for the A strip to be released, for a free B stage
                 o[1] = w_a;
                 o[2] = w_b;
             }
+#else
+            (void)t_start; (void)w_a; (void)w_b;
+#endif
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -434,6 +455,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                 acc_phase ^= 1;
             }
         }
+#ifdef DRP_DEBUG_HOOKS
         if (p.prof && lane == 0) {
             long long* o = p.prof + 16 * blockIdx.x;
             o[3] = clock64() - t_start;       // MMA issuer: total, waiting for a unit, the A strip, drained accumulators, a B block
@@ -443,6 +465,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
             o[7] = w_b;
             o[8] = n_tiles;
         }
+#else
+        (void)t_start; (void)w_unit; (void)w_a; (void)w_acc; (void)w_b; (void)n_tiles;
+#endif
     } else {
         // ============================ epilogue ================================
         // warp (q, h) owns rows 32q.. and columns 16h.. of the 128x64 tile; thread t holds, for row select i = 0..3,
@@ -590,12 +615,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
                 }
             }
         }
+#ifdef DRP_DEBUG_HOOKS
         if (p.prof && warp == 2 && lane == 0) {
             long long* o = p.prof + 16 * blockIdx.x;
             o[9] = clock64() - t_start;       // epilogue warp 2: total, waiting for a unit, for completed accumulators
             o[10] = w_unit;
             o[11] = w_acc;
         }
+#else
+        (void)t_start; (void)w_unit; (void)w_acc;
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -606,20 +635,18 @@ template <int S, int KBN>
 int oz_launch(const OzParams& p, int z, int k0, int Kcols, cudaStream_t st, double flops)
 {
     using Cfg = OzCfg<S, KBN>;
-    static bool attr_done = false;
     static int n_sm = 0;
-    if (!attr_done) {
+    if (drp_first_on_device(8 + S * 2 + KBN)) {
         cudaFuncSetAttribute(oz_syrk_kernel<S, KBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        attr_done = true;
     }
     {
         DRP_LAUNCH(DRP_K_SLICE, (double)z * p.Rpad * KBN * 128 * (8.0 + S), st);
         oz_slice_kernel<S><<<dim3((p.Rpad + 7) / 8, z), 256, 0, st>>>(p.M, p.ld, p.bs, k0, Kcols, KBN, p.rb, p.c1, p.R, p.Rpad,
                                                                      const_cast<uint8_t*>(p.sl), p.sl_bs,
-                                                                     const_cast<int32_t*>(p.scl), p.counter);
+                                                                     const_cast<int32_t*>(p.scl), p.counter, p.zmap);
     }
     {
         DRP_LAUNCH(DRP_K_SYRK_TC, flops, st);
@@ -631,19 +658,43 @@ int oz_launch(const OzParams& p, int z, int k0, int Kcols, cudaStream_t st, doub
 
 }  // namespace
 
+// The phase-accounting / event-trace hooks of the update kernel are process-global debug state and therefore NOT part of
+// the product library: they exist only in a -DDRP_DEBUG_HOOKS build (profiles/build_debug.sh -> libdraupnir_b200_debug.so),
+// which the profiling scripts under profiles/ load instead.
+#ifdef DRP_DEBUG_HOOKS
 static long long* g_oz_trace = nullptr;
 static long long* g_oz_prof = nullptr;
-// Debug hook: device buffer of >= 16 * (number of SMs) int64; every CTA of the following updates stores the cycles its
+// device buffer of >= 16 * (number of SMs) int64; every CTA of the following updates stores the cycles its
 // producer / MMA issuer / epilogue warp 2 spent in total and blocked on each barrier (layout: see the kernel).
 DRP_API void drp_ozaki_set_prof(void* buf) { g_oz_prof = (long long*)buf; }
-// Debug hook: device buffer of >= 8002 int64 ([0] = event count) that CTA 0 of every following update appends to.
+// device buffer of >= 8002 int64 ([0] = event count) that CTA 0 of every following update appends to.
 DRP_API void drp_ozaki_set_trace(void* buf) { g_oz_trace = (long long*)buf; }
+#else
+static long long* const g_oz_trace = nullptr;
+static long long* const g_oz_prof = nullptr;
+#endif
 
-// Bytes of workspace drp_ozaki_syrk may need for matrices with at most R_full rows.
+int64_t drp_zmap_bytes(int z) { return (((int64_t)z * 8 + 8 + 255) / 256) * 256; }
+
+// Bytes of workspace the tensor path may need for matrices with at most R_full rows (slices, row scales, the work-unit
+// counter, and the precision gate's index lists at the very end).
 int64_t drp_ozaki_workspace_bytes(int R_full, int z)
 {
     const int64_t Rpad = (((int64_t)R_full + 127) / 128 + 1) * 128;
-    return (int64_t)z * Rpad * (12 * OZ_ROWB + 8) + 2048;
+    return (int64_t)z * Rpad * (12 * OZ_ROWB + 8) + 2048 + drp_zmap_bytes(z);
+}
+
+// Largest condition-number bound a matrix may have to take the split-integer update: eps_S * cond <= 1e-5 with the
+// backward error eps_S ~ 2^-(8S-13) |K| of a whole factorisation (S = 6: 2.9e-11; measured < 2e-11 at 1,100-1,500 leaves).
+double drp_ozaki_cond_limit()
+{
+    static double v = -1.0;
+    if (v < 0.0) {
+        const char* e = getenv("DRP_OZAKI_COND_LIMIT");
+        const int S = drp_ozaki_slices();
+        v = e ? atof(e) : 1e-5 * ldexp(1.0, 8 * (S ? S : 6) - 13);
+    }
+    return v;
 }
 
 int drp_ozaki_slices()
@@ -660,7 +711,7 @@ int drp_ozaki_slices()
 // Trailing update through the int8 tensor pipe.  Returns 0 when it ran, 1 when the shape/workspace does not qualify
 // (the caller then uses the fp64 mma.sync kernel), otherwise a launch error code.
 int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, int S, void* ws,
-                   int64_t ws_bytes, cudaStream_t st)
+                   int64_t ws_bytes, const int* zmap, cudaStream_t st)
 {
     if (S == 0 || !ws) return 1;
     if (K < 32 || K > 256) return 1;
@@ -680,6 +731,7 @@ int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     p.K = K;
     p.trace = g_oz_trace;
     p.prof = g_oz_prof;
+    p.zmap = zmap;
     p.nTi = (R - p.rb + OZ_TM - 1) / OZ_TM;
     p.nTj = (cmax - p.rb + OZ_TN - 1) / OZ_TN;
     p.Rpad = p.nTi * OZ_TM;

@@ -10,6 +10,7 @@
 // no N x log N tables, output written once, coalesced, in the reference's row-major level-order layout.
 #include "common.cuh"
 #include "instrument.cuh"
+#include "factor.cuh"
 
 namespace {
 
@@ -325,11 +326,9 @@ DRP_API int drp_lca_patristic_f64(const int32_t* parent, const int32_t* depth, c
     if (ws_bytes < drp_lca_workspace_bytes(nr, max_depth) || (ws_bytes > 0 && !ws)) return -16;
     {
         DRP_LAUNCH(DRP_K_PATRISTIC, ((double)nr * nc * ((dist_out ? 8.0 : 0.0) + (clad_out ? 8.0 : 0.0) + (lca_out ? 4.0 : 0.0))), st);
-        static bool attr_done = false;
-        if (!attr_done) {
+        if (drp_first_on_device(58)) {
             cudaFuncSetAttribute(lca_patristic_kernel<true, 2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_SMEM_MAX);
             cudaFuncSetAttribute(lca_patristic_kernel<true, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_SMEM_MAX);
-            attr_done = true;
         }
         const size_t row_bytes = (size_t)n_nodes * sizeof(uint16_t);
         // two rows per CTA of 512 threads: the per-column operands and the ancestor scan (both L2 traffic, which is what

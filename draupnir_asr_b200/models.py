@@ -83,6 +83,7 @@ class DRAUPNIRModelClass(nn.Module):
         self._prefetched = None
         self._hyper_sites = ()
         self.shard = None          # zshard.ShardContext when the run is spread over several GPUs
+        self.map_consumes_rng = True   # conditional_samplingMAP advances the generator like the reference (S/models.py:239)
         for name in ("blosum_weighted", "dataset_train_blosum", "internal_nodes", "leaves_nodes", "aa_frequencies",
                      "blosum", "blosum_max"):
             t = getattr(self, name)
@@ -214,7 +215,9 @@ class DRAUPNIRModelClass(nn.Module):
         if hit is not None and len(hit[0]) == len(keys) and all(a is b for a, b in zip(hit[0], keys)) and hit[1] == stamp:
             return hit[2], hit[3]
         mean, cov = self._conditional(map_estimates, patristic_matrix, self.internal_nodes, self.n_internal, 0.0, 1e-6, True)
-        tril = ops.potrf(cov)
+        # the Schur complement of an OU covariance inherits lambda_min >= sigma_n^2 and a norm below the joint trace
+        tril = ops.potrf(cov, cond_bound=ops.ou_cond_bound(squeeze_tensor(1, map_estimates["sigma_f"]),
+                                                           squeeze_tensor(1, map_estimates["sigma_n"]), self.n_all))
         del cov
         self._cond_cache = (keys, stamp, mean, tril)
         return mean, tril
@@ -240,12 +243,16 @@ class DRAUPNIRModelClass(nn.Module):
         return latent_space
 
     def conditional_samplingMAP(self, map_estimates, patristic_matrix):
-        """Conditional MEAN of the internal nodes (S/models.py:197-242).  The reference also draws and discards one
-        sample (:239); that draw only advances the RNG and is not reproduced."""
+        """Conditional MEAN of the internal nodes (S/models.py:197-242).  The reference also draws one sample from the
+        conditional distribution and discards it (:239); all that is left of that draw is that the device's random
+        generator advances by `[z, n_internal]` standard-normal numbers, which `map_consumes_rng` (default True = the
+        reference's behaviour) reproduces, so that whatever is sampled AFTER a MAP call sees the same generator state."""
         assert patristic_matrix[1:, 1:].shape == (self.n_all, self.n_all), \
             "Remember to use the entire/full patristic matrix for conditional sampling!"
         mean, _ = self._conditional(map_estimates, patristic_matrix, self.internal_nodes, self.n_internal, 0.0, 0.0, False)
         assert mean.shape == (self.z_dim, self.n_internal)
+        if self.map_consumes_rng:        # MultivariateNormal.sample() = loc + L @ _standard_normal(loc.shape)
+            torch.distributions.utils._standard_normal(mean.shape, dtype=mean.dtype, device=mean.device)
         return mean.T
 
     def conditional_sampling_batch(self, map_estimates, patristic_matrix):

@@ -78,10 +78,7 @@ class RNNDecoder_Tiling(nn.Module):
         (S/models.py:339-342): since x[i,l] = [latent_i ; blosum_l], W_ih x + b_ih = W_z latent_i + (W_b blosum_l + b_ih)
         is a broadcast sum of an `[n,3H]` and an `[L,3H]` term per direction."""
         H, z = self.gru_hidden_dim, latent_space.shape[1]
-        if H != ops.GRU_HIDDEN:
-            n, L = latent_space.shape[0], blosum.shape[0]
-            x = torch.cat((latent_space[:, None, :].expand(n, L, z), blosum[None].expand(n, L, blosum.shape[1])), dim=2)
-            return self.scores(x, hidden)
+        ops.require_gru_hidden(H)
         wih, whh, bih, bhh = ops.gru_stacked_params(self.rnn)
         U = latent_space @ wih[:, :, :z].reshape(6 * H, z).t()                               # [n, 2*3H]
         V = torch.addmm(bih.reshape(-1), blosum, wih[:, :, z:].reshape(6 * H, -1).t())      # [L, 2*3H]
@@ -110,7 +107,7 @@ class EmbedComplex(nn.Module):
         # (W2 W1, W2 b1 + b2) — the encoder's copy runs on n*L rows, where this saves the [n*L, embedding_dim]
         # intermediate and two thirds of the flops; autograd still delivers the gradients of fc1 / fc2 themselves
         if not input.is_cuda:
-            return self.softmax(self.fc2(self.fc1(input)))
+            raise RuntimeError("EmbedComplex: expected a CUDA tensor (draupnir_asr_b200 has no CPU path)")
         W = self.fc2.weight @ self.fc1.weight
         b = torch.addmv(self.fc2.bias, self.fc2.weight, self.fc1.bias)
         A = input.shape[-1]

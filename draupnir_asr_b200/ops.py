@@ -71,9 +71,29 @@ def defer_info_checks():
     prev, _DEFERRED = _DEFERRED, []
     try:
         yield
-    finally:
+    except BaseException:
+        _DEFERRED = prev                 # unwinding from another error: do not synchronise, do not mask it
+        raise
+    else:
         pending, _DEFERRED = _DEFERRED, prev
         _raise_if_failed(pending)
+
+
+def flush_info_checks():
+    """Examine (and clear) the pivot flags queued so far inside `defer_info_checks()`: raises `torch.linalg.LinAlgError`
+    for the first failed factorisation.  Synchronises; call it where the host waits for the device anyway."""
+    global _DEFERRED
+    if _DEFERRED:
+        pending, _DEFERRED = _DEFERRED, []
+        _raise_if_failed(pending)
+
+
+def pending_failures() -> Optional[torch.Tensor]:
+    """Device scalar (int64): how many of the queued pivot-flag vectors report a failure; None if nothing is queued.  Lets a
+    sharded step add the flag to its all-reduce so that every rank raises together."""
+    if not _DEFERRED:
+        return None
+    return torch.stack([(info != 0).any() for info, _ in _DEFERRED]).sum()
 
 
 def _raise_if_failed(pending):
@@ -127,21 +147,43 @@ def ou_cov(t: torch.Tensor, sigma_f: torch.Tensor, sigma_n: torch.Tensor, lamb: 
 # ------------------------------------------------------------------------------------------------------------------
 # K3  Cholesky, potri
 # ------------------------------------------------------------------------------------------------------------------
-def potrf(A: torch.Tensor, check: bool = True) -> torch.Tensor:
-    """Batched lower Cholesky factor with zeros above the diagonal, like `torch.linalg.cholesky` (out of place)."""
+def _cond_arg(cond_bound, z: int, device):
+    """Per-matrix upper bounds of the 2-norm condition number (`[z]` CUDA fp64) for the precision gate of the
+    factorisation, or None: without a bound no matrix takes the split-integer tensor-core update."""
+    if cond_bound is None:
+        return None
+    c = _req(torch.as_tensor(cond_bound, dtype=torch.float64, device=device).reshape(-1), "cond_bound").contiguous()
+    if c.numel() == 1 and z != 1:
+        c = c.expand(z).contiguous()
+    if c.numel() != z:
+        raise RuntimeError(f"cond_bound: expected {z} entries, got {c.numel()}")
+    return c
+
+
+def ou_cond_bound(sigma_f: torch.Tensor, sigma_n: torch.Tensor, n_nodes: int) -> torch.Tensor:
+    """`(n sf^2 + sn^2) / sn^2 >= cond_2` of an OU covariance over `n_nodes` nodes and of every Schur complement of it
+    (lambda_min >= sn^2, the norm is at most the trace): the bound the OU entry points of the library use themselves."""
+    f2, n2 = sigma_f.detach() ** 2, sigma_n.detach() ** 2
+    return (float(n_nodes) * f2 + n2) / n2
+
+
+def potrf(A: torch.Tensor, check: bool = True, cond_bound=None) -> torch.Tensor:
+    """Batched lower Cholesky factor with zeros above the diagonal, like `torch.linalg.cholesky` (out of place).
+    `cond_bound` (optional, per matrix): see `_cond_arg`."""
     _req(A, "A")
     n = A.shape[-1]
     L = A.reshape(-1, n, n).clone()
     info = torch.empty(L.shape[0], dtype=torch.int32, device=A.device)
-    wsb = lib.drp_factor_workspace_bytes(n, L.shape[0]) if n >= 1024 else 0
+    cb = _cond_arg(cond_bound, L.shape[0], A.device)
+    wsb = lib.drp_factor_workspace_bytes(n, L.shape[0]) if (n >= 1024 and cb is not None) else 0
     ws = torch.empty(wsb, dtype=torch.uint8, device=A.device) if wsb else None
-    _rc(lib.drp_potrf_batched_f64(_p(L), n, L.shape[0], 1, _p(info), _p(ws), wsb, _stream()), "drp_potrf_batched_f64")
+    _rc(lib.drp_potrf_batched_f64(_p(L), n, L.shape[0], 1, _p(info), _p(cb), _p(ws), wsb, _stream()), "drp_potrf_batched_f64")
     if check:
         _info_done(info, "linalg.cholesky")
     return L.reshape(A.shape)
 
 
-def potri(K: torch.Tensor) -> torch.Tensor:
+def potri(K: torch.Tensor, cond_bound=None) -> torch.Tensor:
     """Inverse of a batch of SPD matrices through the partial-Cholesky engine."""
     _req(K, "K")
     n = K.shape[-1]
@@ -150,7 +192,8 @@ def potri(K: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(Kc)
     M = torch.empty(lib.drp_ou_workspace_elems(n, n, z), dtype=torch.float64, device=K.device)
     info = torch.empty(z, dtype=torch.int32, device=K.device)
-    _rc(lib.drp_potri_batched_f64(_p(Kc), n, z, _p(out), _p(M), _p(info), _stream()), "drp_potri_batched_f64")
+    _rc(lib.drp_potri_batched_f64(_p(Kc), n, z, _p(out), _p(M), _p(info), _p(_cond_arg(cond_bound, z, K.device)), _stream()),
+        "drp_potri_batched_f64")
     _info_done(info, "potri")
     return out.reshape(K.shape)
 
@@ -300,7 +343,7 @@ class _MVNLogProb(torch.autograd.Function):
         info = torch.empty(z, dtype=torch.int32, device=dev)
         M = torch.empty(lib.drp_ou_workspace_elems(n, n if want else 0, z), dtype=torch.float64, device=dev)
         alpha = torch.empty((z, n), dtype=torch.float64, device=dev) if want else None
-        _rc(lib.drp_mvn_logprob_f64(_p(K), _p(x), n, z, int(want), _p(logp), _p(alpha), _p(M), _p(info), _stream()),
+        _rc(lib.drp_mvn_logprob_f64(_p(K), _p(x), n, z, int(want), _p(logp), _p(alpha), _p(M), _p(info), None, _stream()),
             "drp_mvn_logprob_f64")
         _info_done(info, "linalg.cholesky")
         if want:
@@ -432,6 +475,14 @@ def tree_distances(parent: torch.Tensor, branch: torch.Tensor, rows: Optional[to
 GRU_HIDDEN = lib.drp_gru_hidden_size()
 
 
+def require_gru_hidden(H: int):
+    """The recurrence kernels are built for the reference's gru_hidden_dim (60, S/main.py:2777).  Another size is refused
+    rather than sent to cuDNN's `nn.GRU` behind the caller's back: this package has no library fallback."""
+    if H != GRU_HIDDEN:
+        raise RuntimeError(f"gru_hidden_dim = {H}: the sm_100a GRU kernels of draupnir_asr_b200 are built for {GRU_HIDDEN} "
+                           "(rebuild csrc/gru.cu with another GH); there is no cuDNN fallback")
+
+
 class _GRUBidir(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gi, whh, bhh, h0):
@@ -526,6 +577,13 @@ def gru_bidirectional_uv(U: torch.Tensor, V: torch.Tensor, weight_hh, bias_hh, h
 _GRAM_OFF = os.environ.get("DRP_GRAM", "1") == "0"      # A/B switch for measurements
 
 
+def _aligned16(t: torch.Tensor) -> torch.Tensor:
+    """The TMA bulk copies of `tall_gemm` / `gram_tn` need 16-byte-aligned bases.  A contiguous row slice such as
+    `data_blosum[leaf_lo:leaf_hi]` (the sharded encoder's input) starts at `leaf_lo * L * 21` doubles, which is odd when
+    `leaf_lo` and `L` are: such a view is copied to a fresh (512-byte-aligned) allocation once, instead of failing."""
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
 def gram_tn(A: torch.Tensor, B: torch.Tensor):
     """`(A.t() @ B, A.sum(0))` for tall-skinny fp64 `A [K,M]`, `B [K,N]` (K huge, M, N <= 192): the weight / bias gradient
     shapes of the dense layers around the recurrences, as one split-K kernel instead of a cuBLAS "tn" GEMM + a reduction."""
@@ -533,9 +591,11 @@ def gram_tn(A: torch.Tensor, B: torch.Tensor):
     K, M = A.shape
     N = B.shape[1]
     tiles = ((M + 7) // 8) * ((N + 8) // 8)
-    if (_GRAM_OFF or not A.is_contiguous() or not B.is_contiguous() or A.data_ptr() % 16 or B.data_ptr() % 16 or M > 192 or N > 192
-            or tiles > 96 or 3 * 32 * (M + N) * 8 + 64 > 200 * 1024 or B.shape[0] != K):
-        return A.t() @ B, A.sum(0)
+    if B.shape[0] != K:
+        raise RuntimeError(f"gram_tn: A has {K} rows, B has {B.shape[0]}")
+    if _GRAM_OFF or M > 192 or N > 192 or tiles > 96 or 3 * 32 * (M + N) * 8 + 64 > 200 * 1024:
+        return A.t() @ B, A.sum(0)                  # shapes outside the kernel's range (never on the DRAUPNIR path): cuBLAS
+    A, B = _aligned16(A.contiguous()), _aligned16(B.contiguous())
     C = torch.empty((M, N), dtype=torch.float64, device=A.device)
     cs = torch.empty(M, dtype=torch.float64, device=A.device)
     wse = lib.drp_gram_workspace_elems(M, N)
@@ -555,7 +615,7 @@ def tall_gemm(x: torch.Tensor, Wt: torch.Tensor, bias: Optional[torch.Tensor] = 
     N = Wt.shape[1]
     if _TALL_OFF or K > 192 or N > 184 or M == 0:
         return torch.addmm(bias, x, Wt) if bias is not None else x @ Wt
-    x, Wt = x.contiguous(), Wt.contiguous()
+    x, Wt = _aligned16(x.contiguous()), Wt.contiguous()
     b = None if bias is None else _req(bias, "bias").contiguous()
     y = torch.empty((M, N), dtype=torch.float64, device=x.device)
     rc = lib.drp_tall_gemm_f64(_p(x), _p(Wt), _p(b), M, K, N, _p(y), _stream())
@@ -671,9 +731,8 @@ def gru_encoder_last(rnn: torch.nn.GRU, x: torch.Tensor, h0: torch.Tensor):
     call (`gru_stacked_params` copies them)."""
     from .utils import Deferred
     H = rnn.hidden_size
-    if H != GRU_HIDDEN or not x.is_cuda:
-        out, hn = rnn(x, h0)
-        return out[:, -1], Deferred(lambda: (out.detach(), hn.detach()))
+    require_gru_hidden(H)
+    _req(x, "input")
     wih, whh, bih, bhh = gru_stacked_params(rnn)
     last = _GRUEncoderLast.apply(x, wih, bih, whh, bhh, h0)
     snap = tuple(t.detach() for t in (x, wih, bih, whh, bhh, h0))
@@ -706,8 +765,8 @@ def gru_stacked_params(rnn: torch.nn.GRU):
 def gru_module_forward(rnn: torch.nn.GRU, x: torch.Tensor, h0: torch.Tensor):
     """Drop-in for `rnn(x, h0)` of a one-layer bidirectional batch-first `nn.GRU`: returns `(output, h_n)`."""
     H = rnn.hidden_size
-    if H != GRU_HIDDEN or not x.is_cuda:
-        return rnn(x, h0)
+    require_gru_hidden(H)
+    _req(x, "input")
     wih, whh, bih, bhh = gru_stacked_params(rnn)
     n, L, I = x.shape
     gi = torch.addmm(bih.reshape(-1), x.reshape(n * L, I), wih.reshape(6 * H, I).t()).reshape(n, L, 2, 3 * H)

@@ -153,7 +153,7 @@ class MultivariateNormal(td.Distribution, TorchDistributionMixin):
     def rsample(self, sample_shape=torch.Size()):
         shape = torch.Size(sample_shape) + self.loc.shape
         eps = torch.randn(shape, dtype=self.loc.dtype, device=self.loc.device)
-        return self.loc + (self.scale_tril * eps.unsqueeze(-2)).sum(-1)
+        return self.loc + torch.matmul(self.scale_tril, eps.unsqueeze(-1)).squeeze(-1)      # no [S,z,n,n] intermediate
 
 
 class _TorchMVN(td.MultivariateNormal, TorchDistributionMixin):
@@ -274,10 +274,11 @@ class OUProcessPrior(td.Distribution, TorchDistributionMixin):
 
     def rsample(self, sample_shape=torch.Size()):
         from .. import ops
-        L = ops.potrf(self.covariance_matrix.detach())
+        L = ops.potrf(self.covariance_matrix.detach(),
+                      cond_bound=ops.ou_cond_bound(self.sigma_f, self.sigma_n, self.patristic.shape[0]))
         shape = torch.Size(sample_shape) + self.batch_shape + self.event_shape
         eps = torch.randn(shape, dtype=L.dtype, device=L.device)
-        return (L * eps.unsqueeze(-2)).sum(-1)
+        return torch.matmul(L, eps.unsqueeze(-1)).squeeze(-1)          # [S,z,n]; never a [S,z,n,n] intermediate
 
 
 class TorchDistribution(td.Distribution, TorchDistributionMixin):

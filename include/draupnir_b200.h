@@ -8,7 +8,9 @@
  * Conventions
  *   - every pointer is a DEVICE pointer into row-major contiguous storage unless a leading dimension is given;
  *   - the caller owns every buffer including workspaces (sizes from the *_workspace_* helpers); the library
- *     allocates nothing and keeps no state, so calls are re-entrant per stream and CUDA-graph capturable;
+ *     allocates nothing and keeps no state that affects results (the only process-wide data are the launch counter /
+ *     opt-in CUDA-event timing of the instrumentation block below and the "opt-in shared memory configured on this
+ *     device" bits), so calls are re-entrant per stream and CUDA-graph capturable;
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
  *   - return value: 0 ok, -k = argument group k invalid, 1000+e = CUDA runtime error e;
  *   - `info[z]` (int32, device): 0, or the 1-based index of the first non-positive pivot of matrix z (LAPACK potrf
@@ -62,17 +64,19 @@ int drp_ou_cov_bwd_f64(const double* D, int64_t ldd, int n, const double* lam, i
 
 /* ---- K3  torch.linalg.cholesky inside MultivariateNormal.__init__: S/models.py:118 ----------------------------- */
 /* ws (nullable): drp_factor_workspace_bytes(n, z) bytes; with it, trailing updates of large matrices run on the int8
- * tcgen05 tensor pipe (split-integer, fp64-accurate; DRP_OZAKI_SLICES = 0 disables, 4..7 selects the slice count). */
+ * tcgen05 tensor pipe (split-integer; DRP_OZAKI_SLICES = 0 disables, 4..7 selects the slice count) — but only for the
+ * matrices whose condition number is known to be small enough for its ~2e-11 |K| backward error to stay invisible:
+ * cond_bound (nullable, DEVICE [z]) holds upper bounds of cond_2(K_z); matrix z takes the tensor path iff
+ * cond_bound[z] <= drp_ozaki_cond_limit() (1e-5 / 2^-(8S-13): 3.4e5 for S = 6; DRP_OZAKI_COND_LIMIT overrides), decided
+ * on the device.  Every other matrix — and every matrix when cond_bound is NULL — gets fp64 (mma.sync) updates, i.e. the
+ * accuracy of the LAPACK routine the reference calls.  The OU entry points below derive the bound from the
+ * hyper-parameters themselves: (nodes * sf^2 + sn^2) / sn^2.                                                        */
 int64_t drp_factor_workspace_bytes(int rows, int z);
-int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info, void* ws, int64_t ws_bytes, void* stream);
+double drp_ozaki_cond_limit_f64(void);
+int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info, const double* cond_bound, void* ws,
+                          int64_t ws_bytes, void* stream);
 /* Test hook: ONE trailing update C[r][c] -= sum_{k0 <= k < k0+K} P[r][k] P[c][k], rows [c1,R), cols [c1,min(R,col_limit)),
  * c <= r; slices = 0 -> fp64 mma.sync kernel, 4..7 -> int8 tcgen05 kernel.  Returns 1 if tcgen05 rejects the shape.  */
-/* Debug hook: device buffer of >= 8002 int64 ([0] = event count, then (event id, clock64) pairs) that CTA 0 of every
- * following tcgen05 update appends to; NULL switches tracing off (the default).                                     */
-void drp_ozaki_set_trace(void* buf);
-/* Debug hook: device buffer of >= 16 int64 per SM; every CTA of the following tcgen05 updates stores the cycles its
- * producer, MMA issuer and first epilogue warp ran in total and blocked on each barrier; NULL (default) = off.       */
-void drp_ozaki_set_prof(void* buf);
 int drp_syrk_update_f64(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, int slices,
                         void* ws, int64_t ws_bytes, void* stream);
 
@@ -96,10 +100,12 @@ int drp_ou_prior_apply_f64(const double* D, int64_t ldd, int n, const double* la
                            double* logp, double* alpha, double* gsum, double* part, double* ypart, void* stream);
 
 /* ---- K4/K5  MultivariateNormal(0, K).log_prob(x) for an explicit covariance batch ------------------------------ */
+/* cond_bound: as for drp_potrf_batched_f64 (NULL = fp64 updates only).                                               */
 int drp_mvn_logprob_f64(const double* K, const double* x, int n, int z, int want_grad, double* logp, double* alpha,
-                        double* M, int32_t* info, void* stream);
+                        double* M, int32_t* info, const double* cond_bound, void* stream);
 int drp_mvn_grad_cov_f64(const double* M, int n, int z, const double* gscale, double* G, void* stream);
-int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, double* M, int32_t* info, void* stream);
+int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, double* M, int32_t* info, const double* cond_bound,
+                          void* stream);
 
 /* ---- K6  conditional_sampling / conditional_samplingMAP: S/models.py:149-242 ----------------------------------- */
 /* idx = [leaf rows of D (n) | internal rows of D (ni)]; mean [z,ni]; cov [z,ni,ni] nullable (+jitter everywhere).  */

@@ -98,8 +98,50 @@ def test_potrf_large_through_tensor_path(cuda, n):
     sn = torch.tensor([0.6, 1.1], dtype=torch.float64)
     lam = torch.tensor([0.9, 1.4], dtype=torch.float64)
     K = sf[:, None, None] ** 2 * torch.exp(-D[None] / lam[:, None, None]) + sn[:, None, None] ** 2 * torch.eye(n, dtype=torch.float64)
-    L = ops.potrf(K.to(cuda)).cpu()
+    L = ops.potrf(K.to(cuda), cond_bound=ops.ou_cond_bound(sf, sn, n)).cpu()
     L_ref = torch.linalg.cholesky(K)
     assert float((L - L_ref).abs().max() / L_ref.abs().max()) < 1e-10
     back = float((L @ L.transpose(-1, -2) - K).abs().max() / K.abs().max())
-    assert back < 2e-11, back          # S = 6 slices: ~1e-11 |K| backward error
+    assert 1e-15 < back < 2e-11, back  # S = 6 slices: ~1e-11 |K| backward error; above fp64 level = the tensor path ran
+    # without a bound on the condition number nothing takes the split-integer update: LAPACK-level backward error
+    L64 = ops.potrf(K.to(cuda)).cpu()
+    back64 = float((L64 @ L64.transpose(-1, -2) - K).abs().max() / K.abs().max())
+    assert back64 < 2e-15, back64
+
+
+def test_precision_gate_is_per_matrix(cuda):
+    """sigma_n -> 0 makes K ill-conditioned; the ~2e-11 |K| backward error of the split-integer update would
+    then ruin log-det and gradients (or the pivots) where the reference's fp64 LAPACK factorisation still succeeds.  The
+    gate decides per matrix, on the device, from (n sf^2 + sn^2) / sn^2: the well-conditioned matrix of the batch takes the
+    tensor path, the ill-conditioned one the fp64 kernel, in the same launches; and the fused prior stays at oracle level."""
+    from draupnir_asr_b200 import ops
+    from draupnir_asr_b200 import synthetic as S
+    from oracle import draupnir_oracle as O
+    n = 1100
+    t = S.random_tree(n, seed=2)
+    D = torch.from_numpy(S.patristic_host(t)[np.ix_(t.leaves, t.leaves)])
+    sf = torch.tensor([1.3, 0.9, 1.1], dtype=torch.float64)
+    sn = torch.tensor([0.6, 2e-4, 1e-3], dtype=torch.float64)          # cond bounds 5e3, 2e10, 1.3e9 (limit 3.4e5)
+    lam = torch.tensor([0.9, 1.4, 0.7], dtype=torch.float64)
+    assert ops.ou_cond_bound(sf, sn, n)[0] < ops.lib.drp_ozaki_cond_limit_f64() < ops.ou_cond_bound(sf, sn, n)[2]
+    K = O.ou_covariance(D, sf, sn, lam)
+    L = ops.potrf(K.to(cuda), cond_bound=ops.ou_cond_bound(sf, sn, n)).cpu()
+    back = ((L @ L.transpose(-1, -2) - K).abs().amax((1, 2)) / K.abs().amax((1, 2))).tolist()
+    assert 1e-15 < back[0] < 2e-11 and back[1] < 2e-15 and back[2] < 2e-15, back
+    # fused prior + gradients with the same hyper-parameters against the oracle (autograd through torch's Cholesky)
+    x = torch.randn(3, n, dtype=torch.float64, generator=torch.Generator().manual_seed(4)) * 0.3
+    ps = [v.clone().requires_grad_(True) for v in (sf, sn, lam, x)]
+    lp_ref = torch.distributions.MultivariateNormal(torch.zeros(1, n, dtype=torch.float64),
+                                                    O.ou_covariance(D, *ps[:3])).log_prob(ps[3])
+    lp_ref.sum().backward()
+    pg = [v.clone().to(cuda).requires_grad_(True) for v in (sf, sn, lam, x)]
+    lp = ops.ou_prior_logp(D.to(cuda), *pg)
+    lp.sum().backward()
+    # two fp64 computations of a problem with cond ~1e10 agree to ~cond * 1e-16; the gates are 1e-4 (ELBO) / 1e-3 (gradients)
+    assert torch.allclose(lp.detach().cpu(), lp_ref.detach(), rtol=1e-6)
+    assert abs(float(lp[0]) - float(lp_ref[0])) <= 1e-9 * abs(float(lp_ref[0]))
+    for a, b, name in zip(pg, ps, ("sf", "sn", "lam", "x")):
+        ga, gb = a.grad.cpu(), b.grad
+        for zz in range(3):
+            err = float((ga[zz] - gb[zz]).norm() / gb[zz].norm())
+            assert err < (1e-7 if zz == 0 else 1e-4), (name, zz, err)
