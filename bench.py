@@ -1,11 +1,20 @@
 #!/usr/bin/env python
 """bench.py — SVI steps/s of DRAUPNIR's tree-OU prior + decoder ELBO path on B200 (contract: see the task prompt).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl ours|reference]
 
 A "step" is one full `svi.step` (guide forward, model log-joint, backward, ClippedAdam update) on a seeded synthetic
 tree + alignment.  Default workload: c4 = 2,000 leaves / 500 sites / variational guide / z = 30 (the configuration
-BASELINE.json's target is quoted on; it fits one GPU).  One JSON line goes to stdout; everything else to stderr.
+BASELINE.json's target is quoted on; it fits one GPU).  c5 is BASELINE.json's patristic-matrix + OU-covariance build sweep
+(100-8,000 leaves; a "step" there is one build of both at the largest size).  One JSON line goes to stdout; everything
+else to stderr.
+
+What the line's numbers are: `value` — steps/s with device-resident inputs, the step replayed from its CUDA
+graph; `e2e` — the same through `Run.step_from_host` (pinned host inputs copied every step inside the graph, loss read
+back); `kernels` — per-kernel device time / achieved rate from an extra, EAGER, instrumented pass after the timed regions
+(CUDA events around every launch of the library on its launching stream); `roofline` — the kernel with the largest share
+of that pass; `north_star_kernel` — always the tcgen05 trailing update; `conditional` — K6 at this size; `cpu_baseline` —
+the oracle port on the host cores.
 """
 from __future__ import annotations
 
@@ -26,14 +35,16 @@ WORKLOADS = {
     "c2": dict(n=200, L=300, guide="variational", desc="200-leaf random tree, 300 sites, variational"),
     "c3": dict(n=800, L=400, guide="delta_map", desc="800-leaf tree, 400 sites, delta_map"),
     "c4": dict(n=2000, L=500, guide="variational", desc="2,000-leaf tree, 500 sites, variational"),
+    "c5": dict(n=8000, L=0, guide=None, desc="patristic-matrix + OU-covariance build sweep, 100-8,000 leaves"),
 }
+C5_SIZES = (100, 200, 500, 1000, 2000, 4000, 8000)
 Z_DIM = 30
 METRIC = "svi_steps_per_sec"
 UNIT = "steps/s"
+# Builder constants (NOT in MEASURED_PEAKS.json; every line that uses them says so in `peak_source`):
 FP64_TENSOR_NOMINAL_TFLOPS = 40.0          # B200 data sheet, dense fp64 (tensor and CUDA-core figures coincide)
 FP64_DMMA_MEASURED_TFLOPS = 37.15          # mma.sync.m8n8k4.f64 issue-bound loop on this pool (profiles/microbench/dmma_shapes.cu)
-KCLASS = ["syrk", "trsm", "potf2", "assemble", "reduce", "catlik", "patristic", "other", "syrk_tcgen05", "slice", "gru"]
-FLOP_CLASSES = (0, 1, 2, 8, 10)
+INT8_OVER_BF16 = 2.0                       # dense int8 tensor rate / dense bf16 rate (data sheet ratio; the int8 rate itself is unmeasured)
 
 
 _REAL_STDOUT = None
@@ -191,10 +202,26 @@ def make_clock_sampler(gpu_index: int):
         return SmiClockSampler(gpu_index)
 
 
-def oracle_steps_per_sec(w, budget_s: float, max_steps: int, warmup: int):
+def load_synthetic_standalone():
+    """`draupnir_asr_b200/synthetic.py` as a stand-alone module: the reference arm needs the seeded inputs but must not
+    import the package, whose `__init__` loads the CUDA library (numpy / torch only; nothing of the product runs)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_drp_synthetic", os.path.join(ROOT, "draupnir_asr_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_drp_synthetic"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def config_dict(args, w, world):
+    """Identical keys and values in both arms (the driver compares them)."""
+    return {"workload": f"{args.workload}: {w['desc']}, z_dim={Z_DIM}", "n_leaves": w["n"], "sites": w["L"], "guide": w["guide"],
+            "z_dim": Z_DIM, "gru_hidden_dim": 60, "l2": "flushed between timed iterations", "ranks": world}
+
+
+def oracle_steps_per_sec(w, budget_s: float, max_steps: int, warmup: int, synthetic):
     """The reference's arithmetic (fp64 torch restatement = oracle port) on the host cores; wall-clock bounded."""
     import torch
-    from draupnir_asr_b200 import synthetic
     from oracle import draupnir_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -207,7 +234,7 @@ def oracle_steps_per_sec(w, budget_s: float, max_steps: int, warmup: int):
     t_begin = time.perf_counter()
     done_w = 0
     for _ in range(warmup):
-        if time.perf_counter() - t_begin > 0.35 * budget_s:
+        if done_w >= 1 and time.perf_counter() - t_begin > 0.35 * budget_s:
             break
         svi.step(*args)
         done_w += 1
@@ -219,23 +246,151 @@ def oracle_steps_per_sec(w, budget_s: float, max_steps: int, warmup: int):
         if time.perf_counter() - t_begin > budget_s:
             break
     sps = len(times) / sum(times)
-    return sps, cores, f"{len(times)} full SVI step(s) of the same workload after {done_w} warm-up, {cores} threads, fp64"
+    return sps, cores, len(times), f"{len(times)} full SVI step(s) of the same workload after {done_w} warm-up, {cores} threads, fp64"
+
+
+def c5_cpu_sample(synthetic, budget_s: float):
+    """C5 on the host: parent-walk LCA patristic rows (scalar C oracle) and OUKernel_Fast in torch, on a bounded sample."""
+    import numpy as np
+    import torch
+    from oracle import draupnir_oracle as O
+    from oracle import patristic_oracle as P
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = WORKLOADS["c5"]["n"]
+    t = synthetic.random_tree(n, seed=n)
+    N = t.n_nodes
+    rows = np.arange(0, N, max(1, N // 1024), dtype=np.int32)[:1024]
+    cols = np.arange(N, dtype=np.int32)
+    P.patristic_c(t.parent, t.branch, t.depth, rows[:8], cols, want_lca=False)         # warm-up (loads the library)
+    t0 = time.perf_counter()
+    P.patristic_c(t.parent, t.branch, t.depth, rows, cols, want_lca=False)
+    t_pat = time.perf_counter() - t0
+    b_pat = len(rows) * N * 8
+    m = 2000
+    g = torch.Generator().manual_seed(0)
+    D = torch.rand(m, m, generator=g, dtype=torch.float64)
+    sf, sn, lam = (torch.rand(Z_DIM, generator=g, dtype=torch.float64) + 0.5 for _ in range(3))
+    O.ou_covariance(D[:200, :200], sf, sn, lam)
+    reps, t_ou = 0, 0.0
+    while reps < 1 or (t_ou < min(10.0, budget_s) and reps < 5):
+        t0 = time.perf_counter()
+        O.ou_covariance(D, sf, sn, lam)
+        t_ou += time.perf_counter() - t0
+        reps += 1
+    t_ou /= reps
+    b_ou = m * m * 8 * (Z_DIM + 1)
+    gbs = (b_pat + b_ou) / (t_pat + t_ou) / 1e9
+    return {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": (f"{len(rows)} of {N} patristic rows at {n} leaves (scalar C parent-walk, 1 thread: {b_pat / t_pat / 1e9:.3f} GB/s) + "
+                       f"OUKernel_Fast [30,{m},{m}] in torch on {cores} threads ({b_ou / t_ou / 1e9:.3f} GB/s), fp64"),
+            "patristic_gbs": b_pat / t_pat / 1e9, "ou_cov_gbs": b_ou / t_ou / 1e9}
 
 
 def run_reference(args, w, rank, world):
     if rank != 0:
         return
+    synthetic = load_synthetic_standalone()
     budget = float(os.environ.get("DRP_REF_BUDGET_S", "150"))
-    sps, cores, sample = oracle_steps_per_sec(w, budget, max(1, args.steps), args.warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 / sps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}, z_dim={Z_DIM}", "n_leaves": w["n"], "sites": w["L"],
-                       "guide": w["guide"], "z_dim": Z_DIM, "device": "host CPU"},
+    if args.workload == "c5":
+        cpu = c5_cpu_sample(synthetic, budget)
+        line = {"impl": "reference", "metric": C5_METRIC, "value": cpu["value"], "unit": "GB/s", "n_gpus": args.gpus, "steps": 1,
+                "warmup": 1, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config_dict(args, w, world), "cpu_baseline": cpu,
+                "e2e": {"value": cpu["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        emit(line)
+        return
+    sps, cores, timed, sample = oracle_steps_per_sec(w, budget, max(1, args.steps), max(1, args.warmup), synthetic)
+    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": timed,
+            "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / sps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, w, world),
             "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _event_ms(fn, reps, flush=None, warm=1):
+    import torch
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def read_kernel_table(lib, steps, peaks):
+    """Per-kernel device time and achieved rate from the library's instrumentation (CUDA events around every launch on the
+    launching stream).  Flop-counted kernels are set against the measured dense bf16 rate (the contract's tensor peak;
+    fp64 arithmetic cannot reach it, so the fraction of the fp64 DMMA rate - a builder constant - rides along), byte-counted
+    kernels against the measured HBM copy rate."""
+    import ctypes
+    NK = lib.drp_timing_classes()
+    kms, kln, kwk = (ctypes.c_double * NK)(), (ctypes.c_int64 * NK)(), (ctypes.c_double * NK)()
+    lib.drp_timing_read(kms, kln, kwk)
+    table = {}
+    for k in range(NK):
+        if not kln[k]:
+            continue
+        name = lib.drp_timing_class_name(k).decode()
+        flop = bool(lib.drp_timing_class_is_flops(k))
+        row = {"ms_per_step": kms[k] / steps, "launches_per_step": kln[k] / steps, "avg_launch_ms": kms[k] / kln[k],
+               "work_per_step": kwk[k] / steps, "bound": "tensor" if flop else "hbm"}
+        if kms[k] > 0 and kwk[k] > 0:
+            rate = kwk[k] / (kms[k] * 1e-3) / (1e12 if flop else 1e9)
+            pk = peaks["tensor_sustained"] if flop else peaks["hbm"]
+            row.update(achieved=rate, unit="TFLOP/s" if flop else "GB/s", peak=pk, frac=rate / pk)
+            if flop:
+                row["frac_of_fp64_dmma_builder_constant"] = rate / FP64_DMMA_MEASURED_TFLOPS
+        table[name] = row
+    return table
+
+
+def roofline_entry(name, row, step_ms, peaks, traffic):
+    if row is None or "achieved" not in row:
+        return None
+    tensor = row["bound"] == "tensor"
+    out = {"bound": row["bound"], "kernel": name, "achieved": row["achieved"], "peak": row["peak"], "unit": row["unit"],
+           "frac": row["frac"], "traffic": traffic.get(name),
+           "peak_source": (f"{peaks['source']} MEASURED_PEAKS.json: " + ("dense bf16, sustained" if tensor else "HBM copy")),
+           "avg_launch_ms": row["avg_launch_ms"], "launches_per_step": row["launches_per_step"],
+           "algorithmic_work_per_launch": row["work_per_step"] / row["launches_per_step"],
+           "ms_per_step": row["ms_per_step"], "share_of_step": row["ms_per_step"] / step_ms,
+           "timed": "CUDA events around each launch on its launching stream, eager instrumented pass after the timed region"}
+    if tensor:
+        out["frac_of_fp64_dmma"] = row["achieved"] / FP64_DMMA_MEASURED_TFLOPS
+        out["fp64_dmma_peak_source"] = f"builder constant {FP64_DMMA_MEASURED_TFLOPS} TFLOP/s (profiles/microbench/dmma_shapes.cu), not in MEASURED_PEAKS.json"
+    if name == "oz_syrk_kernel":       # split-integer update: every fp64-equivalent flop costs S(S+1)/2 int8 MACs on the tensor pipe
+        S = int(os.environ.get("DRP_OZAKI_SLICES", "6") or 6)
+        pairs = S * (S + 1) // 2
+        int8_peak = INT8_OVER_BF16 * row["peak"]
+        out["int8_tops_executed"] = row["achieved"] * pairs
+        out["frac_of_int8_peak"] = row["achieved"] * pairs / int8_peak
+        out["int8_peak_source"] = f"{INT8_OVER_BF16} x measured dense bf16 (data-sheet ratio, a builder assumption; the int8 rate is not in MEASURED_PEAKS.json)"
+        out["note"] = (f"fp64-accurate trailing update executed as {pairs} int8 GEMMs (S = {S} byte slices) on tcgen05.mma.kind::i8; "
+                       "'achieved' counts fp64-equivalent flops (2 K per updated entry)")
+    elif tensor:
+        out["note"] = "fp64 kernel (the reference dtype) on mma.sync.m8n8k4.f64: the bf16 peak in 'peak' is not reachable by fp64 arithmetic"
+    return out
+
+
+def load_traffic():
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        return json.load(open(path)).get("kernels", {})
+    except Exception:
+        return {}
 
 
 def run_ours(args, w, rank, world, local_rank):
@@ -245,7 +400,6 @@ def run_ours(args, w, rank, world, local_rank):
     entry.build()
     from draupnir_asr_b200 import runtime, synthetic, zshard
     from draupnir_asr_b200._lib import lib
-    import ctypes
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -253,7 +407,8 @@ def run_ours(args, w, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     shard = zshard.ShardContext(rank, world, Z_DIM, w["n"]) if world > 1 else None
 
-    problem = synthetic.make_problem(w["n"], w["L"], seed=0)
+    # the patristic matrices come from the product's own builder (K1, csrc/patristic.cu)
+    problem = synthetic.make_problem(w["n"], w["L"], seed=0, builder="device", device=dev)
     init = synthetic.make_parameters(w["n"], z_dim=Z_DIM, seed=0)
     run = runtime.build_run(problem, w["guide"], device=dev, init=init, z_dim=Z_DIM, shard=shard)
     host = run.make_host_inputs()
@@ -272,129 +427,271 @@ def run_ours(args, w, rank, world, local_rank):
         gc.collect()
         gc.disable()
         try:
-            return _timed(fn, k)
+            evs = []
+            for _ in range(k):
+                flush.zero_()                                             # L2 flush between timed iterations (untimed)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            per = [a.elapsed_time(b) for a, b in evs]
+            log(f"[rank {rank}] per-step ms: " + " ".join(f"{v:.2f}" for v in per))
+            return sum(per)
         finally:
             gc.enable()
-
-    def _timed(fn, k):
-        evs = []
-        for _ in range(k):
-            flush.zero_()                                             # L2 flush between timed iterations (untimed)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn()
-            b.record()
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        per = [a.elapsed_time(b) for a, b in evs]
-        log(f"[rank {rank}] per-step ms: " + " ".join(f"{v:.2f}" for v in per))
-        return sum(per)
 
     # the sampler starts BEFORE the warm-up: NVML's start-up (attaching to every GPU of the box) can stall the launches
     # of a running context for tens of ms, which must not land inside a timed step; its polling does not
     sampler = make_clock_sampler(local_rank)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        lw = lib.drp_launch_count()
+    W = max(args.warmup, 3)
+    for _ in range(W):                                   # two eager steps, then the step is captured and replayed
         loss = run.step()
-        launches_warm = lib.drp_launch_count() - lw
-    log(f"[rank {rank}] warm-up done, -ELBO {loss:.4f}; {launches_warm} launches of this library per step")
+    graphed = bool(run.svi.last_step_was_replay)
+    log(f"[rank {rank}] warm-up done, -ELBO {loss:.4f}; step replayed from a CUDA graph: {graphed}")
     sampler.wait_first_sample()
-    torch.cuda.synchronize()
-    lib.drp_timing_enable(int(launches_warm * (args.steps + 1)) + 64)   # events for the whole timed region, created now
     barrier()                                                          # ranks leave the (rank-dependent) set-up together
-    l0 = lib.drp_launch_count()
     ms = timed(run.step, args.steps)
-    launches = lib.drp_launch_count() - l0
-    NK = lib.drp_timing_classes()
-    kms = (ctypes.c_double * NK)()
-    kln = (ctypes.c_int64 * NK)()
-    kwk = (ctypes.c_double * NK)()
-    lib.drp_timing_read(kms, kln, kwk)
-    lib.drp_timing_enable(0)
-    for _ in range(max(args.warmup, 3)):                                # the host-fed path has its own warm-up (copy stream, events)
+    for _ in range(W):                                                 # the host-fed path has its own warm-up / capture
         run.step_from_host(host)
+    graphed_e2e = bool(run.svi.last_step_was_replay)
     barrier()
     ms_e2e = timed(lambda: run.step_from_host(host), args.steps)
     barrier()
     clocks = sampler.stop()
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    # ---- instrumented pass: the same step, eager, with CUDA events around every launch of the library
+    P = max(2, min(args.steps, 5))
+    run.svi.cuda_graph = False
+    l0 = lib.drp_launch_count()
+    run.step()
+    launches_per_step = int(lib.drp_launch_count() - l0)
+    torch.cuda.synchronize()
+    lib.drp_timing_enable(int(launches_per_step * (P + 1)) + 64)
+    ms_eager = timed(run.step, P)
+    peaks = measured_peaks()
+    kernels = read_kernel_table(lib, P, peaks)
+    lib.drp_timing_enable(0)
+    run.svi.cuda_graph = True
+
+    # ---- K6: conditional posterior of the internal nodes at this size (S/models.py:149-242), z-sharded like the prior
+    with torch.no_grad():
+        est = run.guide(*run.step_args())
+        est = {k: est[k].detach() for k in ("sigma_f", "sigma_n", "lambd", "latent_z")}
+        D = run.Draupnir
+        n, ni, N = problem.n_leaves, problem.n_internal, problem.n_leaves + problem.n_internal
+        reps = 3 if w["n"] <= 800 else 2
+        ms_map = _event_ms(lambda: D.conditional_samplingMAP(est, run.patristic_matrix_full), reps, flush)
+        ms_cov = _event_ms(lambda: D._conditional(est, run.patristic_matrix_full, D.internal_nodes, D.n_internal, 0.0, 1e-6, True),
+                           reps, flush)
+    t2 = torch.tensor([ms, ms_e2e, ms_map, ms_cov], dtype=torch.float64, device=dev)
     h2d = torch.tensor([float(run.host_bytes_per_step(host))], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)                     # max over ranks
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)                    # max over ranks
         dist.all_reduce(h2d, op=dist.ReduceOp.SUM)                   # bytes copied by all ranks together
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e, ms_map, ms_cov = (float(v) for v in t2)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks = measured_peaks()
-    per_class = {KCLASS[k]: {"ms_per_step": kms[k] / args.steps, "launches_per_step": kln[k] / args.steps,
-                             "work_per_step": kwk[k] / args.steps} for k in range(NK) if kln[k]}
-    # achieved rate of every class against the peak that bounds it (north star: tensor-pipe utilisation for the
-    # Cholesky / GEMM kernels, HBM GB/s for assembly and likelihood); with the prior on a side stream the classes overlap,
-    # so these per-class rates are lower bounds of what each kernel does alone (DRP_PRIOR_STREAM=0 gives the unshared ones)
-    for k in range(NK):
-        if kln[k] and kms[k] > 0:
-            flop = k in FLOP_CLASSES
-            rate = kwk[k] / (kms[k] * 1e-3) / (1e12 if flop else 1e9)
-            pk = peaks["tensor_sustained"] if flop else peaks["hbm"]
-            per_class[KCLASS[k]].update({"achieved": rate, "unit": "TFLOP/s" if flop else "GB/s", "frac_of_peak": rate / pk,
-                                         "bound": "tensor" if flop else "hbm"})
-    dom = max(range(NK), key=lambda k: kms[k])
-    tensor_bound = dom in FLOP_CLASSES
-    avg_ms = kms[dom] / max(kln[dom], 1)
-    work_per_launch = kwk[dom] / max(kln[dom], 1)
-    achieved = work_per_launch / (avg_ms * 1e-3) / (1e12 if tensor_bound else 1e9)
-    peak = peaks["tensor_sustained"] if tensor_bound else peaks["hbm"]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get(KCLASS[dom])
-        except Exception:
-            traffic = None
-    roofline = {"bound": "tensor" if tensor_bound else "hbm", "kernel": KCLASS[dom] + "_kernel", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": f"{peaks['source']} ({'bf16 dense sustained' if tensor_bound else 'HBM copy'})",
-                "avg_launch_ms": avg_ms, "algorithmic_work_per_launch": work_per_launch,
-                "share_of_step": kms[dom] / ms}
-    if tensor_bound:
-        roofline["frac_of_fp64_dmma_measured"] = achieved / FP64_DMMA_MEASURED_TFLOPS
-        if dom == 8:      # split-integer update: every fp64-equivalent flop costs S(S+1)/2 int8 MACs on the tensor pipe
-            S = int(os.environ.get("DRP_OZAKI_SLICES", "6") or 6)
-            pairs = S * (S + 1) // 2
-            int8_peak = 2.0 * peak                               # dense int8 = 2 x dense bf16
-            roofline["int8_tops_executed"] = achieved * pairs
-            roofline["frac_of_int8_peak"] = achieved * pairs / int8_peak
-            roofline["note"] = (f"fp64-accurate update executed as {pairs} int8 GEMMs (S = {S} slices) on tcgen05.mma.kind::i8; "
-                                f"'achieved' counts fp64-equivalent flops, the tensor pipe itself runs {achieved * pairs:.0f} TOP/s = "
-                                f"{achieved * pairs / int8_peak:.3f} of the int8 peak (2 x measured bf16)")
-        else:
-            roofline["note"] = ("fp64 kernel (reference dtype) on mma.sync.m8n8k4.f64; against the measured fp64 DMMA peak of "
-                                f"{FP64_DMMA_MEASURED_TFLOPS} TFLOP/s the fraction is {achieved / FP64_DMMA_MEASURED_TFLOPS:.3f} "
-                                "(the bf16 peak in 'peak' is not reachable by fp64 arithmetic)")
-        roofline["frac_of_fp64_nominal"] = achieved / FP64_TENSOR_NOMINAL_TFLOPS
+    step_ms = ms / args.steps
+    traffic = load_traffic()
+    timed_rows = {k: v for k, v in kernels.items() if "achieved" in v and k not in ("misc", "small_reductions")}
+    dom = max(timed_rows, key=lambda k: timed_rows[k]["ms_per_step"]) if timed_rows else None
+    eager_step_ms = ms_eager / P
+    roofline = roofline_entry(dom, kernels.get(dom), eager_step_ms, peaks, traffic) if dom else None
+    north = roofline_entry("oz_syrk_kernel", kernels.get("oz_syrk_kernel"), eager_step_ms, peaks, traffic)
+    ours_map = Z_DIM * (n ** 3 / 3.0 + n * n * ni)                  # elimination of the leaf block, mean only
+    ours_cov = Z_DIM * (n ** 3 / 3.0 + n * n * ni + n * ni * ni)
+    ref_flops = Z_DIM * (2.0 * N ** 3 + 4.0 * ni ** 3)                # the reference's three dense inverses
+    conditional = {"mean_only_ms": ms_map, "mean_and_covariance_ms": ms_cov,
+                   "algorithmic_tflops_mean_only": ours_map / (ms_map * 1e-3) / 1e12,
+                   "algorithmic_tflops_mean_and_covariance": ours_cov / (ms_cov * 1e-3) / 1e12,
+                   "reference_flops": ref_flops, "reference_equivalent_tflops": ref_flops / (ms_cov * 1e-3) / 1e12,
+                   "flop_saving_vs_reference": ref_flops / ours_cov,
+                   "what": "conditional_samplingMAP (mean [z,ni]) and conditional mean + covariance [z,ni,ni] of the internal nodes given "
+                           "the leaves, Schur complement on the leaf block (S/models.py:149-242), CUDA events, median"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         budget = float(os.environ.get("DRP_CPU_BUDGET_S", "25"))
-        sps, cores, sample = oracle_steps_per_sec(w, budget, 8, 1 if w["n"] <= 800 else 0)
+        sps, cores, _, sample = oracle_steps_per_sec(w, budget, 8, 1, load_synthetic_standalone())
         cpu = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     value = args.steps / (ms * 1e-3)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}, z_dim={Z_DIM}", "n_leaves": w["n"], "sites": w["L"],
-                       "guide": w["guide"], "z_dim": Z_DIM, "gru_hidden_dim": 60, "l2": "flushed between timed iterations",
-                       "parallelism": "single GPU" if world == 1 else f"z-sharded OU prior + leaf-sharded decoder over {world} GPUs"},
-            "roofline": roofline, "cpu_baseline": cpu,
+    cfg = config_dict(args, w, world)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg,
+            "parallelism": "single GPU" if world == 1 else f"z-sharded OU prior + leaf-sharded decoder over {world} GPUs", "roofline": roofline, "north_star_kernel": north, "cpu_baseline": cpu,
             "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d[0]),
-                    "d2h_bytes_per_step": 8 + 4 * Z_DIM, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "kernel_classes": per_class}
+                    "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps, "cuda_graph": graphed_e2e},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_note": (f"{launches_per_step} kernels of libdraupnir_b200.so per step (counted on an eager step) x {args.steps} timed steps; "
+                                  + ("in the timed region they are nodes of the replayed CUDA graph" if graphed else "launched eagerly")),
+            "cuda_graph": graphed, "eager_ms_per_step": eager_step_ms, "clocks": clocks, "conditional": conditional,
+            "kernels": kernels}
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+C5_METRIC = "patristic_plus_ou_covariance_build_gbs"
+
+
+def run_c5(args, w, rank, world, local_rank):
+    """BASELINE.json config 5: all-node patristic matrix (K1) + [30, n, n] OU covariance over the leaves (K2), 100-8,000
+    leaves.  Independent trees shard trivially: with N ranks every rank builds its own copy (weak scaling, no collective)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    entry.build()
+    from draupnir_asr_b200 import ops, synthetic as S
+    from draupnir_asr_b200._lib import lib
+    from oracle import patristic_oracle as P
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = measured_peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = make_clock_sampler(local_rank)
+    sampler.start()
+    g = torch.Generator().manual_seed(0)
+    sf, sn, lam = (torch.rand(Z_DIM, generator=g, dtype=torch.float64).add(0.5).to(dev) for _ in range(3))
+    sweep = []
+    K = None
+    for n in C5_SIZES:
+        t = S.random_tree(n, seed=n)
+        N = t.n_nodes
+        parent, branch = torch.from_numpy(t.parent).to(dev), torch.from_numpy(t.branch).to(dev)
+        row = {"n_leaves": n, "n_nodes": N}
+        # parity: LCA indices bit-exact against the scalar C oracle (all pairs up to 2,000 leaves, a 256 x 256 sample above)
+        if n <= 2000:
+            pat, _, lca = ops.tree_distances(parent, branch, want_lca=True)
+            lca_ref, pat_ref, _ = P.patristic_c(t.parent, t.branch, t.depth)
+        else:
+            rng = np.random.default_rng(n)
+            rows = np.sort(rng.choice(N, 256, replace=False)).astype(np.int32)
+            cols = np.sort(rng.choice(N, 256, replace=False)).astype(np.int32)
+            pat, _, lca = ops.tree_distances(parent, branch, rows=torch.from_numpy(rows), cols=torch.from_numpy(cols), want_lca=True)
+            lca_ref, pat_ref, _ = P.patristic_c(t.parent, t.branch, t.depth, rows, cols)
+        row["lca_bit_exact"] = bool(np.array_equal(lca.cpu().numpy(), lca_ref))
+        row["patristic_max_rel_err"] = float(np.max(np.abs(pat.cpu().numpy() - pat_ref) / np.maximum(np.abs(pat_ref), 1e-300)))
+        del pat, lca
+        ms = _event_ms(lambda: ops.tree_distances(parent, branch), 7, flush, warm=3)
+        row.update(patristic_ms=ms, patristic_bytes=N * N * 8, patristic_gbs=N * N * 8 / (ms * 1e-3) / 1e9)
+        ms = _event_ms(lambda: ops.tree_distances(parent, branch, want_lca=True), 5, flush, warm=1)
+        row.update(patristic_lca_ms=ms, patristic_lca_gbs=N * N * 12 / (ms * 1e-3) / 1e9)
+        leaves = torch.from_numpy(t.leaves).to(dev)
+        D = ops.tree_distances(parent, branch, rows=leaves, cols=leaves)[0]
+
+        def build_cov():
+            nonlocal K
+            K = None
+            K = ops.ou_cov(D, sf, sn, lam)
+
+        ms = _event_ms(build_cov, 5, flush, warm=2)
+        row.update(ou_cov_ms=ms, ou_cov_bytes=n * n * 8 * (Z_DIM + 1), ou_cov_gbs=n * n * 8 * (Z_DIM + 1) / (ms * 1e-3) / 1e9)
+        K = None
+        for k in ("patristic_gbs", "patristic_lca_gbs", "ou_cov_gbs"):
+            row[k.replace("_gbs", "_frac_of_hbm_peak")] = row[k] / peaks["hbm"]
+        sweep.append(row)
+        log(json.dumps(row))
+    # ---- the timed "steps": one build of both at the largest size, K of them; then per-kernel events for the roofline
+    n = C5_SIZES[-1]
+    t = S.random_tree(n, seed=n)
+    N = t.n_nodes
+    parent_h = torch.from_numpy(t.parent).pin_memory()
+    branch_h = torch.from_numpy(t.branch).pin_memory()
+    parent, branch = parent_h.to(dev), branch_h.to(dev)
+    leaves = torch.from_numpy(t.leaves).to(dev)
+    out_h = torch.zeros(2, dtype=torch.float64).pin_memory()
+
+    def build(parent, branch):
+        nonlocal K
+        K = None
+        full = ops.tree_distances(parent, branch)[0]
+        D = ops.tree_distances(parent, branch, rows=leaves, cols=leaves)[0]          # the leaves' matrix the prior consumes
+        K = ops.ou_cov(D, sf, sn, lam)
+        return full, K
+
+    def step_resident():
+        build(parent, branch)
+
+    def step_host():
+        p, b = parent_h.to(dev, non_blocking=True), branch_h.to(dev, non_blocking=True)
+        full, Kc = build(p, b)
+        out_h.copy_(torch.stack((full[N - 1].sum(), Kc[Z_DIM - 1, n - 1].sum())), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step_resident()
+    sampler.wait_first_sample()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step_resident(); b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    for _ in range(W):
+        step_host()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step_host(); b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ms_e2e = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop()
+    l0 = lib.drp_launch_count()
+    step_resident()
+    launches_per_step = int(lib.drp_launch_count() - l0)
+    P_ = 5
+    lib.drp_timing_enable(launches_per_step * (P_ + 1) + 64)
+    for _ in range(P_):
+        flush.zero_()
+        step_resident()
+    kernels = read_kernel_table(lib, P_, peaks)
+    lib.drp_timing_enable(0)
+    t2 = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t2[0]), float(t2[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    bytes_step = N * N * 8 + n * n * 8 + n * n * 8 * (Z_DIM + 1)      # all-node matrix + leaf matrix + D read once, K written
+    traffic = load_traffic()
+    step_ms = ms / args.steps
+    dom = max((k for k in kernels if "achieved" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = c5_cpu_sample(load_synthetic_standalone(), float(os.environ.get("DRP_CPU_BUDGET_S", "25")))
+    cfg = config_dict(args, w, world)
+    line = {"parallelism": "single GPU" if world == 1 else f"{world} independent builds, one per GPU (no collective)",
+            "metric": C5_METRIC, "value": world * bytes_step * args.steps / (ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "roofline": roofline_entry(dom, kernels[dom], step_ms, peaks, traffic), "cpu_baseline": cpu,
+            "e2e": {"value": world * bytes_step * args.steps / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s",
+                    "h2d_bytes_per_step": int(N * 12), "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "kernels": kernels, "sweep": sweep,
+            "all_lca_bit_exact": all(r["lca_bit_exact"] for r in sweep), "hbm_peak_gbs": peaks["hbm"]}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -421,6 +718,8 @@ def main():
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w, rank, world)
+    elif args.workload == "c5":
+        run_c5(args, w, rank, world, local_rank)
     else:
         run_ours(args, w, rank, world, local_rank)
 

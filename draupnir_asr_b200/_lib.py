@@ -21,6 +21,8 @@ SIGNATURES = {
     "drp_abi_version": (_i32, []),
     "drp_launch_count": (_i64, []),
     "drp_timing_classes": (_i32, []),
+    "drp_timing_class_name": (ctypes.c_char_p, [_i32]),
+    "drp_timing_class_is_flops": (_i32, [_i32]),
     "drp_timing_enable": (_i32, [_i32]),
     "drp_timing_read": (_i32, [_p, _p, _p]),
     "drp_tree_prepare": (_i32, [_p, _p, _i32, _p, _p, _p, _p, _p, _p]),
@@ -57,6 +59,8 @@ SIGNATURES = {
     "drp_gram_workspace_elems": (_i64, [_i32, _i32]),
     "drp_gram_tn_f64": (_i32, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _i64, _p]),
     "drp_tall_gemm_f64": (_i32, [_p, _p, _p, _i64, _i32, _i32, _p, _p]),
+    "drp_clipped_adam_max_tensors": (_i32, []),
+    "drp_clipped_adam_f64": (_i32, [_p, _p, _p, _i32, _i32, _p, _f64, _f64, _f64, _f64, _f64, _f64, _p]),
     "drp_cat_loglik_partials": (_i64, [_i64]),
     "drp_cat_loglik_fwd_f64": (_i32, [_p, _p, _i32, _i64, _i32, _p, _p, _p, _p]),
     "drp_cat_loglik_bwd_f64": (_i32, [_p, _p, _i32, _p, _p, _i64, _i32, _p, _p]),

@@ -198,12 +198,9 @@ __global__ void __launch_bounds__(PR) trsm_kernel(double* __restrict__ Mb, int64
 // syrk: C[r][c] -= sum_{k in [k0, k0+K)} P[r][k] P[c][k] for r in [c1, R), c in [c1, min(R, col_limit)), c <= r.
 // 64x64 output tile per CTA, 4 warps (2x2) of 32x32, fp64 mma.sync m8n8k4, K consumed in chunks of 64.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) syrk_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int k0, int K, int c1,
-                                                   int R, int col_limit, const int* __restrict__ zmap, int z)
+__device__ __forceinline__ void syrk_tile(double* __restrict__ A, int64_t ld, int k0, int K, int c1, int R, int col_limit,
+                                          int ti, int tj, double* sm, bool sync_first)
 {
-    const int tj = blockIdx.x, ti = blockIdx.y;
-    if (tj > ti) return;
-    extern __shared__ double sm[];
     double* As = sm;
     double* Bs = (ti == tj) ? As : sm + TS * SLD;
     const int tid = threadIdx.x;
@@ -212,55 +209,89 @@ __global__ void __launch_bounds__(128) syrk_kernel(double* __restrict__ Mb, int6
     const int wm = warp >> 1, wn = warp & 1;
     const double* ap = As + (wm * 32 + gid) * SLD + tig;
     const double* bp = Bs + (wn * 32 + gid) * SLD + tig;
-    // without a zmap: one matrix per blockIdx.z; with one: this CTA walks the matrices of the fp64 list (usually none)
-    const int nq = zmap ? zmap[1] : 1;
-    for (int q = 0; q < nq; ++q) {
-        double* A = Mb + (int64_t)(zmap ? zmap[2 + z + q] : (int)blockIdx.z) * bs;
-        double acc[4][4][2];
+    double acc[4][4][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        for (int kc = 0; kc < K; kc += NB) {
-            const int kb = min(NB, K - kc);
-            if (kc || q) __syncthreads();
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kc = 0; kc < K; kc += NB) {
+        const int kb = min(NB, K - kc);
+        if (kc || sync_first) __syncthreads();
+        for (int idx = tid; idx < TS * NB; idx += 128) {
+            const int r = idx / NB, k = idx - r * NB;
+            As[r * SLD + k] = (r0 + r < R && k < kb) ? A[(int64_t)(r0 + r) * ld + k0 + kc + k] : 0.0;
+        }
+        if (ti != tj) {
             for (int idx = tid; idx < TS * NB; idx += 128) {
                 const int r = idx / NB, k = idx - r * NB;
-                As[r * SLD + k] = (r0 + r < R && k < kb) ? A[(int64_t)(r0 + r) * ld + k0 + kc + k] : 0.0;
-            }
-            if (ti != tj) {
-                for (int idx = tid; idx < TS * NB; idx += 128) {
-                    const int r = idx / NB, k = idx - r * NB;
-                    Bs[r * SLD + k] = (q0 + r < R && k < kb) ? A[(int64_t)(q0 + r) * ld + k0 + kc + k] : 0.0;
-                }
-            }
-            __syncthreads();
-            const int kmax = (kb + 3) & ~3;
-            for (int k = 0; k < kmax; k += 4) {
-                double a[4], b[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = ap[i * 8 * SLD + k];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = bp[j * 8 * SLD + k];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                Bs[r * SLD + k] = (q0 + r < R && k < kb) ? A[(int64_t)(q0 + r) * ld + k0 + kc + k] : 0.0;
             }
         }
-        const int cmax = min(R, col_limit);
+        __syncthreads();
+        const int kmax = (kb + 3) & ~3;
+        for (int k = 0; k < kmax; k += 4) {
+            double a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int row = r0 + wm * 32 + i * 8 + gid;
-            if (row >= R) continue;
-            double* crow = A + (int64_t)row * ld;
+            for (int i = 0; i < 4; ++i) a[i] = ap[i * 8 * SLD + k];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int col = q0 + wn * 32 + j * 8 + 2 * tig;
-                if (col <= row && col < cmax) crow[col] -= acc[i][j][0];
-                if (col + 1 <= row && col + 1 < cmax) crow[col + 1] -= acc[i][j][1];
-            }
+            for (int j = 0; j < 4; ++j) b[j] = bp[j * 8 * SLD + k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
+    }
+    const int cmax = min(R, col_limit);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = r0 + wm * 32 + i * 8 + gid;
+        if (row >= R) continue;
+        double* crow = A + (int64_t)row * ld;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = q0 + wn * 32 + j * 8 + 2 * tig;
+            if (col <= row && col < cmax) crow[col] -= acc[i][j][0];
+            if (col + 1 <= row && col + 1 < cmax) crow[col + 1] -= acc[i][j][1];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) syrk_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int k0, int K, int c1,
+                                                   int R, int col_limit)
+{
+    const int tj = blockIdx.x, ti = blockIdx.y;
+    if (tj > ti) return;
+    extern __shared__ double sm[];
+    syrk_tile(Mb + (int64_t)blockIdx.z * bs, ld, k0, K, c1, R, col_limit, ti, tj, sm, false);
+}
+
+// The same update for the matrices the precision gate (factor.cuh) kept off the tensor path: a small persistent grid
+// whose CTAs find an EMPTY list in the normal case and exit at once (a (Tc, T) grid of 69 KB CTAs that only exit costs
+// ~75 us per launch, 2.4 ms per 2,000-leaf step).  Work item w -> (matrix of the fp64 list, tile row, tile column).
+__global__ void __launch_bounds__(128) syrk_gated_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int k0, int K, int c1,
+                                                         int R, int col_limit, const int* __restrict__ zmap, int z, int T,
+                                                         int Tc)
+{
+    const int nq = zmap[1];
+    if (nq == 0) return;
+    extern __shared__ double sm[];
+    const int tri = Tc * (Tc + 1) / 2, pairs = tri + (T - Tc) * Tc;
+    bool later = false;
+    for (int w = blockIdx.x; w < nq * pairs; w += gridDim.x) {
+        const int q = w / pairs;
+        int v = w - q * pairs, ti, tj;
+        if (v < tri) {                                 // triangular part: rows 0..Tc-1 with ti + 1 tiles each
+            ti = (int)((sqrt(8.0 * v + 1.0) - 1.0) * 0.5);
+            while (ti * (ti + 1) / 2 > v) --ti;
+            while ((ti + 1) * (ti + 2) / 2 <= v) ++ti;
+            tj = v - ti * (ti + 1) / 2;
+        } else {                                       // rows below: Tc tiles each
+            v -= tri;
+            ti = Tc + v / Tc;
+            tj = v - (ti - Tc) * Tc;
+        }
+        syrk_tile(Mb + (int64_t)zmap[2 + z + q] * bs, ld, k0, K, c1, R, col_limit, ti, tj, sm, later);
+        later = true;
     }
 }
 
@@ -294,7 +325,10 @@ static const int SYRK_SMEM = 2 * TS * SLD * (int)sizeof(double);
 void drp_dmma_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, const int* zmap,
                    cudaStream_t st)
 {
-    if (drp_first_on_device(0)) cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM);
+    if (drp_first_on_device(0)) {
+        cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM);
+        cudaFuncSetAttribute(syrk_gated_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM);
+    }
     const int below = R - c1;
     const int cl = min(R, col_limit) - c1;
     if (below <= 0 || cl <= 0) return;
@@ -302,8 +336,13 @@ void drp_dmma_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     const int Tc = min(T, (cl + TS - 1) / TS);
     // algorithmic flops: 2*K per updated entry of the lower trapezoid rows [c1,R) x cols [c1,c1+cl)
     const double entries = (double)cl * (cl + 1) / 2.0 + (double)(below - cl) * cl;
+    if (zmap) {                 // gated: normally nothing to do (work is not attributed; the tensor-path launch carries it)
+        DRP_LAUNCH(DRP_K_SYRK, 0.0, st);
+        syrk_gated_kernel<<<296, 128, SYRK_SMEM, st>>>(M, ld, bs, k0, K, c1, R, col_limit, zmap, z, T, Tc);
+        return;
+    }
     DRP_LAUNCH(DRP_K_SYRK, (double)z * entries * 2.0 * K, st);
-    syrk_kernel<<<dim3(Tc, T, zmap ? 1 : z), 128, SYRK_SMEM, st>>>(M, ld, bs, k0, K, c1, R, col_limit, zmap, z);
+    syrk_kernel<<<dim3(Tc, T, z), 128, SYRK_SMEM, st>>>(M, ld, bs, k0, K, c1, R, col_limit);
 }
 
 // Trailing update: int8 tcgen05 pipe when a workspace is given and the update is large, fp64 mma.sync otherwise.

@@ -906,7 +906,7 @@ static void gru_fwd2_launch(const double* gi, const double* v, const double* whh
     if (drp_first_on_device(32 + 8 * (int)UV + MT)) {
         cudaFuncSetAttribute(gru_fwd2_kernel<UV, MT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     }
-    DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * ndir * G3 * GH, st);
+    DRP_LAUNCH(DRP_K_GRU_FWD, 2.0 * (double)n * L * ndir * G3 * GH, st);
     static int stagger = -1;
     if (stagger < 0) {
         const char* e = getenv("DRP_GRU_HANDOFF");
@@ -928,7 +928,7 @@ static void gru_fwd_launch(const double* gi, const double* v, const double* whh,
     if (drp_first_on_device(44 + 8 * (int)UV + MT)) {
         cudaFuncSetAttribute(gru_fwd_kernel<UV, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     }
-    DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * ndir * G3 * GH, st);
+    DRP_LAUNCH(DRP_K_GRU_FWD, 2.0 * (double)n * L * ndir * G3 * GH, st);
     gru_fwd_kernel<UV, MT><<<dim3((n + 8 * MT - 1) / (8 * MT), ndir), GTHREADS, smem, st>>>(gi, v, whh, bhh, h0, n, L, out, gates,
                                                                                         ndir);
 }
@@ -941,7 +941,7 @@ static void gru_bwd_launch(const double* dout, const double* out, const double* 
     if (drp_first_on_device(24 + MT)) {
         cudaFuncSetAttribute(gru_bwd_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     }
-    DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * ndir * G3 * GH, st);
+    DRP_LAUNCH(DRP_K_GRU_BWD, 2.0 * (double)n * L * ndir * G3 * GH, st);
     gru_bwd_kernel<MT><<<dim3((n + 8 * MT - 1) / (8 * MT), ndir), GTHREADS, smem, st>>>(dout, out, gates, whh, h0, n, L, dgi, dh0,
                                                                                     dgi_dirs, dout_last);
 }
@@ -1093,7 +1093,7 @@ DRP_API int drp_gru_input_sums_f64(const double* dgi, int n, int L, int C, doubl
     cudaStream_t st = (cudaStream_t)stream;
     const int nblk = drp_gru_input_sums_blocks(n);
     const int rows = (n + nblk - 1) / nblk;
-    DRP_LAUNCH(DRP_K_REDUCE, (double)n * L * C * 8.0 + (double)nblk * L * C * 8.0, st);
+    DRP_LAUNCH(DRP_K_GRU_SUMS, (double)n * L * C * 8.0 + (double)nblk * L * C * 8.0, st);
     gru_input_sums_kernel<<<nblk, 256, 0, st>>>(dgi, n, L, C, rows, dU, dVpart);
     return drp_launch_status();
 }
@@ -1128,11 +1128,11 @@ static int gru_wgrad_dispatch(const double* dgi, const double* gates, const doub
     if (nchunks > nblk) nchunks = (int)nblk;
     if (!ws || ws_elems < (int64_t)nchunks * 2 * (GW_MT * 8) * 64) return -10;
     {
-        DRP_LAUNCH(DRP_K_GRU, 2.0 * (double)n * L * ndir * G3 * (GH + 1), st);
+        DRP_LAUNCH(DRP_K_GRU_WGRAD, 2.0 * (double)n * L * ndir * G3 * (GH + 1), st);
         gru_wgrad_kernel<<<ndir * nchunks, GW_THREADS, GW_SMEM, st>>>(dgi, gates, out, h0, n, L, ws, ndir, ndir);
     }
     {
-        DRP_LAUNCH(DRP_K_REDUCE, (double)nchunks * ndir * G3 * (GH + 1) * 8.0, st);
+        DRP_LAUNCH(DRP_K_GRU_WGRAD, (double)nchunks * ndir * G3 * (GH + 1) * 8.0, st);
         gru_wgrad_reduce_kernel<<<(ndir * G3 * (GH + 1) + 255) / 256, 256, 0, st>>>(ws, nchunks, dwhh, dbhh, ndir);
     }
     return drp_launch_status();
@@ -1418,11 +1418,11 @@ DRP_API int drp_gram_tn_f64(const double* A, const double* B, int64_t K, int M, 
     const int grid = (int)(nblk < n_sm ? nblk : n_sm);
     if (!ws || ws_elems < (int64_t)grid * (((M + 7) / 8) * 8) * (((N + 1 + 7) / 8) * 8)) return -8;
     {
-        DRP_LAUNCH(DRP_K_REDUCE, (double)K * (M + N) * 8.0, st);
+        DRP_LAUNCH(DRP_K_GRAM, (double)K * (M + N) * 8.0, st);
         gram_tn_kernel<<<grid, GTHREADS, smem, st>>>(A, B, K, M, N, ws);
     }
     {
-        DRP_LAUNCH(DRP_K_REDUCE, (double)grid * M * (N + 1) * 8.0, st);
+        DRP_LAUNCH(DRP_K_GRAM, (double)grid * M * (N + 1) * 8.0, st);
         gram_reduce_kernel<<<(M * (N + 1) + 255) / 256, 256, 0, st>>>(ws, grid, M, N, C, colsum);
     }
     return drp_launch_status();
@@ -1437,7 +1437,7 @@ static void tall_gemm_launch(const double* X, const double* Wt, const double* bi
     const int64_t ntiles = (M + 8 * MTW - 1) / (8 * MTW);
     const int64_t want = (ntiles + 7) / 8;                        // at least one tile per warp
     const int grid = (int)(want < n_sm ? want : n_sm);
-    DRP_LAUNCH(DRP_K_OTHER, (double)M * (K + N) * 8.0, st);
+    DRP_LAUNCH(DRP_K_TALL_GEMM, (double)M * (K + N) * 8.0, st);
     tall_gemm_kernel<NT, MTW><<<grid, GTHREADS, smem, st>>>(X, Wt, bias, M, K, N, Y);
 }
 

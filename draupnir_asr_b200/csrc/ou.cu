@@ -342,7 +342,7 @@ DRP_API int drp_ou_cov_bwd_f64(const double* D, int64_t ldd, int n, const double
     if (!G || !part || !out) return -6;
     cudaStream_t st = (cudaStream_t)stream;
     {
-        DRP_LAUNCH(DRP_K_REDUCE, ((double)n * n * 8.0 * (z + 1)), st);
+        DRP_LAUNCH(DRP_K_OU_GRAD, ((double)n * n * 8.0 * (z + 1)), st);
         ou_cov_bwd_kernel<<<dim3(n, z), 256, 0, st>>>(D, ldd, n, lam, G, part);
     }
     {
@@ -388,7 +388,7 @@ DRP_API int drp_ou_prior_f64(const double* D, int64_t ldd, int n, const double* 
             alpha_extract_kernel<<<dim3((n + 255) / 256, z), 256, 0, st>>>(M, ld, bs, n, n, alpha);
         }
         {
-            DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * n * 4.0 + (double)n * n * 4.0), st);
+            DRP_LAUNCH(DRP_K_OU_GRAD, ((double)z * n * n * 4.0 + (double)n * n * 4.0), st);
             ou_grad_kernel<<<dim3(n, z), 256, 0, st>>>(M, ld, bs, n, D, ldd, lam, part);
         }
         {
@@ -445,7 +445,7 @@ DRP_API int drp_ou_prior_apply_f64(const double* D, int64_t ldd, int n, const do
     const int64_t ld = drp_ou_workspace_ld(n, n), bs = (int64_t)R * ld;
     const int nb = (n + SYMV_TB - 1) / SYMV_TB;
     {
-        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * n * 4.0), st);
+        DRP_LAUNCH(DRP_K_SYMV, ((double)z * n * n * 4.0), st);
         ou_symv_tile_kernel<<<dim3(nb * (nb + 1) / 2, z), 128, 0, st>>>(M, ld, bs, n, x, nb, ypart);
     }
     {
@@ -457,7 +457,7 @@ DRP_API int drp_ou_prior_apply_f64(const double* D, int64_t ldd, int n, const do
         mvn_finish_kernel<<<z, 256, 0, st>>>(M, ld, bs, n, logp);
     }
     {
-        DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * n * 4.0 + (double)n * n * 4.0), st);
+        DRP_LAUNCH(DRP_K_OU_GRAD, ((double)z * n * n * 4.0 + (double)n * n * 4.0), st);
         ou_grad_kernel<<<dim3(n, z), 256, 0, st>>>(M, ld, bs, n, D, ldd, lam, part);
     }
     {

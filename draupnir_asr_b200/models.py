@@ -157,6 +157,7 @@ class DRAUPNIRModelClass(nn.Module):
         factor, self._prefetched = self._prefetched, None
         if factor is not None and not factor.matches(patristic_matrix, self._hyper_sites):
             factor = None
+        self._hyper_sites = ()             # no reference to this step's autograd graph survives the step
         latent_space = pyro.sample("latent_z", dist.OUProcessPrior(patristic_matrix, sigma_f, sigma_n, lambd,
                                                                    z_slice=z_slice, factor=factor).to_event(1))  # [z, n]
         return latent_space.T
@@ -200,8 +201,24 @@ class DRAUPNIRModelClass(nn.Module):
         if self.leaves_testing:
             leaves_indexes = (patristic_matrix[1:, 0][..., None] == self.leaves_nodes.to(xb.device)).any(-1)
             xb = xb[:, leaves_indexes]
-        return ops.ou_conditional(patristic_matrix[1:, 1:], leaf_pos, int_pos, sigma_f.detach(), sigma_n.detach(),
-                                  lambd.detach(), xb.detach(), jitter=jitter, want_cov=want_cov)
+        sigma_f, sigma_n, lambd, xb = sigma_f.detach(), sigma_n.detach(), lambd.detach(), xb.detach()
+        if self._z_sharded():
+            # the z conditional posteriors are as independent as the z priors.  This rank eliminates the leaf
+            # block of ITS latent dimensions only; one all-gather rebuilds the means [z, ni].  The covariance (needed for
+            # draws) stays sharded: `cov` holds the rows z_lo:z_hi and `conditional_sampling_many` gathers the draws.
+            lo, hi = self.shard.z_lo, self.shard.z_hi
+            if hi > lo:
+                mean, cov = ops.ou_conditional(patristic_matrix[1:, 1:], leaf_pos, int_pos, sigma_f[lo:hi], sigma_n[lo:hi],
+                                               lambd[lo:hi], xb[lo:hi].contiguous(), jitter=jitter, want_cov=want_cov)
+            else:
+                mean = xb.new_zeros((0, n_internal))
+                cov = xb.new_zeros((0, n_internal, n_internal)) if want_cov else None
+            return self.shard.gather_z_rows(mean), cov
+        return ops.ou_conditional(patristic_matrix[1:, 1:], leaf_pos, int_pos, sigma_f, sigma_n, lambd, xb, jitter=jitter,
+                                  want_cov=want_cov)
+
+    def _z_sharded(self) -> bool:
+        return self.shard is not None and self.shard.world > 1
 
     def _conditional_factor(self, map_estimates, patristic_matrix):
         """Conditional mean `[z,ni]` and Cholesky factor `[z,ni,ni]` of the conditional covariance (+1e-6 on every
@@ -216,8 +233,11 @@ class DRAUPNIRModelClass(nn.Module):
             return hit[2], hit[3]
         mean, cov = self._conditional(map_estimates, patristic_matrix, self.internal_nodes, self.n_internal, 0.0, 1e-6, True)
         # the Schur complement of an OU covariance inherits lambda_min >= sigma_n^2 and a norm below the joint trace
-        tril = ops.potrf(cov, cond_bound=ops.ou_cond_bound(squeeze_tensor(1, map_estimates["sigma_f"]),
-                                                           squeeze_tensor(1, map_estimates["sigma_n"]), self.n_all))
+        bound = ops.ou_cond_bound(squeeze_tensor(1, map_estimates["sigma_f"]), squeeze_tensor(1, map_estimates["sigma_n"]),
+                                  self.n_all)
+        if self._z_sharded():                       # cov holds this rank's latent dimensions only
+            bound = bound[self.shard.z_lo:self.shard.z_hi]
+        tril = ops.potrf(cov, cond_bound=bound) if cov.shape[0] else cov
         del cov
         self._cond_cache = (keys, stamp, mean, tril)
         return mean, tril
@@ -236,8 +256,14 @@ class DRAUPNIRModelClass(nn.Module):
         mean, tril = self._conditional_factor(map_estimates, patristic_matrix)
         if eps is None:
             eps = torch.randn((self.z_dim, self.n_internal, int(n_samples)), dtype=mean.dtype, device=mean.device)
+            if self._z_sharded():
+                eps = self.shard.broadcast_from_rank0(eps)                      # all ranks must draw the same numbers
         assert eps.shape == (self.z_dim, self.n_internal, int(n_samples))
-        draws = mean.unsqueeze(-1) + torch.bmm(tril, eps)                       # [z, ni, S]
+        if self._z_sharded():                       # this rank's latent dimensions, then one all-gather of the draws
+            lo, hi = self.shard.z_lo, self.shard.z_hi
+            draws = self.shard.gather_z_rows(mean[lo:hi].unsqueeze(-1) + torch.bmm(tril, eps[lo:hi]))
+        else:
+            draws = mean.unsqueeze(-1) + torch.bmm(tril, eps)                   # [z, ni, S]
         latent_space = draws.permute(2, 1, 0).contiguous()
         assert latent_space.shape == (int(n_samples), self.n_internal, self.z_dim)
         return latent_space
@@ -258,6 +284,7 @@ class DRAUPNIRModelClass(nn.Module):
     def conditional_sampling_batch(self, map_estimates, patristic_matrix):
         """S/models.py:243-287 (batched variant: +1e-6 on the hyper-parameters, no jitter on the covariance)."""
         internal = self.internal_nodes_batch
+        assert not self._z_sharded(), "the batched variant is outside the sharded path"
         mean, cov = self._conditional(map_estimates, patristic_matrix, internal, len(internal), 1e-6, 0.0, True)
         return dist.MultivariateNormal(mean, cov).to_event(1).sample().T
 

@@ -79,6 +79,21 @@ def defer_info_checks():
         _raise_if_failed(pending)
 
 
+def begin_deferred():
+    """Open a deferred-check scope without the context manager (a CUDA-graph capture must not examine the flags when it
+    ends — nothing has run yet).  Returns the token `end_deferred` needs."""
+    global _DEFERRED
+    prev, _DEFERRED = _DEFERRED, []
+    return (prev,)
+
+
+def end_deferred(token):
+    """Close the scope opened by `begin_deferred` and hand back the queued `(info, what)` pairs unexamined."""
+    global _DEFERRED
+    pending, _DEFERRED = _DEFERRED, token[0]
+    return pending or []
+
+
 def flush_info_checks():
     """Examine (and clear) the pivot flags queued so far inside `defer_info_checks()`: raises `torch.linalg.LinAlgError`
     for the first failed factorisation.  Synchronises; call it where the host waits for the device anyway."""

@@ -51,22 +51,27 @@ class Trace_ELBO:
             return float(self.differentiable_loss(model, guide, *args, **kwargs))
 
     def loss_and_grads(self, model, guide, *args, **kwargs):
+        """Loss and gradients of one particle.  The gradients are taken with `torch.autograd.grad` w.r.t. the parameters
+        the two traces saw and then stored in `.grad` — the result `loss.backward()` leaves behind, but without going
+        through the parameters' AccumulateGrad nodes: those are bound to the stream they were created on and outlive a
+        step whenever anything (a loss the caller kept, an earlier trace) still references an old autograd graph, which a
+        CUDA-graph capture of the step cannot tolerate."""
         model_trace, guide_trace = self._traces(model, guide, args, kwargs)
         self.last_traces = (model_trace, guide_trace)
         model_lp, pending = model_trace.split_log_prob()
         loss = -(model_lp - guide_trace.log_prob_sum())
-        if not pending:
-            if isinstance(loss, torch.Tensor) and loss.requires_grad:
-                loss.backward()
-            return loss
-        # terms still running on a side stream are separate roots of ONE backward call: autograd runs every node on the
+        params = _unconstrained_params(model_trace, guide_trace)
+        # terms still running on a side stream are separate roots of ONE backward pass: autograd runs every node on the
         # stream of its forward op, so the recurrences' back-propagation (this stream) does not wait for the OU prior
         terms = [site["log_prob_async"].value for site in pending]
         roots = [loss] + terms
-        grads = [torch.ones_like(loss)] + [-torch.ones_like(loss)] * len(terms)
-        keep = [(r, g) for r, g in zip(roots, grads) if isinstance(r, torch.Tensor) and r.requires_grad]
-        if keep:
-            torch.autograd.backward([r for r, _ in keep], [g for _, g in keep])
+        seeds = [torch.ones_like(loss)] + [-torch.ones_like(t) for t in terms] if isinstance(loss, torch.Tensor) else []
+        keep = [(r, g) for r, g in zip(roots, seeds) if isinstance(r, torch.Tensor) and r.requires_grad]
+        if keep and params:
+            grads = torch.autograd.grad([r for r, _ in keep], params, [g for _, g in keep], allow_unused=True)
+            for p, g in zip(params, grads):
+                if g is not None:
+                    p.grad = g if p.grad is None else p.grad + g
         for site in pending:
             site["log_prob_sum"] = site["log_prob_async"].join()
             loss = loss - site["log_prob_sum"].detach()
@@ -76,24 +81,171 @@ class Trace_ELBO:
         return "Trace_ELBO()"
 
 
+def _recover_generator(device, rng_state):
+    """A capture that dies half-way leaves the device's default generator in capture mode (every later random draw would
+    raise).  Swap in a fresh generator state carrying the seed / offset the capture started from."""
+    try:
+        torch.cuda.synchronize(device)
+    except Exception:       # noqa: BLE001 - the error of the failed capture may surface here once more
+        pass
+    try:
+        fresh = torch.Generator(device=device)
+        fresh.set_state(rng_state)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        torch.cuda.default_generators[idx].graphsafe_set_state(fresh)
+    except Exception:       # noqa: BLE001 - best effort
+        pass
+
+
+class _CapturedStep:
+    """One `svi.step` recorded as a CUDA graph for one set of argument tensors."""
+    __slots__ = ("graph", "out_host", "infos", "params", "grads", "traces", "stream")
+
+
 class SVI:
-    def __init__(self, model, guide, optim, loss, shard=None, **kwargs):
+    """`pyro.infer.SVI` (S/main.py:1059) — `step(*args)` is one ELBO evaluation, its backward pass and one optimiser update
+    (S/train.py:75), returning the loss as a Python float.
+
+    CUDA-graph replay.  With static shapes the whole of guide -> model -> backward (and, sharded, the
+    NCCL all-reduce) is a fixed sequence of a few hundred kernels on two or three streams, re-derived by the Python trace
+    machinery every step: ~6.5 ms of host work, which IS the step below ~800 leaves and on 8 GPUs.  After `graph_warmup`
+    eager steps with the same argument tensors (same storage, shape, dtype) the step is therefore captured once
+    (`torch.cuda.graph`, the side streams forked and joined inside the capture) and replayed afterwards: one graph launch,
+    then the loss and the pivot-failure flag arrive in pinned host memory (a memcpy node of the graph), the host checks the
+    flag — a failed Cholesky raises `torch.linalg.LinAlgError` BEFORE any parameter is touched, as in the reference — and
+    the optimiser (two launches, csrc/adam.cu, counters on the device) runs on the captured gradient buffers.  The values
+    a caller reads afterwards (`loss.last_traces`, the guide's returned dictionary) are the graph's static tensors and hold
+    the latest step's numbers.  `cuda_graph=False` / DRP_CUDA_GRAPH=0 keeps every step eager; a capture that fails (an
+    operation that cannot be captured somewhere in user code) falls back to eager steps for good, with a warning.
+    """
+
+    def __init__(self, model, guide, optim, loss, shard=None, cuda_graph=None, graph_warmup: int = 2, **kwargs):
+        import os
         self.model, self.guide, self.optim, self.loss = model, guide, optim, loss
         self.shard = shard     # zshard.ShardContext: local losses/gradients are summed over the ranks before the update
+        self.cuda_graph = (os.environ.get("DRP_CUDA_GRAPH", "1") != "0") if cuda_graph is None else bool(cuda_graph)
+        self.graph_warmup = int(graph_warmup)
+        self.step_prologue = None          # callable run at the start of every step (host-fed steps enqueue their copies there)
+        self._graphs = {}                  # key -> _CapturedStep | number of eager steps so far | False (not capturable)
+        self.last_step_was_replay = False
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def reset_graphs(self):
+        """Forget every captured step (after swapping tensors the model reads that are not arguments of `step`)."""
+        self._graphs.clear()
+
+    def _graph_key(self, args):
+        key, device = [], None
+        for a in args:
+            if a is None:
+                key.append(None)
+            elif isinstance(a, torch.Tensor) and a.is_cuda:
+                key.append((a.data_ptr(), tuple(a.shape), tuple(a.stride()), a.dtype, a.device.index))
+                device = a.device
+            else:
+                return None, None
+        if device is None or not torch.is_grad_enabled():
+            return None, None
+        if self.shard is not None:
+            import torch.distributed as dist
+            if dist.get_backend(self.shard.group) != "nccl":      # gloo moves CUDA tensors through the host: not capturable
+                return None, None
+        return (tuple(key), id(self.step_prologue)), device
+
+    def _evaluate(self, args, kwargs):
+        """Prologue, ELBO and gradients, cross-rank reduction: everything of a step up to (not including) the optimiser.
+        Returns (loss, failure flag or None, parameters)."""
+        from ... import ops
+        if self.step_prologue is not None:
+            self.step_prologue()
+        loss = self.loss.loss_and_grads(self.model, self.guide, *args, **kwargs)
+        params = _unconstrained_params(*self.loss.last_traces)
+        flag = ops.pending_failures()
+        if self.shard is not None:
+            loss, flag = self.shard.reduce_step(params, loss, flag)
+        return loss, flag, params
+
+    def _eager_step(self, args, kwargs) -> float:
+        from ... import ops
+        with ops.defer_info_checks():
+            loss, flag, params = self._evaluate(args, kwargs)
+            value = float(loss.detach())   # synchronises; the deferred pivot checks piggy-back on it
+            ops.flush_info_checks()        # a failed factorisation raises here, before any parameter is updated
+            if self.shard is not None and flag is not None and float(flag) != 0.0:
+                raise torch.linalg.LinAlgError("linalg.cholesky: the factorisation failed on another rank of the sharded run")
+        self.optim(params)
+        for p in params:
+            p.grad = None
+        self.last_step_was_replay = False
+        return value
+
+    def _capture(self, args, device) -> "_CapturedStep":
+        from ... import ops
+        cs = _CapturedStep()
+        cs.graph = torch.cuda.CUDAGraph()
+        cs.out_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+        self.loss.last_traces = None       # the previous step's autograd graph is not needed any more
+        rng_state = torch.cuda.get_rng_state(device)
+        token = ops.begin_deferred()
+        try:
+            with torch.cuda.graph(cs.graph):
+                loss, flag, params = self._evaluate(args, {})
+                zero = torch.zeros((), dtype=torch.float64, device=device)
+                out = torch.stack((loss.detach().reshape(()).to(torch.float64), zero if flag is None else flag.to(torch.float64)))
+                cs.out_host.copy_(out, non_blocking=True)
+            cs.infos = ops.end_deferred(token)
+        except BaseException:
+            ops.end_deferred(token)
+            _recover_generator(device, rng_state)
+            raise
+        cs.params = params
+        cs.grads = [p.grad for p in params]
+        cs.traces = self.loss.last_traces
+        for p in params:                   # nothing has run yet: the capture only recorded the work
+            p.grad = None
+        return cs
+
+    def _replay(self, cs: "_CapturedStep") -> float:
+        from ... import ops
+        cs.graph.replay()
+        torch.cuda.current_stream().synchronize()
+        value, failed = float(cs.out_host[0]), float(cs.out_host[1])
+        self.loss.last_traces = cs.traces
+        if failed != 0.0:
+            ops._raise_if_failed(cs.infos)
+            raise torch.linalg.LinAlgError("linalg.cholesky: the factorisation failed on another rank of the sharded run")
+        live = [(p, g) for p, g in zip(cs.params, cs.grads) if g is not None]
+        for p, g in live:
+            p.grad = g
+        self.optim([p for p, _ in live])
+        for p, _ in live:
+            p.grad = None
+        self.last_step_was_replay = True
+        return value
 
     def step(self, *args, **kwargs) -> float:
         """One gradient step; returns the loss as a Python float (the only host<->device synchronisation)."""
-        from ... import ops
-        with ops.defer_info_checks():
-            loss = self.loss.loss_and_grads(self.model, self.guide, *args, **kwargs)
-            params = _unconstrained_params(*self.loss.last_traces)
-            if self.shard is not None:
-                loss = self.shard.reduce_step(params, loss)
-            self.optim(params)
-            for p in params:
-                p.grad = None
-            value = float(loss.detach())   # synchronises; the deferred pivot checks piggy-back on it
-        return value
+        if self.cuda_graph and not kwargs:
+            key, device = self._graph_key(args)
+            if key is not None:
+                entry = self._graphs.get(key, 0)
+                if isinstance(entry, _CapturedStep):
+                    return self._replay(entry)
+                if entry is not False:
+                    if entry < self.graph_warmup:
+                        self._graphs[key] = entry + 1
+                    else:
+                        try:
+                            entry = self._graphs[key] = self._capture(args, device)
+                        except Exception as e:        # noqa: BLE001 - whatever broke the capture, the eager path still works
+                            import warnings
+                            self._graphs[key] = False
+                            torch.cuda.synchronize()
+                            warnings.warn(f"svi.step could not be captured in a CUDA graph ({type(e).__name__}: {e}); "
+                                          "continuing with eager steps")
+                        else:
+                            return self._replay(entry)
+        return self._eager_step(args, kwargs)
 
     def evaluate_loss(self, *args, **kwargs) -> float:
         return self.loss.loss(self.model, self.guide, *args, **kwargs)

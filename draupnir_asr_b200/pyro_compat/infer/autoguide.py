@@ -40,7 +40,10 @@ class AutoDelta(torch.nn.Module):
         self._sites = []
 
     def _setup_prototype(self, *args, **kwargs):
-        with poutine.block():
+        # no_grad: the prototype only records names, shapes and supports.  A trace with an autograd graph would keep the
+        # networks' AccumulateGrad nodes (bound to the stream of this very first call) alive for the life of the guide,
+        # which breaks a later CUDA-graph capture of the step (pyro_compat/infer: Trace_ELBO.loss_and_grads).
+        with torch.no_grad(), poutine.block():
             self.prototype_trace = poutine.trace(self.model).get_trace(*args, **kwargs)
         for name, site in self.prototype_trace.sample_sites():
             if site["is_observed"]:
@@ -107,7 +110,7 @@ class _AutoMeanField(torch.nn.Module):
         self._sites = []          # (name, transform, site event_dim, unconstrained shape)
 
     def _latent_sites(self, *args, **kwargs):
-        with poutine.block():
+        with torch.no_grad(), poutine.block():          # see AutoDelta._setup_prototype
             self.prototype_trace = poutine.trace(self.model).get_trace(*args, **kwargs)
         out = []
         for name, site in self.prototype_trace.sample_sites():

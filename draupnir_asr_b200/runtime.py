@@ -101,8 +101,6 @@ class Run(SimpleNamespace):
         only (stream-waits, no host synchronisation): the patristic matrix first — the guide hands it to the prior's
         factorisation before anything else happens; the BLOSUM-encoded data set is awaited in front of the encoder; the
         data set itself when the likelihood is scored, after both networks ran."""
-        lo, hi = self._leaf_rows()
-        main = torch.cuda.current_stream()
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._events = [torch.cuda.Event() for _ in range(3)]      # 0 patristic, 1 blosum, 2 data set
@@ -132,26 +130,40 @@ class Run(SimpleNamespace):
                 self._model_level = 1
             else:                                   # an ELBO without the hook (real Pyro): the model waits for everything
                 self._model_level = 2
-        cs = self._copy_stream
-        cs.wait_stream(main)                       # the previous step has finished reading the staging buffers
-        with torch.cuda.stream(cs):
-            self._staging["patristic"].copy_(host["patristic"], non_blocking=True)
-            self._events[0].record(cs)
-            if "blosum" in host:
-                self._staging["blosum"][lo:hi].copy_(host["blosum"][lo:hi], non_blocking=True)
-            self._events[1].record(cs)
-            self._staging["dataset"][lo:hi].copy_(host["dataset"][lo:hi], non_blocking=True)
-            self._events[2].record(cs)
-        self._pending = [(k, e) for k, e in enumerate(self._events)]
+            self._host_prologues = {}
+        key = tuple(id(v) for v in host.values())
+        prologue = self._host_prologues.get(key)
+        if prologue is None:
+            lo, hi = self._leaf_rows()
+
+            def prologue():
+                # runs at the start of the step — eagerly, or ONCE inside the CUDA-graph capture of the step, where the
+                # copies become memcpy nodes from the pinned buffers and the event waits become graph dependencies
+                main, cs = torch.cuda.current_stream(), self._copy_stream
+                cs.wait_stream(main)               # the previous step has finished reading the staging buffers
+                with torch.cuda.stream(cs):
+                    self._staging["patristic"].copy_(host["patristic"], non_blocking=True)
+                    self._events[0].record(cs)
+                    if "blosum" in host:
+                        self._staging["blosum"][lo:hi].copy_(host["blosum"][lo:hi], non_blocking=True)
+                    self._events[1].record(cs)
+                    self._staging["dataset"][lo:hi].copy_(host["dataset"][lo:hi], non_blocking=True)
+                    self._events[2].record(cs)
+                self._pending = [(k, e) for k, e in enumerate(self._events)]
+
+            self._host_prologues[key] = prologue
         st = self._staging
-        loss = self.svi.step(st["dataset"], st["patristic"], None, st.get("blosum"), None, None)
-        self._wait_for(2)                          # nothing may be left waiting when the step returns
+        self.svi.step_prologue = prologue
+        try:
+            loss = self.svi.step(st["dataset"], st["patristic"], None, st.get("blosum"), None, None)
+        finally:
+            self.svi.step_prologue = None
         return loss
 
 
 def build_run(problem: SyntheticProblem, select_guide: str, device="cuda", init: Optional[Dict[str, torch.Tensor]] = None,
               z_dim=30, gru_hidden_dim=60, embedding_dim=50, config: Optional[dict] = None, seed: int = 0,
-              shard=None) -> Run:
+              shard=None, cuda_graph: Optional[bool] = None) -> Run:
     """Mirror of `draupnir_train`'s setup (S/main.py:991-1059): ModelLoad -> DRAUPNIRModel_classic -> guide
     (`AutoDelta` for delta_map, `DRAUPNIRGUIDES` otherwise) -> Trace_ELBO -> ClippedAdam -> SVI."""
     assert select_guide in ("delta_map", "variational", "normal", "diagonal_normal")          # S/main.py:511-524
@@ -183,7 +195,7 @@ def build_run(problem: SyntheticProblem, select_guide: str, device="cuda", init:
         torch.random.set_rng_state(gen_state)
     optim = ClippedAdam({"lr": cfg["lr"], "betas": (cfg["beta1"], cfg["beta2"]), "eps": cfg["eps"],
                          "weight_decay": cfg["weight_decay"], "clip_norm": cfg["clip_norm"], "lrd": cfg["lrd"]})
-    svi = SVI(Draupnir.model, guide, optim, Trace_ELBO(), shard=shard)
+    svi = SVI(Draupnir.model, guide, optim, Trace_ELBO(), shard=shard, cuda_graph=cuda_graph)
     dev = ml.device
     return Run(Draupnir=Draupnir, guide=guide, svi=svi, optim=optim, model_load=ml, device=dev,
                dataset_train=problem.dataset_train.to(dev), patristic_matrix_train=problem.patristic_matrix_train.to(dev),

@@ -236,13 +236,31 @@ def _dataset(ids: np.ndarray, residues: np.ndarray, tree: SyntheticTree) -> torc
     return torch.from_numpy(d)
 
 
+def patristic_device(tree: SyntheticTree, device="cuda") -> np.ndarray:
+    """The same `[N,N]` matrix from the product's builder (K1: `ops.tree_distances`, the LCA kernel that replaces the
+    reference's ete3 / R path, S/utils.py:496-579), brought back to the host in the layout `make_problem` stores."""
+    from . import ops
+    parent = torch.from_numpy(tree.parent).to(device)
+    branch = torch.from_numpy(tree.branch).to(device)
+    return ops.tree_distances(parent, branch)[0].cpu().numpy()
+
+
 def make_problem(n_leaves: int, seq_len: int, seed: int = 0, shape: str = "agglomerate",
-                 aa_probs: int = 21, patristic_full: Optional[np.ndarray] = None) -> SyntheticProblem:
-    """Tree + alignment + every host tensor the model/guide constructors and `svi.step` consume."""
+                 aa_probs: int = 21, patristic_full: Optional[np.ndarray] = None, builder: str = "host",
+                 device="cuda") -> SyntheticProblem:
+    """Tree + alignment + every host tensor the model/guide constructors and `svi.step` consume.  `builder` = "host"
+    (numpy propagation; CPU tests, the oracle's and the reference arm's inputs) or "device" (the CUDA patristic builder:
+    what bench.py's own arm and smoke() feed the model with)."""
     tree = random_tree(n_leaves, seed=seed, shape=shape)
     x = evolve_alignment(tree, seq_len, seed=seed)
     leaves, internal = tree.leaves, tree.internal
-    d_full = patristic_host(tree) if patristic_full is None else patristic_full
+    if patristic_full is not None:
+        d_full = patristic_full
+    elif builder == "device":
+        d_full = patristic_device(tree, device)
+    else:
+        assert builder == "host", builder
+        d_full = patristic_host(tree)
     pm_full = torch.from_numpy(with_id_header(d_full, np.arange(tree.n_nodes)))
     pm_train = torch.from_numpy(with_id_header(d_full[np.ix_(leaves, leaves)], leaves))
     ds_train = _dataset(leaves, x[leaves], tree)

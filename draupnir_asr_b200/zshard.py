@@ -65,14 +65,31 @@ class ShardContext:
     def gather_leaf_rows(self, x_local: torch.Tensor) -> torch.Tensor:
         return _AllGatherRows.apply(x_local, self)
 
-    def reduce_step(self, params: List[torch.Tensor], loss: torch.Tensor) -> torch.Tensor:
-        """One all-reduce(SUM) over [every gradient | loss]; returns the global loss (detached)."""
+    def gather_z_rows(self, x_local: torch.Tensor) -> torch.Tensor:
+        """Concatenate the ranks' z-slices (dimension 0, uneven allowed) of a tensor without gradient: the conditional
+        posterior means `[z_r, ni]` / draws `[z_r, ni, S]` of the z-sharded K6.  One all-gather."""
+        pad = max(hi - lo for lo, hi in self.z_ranges)
+        buf = x_local.new_zeros((pad,) + tuple(x_local.shape[1:]))
+        buf[: x_local.shape[0]] = x_local
+        outs = [torch.empty_like(buf) for _ in range(self.world)]
+        dist.all_gather(outs, buf.contiguous(), group=self.group)
+        return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, self.z_ranges)], dim=0)
+
+    def broadcast_from_rank0(self, x: torch.Tensor) -> torch.Tensor:
+        """Every rank continues with rank 0's tensor (random numbers that all ranks must agree on)."""
+        dist.broadcast(x, src=0 if self.group is None else dist.get_global_rank(self.group, 0), group=self.group)
+        return x
+
+    def reduce_step(self, params: List[torch.Tensor], loss: torch.Tensor, flag=None):
+        """One all-reduce(SUM) over [every gradient | loss | pivot-failure count]; returns (global loss, global failure
+        count) — detached device scalars, so that every rank sees a failed factorisation of any rank's z-slice."""
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
-        flat = torch.cat([g.reshape(-1) for g in grads] + [loss.detach().reshape(1)])
+        fl = torch.zeros(1, dtype=loss.dtype, device=loss.device) if flag is None else flag.detach().reshape(1).to(loss.dtype)
+        flat = torch.cat([g.reshape(-1) for g in grads] + [loss.detach().reshape(1), fl])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         off = 0
         for p, g in zip(params, grads):
             k = g.numel()
             p.grad = flat[off: off + k].view_as(g).clone() if p.grad is None else p.grad.copy_(flat[off: off + k].view_as(g))
             off += k
-        return flat[off]
+        return flat[off], flat[off + 1]

@@ -33,13 +33,14 @@ int drp_abi_version(void);
 /* ---- instrumentation (bench.py: `gpu_launches` and the live per-kernel roofline) -------------------------------- */
 /* Cumulative number of kernels launched by this library.                                                            */
 int64_t drp_launch_count(void);
-/* CUDA-event timing of every launch, by kernel class: 0 syrk (fp64 mma.sync), 1 trsm, 2 potf2 (work = flops),
- * 3 assembly, 4 reductions, 5 categorical, 6 patristic (work = bytes), 7 other, 8 syrk on the int8 tcgen05 pipe
- * (work = fp64-equivalent flops), 9 int8 slicing (work = bytes), 10 GRU recurrence (work = flops).  enable(on >= 1) clears
- * earlier records (on > 1 additionally pre-creates the events for `on` launches, keeping event creation out of the
- * caller's timed region); read() synchronises the device and fills three arrays of drp_timing_classes() entries (HOST
- * pointers).                                                                                                        */
+/* CUDA-event timing of every launch, by kernel class (one class per kernel of the path; drp_timing_class_name(k) names it,
+ * drp_timing_class_is_flops(k) says whether work[k] counts flops or bytes).  enable(on >= 1) clears earlier records
+ * (on > 1 additionally pre-creates the events for `on` launches, keeping event creation out of the caller's timed
+ * region); read() synchronises the device and fills three arrays of drp_timing_classes() entries (HOST pointers).
+ * Not to be enabled while a CUDA graph is being captured.  This block is the library's only process-wide state.       */
 int drp_timing_classes(void);
+const char* drp_timing_class_name(int k);   /* the kernel behind class k ("oz_syrk_kernel", "gru_fwd2_kernel", ...)    */
+int drp_timing_class_is_flops(int k);       /* 1: work[k] counts flops, 0: bytes                                        */
 int drp_timing_enable(int on);
 int drp_timing_read(double* ms, int64_t* launches, double* work);
 
@@ -174,6 +175,18 @@ int drp_cat_loglik_fwd_f64(const double* scores, const void* obs, int obs_is_f64
                            double* lse, double* part, void* stream);
 int drp_cat_loglik_bwd_f64(const double* scores, const void* obs, int obs_is_f64, const double* lse, const double* g,
                            int64_t rows, int A, double* dscores, void* stream);
+
+/* ---- pyro.optim.ClippedAdam over all parameters of the step: S/main.py:1036-1041 (the update that ends svi.step,
+ *      S/train.py:75).  lr <- lr * lrd; g = clamp(grad, +-clip) + weight_decay * p; Adam moments; p -= lr sqrt(1 - b2^t) /
+ *      (1 - b1^t) * m / (sqrt(v) + eps).  Step counters and lr live on the DEVICE (state [1 + 2 * slots] doubles: lr, then
+ *      (t, step size) per slot; the caller sets state[0] = lr and zeroes the rest), so the update is a fixed launch
+ *      sequence: CUDA-graph capturable.  ptrs: HOST array of 4 * count device pointers (p, grad, exp_avg, exp_avg_sq per
+ *      tensor); numel, slot: HOST arrays [count].  count <= drp_clipped_adam_max_tensors(); longer lists are split by the
+ *      caller, first = 1 only for the first part (it applies lrd).                                                      */
+int drp_clipped_adam_max_tensors(void);
+int drp_clipped_adam_f64(const void* const* ptrs, const int64_t* numel, const int64_t* slot, int count, int first,
+                         double* state, double lrd, double beta1, double beta2, double eps, double weight_decay, double clip,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,55 @@ def test_patristic_rows_cols_subset(cuda):
     np.testing.assert_allclose(pat.cpu().numpy(), pat_ref, rtol=1e-12, atol=1e-13)
 
 
+def _sampled_lca_check(cuda, n, seed, nrows, ncols, shape="agglomerate"):
+    from draupnir_asr_b200 import ops
+    t = S.random_tree(n, seed=seed, shape=shape)
+    N = t.n_nodes
+    rng = np.random.default_rng(seed)
+    rows = np.sort(rng.choice(N, nrows, replace=False)).astype(np.int32)
+    cols = np.sort(rng.choice(N, ncols, replace=False)).astype(np.int32)
+    parent, branch = torch.from_numpy(t.parent).to(cuda), torch.from_numpy(t.branch).to(cuda)
+    pat, cla, lca = ops.tree_distances(parent, branch, rows=torch.from_numpy(rows), cols=torch.from_numpy(cols), want_lca=True,
+                                       want_cladistic=True)
+    lca_ref, pat_ref, cla_ref = P.patristic_c(t.parent, t.branch, t.depth, rows, cols, want_cladistic=True)
+    assert np.array_equal(lca.cpu().numpy(), lca_ref)
+    assert np.array_equal(cla.cpu().numpy(), cla_ref)
+    np.testing.assert_allclose(pat.cpu().numpy(), pat_ref, rtol=1e-12, atol=1e-13)
+    return t, parent, branch
+
+
+def test_patristic_lca_bit_exact_c4_and_c5_sizes(cuda):
+    """BASELINE configs 4 and 5: ALL pairs of the 3,999-node tree of C4, and at the top of the C5 sweep (8,000 leaves,
+    15,999 nodes) 96 complete rows plus a 512 x 512 random sample, bit-exact against the scalar C oracle."""
+    from draupnir_asr_b200 import ops
+    t = S.random_tree(2000, seed=2000)
+    parent, branch = torch.from_numpy(t.parent).to(cuda), torch.from_numpy(t.branch).to(cuda)
+    pat, _, lca = ops.tree_distances(parent, branch, want_lca=True)
+    lca_ref, pat_ref, _ = P.patristic_c(t.parent, t.branch, t.depth)
+    assert lca.shape == (3999, 3999) and np.array_equal(lca.cpu().numpy(), lca_ref)
+    np.testing.assert_allclose(pat.cpu().numpy(), pat_ref, rtol=1e-12, atol=1e-13)
+    del pat, lca
+    t, parent, branch = _sampled_lca_check(cuda, 8000, 8000, 512, 512)
+    rows = np.sort(np.random.default_rng(1).choice(t.n_nodes, 96, replace=False)).astype(np.int32)
+    pat, _, lca = ops.tree_distances(parent, branch, rows=torch.from_numpy(rows), want_lca=True)
+    lca_ref, pat_ref, _ = P.patristic_c(t.parent, t.branch, t.depth, rows, np.arange(t.n_nodes, dtype=np.int32))
+    assert lca.shape == (96, 15999) and np.array_equal(lca.cpu().numpy(), lca_ref)
+    np.testing.assert_allclose(pat.cpu().numpy(), pat_ref, rtol=1e-12, atol=1e-13)
+    # the all-pairs matrix at that size is symmetric with a zero diagonal (2 GB; checked on the device)
+    full = ops.tree_distances(parent, branch)[0]
+    assert full.shape == (15999, 15999) and bool((full.diagonal() == 0).all())
+    assert torch.equal(full[:4000, 12000:], full[12000:, :4000].T)
+
+
+@pytest.mark.parametrize("n,shape", [(35000, "agglomerate"), (45000, "agglomerate"), (1400, "caterpillar")])
+def test_patristic_beyond_the_table_limits(cuda, n, shape):
+    """Nothing on this path is limited to 65,535 nodes: the preorder lookup table stores CHAIN indices (uint16, bounded by
+    the depth, which is checked), not node ids.  69,999 nodes still use the table (one row per CTA), 89,999 nodes exceed
+    its shared memory and take the binary-search kernel, a 1,399-deep caterpillar exceeds the shared-memory chain and
+    spills it to the workspace - all bit-exact on a random sample of pairs."""
+    _sampled_lca_check(cuda, n, n, 192, 256, shape=shape)
+
+
 # ---------------------------------------------------------------- K2 ---------------------------------------------
 @pytest.mark.parametrize("n,z", [(1, 1), (19, 30), (257, 7), (600, 30)])
 def test_ou_cov_forward_backward(cuda, n, z):
@@ -156,6 +205,29 @@ def test_ou_prior_two_phase(cuda, n, z):
         assert rel(a.grad.cpu(), b.grad) < 1e-7, name
 
 
+def test_ou_prior_through_the_tensor_path_at_1100_leaves(cuda):
+    """value AND gradients (sigma_f, sigma_n, lambd, latent_z) of the fused prior at a size whose trailing
+    updates run on tcgen05 (R = 2n+1 = 2201 rows, three-level blocking, col_limit, ragged last panel), one-call and
+    two-phase form, against autograd through torch's fp64 Cholesky on the CPU.  Gates: 1e-4 (ELBO) / 1e-3 (gradients)."""
+    from draupnir_asr_b200 import ops
+    n, z = 1100, 2
+    D, sf, sn, lam, x = _spd_problem(n, z, seed=11)
+    ps = [v.clone().requires_grad_(True) for v in (sf, sn, lam, x)]
+    lp_ref = torch.distributions.MultivariateNormal(torch.zeros(1, n, dtype=torch.float64),
+                                                    O.ou_covariance(D, *ps[:3])).log_prob(ps[3])
+    w = torch.tensor([0.7, 1.3], dtype=torch.float64)
+    (lp_ref * w).sum().backward()
+    Dg = D.to(cuda)
+    for two_phase in (False, True):
+        pg = [v.clone().to(cuda).requires_grad_(True) for v in (sf, sn, lam, x)]
+        f = ops.ou_prior_factor(Dg, *pg[:3], key=tuple(pg[:3])) if two_phase else None
+        lp = ops.ou_prior_logp(Dg, *pg, factor=f)
+        (lp * w.to(cuda)).sum().backward()
+        assert rel(lp.detach().cpu(), lp_ref.detach()) < 1e-9, two_phase
+        for a, b, name in zip(pg, ps, ("sigma_f", "sigma_n", "lambd", "latent_z")):
+            assert rel(a.grad.cpu(), b.grad) < 1e-6, (two_phase, name, rel(a.grad.cpu(), b.grad))
+
+
 def test_mvn_logprob_explicit_cov(cuda):
     from draupnir_asr_b200 import ops
     n, z = 90, 4
@@ -190,6 +262,25 @@ def test_conditional_matches_precision_partition(cuda, n):
     mean2, none = ops.ou_conditional(pm[1:, 1:], leaf, inte, par["sigma_f"].to(cuda), par["sigma_n"].to(cuda),
                                      par["lambd"].to(cuda), par["latent_z"].to(cuda), want_cov=False)
     assert none is None and rel(mean2.cpu(), mean_ref) < 1e-9
+
+
+@pytest.mark.parametrize("n,z", [(1100, 2), (800, 3)])
+def test_conditional_full_size_through_the_tensor_path(cuda, n, z):
+    """Row a10 at the sizes where the elimination of the leaf block runs on tcgen05 with `col_limit` (N = 2,199 and the
+    1,599 nodes of C3): conditional mean and covariance against the reference's precision-partition arithmetic
+    (three dense fp64 inverses on the CPU)."""
+    from draupnir_asr_b200 import ops
+    pr = S.make_problem(n, 4, seed=n)
+    par = S.make_parameters(n, z_dim=z, seed=n)
+    mean_ref, cov_ref = O.conditional_moments(par, pr.patristic_matrix_full, pr.internal_nodes, jitter=1e-6)
+    pm = pr.patristic_matrix_full.to(cuda)
+    leaf, inte = torch.from_numpy(pr.tree.leaves), torch.from_numpy(pr.tree.internal)
+    hp = [par[k].to(cuda) for k in ("sigma_f", "sigma_n", "lambd", "latent_z")]
+    mean, cov = ops.ou_conditional(pm[1:, 1:], leaf, inte, *hp, jitter=1e-6, want_cov=True)
+    assert rel(mean.cpu(), mean_ref) < 1e-8, rel(mean.cpu(), mean_ref)
+    assert rel(cov.cpu(), cov_ref) < 1e-8, rel(cov.cpu(), cov_ref)
+    mean2, _ = ops.ou_conditional(pm[1:, 1:], leaf, inte, *hp, want_cov=False)          # the MAP shape: col_limit = n + 1
+    assert rel(mean2.cpu(), mean_ref) < 1e-8
 
 
 # ---------------------------------------------------------------- K10 --------------------------------------------

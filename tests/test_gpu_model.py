@@ -12,12 +12,12 @@ from draupnir_asr_b200 import synthetic as S  # noqa: E402
 from oracle import draupnir_oracle as O  # noqa: E402
 
 
-def _pair(n, L, guide, cuda, seed=0, z=30):
+def _pair(n, L, guide, cuda, seed=0, z=30, cuda_graph=None):
     from draupnir_asr_b200 import runtime
     problem = S.make_problem(n, L, seed=seed)
     init = S.make_parameters(n, z_dim=z, seed=seed)
     nets = O.Networks(z_dim=z, variational=(guide == "variational"), seed=seed)
-    run = runtime.build_run(problem, guide, device=cuda, init=init, z_dim=z)
+    run = runtime.build_run(problem, guide, device=cuda, init=init, z_dim=z, cuda_graph=cuda_graph)
     state = {"decoder": nets.decoder.state_dict(), "embed": nets.embed.state_dict(), "h_0_MODEL": nets.h_0_MODEL}
     if guide == "variational":
         state.update(encoder=nets.encoder.state_dict(), embeddingencoder=nets.embeddingencoder.state_dict(),
@@ -30,17 +30,22 @@ def _pair(n, L, guide, cuda, seed=0, z=30):
 class _FixedNoise:
     """Makes torch's Normal.rsample use a given standard-normal draw so the variational guide is deterministic."""
 
+    _cache = {}         # (id(eps), device, dtype) -> device copy, shared by all instances: see `fixed`
+
     def __init__(self, eps):
         self.eps = eps
 
     def __enter__(self):
         import torch.distributions.normal as tn
         self._mod, self._orig = tn, tn._standard_normal
-        eps, orig = self.eps, self._orig
+        eps, orig, cache = self.eps, self._orig, _FixedNoise._cache
 
         def fixed(shape, dtype, device):
             if torch.Size(shape).numel() == eps.numel():
-                return eps.to(device=device, dtype=dtype).reshape(shape)
+                key = (id(eps), eps._version, str(device), dtype)   # ONE device copy per draw: a step captured in a CUDA graph must not copy from the host
+                if key not in cache:
+                    cache[key] = (eps, eps.to(device=device, dtype=dtype))      # holding eps keeps its id from being reused
+                return cache[key][1].reshape(shape)
             return orig(shape, dtype=dtype, device=device)      # e.g. the prior draws of AutoDelta's prototype trace
 
         tn._standard_normal = fixed
@@ -182,6 +187,65 @@ def test_host_fed_step_equals_resident_step(cuda, guide):
         with _FixedNoise(eps):
             lb = run_b.step_from_host(host)
         assert abs(la - lb) <= 1e-10 * abs(la), (la, lb)
+
+
+@pytest.mark.parametrize("guide,n,L", [("delta_map", 19, 225), ("variational", 60, 40), ("variational", 450, 24)])
+def test_graph_replay_walks_the_eager_trajectory(cuda, guide, n, L):
+    """after two eager steps `svi.step` is captured in a CUDA graph and replayed.  Same losses,
+    same parameters and the same random stream as a run that stays eager (the variational guide's draws are NOT fixed here:
+    the captured Philox state advances exactly as the eager one does); 450 leaves puts the prior's side stream and the
+    factorisation prefetched from the guide inside the capture."""
+    torch.manual_seed(0)
+    _, run_e, _ = _pair(n, L, guide, cuda, cuda_graph=False)
+    torch.manual_seed(0)
+    _, run_g, _ = _pair(n, L, guide, cuda, cuda_graph=True)
+    torch.manual_seed(123)
+    want = [run_e.step() for _ in range(6)]
+    assert not run_e.svi.last_step_was_replay
+    torch.manual_seed(123)
+    got = []
+    for k in range(6):
+        got.append(run_g.step())
+        assert run_g.svi.last_step_was_replay == (k >= 2), k
+    assert got == pytest.approx(want, rel=1e-11)
+    for (name, a), (_, b) in zip(run_e.Draupnir.named_parameters(), run_g.Draupnir.named_parameters()):
+        assert torch.allclose(a, b, rtol=1e-9, atol=1e-12), name
+    for (name, a), (_, b) in zip(run_e.guide.named_parameters(), run_g.guide.named_parameters()):
+        assert torch.allclose(a, b, rtol=1e-9, atol=1e-12), name
+    assert run_g.optim.step_count == run_e.optim.step_count == 6
+    # what a caller reads after a replayed step is that step's: the guide's recorded return value (epochs.run_epochs)
+    est = run_g.svi.loss.last_traces[1].return_value
+    with torch.no_grad():
+        torch.manual_seed(5)
+        fresh = run_e.guide(*run_e.step_args())
+    assert set(est.keys()) == set(fresh.keys())
+    # host-fed replay: the copies are memcpy nodes of a second graph; the trajectory continues identically
+    host_e, host_g = run_e.make_host_inputs(), run_g.make_host_inputs()
+    torch.manual_seed(77)
+    want2 = [run_e.step_from_host(host_e) for _ in range(4)]
+    torch.manual_seed(77)
+    got2 = [run_g.step_from_host(host_g) for _ in range(4)]
+    assert run_g.svi.last_step_was_replay
+    assert got2 == pytest.approx(want2, rel=1e-11)
+
+
+def test_graph_replay_raises_before_the_update(cuda):
+    """A factorisation that fails inside a replayed step raises torch.linalg.LinAlgError (the reference's behaviour,
+    S/models.py:118) and leaves every parameter and the optimiser's counters untouched."""
+    problem, run, _ = _pair(40, 12, "delta_map", cuda, cuda_graph=True)
+    for _ in range(4):
+        run.step()
+    assert run.svi.last_step_was_replay
+    before = [p.detach().clone() for p in run.guide.parameters()] + [p.detach().clone() for p in run.Draupnir.parameters()]
+    steps = run.optim.step_count
+    run.patristic_matrix_train[1:, 1:].mul_(-50.0)          # exp(+50 d / lambda): the covariance is no longer positive definite
+    with pytest.raises(torch.linalg.LinAlgError):
+        run.step()
+    after = [p.detach() for p in run.guide.parameters()] + [p.detach() for p in run.Draupnir.parameters()]
+    assert all(torch.equal(a, b) for a, b in zip(before, after)) and run.optim.step_count == steps
+    run.patristic_matrix_train[1:, 1:].div_(-50.0)
+    l1, l2 = run.step(), run.step()                        # the graph is still usable afterwards
+    assert run.svi.last_step_was_replay and l1 == l1 and l2 < l1 + abs(l1) and run.optim.step_count == steps + 2
 
 
 @pytest.mark.parametrize("guide", ["delta_map", "variational"])

@@ -39,10 +39,17 @@ def _cpu_worker(rank, world, port, q):
         p2 = torch.ones(2, 2, dtype=torch.float64, requires_grad=True)
         p1.grad = torch.full((4,), float(rank + 1), dtype=torch.float64)
         p2.grad = None if rank == 1 else torch.full((2, 2), 0.5, dtype=torch.float64)
-        loss = sh.reduce_step([p1, p2], torch.tensor(10.0 * (rank + 1), dtype=torch.float64))
+        loss, failed = sh.reduce_step([p1, p2], torch.tensor(10.0 * (rank + 1), dtype=torch.float64),
+                                      torch.tensor(rank, dtype=torch.int64))
+        assert float(failed) == 1.0                                      # rank 1's failure is seen by both
         assert float(loss) == 30.0 and torch.equal(p1.grad, torch.full((4,), 3.0, dtype=torch.float64))
         assert torch.equal(p2.grad, torch.full((2, 2), 0.5, dtype=torch.float64))
         assert (sh.replicated_scale == 1.0) == (rank == 0)
+        # z-slices of the conditional posterior (K6): uneven 3 + 2, gathered in order; rank 0's random numbers win
+        zfull = torch.arange(z * 4, dtype=torch.float64).reshape(z, 4)
+        assert torch.equal(sh.gather_z_rows(zfull[sh.z_lo:sh.z_hi].clone()), zfull)
+        e = torch.full((3,), float(rank + 7), dtype=torch.float64)
+        assert torch.equal(sh.broadcast_from_rank0(e), torch.full((3,), 7.0, dtype=torch.float64))
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
@@ -118,6 +125,55 @@ def _gpu_worker(rank, world, port, q, guide):
     finally:
         if dist.is_initialized():
             dist.destroy_process_group()
+
+
+def _gpu_conditional_worker(rank, world, port, q):
+    """z-sharded K6: each process eliminates the leaf block of its latent dimensions, all-gather of the means
+    [z, ni] / of the draws; equal to the oracle's precision-partition arithmetic over all z."""
+    try:
+        _init(rank, world, port)
+        import __graft_entry__ as entry
+        entry.build()
+        from draupnir_asr_b200 import runtime, synthetic, zshard
+        from oracle import draupnir_oracle as O
+        n, L, z = 45, 12, 30
+        problem = synthetic.make_problem(n, L, seed=4)
+        init = synthetic.make_parameters(n, z_dim=z, seed=4)
+        shard = zshard.ShardContext(rank, world, z, n)
+        run = runtime.build_run(problem, "delta_map", device="cuda:0", init=init, z_dim=z, shard=shard)
+        calls = []
+        from draupnir_asr_b200 import ops
+        real = ops.ou_conditional
+        ops.ou_conditional = lambda *a, **k: (calls.append(a[6].shape[0]), real(*a, **k))[1]
+        est = {k: v.to("cuda:0") for k, v in init.items()}
+        mean = run.Draupnir.conditional_samplingMAP(est, run.patristic_matrix_full)
+        want = O.conditional_samplingMAP(init, problem.patristic_matrix_full, problem.internal_nodes)
+        assert calls == [shard.z_hi - shard.z_lo], calls                  # only this rank's latent dimensions were eliminated
+        assert torch.allclose(mean.cpu(), want, rtol=1e-8, atol=1e-10)
+        eps = torch.randn(z, problem.n_internal, 2, dtype=torch.float64, generator=torch.Generator().manual_seed(9))
+        draws = run.Draupnir.conditional_sampling_many(est, run.patristic_matrix_full, 2, eps=eps.to("cuda:0"))
+        for s in range(2):
+            w = O.conditional_sampling(init, problem.patristic_matrix_full, problem.internal_nodes, eps[:, :, s])
+            assert torch.allclose(draws[s].cpu(), w, rtol=1e-7, atol=1e-8)
+        torch.manual_seed(100 + rank)                                     # different generator states: rank 0's draw is used
+        d2 = run.Draupnir.conditional_sampling_many(est, run.patristic_matrix_full, 1)
+        d2 = d2.cpu()
+        both = [torch.empty_like(d2) for _ in range(world)]
+        dist.all_gather(both, d2)
+        assert torch.equal(both[0], both[1])
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_conditional_two_processes_one_gpu(cuda):
+    res = _spawn(_gpu_conditional_worker, 2)
+    assert res == {0: "ok", 1: "ok"}, res
 
 
 @pytest.mark.gpu
