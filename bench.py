@@ -367,7 +367,8 @@ def roofline_entry(name, row, step_ms, peaks, traffic):
            "avg_launch_ms": row["avg_launch_ms"], "launches_per_step": row["launches_per_step"],
            "algorithmic_work_per_launch": row["work_per_step"] / row["launches_per_step"],
            "ms_per_step": row["ms_per_step"], "share_of_step": row["ms_per_step"] / step_ms,
-           "timed": "CUDA events around each launch on its launching stream, eager instrumented pass after the timed region"}
+           "timed": "CUDA events around each launch on its launching stream; eager, single-stream instrumented pass after the timed "
+                    "regions (share_of_step is relative to that serialised step)"}
     if tensor:
         out["frac_of_fp64_dmma"] = row["achieved"] / FP64_DMMA_MEASURED_TFLOPS
         out["fp64_dmma_peak_source"] = f"builder constant {FP64_DMMA_MEASURED_TFLOPS} TFLOP/s (profiles/microbench/dmma_shapes.cu), not in MEASURED_PEAKS.json"
@@ -391,6 +392,22 @@ def load_traffic():
         return json.load(open(path)).get("kernels", {})
     except Exception:
         return {}
+
+
+def finish_ranks(world):
+    """Multi-rank exit.  Tearing down a NCCL communicator whose collectives are nodes of live CUDA graphs can block for
+    minutes; the ranks meet at a barrier, flush, and leave without running the destructors."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if _REAL_STDOUT is not None:
+        _REAL_STDOUT.flush()
+    os._exit(0)
 
 
 def run_ours(args, w, rank, world, local_rank):
@@ -463,8 +480,12 @@ def run_ours(args, w, rank, world, local_rank):
     clocks = sampler.stop()
 
     # ---- instrumented pass: the same step, eager, with CUDA events around every launch of the library
+    # (the prior's side stream is switched off for it, so that every kernel is timed ALONE: with the overlap on, a kernel's
+    # span includes the time it waits for SMs the other chain holds)
+    from draupnir_asr_b200 import ops as _ops
     P = max(2, min(args.steps, 5))
     run.svi.cuda_graph = False
+    _ops.PRIOR_STREAM_ENABLED = False
     l0 = lib.drp_launch_count()
     run.step()
     launches_per_step = int(lib.drp_launch_count() - l0)
@@ -475,6 +496,7 @@ def run_ours(args, w, rank, world, local_rank):
     kernels = read_kernel_table(lib, P, peaks)
     lib.drp_timing_enable(0)
     run.svi.cuda_graph = True
+    _ops.PRIOR_STREAM_ENABLED = os.environ.get("DRP_PRIOR_STREAM", "1") != "0"
 
     # ---- K6: conditional posterior of the internal nodes at this size (S/models.py:149-242), z-sharded like the prior
     with torch.no_grad():
@@ -493,8 +515,7 @@ def run_ours(args, w, rank, world, local_rank):
         dist.all_reduce(h2d, op=dist.ReduceOp.SUM)                   # bytes copied by all ranks together
     ms, ms_e2e, ms_map, ms_cov = (float(v) for v in t2)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish_ranks(world)
         return
 
     step_ms = ms / args.steps
@@ -535,8 +556,7 @@ def run_ours(args, w, rank, world, local_rank):
             "cuda_graph": graphed, "eager_ms_per_step": eager_step_ms, "clocks": clocks, "conditional": conditional,
             "kernels": kernels}
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    finish_ranks(world)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -672,8 +692,7 @@ def run_c5(args, w, rank, world, local_rank):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t2[0]), float(t2[1])
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish_ranks(world)
         return
     bytes_step = N * N * 8 + n * n * 8 + n * n * 8 * (Z_DIM + 1)      # all-node matrix + leaf matrix + D read once, K written
     traffic = load_traffic()
@@ -693,8 +712,7 @@ def run_c5(args, w, rank, world, local_rank):
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "kernels": kernels, "sweep": sweep,
             "all_lca_bit_exact": all(r["lca_bit_exact"] for r in sweep), "hbm_peak_gbs": peaks["hbm"]}
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    finish_ranks(world)
 
 
 def main():

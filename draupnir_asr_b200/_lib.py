@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # DRP_LIB: another build of the same ABI (profiles/build_debug.sh: the library with the tcgen05 kernel's debug hooks)
 LIB_PATH = os.environ.get("DRP_LIB") or os.path.join(_HERE, "libdraupnir_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _i32, _i64, _f64, _p = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 
@@ -32,18 +32,19 @@ SIGNATURES = {
     "drp_ou_cov_bwd_f64": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _p]),
     "drp_factor_workspace_bytes": (_i64, [_i32, _i32]),
     "drp_ozaki_cond_limit_f64": (_f64, []),
-    "drp_potrf_batched_f64": (_i32, [_p, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),
+    "drp_potrf_batched_f64": (_i32, [_p, _i32, _i32, _i32, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "drp_syrk_update_f64": (_i32, [_p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),
+    "drp_syrk_update_range_f64": (_i32, [_p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _i32, _i32, _p]),
     "drp_ou_workspace_ld": (_i64, [_i32, _i32]),
     "drp_ou_workspace_elems": (_i64, [_i32, _i32, _i32]),
-    "drp_ou_prior_f64": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
-    "drp_ou_prior_factor_f64": (_i32, [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p]),
+    "drp_ou_prior_f64": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "drp_ou_prior_factor_f64": (_i32, [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
     "drp_ou_prior_apply_workspace_elems": (_i64, [_i32, _i32]),
     "drp_ou_prior_apply_f64": (_i32, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
-    "drp_mvn_logprob_f64": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p]),
+    "drp_mvn_logprob_f64": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "drp_mvn_grad_cov_f64": (_i32, [_p, _i32, _i32, _p, _p, _p]),
-    "drp_potri_batched_f64": (_i32, [_p, _i32, _i32, _p, _p, _p, _p, _p]),
-    "drp_ou_conditional_f64": (_i32, [_p, _i64, _p, _i32, _i32, _p, _p, _p, _p, _i32, _f64, _p, _p, _p, _p, _p]),
+    "drp_potri_batched_f64": (_i32, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "drp_ou_conditional_f64": (_i32, [_p, _i64, _p, _i32, _i32, _p, _p, _p, _p, _i32, _f64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "drp_gru_hidden_size": (_i32, []),
     "drp_gru_fwd_f64": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "drp_gru_fwd_dir0_f64": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),

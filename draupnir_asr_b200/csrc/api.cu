@@ -60,7 +60,7 @@ bool drp_first_on_device(int key)
     return (seen[key & 63].fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
 }
 
-DRP_API int drp_abi_version(void) { return 4; }
+DRP_API int drp_abi_version(void) { return 5; }
 
 // Number of kernel classes reported by drp_timing_read (length of its three arrays).
 DRP_API int drp_timing_classes(void) { return DRP_K_CLASSES; }

@@ -345,16 +345,27 @@ void drp_dmma_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     syrk_kernel<<<dim3(Tc, T, z), 128, SYRK_SMEM, st>>>(M, ld, bs, k0, K, c1, R, col_limit);
 }
 
-// Trailing update: int8 tcgen05 pipe when a workspace is given and the update is large, fp64 mma.sync otherwise.
-static int trailing_update(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, void* ws,
-                           int64_t ws_bytes, const int* zmap, cudaStream_t st)
+// Trailing update of rows [c1, R), columns [col_lo, min(R, col_hi)): int8 tcgen05 pipe when a workspace is given and the
+// (whole) update is large, fp64 mma.sync otherwise.  do_slice / buffer / counter_idx: see drp_ozaki_syrk.
+static int trailing_update(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_lo, int col_hi,
+                           void* ws, int64_t ws_bytes, const int* zmap, int do_slice, int buffer, int counter_idx,
+                           cudaStream_t st)
 {
-    const int rc = drp_ozaki_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, drp_ozaki_slices(), ws, ws_bytes, zmap, st);
+    const int rc = drp_ozaki_syrk(M, ld, bs, z, k0, K, c1, R, col_lo, col_hi, drp_ozaki_slices(), ws, ws_bytes, zmap, do_slice,
+                                  buffer, counter_idx, st);
     if (rc > 1 || rc < 0) return rc;
     // rc == 1: the shape does not qualify for the tensor path -> every matrix on the fp64 kernel;
     // rc == 0: the matrices the precision gate kept off the tensor path (normally none: the CTAs find an empty list)
-    drp_dmma_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, rc == 1 ? nullptr : zmap, st);
+    drp_dmma_syrk(M, ld, bs, z, k0, K, col_lo > c1 ? col_lo : c1, R, col_hi, rc == 1 ? nullptr : zmap, st);
     return 0;
+}
+
+// Would the tensor path take an update of this shape?  (Look-ahead only splits updates that do.)
+static bool tensor_update_qualifies(int K, int c1, int R, int col_limit)
+{
+    const int cmax = R < col_limit ? R : col_limit;
+    const int KBN = K > 128 ? 2 : 1;
+    return K >= 32 && K <= 256 && drp_ozaki_slices() * KBN <= 12 && R - c1 >= 384 && cmax - c1 >= 64;
 }
 
 static int outer_block(int R_full, bool tensor_path)
@@ -370,12 +381,36 @@ static int outer_block(int R_full, bool tensor_path)
     return (tensor_path && R_full >= 1024) ? 256 : 128;
 }
 
+static bool lookahead_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DRP_LOOKAHEAD");
+        v = e ? atoi(e) : 0;        // off by default: measured, it does not pay on one GPU (see the comment at drp_factor_run)
+    }
+    return v != 0;
+}
+
 // Two-level right-looking elimination: panels of `outer_block()` columns are factored with NB-wide inner steps whose
 // trailing updates stay inside the panel; the rest of the matrix is then updated once per panel with K = panel width
 // (halves / quarters the read-modify-write traffic of the trailing matrix compared with K = NB, and gives the tensor
 // path a contraction length of 128-256).
+//
+// Look-ahead (aux != null).  The factorisation of an outer panel is a latency chain of ~20 narrow kernels (4 x {potf2, trsm,
+// slicing, in-panel update}) that leaves the GPU idle; the update that follows is throughput work.  They only depend on
+// each other through the columns of the NEXT panel, so the update of panel k is split by columns: part (a), the next
+// panel's columns, runs first on the caller's stream; part (b), everything right of them, goes to the auxiliary stream and
+// runs WHILE panel k+1 is being factored (which reads and writes the next panel's columns only).  Update k+1 waits for
+// part (b) of update k.  Part (b) re-uses the slices part (a) made (buffer 0); the in-panel updates of panel k+1 slice into
+// buffer 1.  Two events, one auxiliary stream, all supplied by the caller; everything is joined back before returning.
+// MEASURED (round 2, profiles/r02/lookahead_ab.txt): parity-green but NO gain at 2,000 leaves on one B200 - 22.14 vs
+// 22.11 ms per step, conditional posterior 10.15 vs 10.15 ms, with persistent or one-unit-per-CTA part (b) kernels and
+// stream priorities either way.  Both the chain's wide kernels (trsm: 930 CTAs, slicing) and part (b) want every SM; what
+// the overlap recovers (idle SMs under potf2, launch gaps) it loses again in contention (trsm 1.35 -> 3.4 ms inside the
+// overlapped region).  Hence opt-in (DRP_LOOKAHEAD=1); the column-range form of the update it needs is exercised by the
+// GPU test-suite either way (tests/test_gpu_ozaki.py::test_split_update_equals_whole).
 int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_full, int grow_base, int col_limit,
-                   int32_t* info, void* ws, int64_t ws_bytes, const DrpGate& gate, cudaStream_t st)
+                   int32_t* info, void* ws, int64_t ws_bytes, const DrpGate& gate, const DrpAux* aux, cudaStream_t st)
 {
     if (drp_first_on_device(1)) cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM);
     if (info) cudaMemsetAsync(info, 0, sizeof(int32_t) * z, st);
@@ -391,16 +426,20 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
         DRP_LAUNCH(DRP_K_OTHER, 16.0 * z, st);
         gate_kernel<<<1, 32, 0, st>>>(gate.cond, gate.sf, gate.sn, gate.nnorm, z, drp_ozaki_cond_limit(), zmap);
     }
-    for (int C0 = 0; C0 < nfactor; C0 += NBO) {
+    const bool look = tensor_path && aux != nullptr && aux->stream != nullptr && aux->ev_fork != nullptr &&
+                      aux->ev_join != nullptr && lookahead_enabled();
+    bool pending_b = false;                                         // a part (b) is in flight on the auxiliary stream
+    int rc = 0;
+    for (int C0 = 0; C0 < nfactor && rc == 0; C0 += NBO) {
         const int W = min(NBO, nfactor - C0);
         const int C1 = C0 + W;
         const int R = grow_base > 0 ? min(R_full, grow_base + C1) : R_full;
         // inside the outer panel: 64-wide steps; with the tensor path the panel is split again into 128-wide
         // sub-panels so that only 64-column-wide updates are left to the fp64 mma.sync kernel
         const int NBM = (tensor_path && W > 2 * NB) ? 2 * NB : W;
-        for (int Q0 = C0; Q0 < C1; Q0 += NBM) {
+        for (int Q0 = C0; Q0 < C1 && rc == 0; Q0 += NBM) {
             const int Q1 = min(Q0 + NBM, C1);
-            for (int c0 = Q0; c0 < Q1; c0 += NB) {
+            for (int c0 = Q0; c0 < Q1 && rc == 0; c0 += NB) {
                 const int nb = min(NB, Q1 - c0);
                 const int c1 = c0 + nb;
                 {
@@ -414,20 +453,35 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
                         DRP_LAUNCH(DRP_K_TRSM, (double)z * below * nb * nb, st);
                         trsm_kernel<<<g, PR, TRSM_SMEM, st>>>(M, ld, bs, c0, nb, R);
                     }
-                    if (c1 < Q1) {                                                              // inside the sub-panel
-                        const int rc = trailing_update(M, ld, bs, z, c0, nb, c1, R, min(col_limit, Q1), tws, ws_bytes, zmap, st);
-                        if (rc) return rc;
-                    }
+                    if (c1 < Q1)                                                                // inside the sub-panel
+                        rc = trailing_update(M, ld, bs, z, c0, nb, c1, R, c1, min(col_limit, Q1), tws, ws_bytes, zmap, 1, 1, 0, st);
                 }
             }
-            if (Q1 < C1) {                                                                              // rest of the outer panel
-                const int rc = trailing_update(M, ld, bs, z, Q0, Q1 - Q0, Q1, R, min(col_limit, C1), tws, ws_bytes, zmap, st);
-                if (rc) return rc;
-            }
+            if (Q1 < C1 && rc == 0)                                                                     // rest of the outer panel
+                rc = trailing_update(M, ld, bs, z, Q0, Q1 - Q0, Q1, R, Q1, min(col_limit, C1), tws, ws_bytes, zmap, 1, 1, 0, st);
         }
-        const int rc = trailing_update(M, ld, bs, z, C0, W, C1, R, col_limit, tws, ws_bytes, zmap, st);          // rest of the matrix
-        if (rc) return rc;
+        if (rc) break;
+        // ---- rest of the matrix
+        if (pending_b) {                                            // part (b) of the previous update writes the same entries
+            cudaStreamWaitEvent(st, aux->ev_join, 0);
+            pending_b = false;
+        }
+        const int Wn = min(NBO, nfactor - C1);                      // width of the next outer panel (0: this was the last)
+        const int cmax = min(R, col_limit);
+        if (look && Wn >= NB && C1 + Wn < cmax && tensor_update_qualifies(W, C1, R, col_limit)) {
+            rc = trailing_update(M, ld, bs, z, C0, W, C1, R, C1, C1 + Wn, tws, ws_bytes, zmap, 1, 0, 0, st);          // (a)
+            if (rc) break;
+            cudaEventRecord(aux->ev_fork, st);
+            cudaStreamWaitEvent(aux->stream, aux->ev_fork, 0);
+            rc = trailing_update(M, ld, bs, z, C0, W, C1, R, C1 + Wn, col_limit, tws, ws_bytes, zmap, 0, 0, 1, aux->stream);   // (b)
+            cudaEventRecord(aux->ev_join, aux->stream);
+            pending_b = true;
+        } else {
+            rc = trailing_update(M, ld, bs, z, C0, W, C1, R, C1, col_limit, tws, ws_bytes, zmap, 1, 0, 0, st);
+        }
     }
+    if (pending_b) cudaStreamWaitEvent(st, aux->ev_join, 0);        // the auxiliary stream is joined before anything follows
+    if (rc) return rc;
     return drp_launch_status();
 }
 
@@ -458,18 +512,35 @@ DRP_API int drp_syrk_update_f64(double* M, int64_t ld, int64_t bs, int z, int k0
         drp_dmma_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, nullptr, st);
         return drp_launch_status();
     }
-    return drp_ozaki_syrk(M, ld, bs, z, k0, K, c1, R, col_limit, slices, ws, ws_bytes, nullptr, st);
+    return drp_ozaki_syrk(M, ld, bs, z, k0, K, c1, R, c1, col_limit, slices, ws, ws_bytes, nullptr, 1, 0, 0, st);
+}
+
+// Test hook: the column range [col_lo, col_hi) of the same update (rows [c1, R), c <= r); do_slice = 0 re-uses the slices of
+// the preceding call with the same panel, counter_idx selects the work-unit counter (two parts may run on two streams).
+DRP_API int drp_syrk_update_range_f64(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_lo,
+                                      int col_hi, int slices, void* ws, int64_t ws_bytes, int do_slice, int counter_idx,
+                                      void* stream)
+{
+    if (!M) return -1;
+    if (z <= 0 || K <= 0 || R <= c1 || col_lo < c1) return -4;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (slices == 0) {
+        drp_dmma_syrk(M, ld, bs, z, k0, K, col_lo, R, col_hi, nullptr, st);
+        return drp_launch_status();
+    }
+    return drp_ozaki_syrk(M, ld, bs, z, k0, K, c1, R, col_lo, col_hi, slices, ws, ws_bytes, nullptr, do_slice, 0, counter_idx, st);
 }
 
 DRP_API int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info, const double* cond_bound, void* ws,
-                                  int64_t ws_bytes, void* stream)
+                                  int64_t ws_bytes, void* aux_stream, void* ev_fork, void* ev_join, void* stream)
 {
+    const DrpAux aux{(cudaStream_t)aux_stream, (cudaEvent_t)ev_fork, (cudaEvent_t)ev_join};
     if (!A) return -1;
     if (n <= 0) return -2;
     if (z <= 0) return -3;
     cudaStream_t st = (cudaStream_t)stream;
     const DrpGate gate{cond_bound, nullptr, nullptr, 0.0};
-    int rc = drp_factor_run(A, n, (int64_t)n * n, z, n, n, 0, n, info, ws, ws_bytes, gate, st);
+    int rc = drp_factor_run(A, n, (int64_t)n * n, z, n, n, 0, n, info, ws, ws_bytes, gate, &aux, st);
     if (rc) return rc;
     if (zero_upper) {
         dim3 g((n + 255) / 256, n, z);

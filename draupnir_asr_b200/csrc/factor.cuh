@@ -28,8 +28,13 @@ struct DrpGate {
     const double* sn;        //       (nnorm * sf^2 + sn^2) / sn^2   (lambda_min(K) >= sn^2, |K|_2 <= trace(K))
     double nnorm;            // all null: no bound known -> fp64 updates only
 };
+// Look-ahead resources, owned by the caller (the library creates no streams or events): an auxiliary stream and two events.
+struct DrpAux {
+    cudaStream_t stream;
+    cudaEvent_t ev_fork, ev_join;
+};
 int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_full, int grow_base, int col_limit,
-                   int32_t* info, void* ws, int64_t ws_bytes, const DrpGate& gate, cudaStream_t st);
+                   int32_t* info, void* ws, int64_t ws_bytes, const DrpGate& gate, const DrpAux* aux, cudaStream_t st);
 
 // ozaki.cu
 int64_t drp_ozaki_workspace_bytes(int R_full, int z);
@@ -38,8 +43,8 @@ double drp_ozaki_cond_limit();
 // zmap (device, nullable = all z matrices): [0] number of matrices on the tensor path, [1] number on the fp64 path,
 // [2 .. 2+z) indices of the former, [2+z .. 2+2z) indices of the latter
 int64_t drp_zmap_bytes(int z);
-int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, int S, void* ws,
-                   int64_t ws_bytes, const int* zmap, cudaStream_t st);
+int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_lo, int col_hi, int S,
+                   void* ws, int64_t ws_bytes, const int* zmap, int do_slice, int buffer, int counter_idx, cudaStream_t st);
 // factor.cu: the fp64 mma.sync trailing update (also exported for kernel-vs-kernel parity tests); with a zmap only the
 // matrices of its fp64 list are updated
 void drp_dmma_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, const int* zmap,

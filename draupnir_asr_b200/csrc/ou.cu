@@ -358,8 +358,9 @@ DRP_API int drp_ou_cov_bwd_f64(const double* D, int64_t ldd, int n, const double
 //   part workspace of z*n*3 doubles (want_grad only)
 DRP_API int drp_ou_prior_f64(const double* D, int64_t ldd, int n, const double* sf, const double* sn, const double* lam,
                              const double* x, int z, int want_grad, double* logp, double* alpha, double* gsum, double* M,
-                             double* part, int32_t* info, void* stream)
+                             double* part, int32_t* info, void* aux_stream, void* ev_fork, void* ev_join, void* stream)
 {
+    const DrpAux aux{(cudaStream_t)aux_stream, (cudaEvent_t)ev_fork, (cudaEvent_t)ev_join};
     if (!D) return -1;
     if (n <= 0 || ldd < n) return -3;
     if (!sf || !sn || !lam || !x) return -4;
@@ -376,7 +377,7 @@ DRP_API int drp_ou_prior_f64(const double* D, int64_t ldd, int n, const double* 
         ou_assemble_kernel<<<g, 256, 3 * z * sizeof(double), st>>>(D, ldd, nullptr, n, n2, 1, sf, sn, lam, x, z, M, ld, bs);
     }
     const DrpGate gate{nullptr, sf, sn, (double)n};
-    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, M + ou_matrix_elems(n, n2, z), drp_ozaki_workspace_bytes(R, z), gate, st);
+    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, M + ou_matrix_elems(n, n2, z), drp_ozaki_workspace_bytes(R, z), gate, &aux, st);
     if (rc) return rc;
     {
         DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 8.0), st);
@@ -403,8 +404,9 @@ DRP_API int drp_ou_prior_f64(const double* D, int64_t ldd, int n, const double* 
 // factorisation, leaving L and -K^-1 in M.  Phase 2 needs the latent vectors: alpha = K^-1 x, log-densities and the
 // hyper-parameter gradient sums.  Same results as the one-call form up to rounding (alpha through the explicit inverse).
 DRP_API int drp_ou_prior_factor_f64(const double* D, int64_t ldd, int n, const double* sf, const double* sn, const double* lam,
-                                    int z, double* M, int32_t* info, void* stream)
+                                    int z, double* M, int32_t* info, void* aux_stream, void* ev_fork, void* ev_join, void* stream)
 {
+    const DrpAux aux{(cudaStream_t)aux_stream, (cudaEvent_t)ev_fork, (cudaEvent_t)ev_join};
     if (!D) return -1;
     if (n <= 0 || ldd < n) return -3;
     if (!sf || !sn || !lam) return -4;
@@ -419,7 +421,7 @@ DRP_API int drp_ou_prior_factor_f64(const double* D, int64_t ldd, int n, const d
         ou_assemble_kernel<<<g, 256, 3 * z * sizeof(double), st>>>(D, ldd, nullptr, n, n, 1, sf, sn, lam, nullptr, z, M, ld, bs);
     }
     const DrpGate gate{nullptr, sf, sn, (double)n};
-    int rc = drp_factor_run(M, ld, bs, z, n, R, n + 1, R, info, M + ou_matrix_elems(n, n, z), drp_ozaki_workspace_bytes(R, z), gate, st);
+    int rc = drp_factor_run(M, ld, bs, z, n, R, n + 1, R, info, M + ou_matrix_elems(n, n, z), drp_ozaki_workspace_bytes(R, z), gate, &aux, st);
     if (rc) return rc;
     return drp_launch_status();
 }
@@ -472,8 +474,9 @@ DRP_API int drp_ou_prior_apply_f64(const double* D, int64_t ldd, int n, const do
 // cond_bound (nullable, device [z]): upper bounds of cond_2(K_z); matrices within drp_ozaki_cond_limit take the
 // split-integer tensor-core update, all others (and all of them without a bound) the fp64 one.
 DRP_API int drp_mvn_logprob_f64(const double* K, const double* x, int n, int z, int want_grad, double* logp, double* alpha,
-                                double* M, int32_t* info, const double* cond_bound, void* stream)
+                                double* M, int32_t* info, const double* cond_bound, void* aux_stream, void* ev_fork, void* ev_join, void* stream)
 {
+    const DrpAux aux{(cudaStream_t)aux_stream, (cudaEvent_t)ev_fork, (cudaEvent_t)ev_join};
     if (!K || !x) return -1;
     if (n <= 0) return -3;
     if (z <= 0) return -4;
@@ -488,7 +491,7 @@ DRP_API int drp_mvn_logprob_f64(const double* K, const double* x, int n, int z, 
         cov_assemble_kernel<<<dim3((R + 255) / 256, R, z), 256, 0, st>>>(K, n, x, M, ld, bs);
     }
     const DrpGate gate{cond_bound, nullptr, nullptr, 0.0};
-    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, M + ou_matrix_elems(n, n2, z), drp_ozaki_workspace_bytes(R, z), gate, st);
+    int rc = drp_factor_run(M, ld, bs, z, n, R, want_grad ? n + 1 : 0, R, info, M + ou_matrix_elems(n, n2, z), drp_ozaki_workspace_bytes(R, z), gate, &aux, st);
     if (rc) return rc;
     {
         DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 8.0), st);
@@ -519,8 +522,9 @@ DRP_API int drp_mvn_grad_cov_f64(const double* M, int n, int z, const double* gs
 
 // K^-1 of z SPD matrices via the same elimination (potri equivalent); Kinv [z,n,n] full symmetric.
 DRP_API int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, double* M, int32_t* info,
-                                  const double* cond_bound, void* stream)
+                                  const double* cond_bound, void* aux_stream, void* ev_fork, void* ev_join, void* stream)
 {
+    const DrpAux aux{(cudaStream_t)aux_stream, (cudaEvent_t)ev_fork, (cudaEvent_t)ev_join};
     if (!K) return -1;
     if (n <= 0 || z <= 0) return -2;
     if (!Kinv || !M) return -4;
@@ -533,7 +537,7 @@ DRP_API int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, d
         cov_assemble_kernel<<<dim3((R + 255) / 256, R, z), 256, 0, st>>>(K, n, Kinv, M, ld, bs);
     }
     const DrpGate gate{cond_bound, nullptr, nullptr, 0.0};
-    int rc = drp_factor_run(M, ld, bs, z, n, R, n + 1, R, info, M + ou_matrix_elems(n, n, z), drp_ozaki_workspace_bytes(R, z), gate, st);
+    int rc = drp_factor_run(M, ld, bs, z, n, R, n + 1, R, info, M + ou_matrix_elems(n, n, z), drp_ozaki_workspace_bytes(R, z), gate, &aux, st);
     if (rc) return rc;
     {
         DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * n * 12.0), st);
@@ -548,8 +552,9 @@ DRP_API int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, d
 //   idx = [leaf_idx (n) | int_idx (ni)] rows of D;  M workspace of drp_ou_workspace_elems(n, ni, z) doubles.
 DRP_API int drp_ou_conditional_f64(const double* D, int64_t ldd, const int32_t* idx, int n, int ni, const double* sf,
                                    const double* sn, const double* lam, const double* x_leaf, int z, double jitter,
-                                   double* mean, double* cov, double* M, int32_t* info, void* stream)
+                                   double* mean, double* cov, double* M, int32_t* info, void* aux_stream, void* ev_fork, void* ev_join, void* stream)
 {
+    const DrpAux aux{(cudaStream_t)aux_stream, (cudaEvent_t)ev_fork, (cudaEvent_t)ev_join};
     if (!D) return -1;
     if (!idx) return -3;
     if (n <= 0 || ni <= 0) return -4;
@@ -565,7 +570,7 @@ DRP_API int drp_ou_conditional_f64(const double* D, int64_t ldd, const int32_t* 
                                                                                   x_leaf, z, M, ld, bs);
     }
     const DrpGate gate{nullptr, sf, sn, (double)(n + ni)};
-    int rc = drp_factor_run(M, ld, bs, z, n, R, 0, cov ? R : n + 1, info, M + ou_matrix_elems(n, ni, z), drp_ozaki_workspace_bytes(R, z), gate, st);
+    int rc = drp_factor_run(M, ld, bs, z, n, R, 0, cov ? R : n + 1, info, M + ou_matrix_elems(n, ni, z), drp_ozaki_workspace_bytes(R, z), gate, &aux, st);
     if (rc) return rc;
     {
         DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 16.0), st);

@@ -62,10 +62,13 @@ struct OzParams {
     const int32_t* scl;        // [z][Rpad]  binary exponent e_r of the row maximum (row scale 2^(e_r - 7))
     int Rpad, rb, c1, R, cmax;
     int nTi, nTj, units_per_z, total_units;
+    int slice_c1;              // first live row of the panel (rows of the slice buffer above it are zeros)
+    int ti0, tj0;              // first 128-row strip / first 64-column tile of this launch (a column-range part of an update)
     int K;                     // real contraction length (columns of the panel); the k-blocks are zero-padded
     long long* trace;          // event trace of CTA 0 (DRP_DEBUG_HOOKS builds only)
     long long* prof;           // per-CTA wait-time sums [grid][16] (DRP_DEBUG_HOOKS builds only)
-    int* counter;              // next work unit (zeroed by the slicing kernel that precedes every update)
+    int* counter;              // next work unit of THIS launch (both counters are zeroed by the slicing kernel of the update)
+    int counter_idx;           // 0 / 1: which of the two
     const int* zmap;           // precision gate (factor.cuh): [0] matrices on this path, [2..] their indices; null = all z
 };
 
@@ -219,19 +222,19 @@ __device__ __forceinline__ void oz_decode(const OzParams& p, int u, int& zz, int
     zz = u / p.units_per_z;
     int v = u - zz * p.units_per_z;
     if (p.zmap) zz = p.zmap[2 + zz];
-    tj0 = 0;
+    tj0 = p.tj0;
     ntj = 0;
-    for (ti = p.nTi - 1; ti >= 0; --ti) {
-        const int tot = min(2 * ti + 2, p.nTj);
-        const int nch = (tot + OZ_CHUNK - 1) / OZ_CHUNK;
+    for (ti = p.nTi - 1; ti >= p.ti0; --ti) {
+        const int tot = min(2 * ti + 2, p.nTj) - p.tj0;        // column tiles [p.tj0, min(2 ti + 2, nTj)) of this strip
+        const int nch = tot > 0 ? (tot + OZ_CHUNK - 1) / OZ_CHUNK : 0;
         if (v < nch) {
-            tj0 = v * OZ_CHUNK;
-            ntj = min(OZ_CHUNK, tot - tj0);
+            tj0 = p.tj0 + v * OZ_CHUNK;
+            ntj = min(OZ_CHUNK, tot - v * OZ_CHUNK);
             return;
         }
         v -= nch;
     }
-    ti = 0;
+    ti = p.ti0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
                                                        int64_t sl_bs, int32_t* __restrict__ scl, int* __restrict__ counter,
                                                        const int* __restrict__ zmap)
 {
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *counter = 0;      // work-unit counter of the update that follows
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) counter[0] = counter[1] = 0;   // work-unit counters of the (up to two) update launches that follow
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rr = blockIdx.x * 8 + warp;
     int zz = blockIdx.y;
@@ -631,8 +634,18 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
     if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_COLS);
 }
 
+static bool oz_yield()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DRP_LOOKAHEAD_YIELD");
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
+}
+
 template <int S, int KBN>
-int oz_launch(const OzParams& p, int z, int k0, int Kcols, cudaStream_t st, double flops)
+int oz_launch(const OzParams& p, int z, int k0, int Kcols, cudaStream_t st, double flops, bool do_slice)
 {
     using Cfg = OzCfg<S, KBN>;
     static int n_sm = 0;
@@ -642,15 +655,18 @@ int oz_launch(const OzParams& p, int z, int k0, int Kcols, cudaStream_t st, doub
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
-    {
+    if (do_slice) {
         DRP_LAUNCH(DRP_K_SLICE, (double)z * p.Rpad * KBN * 128 * (8.0 + S), st);
-        oz_slice_kernel<S><<<dim3((p.Rpad + 7) / 8, z), 256, 0, st>>>(p.M, p.ld, p.bs, k0, Kcols, KBN, p.rb, p.c1, p.R, p.Rpad,
+        oz_slice_kernel<S><<<dim3((p.Rpad + 7) / 8, z), 256, 0, st>>>(p.M, p.ld, p.bs, k0, Kcols, KBN, p.rb, p.slice_c1, p.R, p.Rpad,
                                                                      const_cast<uint8_t*>(p.sl), p.sl_bs,
-                                                                     const_cast<int32_t*>(p.scl), p.counter, p.zmap);
+                                                                     const_cast<int32_t*>(p.scl), p.counter - p.counter_idx, p.zmap);
     }
     {
         DRP_LAUNCH(DRP_K_SYRK_TC, flops, st);
-        const int grid = p.total_units < n_sm ? p.total_units : n_sm;
+        // counter_idx 1 = the look-ahead part of an update, running beside the next panel's factorisation chain: one CTA per
+        // work unit instead of one persistent CTA per SM, so that SMs are handed back every ~50 us and the (higher-priority)
+        // chain kernels get them; CTAs that find the counter exhausted exit at once
+        const int grid = (p.counter_idx == 1 && oz_yield()) ? p.total_units : (p.total_units < n_sm ? p.total_units : n_sm);
         oz_syrk_kernel<S, KBN><<<grid, OZ_THREADS, Cfg::SMEM, st>>>(p);
     }
     return 0;
@@ -676,12 +692,19 @@ static long long* const g_oz_prof = nullptr;
 
 int64_t drp_zmap_bytes(int z) { return (((int64_t)z * 8 + 8 + 255) / 256) * 256; }
 
-// Bytes of workspace the tensor path may need for matrices with at most R_full rows (slices, row scales, the work-unit
-// counter, and the precision gate's index lists at the very end).
-int64_t drp_ozaki_workspace_bytes(int R_full, int z)
+// Bytes of ONE slice buffer (slices, row scales, the two work-unit counters) for matrices with at most R_full rows.
+static int64_t oz_buffer_bytes(int R_full, int z)
 {
     const int64_t Rpad = (((int64_t)R_full + 127) / 128 + 1) * 128;
-    return (int64_t)z * Rpad * (12 * OZ_ROWB + 8) + 2048 + drp_zmap_bytes(z);
+    return (((int64_t)z * Rpad * (12 * OZ_ROWB + 8) + 2048) + 1023) / 1024 * 1024;
+}
+
+// Bytes of workspace the tensor path may need for matrices with at most R_full rows: TWO slice buffers (buffer 0: the
+// updates that leave an outer panel, buffer 1: the updates inside a panel - with look-ahead the latter are sliced while the
+// former are still being multiplied) and the precision gate's index lists at the very end.
+int64_t drp_ozaki_workspace_bytes(int R_full, int z)
+{
+    return 2 * oz_buffer_bytes(R_full, z) + drp_zmap_bytes(z);
 }
 
 // Largest condition-number bound a matrix may have to take the split-integer update: eps_S * cond <= 1e-5 with the
@@ -710,22 +733,30 @@ int drp_ozaki_slices()
 
 // Trailing update through the int8 tensor pipe.  Returns 0 when it ran, 1 when the shape/workspace does not qualify
 // (the caller then uses the fp64 mma.sync kernel), otherwise a launch error code.
-int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, int S, void* ws,
-                   int64_t ws_bytes, const int* zmap, cudaStream_t st)
+//   the panel P = M[c1 .. R) x [k0, k0 + K) is sliced from row c1 down (do_slice; `buffer` 0/1 selects the slice buffer);
+//   updated entries: rows r in [c1, R), columns c in [col_lo, min(R, col_hi)), c <= r  (col_lo >= c1).
+//   do_slice = 0 re-uses the slices a previous call with the same (c1, R, k0, K, buffer) made: the second column-range part
+//   of one update, possibly running on another stream (counter_idx 1).
+int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_lo, int col_hi, int S,
+                   void* ws, int64_t ws_bytes, const int* zmap, int do_slice, int buffer, int counter_idx, cudaStream_t st)
 {
     if (S == 0 || !ws) return 1;
     if (K < 32 || K > 256) return 1;
     const int KBN = K > 128 ? 2 : 1;
     if (S * KBN > 12) return 1;                          // A strip must stay resident in shared memory
-    const int cmax = R < col_limit ? R : col_limit;
-    const int below = R - c1, cl = cmax - c1;
-    if (below < 384 || cl < 64) return 1;                // small updates: launch/slicing overhead dominates
+    const int cmax = R < col_hi ? R : col_hi;
+    if (col_lo < c1) col_lo = c1;
+    const int below = R - c1, cl = cmax - col_lo;
+    // qualification is decided on the WHOLE update (rows below c1, columns up to cmax), so that both parts of a split
+    // update take the same path
+    if (below < 384 || cmax - c1 < 64) return 1;         // small updates: launch/slicing overhead dominates
+    if (cl <= 0) return 0;
     OzParams p;
     p.M = M;
     p.ld = ld;
     p.bs = bs;
     p.rb = c1 & ~7;
-    p.c1 = c1;
+    p.c1 = col_lo;                                       // rows and columns below col_lo are not touched (c <= r)
     p.R = R;
     p.cmax = cmax;
     p.K = K;
@@ -734,36 +765,44 @@ int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     p.zmap = zmap;
     p.nTi = (R - p.rb + OZ_TM - 1) / OZ_TM;
     p.nTj = (cmax - p.rb + OZ_TN - 1) / OZ_TN;
+    p.ti0 = (col_lo - p.rb) / OZ_TM;
+    p.tj0 = (col_lo - p.rb) / OZ_TN;
     p.Rpad = p.nTi * OZ_TM;
     p.sl_bs = (int64_t)S * KBN * p.Rpad * OZ_ROWB;
     const int64_t need = (int64_t)z * p.sl_bs + (int64_t)z * p.Rpad * 8 + 2048;
-    if (need > ws_bytes) return 1;
-    uint8_t* w = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    const int64_t bbytes = (ws_bytes / 2) & ~(int64_t)1023;      // two buffers
+    if (need > bbytes - 1024) return 1;
+    uint8_t* w = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023) + (buffer ? bbytes : 0);
     p.sl = w;
     p.scl = reinterpret_cast<const int32_t*>(w + (int64_t)z * p.sl_bs);
-    p.counter = reinterpret_cast<int*>(w + (int64_t)z * p.sl_bs + (int64_t)z * p.Rpad * 8);
+    p.counter_idx = counter_idx ? 1 : 0;
+    p.counter = reinterpret_cast<int*>(w + (int64_t)z * p.sl_bs + (int64_t)z * p.Rpad * 8) + p.counter_idx;
+    // NOTE: the slicing kernel writes zeros for the rows of the panel outside [c1, R); it is given the panel's own c1
     int upz = 0;
-    for (int ti = 0; ti < p.nTi; ++ti) {
-        const int tot = 2 * ti + 2 < p.nTj ? 2 * ti + 2 : p.nTj;
-        upz += (tot + OZ_CHUNK - 1) / OZ_CHUNK;
+    for (int ti = p.ti0; ti < p.nTi; ++ti) {
+        const int tot = (2 * ti + 2 < p.nTj ? 2 * ti + 2 : p.nTj) - p.tj0;
+        if (tot > 0) upz += (tot + OZ_CHUNK - 1) / OZ_CHUNK;
     }
+    if (upz == 0) return 0;
     p.units_per_z = upz;
     p.total_units = upz * z;
-    const double entries = (double)cl * (cl + 1) / 2.0 + (double)(below - cl) * cl;
+    const double c0 = (double)(col_lo - c1), c1d = (double)(cmax - c1);      // columns [c0, c1d) of the trapezoid below c1
+    const double entries = (double)below * (c1d - c0) - (c1d * (c1d - 1.0) - c0 * (c0 - 1.0)) / 2.0;
     const double flops = (double)z * entries * 2.0 * K;
+    p.slice_c1 = c1;
     int rc = 1;
     if (KBN == 1) {
         switch (S) {
-            case 4: rc = oz_launch<4, 1>(p, z, k0, K, st, flops); break;
-            case 5: rc = oz_launch<5, 1>(p, z, k0, K, st, flops); break;
-            case 6: rc = oz_launch<6, 1>(p, z, k0, K, st, flops); break;
-            case 7: rc = oz_launch<7, 1>(p, z, k0, K, st, flops); break;
+            case 4: rc = oz_launch<4, 1>(p, z, k0, K, st, flops, do_slice != 0); break;
+            case 5: rc = oz_launch<5, 1>(p, z, k0, K, st, flops, do_slice != 0); break;
+            case 6: rc = oz_launch<6, 1>(p, z, k0, K, st, flops, do_slice != 0); break;
+            case 7: rc = oz_launch<7, 1>(p, z, k0, K, st, flops, do_slice != 0); break;
         }
     } else {
         switch (S) {
-            case 4: rc = oz_launch<4, 2>(p, z, k0, K, st, flops); break;
-            case 5: rc = oz_launch<5, 2>(p, z, k0, K, st, flops); break;
-            case 6: rc = oz_launch<6, 2>(p, z, k0, K, st, flops); break;
+            case 4: rc = oz_launch<4, 2>(p, z, k0, K, st, flops, do_slice != 0); break;
+            case 5: rc = oz_launch<5, 2>(p, z, k0, K, st, flops, do_slice != 0); break;
+            case 6: rc = oz_launch<6, 2>(p, z, k0, K, st, flops, do_slice != 0); break;
         }
     }
     if (rc) return rc;

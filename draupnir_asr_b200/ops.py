@@ -19,6 +19,7 @@ _DEFERRED: Optional[List[Tuple[torch.Tensor, str]]] = None
 # recurrences (one CTA per SM on 126 of 148 SMs, latency-bound) are independent until the loss is summed: the prior's
 # log-density is evaluated on a side stream so that the two fill each other's idle SMs.  DRP_PRIOR_STREAM=0 disables.
 PRIOR_STREAM_ENABLED = os.environ.get("DRP_PRIOR_STREAM", "1") != "0"
+LOOKAHEAD_ENABLED = os.environ.get("DRP_LOOKAHEAD", "0") not in ("0", "")     # opt-in: no gain measured (csrc/factor.cu)
 _SIDE_STREAMS = {}
 
 
@@ -27,8 +28,37 @@ def side_stream(device) -> "torch.cuda.Stream":
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     st = _SIDE_STREAMS.get(key)
     if st is None:
-        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+        # priorities: the step's main chain (the graph's capture stream) -2, the prior's chain here -1, the look-ahead part of
+        # the factorisation's updates (`_aux`) 0 = lowest: latency chains get SMs ahead of throughput work
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key, priority=-1)
     return st
+
+
+_AUX = {}
+
+
+def _aux(device):
+    """(stream, fork event, join event) the factorisation's look-ahead runs on (csrc/factor.cu: the update of an outer panel
+    is split by columns and its larger part overlaps the factorisation of the next panel).  The library creates no streams
+    or events of its own; these are per device AND per launching stream (the prior on the side stream and a conditional
+    posterior on the main stream must not share events).  Returned as three ctypes handles."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    hit = _AUX.get(key)
+    if hit is None:
+        if not LOOKAHEAD_ENABLED:
+            hit = (None, None, None, None)
+        else:
+            st = torch.cuda.Stream(device=idx, priority=0)
+            evs = (torch.cuda.Event(), torch.cuda.Event())
+            with torch.cuda.stream(st):
+                for e in evs:
+                    e.record()                      # materialises the cudaEvent_t
+            hit = (ctypes.c_void_p(st.cuda_stream), ctypes.c_void_p(evs[0].cuda_event), ctypes.c_void_p(evs[1].cuda_event),
+                   (st, evs))                       # the torch objects keep the handles alive
+        _AUX[key] = hit
+    return hit[:3]
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -192,7 +222,8 @@ def potrf(A: torch.Tensor, check: bool = True, cond_bound=None) -> torch.Tensor:
     cb = _cond_arg(cond_bound, L.shape[0], A.device)
     wsb = lib.drp_factor_workspace_bytes(n, L.shape[0]) if (n >= 1024 and cb is not None) else 0
     ws = torch.empty(wsb, dtype=torch.uint8, device=A.device) if wsb else None
-    _rc(lib.drp_potrf_batched_f64(_p(L), n, L.shape[0], 1, _p(info), _p(cb), _p(ws), wsb, _stream()), "drp_potrf_batched_f64")
+    _rc(lib.drp_potrf_batched_f64(_p(L), n, L.shape[0], 1, _p(info), _p(cb), _p(ws), wsb, *_aux(A.device), _stream()),
+        "drp_potrf_batched_f64")
     if check:
         _info_done(info, "linalg.cholesky")
     return L.reshape(A.shape)
@@ -207,8 +238,8 @@ def potri(K: torch.Tensor, cond_bound=None) -> torch.Tensor:
     out = torch.empty_like(Kc)
     M = torch.empty(lib.drp_ou_workspace_elems(n, n, z), dtype=torch.float64, device=K.device)
     info = torch.empty(z, dtype=torch.int32, device=K.device)
-    _rc(lib.drp_potri_batched_f64(_p(Kc), n, z, _p(out), _p(M), _p(info), _p(_cond_arg(cond_bound, z, K.device)), _stream()),
-        "drp_potri_batched_f64")
+    _rc(lib.drp_potri_batched_f64(_p(Kc), n, z, _p(out), _p(M), _p(info), _p(_cond_arg(cond_bound, z, K.device)),
+                                  *_aux(K.device), _stream()), "drp_potri_batched_f64")
     _info_done(info, "potri")
     return out.reshape(K.shape)
 
@@ -236,7 +267,7 @@ class _OUPrior(torch.autograd.Function):
             gsum = torch.empty((z, 3), dtype=torch.float64, device=dev)
             part = torch.empty((z, n, 3), dtype=torch.float64, device=dev)
         _rc(lib.drp_ou_prior_f64(_p(Dv), ldd, n, _p(sf), _p(sn), _p(lam), _p(x), z, int(want), _p(logp), _p(alpha),
-                                 _p(gsum), _p(M), _p(part), _p(info), _stream()), "drp_ou_prior_f64")
+                                 _p(gsum), _p(M), _p(part), _p(info), *_aux(dev), _stream()), "drp_ou_prior_f64")
         _info_done(info, "linalg.cholesky")
         if want:
             ctx.save_for_backward(sf, sn, lam, alpha, gsum)
@@ -274,7 +305,7 @@ def in_elbo_scope() -> bool:
 class PriorFactor:
     """Phase 1 of the two-phase OU prior: the factored workspace of `K(sigma_f, sigma_n, lambd)` (L and -K^-1), enqueued on
     `stream`.  `key` are the objects it was derived from: a consumer presents the same ones (`matches`) or does not get it."""
-    __slots__ = ("D", "ldd", "key", "M", "info", "stream", "n", "z", "used")
+    __slots__ = ("D", "ldd", "key", "M", "info", "stream", "n", "z", "used", "inputs")
 
     def matches(self, D, key) -> bool:
         Dv, ldd = _matrix_view(D, "patristic_matrix")
@@ -293,13 +324,19 @@ def ou_prior_factor(patristic: torch.Tensor, sigma_f, sigma_n, lambd, key=(), st
     f.n, f.z = Dv.shape[0], sf.shape[0]
     cur = torch.cuda.current_stream()
     f.stream = cur if stream is None else stream
+    f.inputs = (sf, sn, lam)
     if f.stream != cur:
         f.stream.wait_stream(cur)
+        # these temporaries were allocated on the CURRENT stream and are read by kernels on f.stream: without this the caching
+        # allocator may hand their memory to the next allocation of the current stream as soon as the Python references die,
+        # i.e. while (in a replayed CUDA graph: possibly long before) the other stream's kernels read them
+        for t in (sf, sn, lam):
+            t.record_stream(f.stream)
     with torch.cuda.stream(f.stream):
         f.M = torch.empty(lib.drp_ou_workspace_elems(f.n, f.n, f.z), dtype=torch.float64, device=sf.device)
         f.info = torch.empty(f.z, dtype=torch.int32, device=sf.device)
-        _rc(lib.drp_ou_prior_factor_f64(_p(Dv), ldd, f.n, _p(sf), _p(sn), _p(lam), f.z, _p(f.M), _p(f.info), _stream()),
-            "drp_ou_prior_factor_f64")
+        _rc(lib.drp_ou_prior_factor_f64(_p(Dv), ldd, f.n, _p(sf), _p(sn), _p(lam), f.z, _p(f.M), _p(f.info), *_aux(sf.device),
+                                        _stream()), "drp_ou_prior_factor_f64")
     return f
 
 
@@ -358,8 +395,8 @@ class _MVNLogProb(torch.autograd.Function):
         info = torch.empty(z, dtype=torch.int32, device=dev)
         M = torch.empty(lib.drp_ou_workspace_elems(n, n if want else 0, z), dtype=torch.float64, device=dev)
         alpha = torch.empty((z, n), dtype=torch.float64, device=dev) if want else None
-        _rc(lib.drp_mvn_logprob_f64(_p(K), _p(x), n, z, int(want), _p(logp), _p(alpha), _p(M), _p(info), None, _stream()),
-            "drp_mvn_logprob_f64")
+        _rc(lib.drp_mvn_logprob_f64(_p(K), _p(x), n, z, int(want), _p(logp), _p(alpha), _p(M), _p(info), None, *_aux(dev),
+                                    _stream()), "drp_mvn_logprob_f64")
         _info_done(info, "linalg.cholesky")
         if want:
             ctx.save_for_backward(alpha, M)
@@ -403,7 +440,7 @@ def ou_conditional(patristic_full: torch.Tensor, leaf_pos: torch.Tensor, interna
     info = torch.empty(z, dtype=torch.int32, device=dev)
     M = torch.empty(lib.drp_ou_workspace_elems(n, ni, z), dtype=torch.float64, device=dev)
     _rc(lib.drp_ou_conditional_f64(_p(Dv), ldd, _p(idx), n, ni, _p(sf), _p(sn), _p(lam), _p(x), z, float(jitter), _p(mean),
-                                   _p(cov), _p(M), _p(info), _stream()), "drp_ou_conditional_f64")
+                                   _p(cov), _p(M), _p(info), *_aux(dev), _stream()), "drp_ou_conditional_f64")
     _info_done(info, "linalg.inv")
     return mean, cov
 
@@ -792,6 +829,21 @@ def gru_module_forward(rnn: torch.nn.GRU, x: torch.Tensor, h0: torch.Tensor):
 # ------------------------------------------------------------------------------------------------------------------
 # test hook: one trailing update of the blocked factorisation (fp64 mma.sync kernel or int8 tcgen05 kernel)
 # ------------------------------------------------------------------------------------------------------------------
+def syrk_update_split(M: torch.Tensor, k0: int, K: int, c1: int, R: int, col_mid: int, col_limit: int, slices: int) -> bool:
+    """The same update as `syrk_update` in the two column-range parts the factorisation's look-ahead uses: columns
+    [c1, col_mid) with slicing, then [col_mid, col_limit) from the same slices with the second work-unit counter."""
+    _req(M, "M")
+    z, rows, ld = M.shape
+    wsb = lib.drp_factor_workspace_bytes(rows, z)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=M.device)
+    for lo, hi, do_slice, cidx in ((c1, col_mid, 1, 0), (col_mid, col_limit, 0, 1)):
+        rc = lib.drp_syrk_update_range_f64(_p(M), ld, rows * ld, z, k0, K, c1, R, lo, hi, slices, _p(ws), wsb, do_slice, cidx, _stream())
+        if rc == 1:
+            return False
+        _rc(rc, "drp_syrk_update_range_f64")
+    return True
+
+
 def syrk_update(M: torch.Tensor, k0: int, K: int, c1: int, R: int, col_limit: int, slices: int = 0) -> bool:
     """In place on `M [z, rows, ld]`: `M[r][c] -= sum_{k0<=k<k0+K} M[r][k] M[c][k]` for `c1 <= c <= r < R`, `c < col_limit`.
     `slices = 0` runs the fp64 mma.sync kernel, `4..7` the split-integer tcgen05 kernel.  Returns False when the tcgen05

@@ -252,6 +252,8 @@ class OUProcessPrior(td.Distribution, TorchDistributionMixin):
         if f.stream == cur:
             return self._log_prob_here(value, f)
         f.stream.wait_stream(cur)                     # the value (and whatever else the caller produced) is ready
+        for t in (value, self.sigma_f, self.sigma_n, self.lambd):
+            t.record_stream(f.stream)
         with torch.cuda.stream(f.stream):
             lp = self._log_prob_here(value, f)
         cur.wait_stream(f.stream)
@@ -266,6 +268,8 @@ class OUProcessPrior(td.Distribution, TorchDistributionMixin):
             return None                      # small trees: the prior is a few short kernels, forking costs more than it hides
         side = ops.side_stream(value.device)
         side.wait_stream(torch.cuda.current_stream())
+        for t in (value, self.sigma_f, self.sigma_n, self.lambd):      # allocated on this stream, read on the side stream
+            t.record_stream(side)
         with torch.cuda.stream(side):
             lp = self.log_prob(value).sum()           # a factor started from the guide lives on this same stream
             if scale != 1.0:

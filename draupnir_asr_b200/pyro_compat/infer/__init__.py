@@ -1,6 +1,8 @@
 """`pyro.infer` subset: `Trace_ELBO` and `SVI` (S/main.py:1021,1059; S/train.py:75)."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import poutine
@@ -71,6 +73,8 @@ class Trace_ELBO:
             grads = torch.autograd.grad([r for r, _ in keep], params, [g for _, g in keep], allow_unused=True)
             for p, g in zip(params, grads):
                 if g is not None:
+                    if not g.is_contiguous():      # e.g. the gradient of a transposed view: `.grad` has the parameter's layout
+                        g = g.contiguous()
                     p.grad = g if p.grad is None else p.grad + g
         for site in pending:
             site["log_prob_sum"] = site["log_prob_async"].join()
@@ -120,7 +124,6 @@ class SVI:
     """
 
     def __init__(self, model, guide, optim, loss, shard=None, cuda_graph=None, graph_warmup: int = 2, **kwargs):
-        import os
         self.model, self.guide, self.optim, self.loss = model, guide, optim, loss
         self.shard = shard     # zshard.ShardContext: local losses/gradients are summed over the ranks before the update
         self.cuda_graph = (os.environ.get("DRP_CUDA_GRAPH", "1") != "0") if cuda_graph is None else bool(cuda_graph)
@@ -187,8 +190,14 @@ class SVI:
         self.loss.last_traces = None       # the previous step's autograd graph is not needed any more
         rng_state = torch.cuda.get_rng_state(device)
         token = ops.begin_deferred()
+        # The capture stream has HIGH priority and the kernel nodes inherit it: the step's main chain (the recurrences, one CTA
+        # per SM for milliseconds) gets SMs ahead of the prior's chain on the (default-priority) side stream whenever both have
+        # a kernel pending.  The other order starves the recurrences behind the persistent tcgen05 update kernels: 26-33 ms per
+        # 2,000-leaf step instead of 22.4 (profiles/r02/bench_graph_v1_c4.json).
+        prio = int(os.environ.get("DRP_GRAPH_PRIORITY", "-2"))
+        stream = torch.cuda.Stream(device=device, priority=prio) if prio != 0 else None
         try:
-            with torch.cuda.graph(cs.graph):
+            with torch.cuda.graph(cs.graph, stream=stream):
                 loss, flag, params = self._evaluate(args, {})
                 zero = torch.zeros((), dtype=torch.float64, device=device)
                 out = torch.stack((loss.detach().reshape(()).to(torch.float64), zero if flag is None else flag.to(torch.float64)))

@@ -74,12 +74,21 @@ int drp_ou_cov_bwd_f64(const double* D, int64_t ldd, int n, const double* lam, i
  * hyper-parameters themselves: (nodes * sf^2 + sn^2) / sn^2.                                                        */
 int64_t drp_factor_workspace_bytes(int rows, int z);
 double drp_ozaki_cond_limit_f64(void);
+/* Look-ahead (every entry point that factorises takes the same three arguments): aux_stream, ev_fork, ev_join — a second
+ * cudaStream_t and two cudaEvent_t of the caller's (the library creates none), or NULL.  With them the update that leaves
+ * an outer panel is split by columns: the next panel's columns first, on `stream`; the rest on aux_stream, concurrently with
+ * the next panel's latency-bound factorisation chain.  aux_stream is joined back into `stream` before the call returns
+ * (stream-wise), so the caller sees one stream; the construct is CUDA-graph capturable.  DRP_LOOKAHEAD=0 disables.  */
 int drp_potrf_batched_f64(double* A, int n, int z, int zero_upper, int32_t* info, const double* cond_bound, void* ws,
-                          int64_t ws_bytes, void* stream);
+                          int64_t ws_bytes, void* aux_stream, void* ev_fork, void* ev_join, void* stream);
 /* Test hook: ONE trailing update C[r][c] -= sum_{k0 <= k < k0+K} P[r][k] P[c][k], rows [c1,R), cols [c1,min(R,col_limit)),
  * c <= r; slices = 0 -> fp64 mma.sync kernel, 4..7 -> int8 tcgen05 kernel.  Returns 1 if tcgen05 rejects the shape.  */
 int drp_syrk_update_f64(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_limit, int slices,
                         void* ws, int64_t ws_bytes, void* stream);
+/* Test hook: only the columns [col_lo, col_hi) of that update (what the look-ahead splits an update into); do_slice = 0
+ * re-uses the slices made by the preceding call for the same panel, counter_idx (0/1) picks the work-unit counter.     */
+int drp_syrk_update_range_f64(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_lo, int col_hi,
+                              int slices, void* ws, int64_t ws_bytes, int do_slice, int counter_idx, void* stream);
 
 /* ---- K3+K4+K5  gp_prior's latent_z site, fused: S/models.py:100-118 -------------------------------------------- */
 int64_t drp_ou_workspace_ld(int n, int n2);
@@ -88,14 +97,14 @@ int64_t drp_ou_workspace_elems(int n, int n2, int z);
  * (as drp_ou_cov_bwd_f64 with G = dlogp/dK).  M: drp_ou_workspace_elems(n, want_grad ? n : 0, z) doubles.          */
 int drp_ou_prior_f64(const double* D, int64_t ldd, int n, const double* sf, const double* sn, const double* lam,
                      const double* x, int z, int want_grad, double* logp, double* alpha, double* gsum, double* M,
-                     double* part, int32_t* info, void* stream);
+                     double* part, int32_t* info, void* aux_stream, void* ev_fork, void* ev_join, void* stream);
 
 /* The same in two phases (want_grad = 1 layout, M of drp_ou_workspace_elems(n, n, z) doubles): the factorisation needs
  * only the hyper-parameters (S/models.py:90-92,101-105) and may be enqueued before the latent vectors exist (they come
  * out of the guide's encoder, S/guides.py:116-120); the second call needs x (S/models.py:118) and costs one symmetric
  * matrix-vector product per latent dimension.  ypart: drp_ou_prior_apply_workspace_elems(n, z) doubles.             */
 int drp_ou_prior_factor_f64(const double* D, int64_t ldd, int n, const double* sf, const double* sn, const double* lam,
-                            int z, double* M, int32_t* info, void* stream);
+                            int z, double* M, int32_t* info, void* aux_stream, void* ev_fork, void* ev_join, void* stream);
 int64_t drp_ou_prior_apply_workspace_elems(int n, int z);
 int drp_ou_prior_apply_f64(const double* D, int64_t ldd, int n, const double* lam, const double* x, int z, double* M,
                            double* logp, double* alpha, double* gsum, double* part, double* ypart, void* stream);
@@ -103,16 +112,17 @@ int drp_ou_prior_apply_f64(const double* D, int64_t ldd, int n, const double* la
 /* ---- K4/K5  MultivariateNormal(0, K).log_prob(x) for an explicit covariance batch ------------------------------ */
 /* cond_bound: as for drp_potrf_batched_f64 (NULL = fp64 updates only).                                               */
 int drp_mvn_logprob_f64(const double* K, const double* x, int n, int z, int want_grad, double* logp, double* alpha,
-                        double* M, int32_t* info, const double* cond_bound, void* stream);
+                        double* M, int32_t* info, const double* cond_bound, void* aux_stream, void* ev_fork, void* ev_join,
+                        void* stream);
 int drp_mvn_grad_cov_f64(const double* M, int n, int z, const double* gscale, double* G, void* stream);
 int drp_potri_batched_f64(const double* K, int n, int z, double* Kinv, double* M, int32_t* info, const double* cond_bound,
-                          void* stream);
+                          void* aux_stream, void* ev_fork, void* ev_join, void* stream);
 
 /* ---- K6  conditional_sampling / conditional_samplingMAP: S/models.py:149-242 ----------------------------------- */
 /* idx = [leaf rows of D (n) | internal rows of D (ni)]; mean [z,ni]; cov [z,ni,ni] nullable (+jitter everywhere).  */
 int drp_ou_conditional_f64(const double* D, int64_t ldd, const int32_t* idx, int n, int ni, const double* sf,
                            const double* sn, const double* lam, const double* x_leaf, int z, double jitter, double* mean,
-                           double* cov, double* M, int32_t* info, void* stream);
+                           double* cov, double* M, int32_t* info, void* aux_stream, void* ev_fork, void* ev_join, void* stream);
 
 /* ---- K9  nn.GRU (bidirectional, one layer, hidden 60) inside RNNDecoder_Tiling.forward / RNNEncoder.forward:
  *          S/models_utils.py:93-94 and :54 ----------------------------------------------------------------------- */

@@ -27,13 +27,13 @@ def test_header_symbols_are_exported_and_bound():
 def test_argument_validation_without_a_gpu():
     """Bad-argument paths return before any CUDA call, so they are checkable on a CPU-only box."""
     from draupnir_asr_b200._lib import lib
-    assert lib.drp_potrf_batched_f64(None, 4, 1, 0, None, None, None, 0, None) == -1
+    assert lib.drp_potrf_batched_f64(None, 4, 1, 0, None, None, None, 0, None, None, None, None) == -1
     assert lib.drp_syrk_update_f64(None, 8, 64, 1, 0, 128, 128, 512, 512, 6, None, 0, None) == -1
     assert lib.drp_ou_cov_fwd_f64(None, 4, 4, None, None, None, 1, None, None) == -1
     assert lib.drp_cat_loglik_fwd_f64(None, None, 1, 10, 21, None, None, None, None) == -1
     assert lib.drp_ou_workspace_ld(19, 19) == 40 and lib.drp_ou_workspace_ld(2000, 2000) == 4008
     assert lib.drp_ou_workspace_elems(19, 0, 30) == 30 * 20 * 24 + (lib.drp_factor_workspace_bytes(20, 30) + 7) // 8
-    assert lib.drp_factor_workspace_bytes(2000, 30) == 30 * 2176 * (12 * 128 + 8) + 2048 + 256
+    assert lib.drp_factor_workspace_bytes(2000, 30) == 2 * ((30 * 2176 * (12 * 128 + 8) + 2048 + 1023) // 1024 * 1024) + 256
     assert lib.drp_ozaki_cond_limit_f64() == 1e-5 * 2.0 ** 35
     assert lib.drp_timing_classes() == 18 and lib.drp_timing_class_name(8) == b"oz_syrk_kernel"
     assert lib.drp_gru_hidden_size() == 60

@@ -78,6 +78,21 @@ def test_tcgen05_update_vs_mma_sync_kernel(cuda):
     assert d < 1e-9, d
 
 
+@pytest.mark.parametrize("case", [(2, 1400, 1408, 0, 256, 256, 1400, 512, 1400), (2, 1300, 1304, 100, 128, 250, 1297, 506, 1000),
+                                  (1, 2100, 2104, 512, 256, 768, 2100, 1024, 2100)])
+@pytest.mark.parametrize("slices", [0, 6])
+def test_split_update_equals_whole(cuda, case, slices):
+    """The column-range form of the update (csrc/factor.cu look-ahead: the next panel's columns first, the rest from the
+    same slices) touches exactly the entries of the whole update and gives bit-identical values."""
+    from draupnir_asr_b200 import ops
+    z, rows, ld, k0, K, c1, R, col_mid, col_limit = case
+    M = torch.randn(z, rows, ld, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    A, B = M.to(cuda), M.to(cuda)
+    assert ops.syrk_update(A, k0, K, c1, R, col_limit, slices=slices)
+    assert ops.syrk_update_split(B, k0, K, c1, R, col_mid, col_limit, slices=slices)
+    assert torch.equal(A, B)
+
+
 def test_small_shapes_are_declined(cuda):
     from draupnir_asr_b200 import ops
     M = torch.randn(1, 300, 304, dtype=torch.float64, device=cuda)
