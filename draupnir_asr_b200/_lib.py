@@ -53,6 +53,7 @@ SIGNATURES = {
     "drp_gru_bwd_dir0_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "drp_gru_bwd_last_dir0_f64": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "drp_gru_input_sums_blocks": (_i32, [_i32]),
+    "drp_gru_input_sums_chunks": (_i32, [_i32, _i32]),
     "drp_gru_input_sums_f64": (_i32, [_p, _i32, _i32, _i32, _p, _p, _p]),
     "drp_gru_wgrad_dir0_f64": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),
     "drp_gru_wgrad_workspace_elems": (_i64, []),
@@ -60,6 +61,9 @@ SIGNATURES = {
     "drp_gram_workspace_elems": (_i64, [_i32, _i32]),
     "drp_gram_tn_f64": (_i32, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _i64, _p]),
     "drp_tall_gemm_f64": (_i32, [_p, _p, _p, _i64, _i32, _i32, _p, _p]),
+    "drp_site_logp_workspace_elems": (_i64, []),
+    "drp_site_logp_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p]),
+    "drp_site_logp_bwd_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p]),
     "drp_clipped_adam_max_tensors": (_i32, []),
     "drp_clipped_adam_f64": (_i32, [_p, _p, _p, _i32, _i32, _p, _f64, _f64, _f64, _f64, _f64, _f64, _p]),
     "drp_cat_loglik_partials": (_i64, [_i64]),

@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdraupnir_b200.so")
-SOURCES = ["api.cu", "factor.cu", "ozaki.cu", "ou.cu", "patristic.cu", "catlik.cu", "gru.cu", "adam.cu"]
+SOURCES = ["api.cu", "factor.cu", "ozaki.cu", "ou.cu", "patristic.cu", "catlik.cu", "gru.cu", "adam.cu", "sites.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 

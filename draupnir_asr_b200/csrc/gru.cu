@@ -1042,59 +1042,109 @@ DRP_API int drp_gru_bwd_last_dir0_f64(const double* dlast, const double* out, co
 // 2.9 GB tensor twice).  C even, C / 2 <= 256 threads; the caller adds the nblk partial dV blocks.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int GS_ROWS = 16;                                      // rows per CTA at most
+constexpr int GS_LU = 4;                                         // positions per iteration when a CTA has few rows
+// grid (row blocks, position chunks).  With few rows per CTA (a leaf-sharded rank: 250 rows -> 2 per CTA) one position per
+// iteration leaves two loads in flight per thread and the kernel runs at DRAM latency (0.47 ms for 360 MB); the positions are
+// therefore also split over blockIdx.y (dU then comes out as per-chunk partials the caller adds) and walked four at a time.
 __global__ void __launch_bounds__(256) gru_input_sums_kernel(const double* __restrict__ dgi, int n, int L, int C, int rows_per_blk,
-                                                             double* __restrict__ dU, double* __restrict__ dVpart)
+                                                             int l_per_blk, double* __restrict__ dUpart, double* __restrict__ dVpart)
 {
     const int c2 = threadIdx.x;
     if (2 * c2 >= C) return;
     const int r0 = blockIdx.x * rows_per_blk;
     const int nr = min(rows_per_blk, n - r0);
+    const int l0 = blockIdx.y * l_per_blk, l1 = min(L, l0 + l_per_blk);
     double2 du[GS_ROWS];
 #pragma unroll
     for (int r = 0; r < GS_ROWS; ++r) du[r] = make_double2(0.0, 0.0);
     const double2* base = reinterpret_cast<const double2*>(dgi) + (int64_t)r0 * L * (C / 2) + c2;
     double2* dv = reinterpret_cast<double2*>(dVpart) + (int64_t)blockIdx.x * L * (C / 2) + c2;
-    for (int l = 0; l < L; ++l) {
-        double2 v[GS_ROWS];
+    if (nr <= GS_ROWS / GS_LU) {
+        constexpr int RR = GS_ROWS / GS_LU;
+        for (int l = l0; l < l1; l += GS_LU) {
+            double2 v[GS_LU][RR];
 #pragma unroll
-        for (int r = 0; r < GS_ROWS; ++r)
-            v[r] = r < nr ? __ldcs(base + ((int64_t)r * L + l) * (C / 2)) : make_double2(0.0, 0.0);
-        double2 s = make_double2(0.0, 0.0);
+            for (int u = 0; u < GS_LU; ++u)
 #pragma unroll
-        for (int r = 0; r < GS_ROWS; ++r) {
-            du[r].x += v[r].x, du[r].y += v[r].y;
-            s.x += v[r].x, s.y += v[r].y;
+                for (int r = 0; r < RR; ++r)
+                    v[u][r] = (r < nr && l + u < l1) ? __ldcs(base + ((int64_t)r * L + l + u) * (C / 2)) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < GS_LU; ++u) {
+                double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int r = 0; r < RR; ++r) {
+                    du[r].x += v[u][r].x, du[r].y += v[u][r].y;
+                    s.x += v[u][r].x, s.y += v[u][r].y;
+                }
+                if (l + u < l1) dv[(int64_t)(l + u) * (C / 2)] = s;
+            }
         }
-        dv[(int64_t)l * (C / 2)] = s;
+    } else {
+        for (int l = l0; l < l1; ++l) {
+            double2 v[GS_ROWS];
+#pragma unroll
+            for (int r = 0; r < GS_ROWS; ++r)
+                v[r] = r < nr ? __ldcs(base + ((int64_t)r * L + l) * (C / 2)) : make_double2(0.0, 0.0);
+            double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int r = 0; r < GS_ROWS; ++r) {
+                du[r].x += v[r].x, du[r].y += v[r].y;
+                s.x += v[r].x, s.y += v[r].y;
+            }
+            dv[(int64_t)l * (C / 2)] = s;
+        }
     }
+    double2* duo = reinterpret_cast<double2*>(dUpart) + (int64_t)blockIdx.y * n * (C / 2);
 #pragma unroll
     for (int r = 0; r < GS_ROWS; ++r)
-        if (r < nr) reinterpret_cast<double2*>(dU)[(int64_t)(r0 + r) * (C / 2) + c2] = du[r];
+        if (r < nr) duo[(int64_t)(r0 + r) * (C / 2) + c2] = du[r];
+}
+
+static int gs_sm_count()
+{
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    return n_sm;
 }
 
 // Number of row blocks (= leading dimension of dVpart) drp_gru_input_sums_f64 uses for n rows.
 DRP_API int drp_gru_input_sums_blocks(int n)
 {
     if (n <= 0) return 0;
-    int dev = 0, n_sm = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int n_sm = gs_sm_count();
     int rows = (n + n_sm - 1) / n_sm;
     if (rows > GS_ROWS) rows = GS_ROWS;
     return (n + rows - 1) / rows;
 }
 
-DRP_API int drp_gru_input_sums_f64(const double* dgi, int n, int L, int C, double* dU, double* dVpart, void* stream)
+// Number of position chunks (= leading dimension of dUpart): enough CTAs for two per SM, at least 32 positions each.
+DRP_API int drp_gru_input_sums_chunks(int n, int L)
+{
+    if (n <= 0 || L <= 0) return 0;
+    const int nblk = drp_gru_input_sums_blocks(n);
+    int want = (2 * gs_sm_count() + nblk - 1) / nblk;
+    const int most = (L + 31) / 32;
+    if (want > most) want = most;
+    if (want > 16) want = 16;
+    return want < 1 ? 1 : want;
+}
+
+// dUpart [drp_gru_input_sums_chunks(n, L), n, C] (the caller adds the chunks), dVpart [drp_gru_input_sums_blocks(n), L, C].
+DRP_API int drp_gru_input_sums_f64(const double* dgi, int n, int L, int C, double* dUpart, double* dVpart, void* stream)
 {
     if (!dgi) return -1;
     if (n <= 0 || L <= 0) return -2;
     if (C <= 0 || (C & 1) || C / 2 > 256) return -4;
-    if (!dU || !dVpart) return -5;
+    if (!dUpart || !dVpart) return -5;
     cudaStream_t st = (cudaStream_t)stream;
     const int nblk = drp_gru_input_sums_blocks(n);
     const int rows = (n + nblk - 1) / nblk;
+    const int nch = drp_gru_input_sums_chunks(n, L);
+    int lper = (L + nch - 1) / nch;
+    lper = (lper + GS_LU - 1) / GS_LU * GS_LU;
     DRP_LAUNCH(DRP_K_GRU_SUMS, (double)n * L * C * 8.0 + (double)nblk * L * C * 8.0, st);
-    gru_input_sums_kernel<<<nblk, 256, 0, st>>>(dgi, n, L, C, rows, dU, dVpart);
+    gru_input_sums_kernel<<<dim3(nblk, nch), 256, 0, st>>>(dgi, n, L, C, rows, lper, dUpart, dVpart);
     return drp_launch_status();
 }
 

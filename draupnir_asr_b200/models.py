@@ -82,6 +82,7 @@ class DRAUPNIRModelClass(nn.Module):
         self._cond_cache = None
         self._prefetched = None
         self._hyper_sites = ()
+        self._before_prior = None  # hook: called on the stream that is about to read the patristic matrix (host-fed steps)
         self.shard = None          # zshard.ShardContext when the run is spread over several GPUs
         self.map_consumes_rng = True   # conditional_samplingMAP advances the generator like the reference (S/models.py:239)
         for name in ("blosum_weighted", "dataset_train_blosum", "internal_nodes", "leaves_nodes", "aa_frequencies",
@@ -144,11 +145,14 @@ class DRAUPNIRModelClass(nn.Module):
                 return
             sf, sn, lam = sf[lo:hi], sn[lo:hi], lam[lo:hi]
         self._prefetched = ops.ou_prior_factor(patristic_matrix_sorted[1:, 1:], sf, sn, lam, key=(sigma_f, sigma_n, lambd),
-                                               stream=ops.side_stream(patristic_matrix_sorted.device))
+                                               stream=ops.side_stream(patristic_matrix_sorted.device),
+                                               before_launch=self._before_prior)
 
     def gp_prior(self, patristic_matrix_sorted):
         """Ornstein-Uhlenbeck process prior over the latent space (S/models.py:85-121).  Returns `[n, z]`."""
         alpha, sigma_f, sigma_n, lambd = self._hyper_priors(1e-6)
+        if self._before_prior is not None:
+            self._before_prior()
         patristic_matrix = patristic_matrix_sorted[1:, 1:]
         n_expected = self.n_all if self.leaves_testing else self.n_leaves
         assert patristic_matrix.shape == (n_expected, n_expected), \

@@ -313,7 +313,7 @@ class PriorFactor:
                 and len(key) == len(self.key) and all(a is b for a, b in zip(key, self.key)))
 
 
-def ou_prior_factor(patristic: torch.Tensor, sigma_f, sigma_n, lambd, key=(), stream=None) -> PriorFactor:
+def ou_prior_factor(patristic: torch.Tensor, sigma_f, sigma_n, lambd, key=(), stream=None, before_launch=None) -> PriorFactor:
     """Assemble and factor the OU covariances of all latent dimensions (everything of the prior that costs time) before the
     latent vectors exist; `ou_prior_logp(..., factor=...)` completes the log-density and its gradients.  Runs on `stream`
     (default: the current one) after that stream has waited for the current one."""
@@ -333,6 +333,8 @@ def ou_prior_factor(patristic: torch.Tensor, sigma_f, sigma_n, lambd, key=(), st
         for t in (sf, sn, lam):
             t.record_stream(f.stream)
     with torch.cuda.stream(f.stream):
+        if before_launch is not None:      # e.g. a host-fed step: THIS stream (not the caller's) waits for the matrix to arrive
+            before_launch()
         f.M = torch.empty(lib.drp_ou_workspace_elems(f.n, f.n, f.z), dtype=torch.float64, device=sf.device)
         f.info = torch.empty(f.z, dtype=torch.int32, device=sf.device)
         _rc(lib.drp_ou_prior_factor_f64(_p(Dv), ldd, f.n, _p(sf), _p(sn), _p(lam), f.z, _p(f.M), _p(f.info), *_aux(sf.device),
@@ -487,6 +489,59 @@ def cat_loglik(scores: torch.Tensor, obs: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# the small sample sites: summed HalfNormal / Normal log-densities, one launch each way
+# ------------------------------------------------------------------------------------------------------------------
+def _strides2(t: torch.Tensor):
+    if t.dim() == 0:
+        return 0, 0
+    if t.dim() == 1:
+        return 0, t.stride(0)
+    return t.stride(0), t.stride(1)
+
+
+class _SiteLogP(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, value, loc, scale, mode):
+        rows, cols = (1, max(value.numel(), 1)) if value.dim() < 2 else tuple(value.shape)
+        st = (ctypes.c_int64 * 6)(*_strides2(value), *(_strides2(loc) if loc is not None else (0, 0)), *_strides2(scale))
+        out = torch.empty((), dtype=torch.float64, device=value.device)
+        part = torch.empty(lib.drp_site_logp_workspace_elems(), dtype=torch.float64, device=value.device)
+        _rc(lib.drp_site_logp_f64(_p(value), _p(loc), _p(scale), st, rows, cols, mode, _p(out), _p(part), _stream()),
+            "drp_site_logp_f64")
+        ctx.save_for_backward(value, loc, scale)
+        ctx.geom = (rows, cols, mode, st)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        value, loc, scale = ctx.saved_tensors
+        rows, cols, mode, st = ctx.geom
+        need_v, need_m, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and loc is not None, ctx.needs_input_grad[2]
+        mk = lambda need: torch.empty(value.shape, dtype=torch.float64, device=value.device) if need else None
+        dv, dm, ds = mk(need_v), mk(need_m), mk(need_s)
+        g = g.contiguous()
+        _rc(lib.drp_site_logp_bwd_f64(_p(value), _p(loc), _p(scale), st, rows, cols, mode, _p(g), _p(dv), _p(dm), _p(ds), _stream()),
+            "drp_site_logp_bwd_f64")
+        return dv, dm, ds, None
+
+
+def site_logp_sum(value: torch.Tensor, loc: Optional[torch.Tensor], scale: torch.Tensor) -> torch.Tensor:
+    """Scalar `HalfNormal(scale).log_prob(value).sum()` (loc None) or `Normal(loc, scale).log_prob(value).sum()` for CUDA fp64
+    tensors of at most two dimensions; `loc` / `scale` broadcast against `value` (expanded scalars and transposed views are
+    read in place).  S/models.py:89-92, S/guides.py:118-121."""
+    _req(value, "value"), _req(scale, "scale")
+    # torch's broadcasting, exactly: the variational guide's [k,1]-shaped values meet [k]-shaped scales in the model and the
+    # reference's log_prob is the [k,k] outer broadcast of the two (S/guides.py:33-36 vs S/models.py:89-92) — so is this one
+    if loc is None:
+        value, scale = torch.broadcast_tensors(value, scale)
+    else:
+        value, loc, scale = torch.broadcast_tensors(value, _req(loc, "loc"), scale)
+    if value.dim() > 2:
+        raise RuntimeError("site_logp_sum: at most two dimensions after broadcasting")
+    return _SiteLogP.apply(value, loc, scale, 0 if loc is None else 1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # K1  patristic / cladistic / LCA
 # ------------------------------------------------------------------------------------------------------------------
 def tree_distances(parent: torch.Tensor, branch: torch.Tensor, rows: Optional[torch.Tensor] = None,
@@ -611,11 +666,11 @@ class _GRUBidirUV(torch.autograd.Function):
             # both sums in one pass over dgi (2.9 GB at 2,000 leaves x 500 sites)
             n, L = dgi.shape[0], dgi.shape[1]
             C = dgi.numel() // (n * L)
-            nblk = lib.drp_gru_input_sums_blocks(n)
-            dU = torch.empty((n, C), dtype=torch.float64, device=dgi.device)
+            nblk, nch = lib.drp_gru_input_sums_blocks(n), lib.drp_gru_input_sums_chunks(n, L)
+            dUp = torch.empty((nch, n, C), dtype=torch.float64, device=dgi.device)
             dVp = torch.empty((nblk, L, C), dtype=torch.float64, device=dgi.device)
-            _rc(lib.drp_gru_input_sums_f64(_p(dgi), n, L, C, _p(dU), _p(dVp), _stream()), "drp_gru_input_sums_f64")
-            dU = dU.reshape(ctx.shapes[0])
+            _rc(lib.drp_gru_input_sums_f64(_p(dgi), n, L, C, _p(dUp), _p(dVp), _stream()), "drp_gru_input_sums_f64")
+            dU = (dUp[0] if nch == 1 else dUp.sum(0)).reshape(ctx.shapes[0])
             dV = dVp.sum(0).reshape(ctx.shapes[1])
         return dU, dV, dwhh, dbhh, dh0
 

@@ -97,44 +97,55 @@ class Run(SimpleNamespace):
     def step_from_host(self, host) -> float:
         """H2D of the step inputs (pinned, asynchronous) -> svi.step -> loss back to the host as a float.
 
-        The copies run on a copy stream in the order the step consumes them, and every consumer waits for its own input
-        only (stream-waits, no host synchronisation): the patristic matrix first — the guide hands it to the prior's
-        factorisation before anything else happens; the BLOSUM-encoded data set is awaited in front of the encoder; the
-        data set itself when the likelihood is scored, after both networks ran."""
+        The copies run on a copy stream and every consumer waits for its own input only (event waits on the stream that reads
+        it, no host synchronisation): the patristic matrix is awaited by the stream that assembles the covariances (the
+        prior's side stream when the guide starts the factorisation, so the main stream never waits for it), the
+        BLOSUM-encoded data set in front of the encoder, the data set itself when the likelihood is scored, after both
+        networks ran.  Of the first two the SMALLER goes first: on one GPU that is the matrix (the factorisation then has
+        the machine to itself while the 168 MB BLOSUM tensor crosses PCIe), on a leaf-sharded rank it is the rank's slice of
+        the BLOSUM tensor (the recurrences are the critical path there and must not queue behind 32 MB of matrix)."""
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._events = [torch.cuda.Event() for _ in range(3)]      # 0 patristic, 1 blosum, 2 data set
-            self._pending = []
+            self._events = {k: torch.cuda.Event() for k in ("patristic", "blosum", "dataset")}
+            self._armed = False
             real_model, real_guide = self.svi.model, self.svi.guide
 
-            def wait_for(upto):
-                while self._pending and self._pending[0][0] <= upto:
-                    torch.cuda.current_stream().wait_event(self._pending.pop(0)[1])
+            def wait_for(*keys):
+                if self._armed:
+                    for k in keys:
+                        torch.cuda.current_stream().wait_event(self._events[k])
 
             def guide_after_inputs(*a, **k):
-                wait_for(self._guide_level)
+                wait_for(*self._guide_waits)
                 return real_guide(*a, **k)
 
             def model_after_inputs(*a, **k):
-                wait_for(self._model_level)
+                wait_for(*self._model_waits)
                 return real_model(*a, **k)
 
             self._wait_for = wait_for
             self.svi.model, self.svi.guide = model_after_inputs, guide_after_inputs
-            hooked_guide = hasattr(self.guide, "_encode")              # DRAUPNIRGUIDES: waits for the BLOSUM copy itself
-            if hooked_guide:
-                self.guide.__dict__["_before_encode"] = lambda: wait_for(1)
-            self._guide_level = 0 if hooked_guide else 1
-            if hasattr(self.svi.loss, "pre_score_hook"):
-                self.svi.loss.pre_score_hook = lambda: wait_for(2)
-                self._model_level = 1
+            if hasattr(self.guide, "_encode"):                         # DRAUPNIRGUIDES: waits for the BLOSUM copy itself
+                self.guide.__dict__["_before_encode"] = lambda: wait_for("blosum")
+                self._guide_waits = ()
+            elif hasattr(self.guide, "prototype_trace"):               # auto-guides read no data
+                self._guide_waits = ()
+            else:
+                self._guide_waits = ("patristic", "blosum")
+            hooked_model = hasattr(self.Draupnir, "_before_prior") and hasattr(self.svi.loss, "pre_score_hook")
+            if hooked_model:
+                self.Draupnir._before_prior = lambda: wait_for("patristic")
+                self.svi.loss.pre_score_hook = lambda: wait_for("patristic", "blosum", "dataset")   # joins the copy stream
+                self._model_waits = ()
             else:                                   # an ELBO without the hook (real Pyro): the model waits for everything
-                self._model_level = 2
+                self._model_waits = ("patristic", "blosum", "dataset")
             self._host_prologues = {}
         key = tuple(id(v) for v in host.values())
         prologue = self._host_prologues.get(key)
         if prologue is None:
             lo, hi = self._leaf_rows()
+            blosum_bytes = (hi - lo) * (host["blosum"].numel() // host["blosum"].shape[0]) * 8 if "blosum" in host else 0
+            matrix_first = "blosum" not in host or host["patristic"].numel() * 8 <= blosum_bytes
 
             def prologue():
                 # runs at the start of the step — eagerly, or ONCE inside the CUDA-graph capture of the step, where the
@@ -142,14 +153,20 @@ class Run(SimpleNamespace):
                 main, cs = torch.cuda.current_stream(), self._copy_stream
                 cs.wait_stream(main)               # the previous step has finished reading the staging buffers
                 with torch.cuda.stream(cs):
-                    self._staging["patristic"].copy_(host["patristic"], non_blocking=True)
-                    self._events[0].record(cs)
-                    if "blosum" in host:
-                        self._staging["blosum"][lo:hi].copy_(host["blosum"][lo:hi], non_blocking=True)
-                    self._events[1].record(cs)
+                    def matrix():
+                        self._staging["patristic"].copy_(host["patristic"], non_blocking=True)
+                        self._events["patristic"].record(cs)
+
+                    def blosum():
+                        if "blosum" in host:
+                            self._staging["blosum"][lo:hi].copy_(host["blosum"][lo:hi], non_blocking=True)
+                        self._events["blosum"].record(cs)
+
+                    for fn in ((matrix, blosum) if matrix_first else (blosum, matrix)):
+                        fn()
                     self._staging["dataset"][lo:hi].copy_(host["dataset"][lo:hi], non_blocking=True)
-                    self._events[2].record(cs)
-                self._pending = [(k, e) for k, e in enumerate(self._events)]
+                    self._events["dataset"].record(cs)
+                self._armed = True
 
             self._host_prologues[key] = prologue
         st = self._staging
@@ -158,6 +175,7 @@ class Run(SimpleNamespace):
             loss = self.svi.step(st["dataset"], st["patristic"], None, st.get("blosum"), None, None)
         finally:
             self.svi.step_prologue = None
+            self._armed = False
         return loss
 
 

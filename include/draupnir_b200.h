@@ -153,10 +153,11 @@ int drp_gru_bwd_dir0_f64(const double* dout, const double* out, const double* ga
 int drp_gru_bwd_last_dir0_f64(const double* dlast, const double* out, const double* gates, const double* whh,
                               const double* h0, int n, int L, int H, double* dgi0, double* dh0, void* stream);
 /* Gradients of the decoder's broadcast input terms gi[i][l] = U[i] + V[l] (drp_gru_fwd_uv_f64) in one pass over
- * dgi [n,L,C]: dU [n,C] = sum over l; dVpart [drp_gru_input_sums_blocks(n), L, C] = per-row-block sums over i, which the
- * caller adds up.  C even, C <= 512.                                                                                  */
+ * dgi [n,L,C]: dUpart [drp_gru_input_sums_chunks(n, L), n, C] = sums over the positions of a chunk, dVpart
+ * [drp_gru_input_sums_blocks(n), L, C] = per-row-block sums over i; the caller adds the chunks / blocks up.  C even, C <= 512.                                                                                  */
 int drp_gru_input_sums_blocks(int n);
-int drp_gru_input_sums_f64(const double* dgi, int n, int L, int C, double* dU, double* dVpart, void* stream);
+int drp_gru_input_sums_chunks(int n, int L);
+int drp_gru_input_sums_f64(const double* dgi, int n, int L, int C, double* dUpart, double* dVpart, void* stream);
 int drp_gru_wgrad_dir0_f64(const double* dgi0, const double* gates, const double* out, const double* h0, int n, int L, int H,
                            double* dwhh, double* dbhh, double* ws, int64_t ws_elems, void* stream);
 /* dwhh [2,3H,H] = sum_p dgh[p]^T h_prev[p], dbhh [2,3H] = sum_p dgh[p] (autograd of nn.GRU's weight_hh / bias_hh);
@@ -185,6 +186,19 @@ int drp_cat_loglik_fwd_f64(const double* scores, const void* obs, int obs_is_f64
                            double* lse, double* part, void* stream);
 int drp_cat_loglik_bwd_f64(const double* scores, const void* obs, int obs_is_f64, const double* lse, const double* g,
                            int64_t rows, int A, double* dscores, void* stream);
+
+/* ---- the small sample sites, summed log-density in one launch each way:
+ *      dist.HalfNormal(scale).expand_by([k]).to_event(1) at "alpha", "sigma_f", "sigma_n", "lambd" (S/models.py:89-92) and the
+ *      guide's dist.Normal(z_loc.T, z_scale.T) at "latent_z" (S/guides.py:118-121).  mode 0: HalfNormal(scale) (loc unused),
+ *      mode 1: Normal(loc, scale).  Operands are logical [rows, cols] arrays read through strides[6] (HOST array, elements:
+ *      value row/col, loc row/col, scale row/col; 0 broadcasts, so expanded scalars and transposed views need no copy).
+ *      part: drp_site_logp_workspace_elems() doubles.  bwd: g = device scalar; dvalue / dloc / dscale dense [rows, cols],
+ *      each nullable.                                                                                                    */
+int64_t drp_site_logp_workspace_elems(void);
+int drp_site_logp_f64(const double* value, const double* loc, const double* scale, const int64_t* strides, int64_t rows,
+                      int64_t cols, int mode, double* out, double* part, void* stream);
+int drp_site_logp_bwd_f64(const double* value, const double* loc, const double* scale, const int64_t* strides, int64_t rows,
+                          int64_t cols, int mode, const double* g, double* dvalue, double* dloc, double* dscale, void* stream);
 
 /* ---- pyro.optim.ClippedAdam over all parameters of the step: S/main.py:1036-1041 (the update that ends svi.step,
  *      S/train.py:75).  lr <- lr * lrd; g = clamp(grad, +-clip) + weight_decay * p; Adam moments; p -= lr sqrt(1 - b2^t) /

@@ -6,4 +6,4 @@
 set -e
 cd "$(dirname "$0")/../draupnir_asr_b200/csrc"
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -DDRP_DEBUG_HOOKS -Xcompiler -fPIC,-fvisibility=hidden \
-     -shared -o ../../profiles/libdraupnir_b200_debug.so api.cu factor.cu ozaki.cu ou.cu patristic.cu catlik.cu gru.cu adam.cu -lcudart
+     -shared -o ../../profiles/libdraupnir_b200_debug.so api.cu factor.cu ozaki.cu ou.cu patristic.cu catlik.cu gru.cu adam.cu sites.cu -lcudart

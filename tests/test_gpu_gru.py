@@ -139,9 +139,10 @@ def test_gram_tn(cuda, K, M, N):
     assert float((cs.cpu() - cs_ref).abs().max() / cs_ref.abs().max().clamp_min(1e-30)) < 1e-12
 
 
-@pytest.mark.parametrize("n,L,C", [(1, 1, 360), (37, 5, 360), (300, 17, 360), (2500, 3, 24)])
+@pytest.mark.parametrize("n,L,C", [(1, 1, 360), (37, 5, 360), (300, 17, 360), (2500, 3, 24), (250, 500, 360), (9, 131, 360)])
 def test_input_sums_one_pass(cuda, n, L, C):
-    """drp_gru_input_sums_f64: dU = dgi.sum(1), dV = sum of the row-block partials = dgi.sum(0)."""
+    """drp_gru_input_sums_f64: dU = sum of the position-chunk partials = dgi.sum(1), dV = sum of the row-block partials =
+    dgi.sum(0); (250, 500) is a leaf-sharded rank's shape (two rows per CTA, positions split over the grid)."""
     from draupnir_asr_b200.ops import _p, _rc, _stream
     from draupnir_asr_b200._lib import lib
     g = torch.Generator().manual_seed(n + L)
@@ -149,10 +150,12 @@ def test_input_sums_one_pass(cuda, n, L, C):
     d = dgi.to(cuda)
     nblk = lib.drp_gru_input_sums_blocks(n)
     assert 1 <= nblk <= n
-    dU = torch.empty(n, C, dtype=torch.float64, device=cuda)
+    nch = lib.drp_gru_input_sums_chunks(n, L)
+    assert 1 <= nch <= 16 and (n > 100 or L < 64 or nch > 1)
+    dU = torch.full((nch, n, C), float("nan"), dtype=torch.float64, device=cuda)
     dVp = torch.full((nblk, L, C), float("nan"), dtype=torch.float64, device=cuda)
     _rc(lib.drp_gru_input_sums_f64(_p(d), n, L, C, _p(dU), _p(dVp), _stream()), "drp_gru_input_sums_f64")
-    assert torch.allclose(dU.cpu(), dgi.sum(1), rtol=1e-13, atol=1e-12)
+    assert torch.allclose(dU.sum(0).cpu(), dgi.sum(1), rtol=1e-13, atol=1e-12)
     assert torch.allclose(dVp.sum(0).cpu(), dgi.sum(0), rtol=1e-13, atol=1e-12)
 
 
