@@ -45,6 +45,19 @@ static_assert(PR == 2 * NB, "trsm staging assumes two rows per pass");
 // never read back nor stored.  (A fully unrolled thread-per-row variant was instruction-fetch bound, a column-at-a-time
 // variant paid two barriers per column.)
 // ---------------------------------------------------------------------------------------------------------------
+// 1 / sqrt(x) for x > 0: MUFU.RSQ64H seed + two Newton steps, branch-free (the library rsqrt carries a slow-path CALL in the
+// middle of the 64-step dependent chain of the panel factorisation).  Non-positive / non-finite pivots produce NaN or inf as
+// the library routine does; the caller flags them through `info` before the value is used.
+__device__ __forceinline__ double potf2_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double h = 0.5 * x;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y;
+}
+
 __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb,
                                                     int32_t* __restrict__ info)
 {
@@ -72,7 +85,7 @@ __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ Mb, int
                 const int c = 4 * cb + cc;
                 const double piv = __shfl_sync(mask, a[cc][cc], lane_d);
                 if (ty == 0 && !(piv > 0.0) && sbad == 0) sbad = c + 1;
-                const double rd = rsqrt(piv);
+                const double rd = potf2_rsqrt(piv);
                 double lv[4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
@@ -168,18 +181,24 @@ __global__ void __launch_bounds__(PR) trsm_kernel(double* __restrict__ Mb, int64
     double x[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) x[j] = X[tid * PLD + j];
+    // x_c = (x_c - sum_{p<c} x_p L[c][p]) / L[c][c]: the sum runs in FOUR independent accumulation chains (the solve is a
+    // pure dependent-FMA latency chain per thread at 8 resident warps per SM; two chains took 1.35 ms per 2,000-leaf step)
 #pragma unroll
     for (int c = 0; c < NB; ++c) {
         const double* lc = S + c * NB;
-        double a0 = x[c], a1 = 0.0;
+        double a0 = x[c], a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-        for (int p = 0; p + 1 < c; p += 2) {
-            const double2 l2 = *reinterpret_cast<const double2*>(lc + p);
-            a0 = fma(-x[p], l2.x, a0);
-            a1 = fma(-x[p + 1], l2.y, a1);
+        for (int p = 0; p + 3 < c; p += 4) {
+            const double2 l01 = *reinterpret_cast<const double2*>(lc + p);
+            const double2 l23 = *reinterpret_cast<const double2*>(lc + p + 2);
+            a0 = fma(-x[p], l01.x, a0);
+            a1 = fma(-x[p + 1], l01.y, a1);
+            a2 = fma(-x[p + 2], l23.x, a2);
+            a3 = fma(-x[p + 3], l23.y, a3);
         }
-        if (c & 1) a0 = fma(-x[c - 1], lc[c - 1], a0);
-        x[c] = (a0 + a1) * invd[c];
+#pragma unroll
+        for (int p = c & ~3; p < c; ++p) a0 = fma(-x[p], lc[p], a0);
+        x[c] = ((a0 + a1) + (a2 + a3)) * invd[c];
     }
 #pragma unroll
     for (int j = 0; j < NB; ++j) X[tid * PLD + j] = x[j];
@@ -365,7 +384,7 @@ static bool tensor_update_qualifies(int K, int c1, int R, int col_limit)
 {
     const int cmax = R < col_limit ? R : col_limit;
     const int KBN = K > 128 ? 2 : 1;
-    return K >= 32 && K <= 256 && drp_ozaki_slices() * KBN <= 12 && R - c1 >= 384 && cmax - c1 >= 64;
+    return K >= 32 && K <= 256 && drp_ozaki_slices() * KBN <= 12 && R - c1 >= 384 && cmax - c1 >= 256;
 }
 
 static int outer_block(int R_full, bool tensor_path)

@@ -634,6 +634,18 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzParams p
     if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_COLS);
 }
 
+// Narrowest update (columns) that takes the tensor path.  DRP_OZ_MIN_COLS overrides.
+static int oz_min_cols()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DRP_OZ_MIN_COLS");
+        v = e ? atoi(e) : 64;
+        if (v < 64) v = 64;
+    }
+    return v;
+}
+
 static bool oz_yield()
 {
     static int v = -1;
@@ -749,7 +761,7 @@ int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     const int below = R - c1, cl = cmax - col_lo;
     // qualification is decided on the WHOLE update (rows below c1, columns up to cmax), so that both parts of a split
     // update take the same path
-    if (below < 384 || cmax - c1 < 64) return 1;         // small updates: launch/slicing overhead dominates
+    if (below < 384 || cmax - c1 < oz_min_cols()) return 1;   // small updates: launch/slicing overhead dominates
     if (cl <= 0) return 0;
     OzParams p;
     p.M = M;
