@@ -8,7 +8,7 @@ enum DrpKernelClass {
     DRP_K_SYRK = 0,      // syrk_kernel / syrk_gated_kernel: trailing update, fp64 mma.sync          work = flops
     DRP_K_TRSM = 1,      // trsm_kernel: panel solve                                              work = flops
     DRP_K_POTF2 = 2,     // potf2_kernel: diagonal block                                          work = flops
-    DRP_K_ASSEMBLE = 3,  // ou_assemble_kernel / ou_cov_fwd_kernel / cov_assemble_kernel          work = bytes
+    DRP_K_ASSEMBLE = 3,  // ou_assemble_kernel / cov_assemble_kernel: augmented matrix assembly        work = bytes
     DRP_K_REDUCE = 4,    // small reductions / extractions (mvn_finish, alpha_extract, reduce3 ...) work = bytes
     DRP_K_CATLIK = 5,    // cat_fwd_kernel / cat_bwd_kernel: categorical log-likelihood           work = bytes
     DRP_K_PATRISTIC = 6, // tree_prepare_kernel + lca_patristic_kernel                            work = bytes
@@ -23,7 +23,8 @@ enum DrpKernelClass {
     DRP_K_GRU_SUMS = 15, // gru_input_sums_kernel: dU / dV of the decoder's broadcast input       work = bytes
     DRP_K_OU_GRAD = 16,  // ou_grad_kernel / ou_cov_bwd_kernel: hyper-parameter gradient sums     work = bytes
     DRP_K_SYMV = 17,     // ou_symv_tile_kernel: alpha = K^-1 x from the stored inverse           work = bytes
-    DRP_K_CLASSES = 18
+    DRP_K_OU_COV = 18,   // ou_cov_fwd_kernel: dense [z,n,n] OU covariance (OUKernel_Fast.forward)            work = bytes
+    DRP_K_CLASSES = 19
 };
 
 // Call right before / after a kernel launch of class `k` doing `work` algorithmic flops or bytes.

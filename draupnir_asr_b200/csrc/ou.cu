@@ -324,7 +324,7 @@ DRP_API int drp_ou_cov_fwd_f64(const double* D, int64_t ldd, int n, const double
     if (!K) return -8;
     dim3 g((n + 255) / 256, n);
     {
-        DRP_LAUNCH(DRP_K_ASSEMBLE, ((double)n * n * 8.0 * (z + 1)), st);
+        DRP_LAUNCH(DRP_K_OU_COV, ((double)n * n * 8.0 * (z + 1)), st);
         ou_cov_fwd_kernel<<<g, 256, 3 * z * sizeof(double), (cudaStream_t)stream>>>(D, ldd, n, sf, sn, lam, z, K);
     }
     return drp_launch_status();

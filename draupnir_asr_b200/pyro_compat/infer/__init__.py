@@ -103,7 +103,7 @@ def _recover_generator(device, rng_state):
 
 class _CapturedStep:
     """One `svi.step` recorded as a CUDA graph for one set of argument tensors."""
-    __slots__ = ("graph", "out_host", "infos", "params", "grads", "traces", "stream")
+    __slots__ = ("graph", "out_host", "infos", "params", "grads", "traces", "stream", "static_args")
 
 
 class SVI:
@@ -130,6 +130,7 @@ class SVI:
         self.graph_warmup = int(graph_warmup)
         self.step_prologue = None          # callable run at the start of every step (host-fed steps enqueue their copies there)
         self._graphs = {}                  # key -> _CapturedStep | number of eager steps so far | False (not capturable)
+        self._capture_failures = 0
         self.last_step_was_replay = False
 
     # ---------------------------------------------------------------------------------------------------------------
@@ -138,22 +139,30 @@ class SVI:
         self._graphs.clear()
 
     def _graph_key(self, args):
-        key, device = [], None
+        """(exact key, signature key, device) of a call, or Nones if it cannot be captured.  The exact key names the argument
+        STORAGE (a caller that passes the same tensors every step - `Run.step`, the host-fed staging buffers - replays with no
+        copy at all); the signature key names only shapes / strides / dtypes: a caller that brings a fresh tensor every epoch -
+        the reference's loop takes `dataset` from a DataLoader (S/train.py:73-75) - gets a graph captured on copies the SVI
+        object owns, into which each step's arguments are copied (device to device) before the replay."""
+        exact, sig, device = [], [], None
         for a in args:
             if a is None:
-                key.append(None)
+                exact.append(None)
+                sig.append(None)
             elif isinstance(a, torch.Tensor) and a.is_cuda:
-                key.append((a.data_ptr(), tuple(a.shape), tuple(a.stride()), a.dtype, a.device.index))
+                sig.append((tuple(a.shape), tuple(a.stride()), a.dtype, a.device.index))
+                exact.append((a.data_ptr(),) + sig[-1])
                 device = a.device
             else:
-                return None, None
+                return None, None, None
         if device is None or not torch.is_grad_enabled():
-            return None, None
+            return None, None, None
         if self.shard is not None:
             import torch.distributed as dist
             if dist.get_backend(self.shard.group) != "nccl":      # gloo moves CUDA tensors through the host: not capturable
-                return None, None
-        return (tuple(key), id(self.step_prologue)), device
+                return None, None, None
+        pro = id(self.step_prologue)
+        return (tuple(exact), pro), (tuple(sig), pro, "signature"), device
 
     def _evaluate(self, args, kwargs):
         """Prologue, ELBO and gradients, cross-rank reduction: everything of a step up to (not including) the optimiser.
@@ -207,6 +216,7 @@ class SVI:
             ops.end_deferred(token)
             _recover_generator(device, rng_state)
             raise
+        cs.static_args = args                  # the tensors the graph reads
         cs.params = params
         cs.grads = [p.grad for p in params]
         cs.traces = self.loss.last_traces
@@ -214,8 +224,12 @@ class SVI:
             p.grad = None
         return cs
 
-    def _replay(self, cs: "_CapturedStep") -> float:
+    def _replay(self, cs: "_CapturedStep", args=None) -> float:
         from ... import ops
+        if args is not None:
+            for a, st in zip(args, cs.static_args):
+                if a is not None and a is not st and (a.data_ptr() != st.data_ptr()):
+                    st.copy_(a, non_blocking=True)           # same signature, other storage: device-to-device, stream-ordered
         cs.graph.replay()
         torch.cuda.current_stream().synchronize()
         value, failed = float(cs.out_host[0]), float(cs.out_host[1])
@@ -232,28 +246,49 @@ class SVI:
         self.last_step_was_replay = True
         return value
 
+    def _try_capture(self, key, args, device):
+        try:
+            entry = self._graphs[key] = self._capture(args, device)
+        except Exception as e:        # noqa: BLE001 - whatever broke the capture, the eager path still works
+            import warnings
+            self._capture_failures += 1
+            # the usual cause is transient (somebody still holds an old autograd graph whose AccumulateGrad nodes are bound to
+            # the default stream): try again a few eager steps later, three times in all, before giving up for good
+            self._graphs[key] = False if self._capture_failures >= 3 else -8
+            torch.cuda.synchronize()
+            warnings.warn(f"svi.step could not be captured in a CUDA graph ({type(e).__name__}: {e}); "
+                          + ("continuing with eager steps" if self._capture_failures >= 3 else "eager steps for now, another attempt later"))
+            return None
+        return entry
+
     def step(self, *args, **kwargs) -> float:
         """One gradient step; returns the loss as a Python float (the only host<->device synchronisation)."""
         if self.cuda_graph and not kwargs:
-            key, device = self._graph_key(args)
+            key, sig, device = self._graph_key(args)
             if key is not None:
                 entry = self._graphs.get(key, 0)
                 if isinstance(entry, _CapturedStep):
                     return self._replay(entry)
-                if entry is not False:
-                    if entry < self.graph_warmup:
-                        self._graphs[key] = entry + 1
+                owned = self._graphs.get(sig, 0)
+                if isinstance(owned, _CapturedStep):             # same signature, other storage: copy in, replay
+                    return self._replay(owned, args)
+                if entry is not False and owned is not False:
+                    if entry >= self.graph_warmup:               # the same tensors for the third time: capture on them
+                        got = self._try_capture(key, args, device)
+                        if got is not None:
+                            return self._replay(got)
+                    elif entry == 0 and owned >= self.graph_warmup + 1:
+                        # the storage keeps changing under a constant signature: capture on copies this object owns
+                        own = tuple(None if a is None else a.clone() for a in args)
+                        got = self._try_capture(sig, own, device)
+                        if got is not None:
+                            return self._replay(got, args)
                     else:
-                        try:
-                            entry = self._graphs[key] = self._capture(args, device)
-                        except Exception as e:        # noqa: BLE001 - whatever broke the capture, the eager path still works
-                            import warnings
-                            self._graphs[key] = False
-                            torch.cuda.synchronize()
-                            warnings.warn(f"svi.step could not be captured in a CUDA graph ({type(e).__name__}: {e}); "
-                                          "continuing with eager steps")
-                        else:
-                            return self._replay(entry)
+                        if len(self._graphs) > 256:              # counters of storages that never came back
+                            self._graphs = {k: v for k, v in self._graphs.items() if not isinstance(v, int)}
+                        self._graphs[key] = entry + 1
+                        if entry == 0:
+                            self._graphs[sig] = owned + 1
         return self._eager_step(args, kwargs)
 
     def evaluate_loss(self, *args, **kwargs) -> float:

@@ -35,7 +35,7 @@ def test_argument_validation_without_a_gpu():
     assert lib.drp_ou_workspace_elems(19, 0, 30) == 30 * 20 * 24 + (lib.drp_factor_workspace_bytes(20, 30) + 7) // 8
     assert lib.drp_factor_workspace_bytes(2000, 30) == 2 * ((30 * 2176 * (12 * 128 + 8) + 2048 + 1023) // 1024 * 1024) + 256
     assert lib.drp_ozaki_cond_limit_f64() == 1e-5 * 2.0 ** 35
-    assert lib.drp_timing_classes() == 18 and lib.drp_timing_class_name(8) == b"oz_syrk_kernel"
+    assert lib.drp_timing_classes() == 19 and lib.drp_timing_class_name(8) == b"oz_syrk_kernel"
     assert lib.drp_gru_hidden_size() == 60
     assert lib.drp_gru_fwd_f64(None, None, None, None, 4, 4, 60, None, None, None) == -1
     assert lib.drp_cat_loglik_partials(257) == 2

@@ -229,6 +229,36 @@ def test_graph_replay_walks_the_eager_trajectory(cuda, guide, n, L):
     assert got2 == pytest.approx(want2, rel=1e-11)
 
 
+def test_graph_replay_with_fresh_argument_tensors(cuda):
+    """The reference's loop takes `dataset` from a DataLoader (S/train.py:73-75): a NEW tensor with the same shape every
+    epoch.  The captured step is keyed by the arguments' signature; other storage is copied into its static arguments, so the
+    trajectory equals the eager one — also when the data really changes."""
+    torch.manual_seed(0)
+    problem, run_e, _ = _pair(60, 40, "delta_map", cuda, cuda_graph=False)
+    torch.manual_seed(0)
+    _, run_g, _ = _pair(60, 40, "delta_map", cuda, cuda_graph=True)
+    base = run_e.step_args()
+    other = base[0].clone()
+    other[:, 2:, 0] = torch.roll(other[:, 2:, 0], 1, dims=0)            # a different alignment with the same shape
+    want, got = [], []
+    for k in range(6):
+        data = base[0].clone() if k != 4 else other.clone()            # fresh storage every step; new content at step 4
+        want.append(run_e.svi.step(data, *base[1:]))
+        got.append(run_g.svi.step(data.clone(), *run_g.step_args()[1:]))
+    assert got == pytest.approx(want, rel=1e-11) and abs(want[4] - want[3]) > 1e-3 * abs(want[3])
+    # keep every argument tensor alive so that no address is ever recycled: only the signature-keyed graph can serve these calls
+    keep = []
+    for k in range(8):
+        data = base[0].clone()
+        keep.append(data)
+        run_e.svi.step(base[0], *base[1:])
+        run_g.svi.step(data, *run_g.step_args()[1:])
+    assert run_g.svi.last_step_was_replay
+    assert any(isinstance(k, tuple) and k[-1] == "signature" and not isinstance(v, (int, bool)) for k, v in run_g.svi._graphs.items())
+    la, lb = run_e.svi.step(base[0], *base[1:]), run_g.svi.step(base[0].clone(), *run_g.step_args()[1:])
+    assert lb == pytest.approx(la, rel=1e-11)
+
+
 def test_graph_replay_raises_before_the_update(cuda):
     """A factorisation that fails inside a replayed step raises torch.linalg.LinAlgError (the reference's behaviour,
     S/models.py:118) and leaves every parameter and the optimiser's counters untouched."""
