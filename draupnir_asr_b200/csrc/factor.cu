@@ -142,7 +142,20 @@ __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ Mb, int
 // unrolled forward substitution, two independent accumulation chains); the factored block is read from shared memory
 // with warp-uniform (broadcast) 16-byte loads; rows are staged through shared memory for coalesced global access.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PR) trsm_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb, int R)
+// Optional fused slicing (`sl.sl != nullptr`; only for nb == NB): the solved 64 columns of rows [c0 + 64, R) ARE the panel of
+// the in-panel K = 64 trailing update that follows, so its int8 slices (ozaki.cu: same fixed-point split, same 128-byte
+// swizzled K-major image, bit-identical to oz_slice_kernel) are written from shared memory while the rows are on chip,
+// instead of by a separate kernel that re-reads them (16 launches of ~40 us per 2,000-leaf factorisation, latency-bound).
+struct TrsmSlice {
+    uint8_t* sl;        // nullptr: plain solve
+    int64_t sl_bs;
+    int32_t* scl;
+    int* counter;
+    int Rpad, S;
+};
+
+__global__ void __launch_bounds__(PR) trsm_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb, int R,
+                                                  const TrsmSlice sl)
 {
     extern __shared__ __align__(16) double sm[];
     double* S = sm;                  // [NB][NB] factored diagonal block (identity beyond nb)
@@ -209,6 +222,44 @@ __global__ void __launch_bounds__(PR) trsm_kernel(double* __restrict__ Mb, int64
 #pragma unroll 8
             for (int i = half; i < PR; i += 2)
                 if (i < nrows) A[(int64_t)(r0 + i) * ld + c0 + j] = X[i * PLD + j];
+        }
+    }
+    if (sl.sl == nullptr) return;
+    // ---- slices of this CTA's 128 rows (one 128-row strip of the update; rows >= R are zeros): two rows per warp iteration,
+    //      16 lanes x 4 consecutive columns each, 4-byte stores (64 contiguous bytes per row and slice)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) sl.counter[0] = sl.counter[1] = 0;
+    const int warp = tid >> 5, lane = tid & 31, hl = lane & 15, sub = lane >> 4;
+    const int NS = sl.S;
+    const long long hi = (1LL << (8 * NS - 1)) - 1;
+    uint8_t* dst = sl.sl + (int64_t)blockIdx.y * sl.sl_bs;
+    for (int it = 0; it < PR / 8; ++it) {
+        const int i = warp * (PR / 4) + 2 * it + sub;            // row inside the CTA
+        const int rr = blockIdx.x * PR + i;                      // row of the slice buffer (relative to c0 + nb)
+        double xv[4];
+        double m = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            xv[j] = X[i * PLD + 4 * hl + j];                     // rows >= nrows were staged as zeros and stay zero
+            m = fmax(m, fabs(xv[j]));
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        int e = 0;
+        if (m > 0.0 && m < 1e300) frexp(m, &e);
+        if (hl == 0) sl.scl[(int64_t)blockIdx.y * sl.Rpad + rr] = e;
+        const int sh = 8 * NS - 1 - e;
+        long long Xq[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long q = __double2ll_rn(scalbn(xv[j], sh));
+            Xq[j] = q > hi ? hi : (q < -hi - 1 ? -hi - 1 : q);
+        }
+        const int chunk = ((hl >> 2) ^ (rr & 7)) << 4;           // 16-byte chunk of the row after the 128B swizzle
+        for (int t = 0; t < NS; ++t) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w |= (uint32_t)((Xq[j] >> (8 * (NS - 1 - t))) & 0xFF) << (8 * j);
+            *reinterpret_cast<uint32_t*>(dst + ((int64_t)t * sl.Rpad + rr) * 128 + chunk + ((4 * hl) & 15)) = w;
         }
     }
 }
@@ -400,6 +451,16 @@ static int outer_block(int R_full, bool tensor_path)
     return (tensor_path && R_full >= 1024) ? 256 : 128;
 }
 
+static bool fused_slicing()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DRP_FUSED_SLICING");
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
+}
+
 static bool lookahead_enabled()
 {
     static int v = -1;
@@ -468,12 +529,20 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
                 const int below = R - c1;
                 if (below > 0) {
                     dim3 g((below + PR - 1) / PR, z);
+                    // the in-panel update that follows a full 64-column step takes its slices from the solve itself
+                    TrsmSlice tsl{nullptr, 0, nullptr, nullptr, 0, 0};
+                    DrpOzLayout lay;
+                    const bool fused = fused_slicing() && tws != nullptr && c1 < Q1 && nb == NB && (c1 & 7) == 0 &&
+                                       drp_ozaki_layout(z, nb, c1, R, min(col_limit, Q1), drp_ozaki_slices(), tws, ws_bytes, 1, &lay) &&
+                                       lay.Rpad == (int)g.x * PR;
+                    if (fused) tsl = TrsmSlice{lay.sl, lay.sl_bs, lay.scl, lay.counter, lay.Rpad, drp_ozaki_slices()};
                     {
                         DRP_LAUNCH(DRP_K_TRSM, (double)z * below * nb * nb, st);
-                        trsm_kernel<<<g, PR, TRSM_SMEM, st>>>(M, ld, bs, c0, nb, R);
+                        trsm_kernel<<<g, PR, TRSM_SMEM, st>>>(M, ld, bs, c0, nb, R, tsl);
                     }
                     if (c1 < Q1)                                                                // inside the sub-panel
-                        rc = trailing_update(M, ld, bs, z, c0, nb, c1, R, c1, min(col_limit, Q1), tws, ws_bytes, zmap, 1, 1, 0, st);
+                        rc = trailing_update(M, ld, bs, z, c0, nb, c1, R, c1, min(col_limit, Q1), tws, ws_bytes, zmap, fused ? 0 : 1, 1,
+                                             0, st);
                 }
             }
             if (Q1 < C1 && rc == 0)                                                                     // rest of the outer panel

@@ -40,6 +40,15 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
 int64_t drp_ozaki_workspace_bytes(int R_full, int z);
 int drp_ozaki_slices();
 double drp_ozaki_cond_limit();
+// slice-buffer geometry of one update's panel (ozaki.cu: drp_ozaki_layout)
+struct DrpOzLayout {
+    uint8_t* sl;        // [z][S][KBN][Rpad][128 B], rows in the 128-byte-swizzled K-major image tcgen05 reads
+    int64_t sl_bs;      // bytes per matrix
+    int32_t* scl;       // [z][Rpad] binary exponent of every row's maximum
+    int* counter;       // two work-unit counters, zeroed by whoever makes the slices
+    int rb, Rpad, KBN;  // first sliced row (c1 rounded down to 8), rows (multiple of 128), 128-column k-blocks
+};
+bool drp_ozaki_layout(int z, int K, int c1, int R, int col_hi, int S, void* ws, int64_t ws_bytes, int buffer, DrpOzLayout* out);
 // zmap (device, nullable = all z matrices): [0] number of matrices on the tensor path, [1] number on the fp64 path,
 // [2 .. 2+z) indices of the former, [2+z .. 2+2z) indices of the latter
 int64_t drp_zmap_bytes(int z);

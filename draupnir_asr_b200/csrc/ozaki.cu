@@ -743,6 +743,33 @@ int drp_ozaki_slices()
     return v;
 }
 
+// Where the slices of the panel P = M[c1 .. R) x [k0, k0 + K) live inside the workspace (the producer may be oz_slice_kernel
+// or, for the 64-column steps inside a panel, the trsm kernel that has just solved those columns: factor.cu).  Returns false
+// when an update of this shape does not take the tensor path at all.
+bool drp_ozaki_layout(int z, int K, int c1, int R, int col_hi, int S, void* ws, int64_t ws_bytes, int buffer, DrpOzLayout* out)
+{
+    if (S == 0 || !ws) return false;
+    if (K < 32 || K > 256) return false;
+    const int KBN = K > 128 ? 2 : 1;
+    if (S * KBN > 12) return false;
+    const int cmax = R < col_hi ? R : col_hi;
+    if (R - c1 < 384 || cmax - c1 < oz_min_cols()) return false;
+    const int rb = c1 & ~7;
+    const int nTi = (R - rb + OZ_TM - 1) / OZ_TM;
+    out->rb = rb;
+    out->Rpad = nTi * OZ_TM;
+    out->KBN = KBN;
+    out->sl_bs = (int64_t)S * KBN * out->Rpad * OZ_ROWB;
+    const int64_t need = (int64_t)z * out->sl_bs + (int64_t)z * out->Rpad * 8 + 2048;
+    const int64_t bbytes = (ws_bytes / 2) & ~(int64_t)1023;      // two buffers
+    if (need > bbytes - 1024) return false;
+    uint8_t* w = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023) + (buffer ? bbytes : 0);
+    out->sl = w;
+    out->scl = reinterpret_cast<int32_t*>(w + (int64_t)z * out->sl_bs);
+    out->counter = reinterpret_cast<int*>(w + (int64_t)z * out->sl_bs + (int64_t)z * out->Rpad * 8);
+    return true;
+}
+
 // Trailing update through the int8 tensor pipe.  Returns 0 when it ran, 1 when the shape/workspace does not qualify
 // (the caller then uses the fp64 mma.sync kernel), otherwise a launch error code.
 //   the panel P = M[c1 .. R) x [k0, k0 + K) is sliced from row c1 down (do_slice; `buffer` 0/1 selects the slice buffer);
@@ -752,22 +779,18 @@ int drp_ozaki_slices()
 int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_lo, int col_hi, int S,
                    void* ws, int64_t ws_bytes, const int* zmap, int do_slice, int buffer, int counter_idx, cudaStream_t st)
 {
-    if (S == 0 || !ws) return 1;
-    if (K < 32 || K > 256) return 1;
-    const int KBN = K > 128 ? 2 : 1;
-    if (S * KBN > 12) return 1;                          // A strip must stay resident in shared memory
+    DrpOzLayout lay;
+    if (!drp_ozaki_layout(z, K, c1, R, col_hi, S, ws, ws_bytes, buffer, &lay)) return 1;
+    const int KBN = lay.KBN;
     const int cmax = R < col_hi ? R : col_hi;
     if (col_lo < c1) col_lo = c1;
     const int below = R - c1, cl = cmax - col_lo;
-    // qualification is decided on the WHOLE update (rows below c1, columns up to cmax), so that both parts of a split
-    // update take the same path
-    if (below < 384 || cmax - c1 < oz_min_cols()) return 1;   // small updates: launch/slicing overhead dominates
     if (cl <= 0) return 0;
     OzParams p;
     p.M = M;
     p.ld = ld;
     p.bs = bs;
-    p.rb = c1 & ~7;
+    p.rb = lay.rb;
     p.c1 = col_lo;                                       // rows and columns below col_lo are not touched (c <= r)
     p.R = R;
     p.cmax = cmax;
@@ -775,20 +798,16 @@ int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int 
     p.trace = g_oz_trace;
     p.prof = g_oz_prof;
     p.zmap = zmap;
-    p.nTi = (R - p.rb + OZ_TM - 1) / OZ_TM;
+    p.nTi = lay.Rpad / OZ_TM;
     p.nTj = (cmax - p.rb + OZ_TN - 1) / OZ_TN;
     p.ti0 = (col_lo - p.rb) / OZ_TM;
     p.tj0 = (col_lo - p.rb) / OZ_TN;
-    p.Rpad = p.nTi * OZ_TM;
-    p.sl_bs = (int64_t)S * KBN * p.Rpad * OZ_ROWB;
-    const int64_t need = (int64_t)z * p.sl_bs + (int64_t)z * p.Rpad * 8 + 2048;
-    const int64_t bbytes = (ws_bytes / 2) & ~(int64_t)1023;      // two buffers
-    if (need > bbytes - 1024) return 1;
-    uint8_t* w = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023) + (buffer ? bbytes : 0);
-    p.sl = w;
-    p.scl = reinterpret_cast<const int32_t*>(w + (int64_t)z * p.sl_bs);
+    p.Rpad = lay.Rpad;
+    p.sl_bs = lay.sl_bs;
+    p.sl = lay.sl;
+    p.scl = lay.scl;
     p.counter_idx = counter_idx ? 1 : 0;
-    p.counter = reinterpret_cast<int*>(w + (int64_t)z * p.sl_bs + (int64_t)z * p.Rpad * 8) + p.counter_idx;
+    p.counter = lay.counter + p.counter_idx;
     // NOTE: the slicing kernel writes zeros for the rows of the panel outside [c1, R); it is given the panel's own c1
     int upz = 0;
     for (int ti = p.ti0; ti < p.nTi; ++ti) {
