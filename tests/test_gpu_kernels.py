@@ -95,8 +95,8 @@ def test_patristic_lca_bit_exact_c4_and_c5_sizes(cuda):
     full = ops.tree_distances(parent, branch)[0]
     assert full.shape == (15999, 15999) and bool((full.diagonal() == 0).all())
     assert torch.equal(full[:4000, 12000:], full[12000:, :4000].T)
-    # the all-pairs call takes the four-rows-per-CTA kernel with byte tables (shallow tree, >= 6,000 nodes); the 96-row call
-    # above took the two-row kernel: same rows, bit for bit, and the LCA ids of the all-pairs call against the C oracle
+    # the all-pairs call (no row / column lists) against the 96-row call above: same rows, bit for bit, and the LCA ids of the
+    # all-pairs call against the C oracle
     rows_t = torch.from_numpy(rows.astype(np.int64)).to(cuda)
     assert torch.equal(full[rows_t], pat)
     del full, pat
