@@ -218,3 +218,42 @@ def test_mean_field_autoguides_elbo_is_the_explicit_formula(kind):
     first = sum(svi.step(data) for _ in range(20)) / 20
     last = sum(svi.step(data) for _ in range(20)) / 20
     assert last < first
+
+
+def test_site_log_prob_sums_equal_torch_and_delta_shortcut():
+    """Round 2: the fused `log_prob_sum` entry points of HalfNormal / Normal fall back to torch on CPU tensors, the Delta
+    shortcut (a guide site scored at its own tensor) equals the generic path, and the reference's [k,1] x [k] outer broadcast
+    (guide value `[3,1]`, model scale `[3]`: S/guides.py:33-36 vs S/models.py:89) is what both compute."""
+    v = torch.tensor([[0.4], [1.3], [0.2]])                                  # the variational guide's alpha: [3, 1]
+    hn = dist.HalfNormal(torch.ones(())).expand_by([3]).to_event(1)
+    want = torch.distributions.HalfNormal(torch.ones(3)).log_prob(v).sum()   # broadcasts to [3, 3]
+    assert want.shape == () and torch.allclose(hn.log_prob_sum(v), want, rtol=1e-15)
+    assert torch.allclose(hn.log_prob_sum(v), 3 * torch.distributions.HalfNormal(torch.ones(())).log_prob(v).sum(), rtol=1e-15)
+    loc, scale = torch.randn(4, 5), torch.rand(4, 5) + 0.5
+    x = torch.randn(4, 5)
+    assert torch.allclose(dist.Normal(loc.T, scale.T).log_prob_sum(x.T), torch.distributions.Normal(loc, scale).log_prob(x).sum(),
+                          rtol=1e-14)
+    d = dist.Delta(v, event_dim=2)
+    assert d.log_prob_sum(d.rsample()) == 0.0 and float(d.log_prob(v).sum()) == 0.0
+    assert float(d.log_prob_sum(v + 1.0)) == float("-inf")                  # another value: the generic path
+    dj = dist.Delta(torch.tensor([0.5, 0.7]), log_density=torch.tensor([-1.0, -2.0]), event_dim=0)
+    assert float(dj.log_prob_sum(dj.v)) == -3.0 == float(dj.log_prob(dj.v).sum())
+    assert float(dist.Delta(torch.zeros(4, 2), log_density=0.25, event_dim=1).log_prob_sum(torch.zeros(4, 2))) == 1.0  # other storage
+    dd = dist.Delta(torch.zeros(4, 2), log_density=0.25, event_dim=1)
+    assert dd.log_prob_sum(dd.v) == 1.0 == float(dd.log_prob(dd.v).sum())
+
+
+def test_svi_without_cuda_arguments_stays_eager_and_checks_before_the_update():
+    """CPU tensors never enter the CUDA-graph path; the step still evaluates, reduces and updates in the order
+    evaluate -> (flags) -> optimiser, and leaves `.grad` cleared."""
+    pyro.clear_param_store()
+    data = torch.tensor([0.3, 1.2, -0.4])
+    init = {"s": torch.tensor([0.8, 1.1]), "mu": torch.tensor(0.25)}
+    guide = AutoDelta(_model, init_loc_fn=init_to_value(values=init))
+    svi = SVI(_model, guide, ClippedAdam({"lr": 0.01}), Trace_ELBO(), cuda_graph=True)
+    l0, l1, l2, l3 = (svi.step(data) for _ in range(4))
+    assert not svi.last_step_was_replay and svi._graph_key((data,)) == (None, None, None) and not svi._graphs
+    assert l3 < l0 and all(p.grad is None for p in guide.parameters())
+    assert guide.prototype_trace is not None
+    assert all(not (isinstance(s.get("value"), torch.Tensor) and s["value"].requires_grad)
+               for _, s in guide.prototype_trace.sample_sites())           # taken under no_grad (DESIGN 4.5)
