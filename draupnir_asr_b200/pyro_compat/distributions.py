@@ -109,6 +109,9 @@ class Delta(td.Distribution, TorchDistributionMixin):
         self.log_density = log_density
         super().__init__(v.shape[:batch_dim], v.shape[batch_dim:], validate_args=False)
 
+    def __repr__(self):
+        return f"Delta(v: {tuple(self.v.shape)}, event_dim: {len(self.event_shape)})"
+
     def expand(self, batch_shape, _instance=None):
         batch_shape = torch.Size(batch_shape)
         return Delta(self.v.expand(batch_shape + self.event_shape), self.log_density, len(self.event_shape))

@@ -160,3 +160,39 @@ def test_precision_gate_is_per_matrix(cuda):
         for zz in range(3):
             err = float((ga[zz] - gb[zz]).norm() / gb[zz].norm())
             assert err < (1e-7 if zz == 0 else 1e-4), (name, zz, err)
+
+
+def test_lookahead_factorisation_equals_the_plain_one(cuda):
+    """DRP_LOOKAHEAD=1 (csrc/factor.cu: the update of an outer panel split by columns, the larger part on an auxiliary stream
+    beside the next panel's factorisation) is opt-in because it does not pay on one GPU, but it must stay correct: the fused
+    prior at 1,100 leaves in a child process with the switch on gives the same log-densities and gradients as this process."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch, numpy as np
+sys.path.insert(0, %r)
+from draupnir_asr_b200 import ops, synthetic as S
+assert ops.LOOKAHEAD_ENABLED
+t = S.random_tree(1100, seed=2)
+D = torch.from_numpy(S.patristic_host(t)[np.ix_(t.leaves, t.leaves)]).cuda()
+g = torch.Generator().manual_seed(2)
+sf, sn, lam = (torch.rand(3, generator=g, dtype=torch.float64).add(0.5).cuda().requires_grad_(True) for _ in range(3))
+x = torch.randn(3, 1100, generator=g, dtype=torch.float64).cuda().requires_grad_(True)
+lp = ops.ou_prior_logp(D, sf, sn, lam, x)
+lp.sum().backward()
+torch.cuda.synchronize()
+print("RESULT", " ".join(repr(float(v)) for v in list(lp.detach().cpu()) + list(sf.grad.cpu()) + list(lam.grad.cpu()) + [float(x.grad.norm())]))
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for la in ("1", "0"):
+        env = dict(os.environ, DRP_LOOKAHEAD=la)
+        if la == "0":
+            code_run = code.replace("assert ops.LOOKAHEAD_ENABLED", "assert not ops.LOOKAHEAD_ENABLED")
+        else:
+            code_run = code
+        r = subprocess.run([sys.executable, "-c", code_run], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][0]
+        outs.append(np.array([float(v) for v in line.split()[1:]]))
+    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-12, atol=0)
