@@ -439,9 +439,9 @@ def run_ours(args, w, rank, world, local_rank):
 
     def timed(fn, k):
         # the cyclic garbage collector is kept out of the timed region (a generation-2 pass over the autograd graphs of a
-        # step costs tens of ms on the host and stalls the launch thread); it runs between the regions instead
+        # step costs tens of ms on the host and stalls the launch thread); the collection itself runs BEFORE the barrier that
+        # opens the region (`quiesce`), so that the GPU does not sit idle between the barrier and the first timed step
         import gc
-        gc.collect()
         gc.disable()
         try:
             evs = []
@@ -459,6 +459,11 @@ def run_ours(args, w, rank, world, local_rank):
         finally:
             gc.enable()
 
+    def quiesce():
+        import gc
+        gc.collect()
+        barrier()
+
     # the sampler starts BEFORE the warm-up: NVML's start-up (attaching to every GPU of the box) can stall the launches
     # of a running context for tens of ms, which must not land inside a timed step; its polling does not
     sampler = make_clock_sampler(local_rank)
@@ -469,12 +474,12 @@ def run_ours(args, w, rank, world, local_rank):
     graphed = bool(run.svi.last_step_was_replay)
     log(f"[rank {rank}] warm-up done, -ELBO {loss:.4f}; step replayed from a CUDA graph: {graphed}")
     sampler.wait_first_sample()
-    barrier()                                                          # ranks leave the (rank-dependent) set-up together
+    quiesce()                                                          # ranks leave the (rank-dependent) set-up together
     ms = timed(run.step, args.steps)
     for _ in range(W):                                                 # the host-fed path has its own warm-up / capture
         run.step_from_host(host)
     graphed_e2e = bool(run.svi.last_step_was_replay)
-    barrier()
+    quiesce()
     ms_e2e = timed(lambda: run.step_from_host(host), args.steps)
     barrier()
     clocks = sampler.stop()
