@@ -10,8 +10,9 @@ BASELINE.json's target is quoted on; it fits one GPU).  c5 is BASELINE.json's pa
 else to stderr.
 
 What the line's numbers are: `value` — steps/s with device-resident inputs, the step replayed from its CUDA
-graph; `e2e` — the same through `Run.step_from_host` (pinned host inputs copied every step inside the graph, loss read
-back); `kernels` — per-kernel device time / achieved rate from an extra, EAGER, instrumented pass after the timed regions
+graph; `e2e` — the same through `Run.step_from_host(host, prefetch=host)`: every step copies its inputs from pinned host
+memory, one step early (double-buffered), and reads the loss back (`ms_per_step_copy_inside_step`: without the overlap, the
+copies being memcpy nodes of the step's own graph); `kernels` — per-kernel device time / achieved rate from an extra, EAGER, instrumented pass after the timed regions
 (CUDA events around every launch of the library on its launching stream); `roofline` — the kernel with the largest share
 of that pass; `north_star_kernel` — always the tcgen05 trailing update; `conditional` — K6 at this size; `cpu_baseline` —
 the oracle port on the host cores.
@@ -478,9 +479,15 @@ def run_ours(args, w, rank, world, local_rank):
     ms = timed(run.step, args.steps)
     for _ in range(W):                                                 # the host-fed path has its own warm-up / capture
         run.step_from_host(host)
+    quiesce()
+    ms_e2e_serial = timed(lambda: run.step_from_host(host), args.steps)     # copies inside the step (memcpy nodes of its graph)
+    # e2e proper: the loop of a double-buffered loader — every step copies its full inputs from pinned host memory, one step
+    # early (while the previous step computes), into the other of two staging sets; each set has its own captured graph
+    for _ in range(max(W, 7)):
+        run.step_from_host(host, prefetch=host)
     graphed_e2e = bool(run.svi.last_step_was_replay)
     quiesce()
-    ms_e2e = timed(lambda: run.step_from_host(host), args.steps)
+    ms_e2e = timed(lambda: run.step_from_host(host, prefetch=host), args.steps)
     barrier()
     clocks = sampler.stop()
 
@@ -513,12 +520,12 @@ def run_ours(args, w, rank, world, local_rank):
         ms_map = _event_ms(lambda: D.conditional_samplingMAP(est, run.patristic_matrix_full), reps, flush)
         ms_cov = _event_ms(lambda: D._conditional(est, run.patristic_matrix_full, D.internal_nodes, D.n_internal, 0.0, 1e-6, True),
                            reps, flush)
-    t2 = torch.tensor([ms, ms_e2e, ms_map, ms_cov], dtype=torch.float64, device=dev)
+    t2 = torch.tensor([ms, ms_e2e, ms_map, ms_cov, ms_e2e_serial], dtype=torch.float64, device=dev)
     h2d = torch.tensor([float(run.host_bytes_per_step(host))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)                    # max over ranks
         dist.all_reduce(h2d, op=dist.ReduceOp.SUM)                   # bytes copied by all ranks together
-    ms, ms_e2e, ms_map, ms_cov = (float(v) for v in t2)
+    ms, ms_e2e, ms_map, ms_cov, ms_e2e_serial = (float(v) for v in t2)
     if rank != 0:
         finish_ranks(world)
         return
@@ -554,7 +561,10 @@ def run_ours(args, w, rank, world, local_rank):
             "data": "synthetic", "config": cfg,
             "parallelism": "single GPU" if world == 1 else f"z-sharded OU prior + leaf-sharded decoder over {world} GPUs", "roofline": roofline, "north_star_kernel": north, "cpu_baseline": cpu,
             "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d[0]),
-                    "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps, "cuda_graph": graphed_e2e},
+                    "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps, "cuda_graph": graphed_e2e,
+                    "pipelining": "double-buffered: Run.step_from_host(host, prefetch=next) copies step k+1's inputs from pinned "
+                                  "host memory while step k computes; every timed step moves h2d_bytes_per_step",
+                    "ms_per_step_copy_inside_step": ms_e2e_serial / args.steps},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_note": (f"{launches_per_step} kernels of libdraupnir_b200.so per step (counted on an eager step) x {args.steps} timed steps; "
                                   + ("in the timed region they are nodes of the replayed CUDA graph" if graphed else "launched eagerly")),

@@ -41,6 +41,10 @@ __device__ __forceinline__ void g_mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void g_mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ uint32_t g_mbar_try_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
@@ -140,7 +144,7 @@ __device__ __forceinline__ double gru_tanh(double x, const double* __restrict__ 
 __device__ long long g_gru_trace[8 * 64 * 2];
 #define GRU_TRACE(slot)                                                                                   \
     do {                                                                                                  \
-        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == (blockDim.x > 256 ? 8 : 7)) && t >= 200 && t < 264) \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == (blockDim.x > 256 ? 8 : (blockDim.x == 160 ? 3 : 7))) && t >= 200 && t < 264) \
             g_gru_trace[((warp ? 1 : 0) * 64 + (t - 200)) * 8 + (slot)] = clock64();                     \
     } while (0)
 extern "C" __attribute__((visibility("default"))) int drp_gru_trace_read(long long* host)
@@ -149,7 +153,7 @@ extern "C" __attribute__((visibility("default"))) int drp_gru_trace_read(long lo
 }
 #define GRU_TRACE_B(slot)                                                                                 \
     do {                                                                                                  \
-        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 7) && tb >= 200 && tb < 264) \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == (blockDim.x == 160 ? 3 : 7)) && tb >= 200 && tb < 264) \
             g_gru_trace[((warp ? 1 : 0) * 64 + (tb - 200)) * 8 + (slot)] = clock64();                    \
     } while (0)
 #define GRU_TRACE_W(slot)                                                                                 \
@@ -727,6 +731,403 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Few rows (at most ~300 sequences per launch: small trees, leaf-sharded ranks): a CLUSTER of two CTAs shares the eight
+// sequences of a row group.
+//
+// With one wave of 8-row CTAs the machine is mostly idle (32 CTAs per direction at 250 sequences) and a step of the
+// recurrence costs what ONE SM needs for it: the recurrent product is 8 warps x 45 DMMAs = 1,440 cycles of that SM's fp64
+// pipe however few rows there are (profiles/r02/trace_gru_rows8.txt), plus the gate arithmetic of 8 x 60 elements.  Here CTA
+// c of the pair owns hidden units 32 c .. 32 c + 31 (four warps, one per SM sub-partition: 45 DMMAs each) and the matching
+// half of the gate arithmetic.  What the other half needs - the new h (forward), dgh (backward) - goes into BOTH CTAs'
+// shared memory: a plain store at home and `st.async` into the partner, which signals the partner's mbarrier with the bytes
+// it delivers.  One mbarrier per operand buffer collects the four local warps' arrivals and the partner's bytes, so a step
+// has a single wait and no fence (a barrier.cluster per step costs 1.3-1.6 k cycles here: its release is a MEMBAR.GPU that
+// waits for the step's global stores, profiles/r02/trace_gru_cluster_v1.txt).  The operand buffers are double-buffered and
+// nothing else is needed: whoever writes buffer b for step t + 2 has consumed everything the readers of step t produced
+// AFTER reading it.  A fifth warp per CTA issues the TMA copies, up to two steps ahead (full / empty mbarriers).
+// Same arguments and layouts as gru_fwd2_kernel / gru_bwd_kernel; rows per cluster: 8.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GC_CL = 2;                      // CTAs per cluster
+constexpr int GC_NW = 8 / GC_CL;              // consumer warps per CTA (one group of 8 hidden units each)
+constexpr int GC_THREADS = 32 * (GC_NW + 1);  // + the producer warp
+constexpr int GC_ROWS = 8;
+constexpr int GC_UNITS1 = GH - 8 * GC_NW;     // hidden units of CTA 1 (28; CTA 0 has 32)
+
+__device__ __forceinline__ uint32_t g_cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t g_mapa(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// 16 bytes into the partner's shared memory; completes 16 bytes of the transaction count of the partner's mbarrier
+__device__ __forceinline__ void g_st_async(uint32_t addr, double a, double b, uint32_t bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(addr), "d"(a),
+                 "d"(b), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void g_cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__host__ __device__ constexpr int gfc_smem(bool uv)
+{
+    // h double buffer | W^T | ring (UV: one V row per stage, + the U rows) | barriers | exponent table
+    return 2 * GC_ROWS * GHS * 8 + (GH * GWS + 8) * 8 + GF2_STAGES * (uv ? 1 : GC_ROWS) * GRS * 8 + (uv ? GC_ROWS * GRS * 8 : 0) + 64 + 256;
+}
+
+template <bool UV>
+__global__ void __launch_bounds__(GC_THREADS, 1) gru_fwdc_kernel(const double* __restrict__ gi, const double* __restrict__ vrow,
+                                                                 const double* __restrict__ whh, const double* __restrict__ bhh,
+                                                                 const double* __restrict__ h0, int n, int L,
+                                                                 double* __restrict__ out, double* __restrict__ gates, int gi_dirs)
+{
+    constexpr int STAGE_ROWS = UV ? 1 : GC_ROWS;
+    extern __shared__ __align__(16) uint8_t gsm[];
+    double* hbuf = reinterpret_cast<double*>(gsm);                                   // [2][8][68]
+    double* wt = hbuf + 2 * GC_ROWS * GHS;                                            // [60][180]: wt[k][c] = W_hh[c][k]
+    double* ring = wt + GH * GWS + 8;                                                 // [stage][8 or 1][184]
+    double* ubuf = ring + GF2_STAGES * STAGE_ROWS * GRS;                              // [8][184] (UV only)
+    double* etab = reinterpret_cast<double*>(gsm + gfc_smem(UV) - 256);
+    const uint32_t full = g_smem_u32(gsm + gfc_smem(UV) - 320);                       // [stages]  ring stage landed
+    const uint32_t empty = full + 8 * GF2_STAGES;                                     // [stages]  ring stage read by the 4 warps
+    const uint32_t hfull = empty + 8 * GF2_STAGES;                                    // [2]       h buffer complete (both halves)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    const uint32_t crank = g_cluster_ctarank();
+    const bool producer = warp == GC_NW;
+    const int wg = (int)crank * GC_NW + warp;                                         // hidden-unit group (consumers)
+    const int dir = blockIdx.y;
+    const int row0 = (blockIdx.x / GC_CL) * GC_ROWS;
+    const int nrows = min(GC_ROWS, n - row0);
+    const int j0 = wg * 8 + 2 * tig;
+    const bool jok = !producer && j0 < GH;
+    const int jb = wg * 8 + gid;
+    const double* W = whh + (int64_t)dir * G3 * GH;
+    // bytes of h the partner delivers per step: all 8 rows of its hidden units
+    const uint32_t rx_bytes = (uint32_t)GC_ROWS * 8u * (crank == 0 ? (uint32_t)GC_UNITS1 : 8u * GC_NW);
+
+    for (int idx = tid; idx < GH * GWS + 8; idx += GC_THREADS) {
+        const int k = idx / GWS, c = idx - k * GWS;
+        wt[idx] = k < GH ? W[(int64_t)c * GH + k] : 0.0;
+    }
+    if (tid < 32) etab[tid] = DRP_EXP2_TAB[tid];
+    double bh[3][2];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        bh[g][0] = jok ? bhh[dir * G3 + g * GH + j0] : 0.0;
+        bh[g][1] = jok ? bhh[dir * G3 + g * GH + j0 + 1] : 0.0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < GF2_STAGES; ++s) {
+            g_mbar_init(full + 8 * s, 1);
+            g_mbar_init(empty + 8 * s, GC_NW);
+        }
+        for (int b = 0; b < 2; ++b) g_mbar_init(hfull + 8 * b, GC_NW);      // warp 0's arrival carries the partner's byte count
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int idx = tid; idx < GC_ROWS * GH; idx += GC_THREADS) {     // every CTA starts from all 60 units of h0
+        const int r = idx / GH, j = idx - r * GH;
+        hbuf[r * GHS + j] = r < nrows ? h0[((int64_t)dir * n + row0 + r) * GH + j] : 0.0;
+    }
+    if (UV) {
+        for (int idx = tid; idx < GC_ROWS * G3; idx += GC_THREADS) {
+            const int r = idx / G3, c = idx - r * G3;
+            ubuf[r * GRS + c] = r < nrows ? gi[((int64_t)(row0 + r) * 2 + dir) * G3 + c] : 0.0;
+        }
+    }
+    __syncthreads();
+    g_cluster_sync();              // the partner is running, its barriers are initialised: remote stores may start
+
+    if (producer) {                // the gi rows (UV: the V row) of step t into ring stage t % 2
+        for (int t = 0; t < L; ++t) {
+            const int s = t % GF2_STAGES;
+            const int l = dir ? L - 1 - t : t;
+            if (t >= GF2_STAGES) g_mbar_wait(empty + 8 * s, (uint32_t)(t / GF2_STAGES - 1) & 1u);
+            if (UV) {
+                if (lane == 0) {
+                    g_mbar_expect_tx(full + 8 * s, G3 * 8);
+                    g_bulk_g2s(g_smem_u32(ring + s * GRS), vrow + ((int64_t)l * 2 + dir) * G3, G3 * 8, full + 8 * s);
+                }
+            } else {
+                if (lane == 0) g_mbar_expect_tx(full + 8 * s, (uint32_t)nrows * G3 * 8);
+                __syncwarp();
+                if (lane < nrows)
+                    g_bulk_g2s(g_smem_u32(ring + (int64_t)s * GC_ROWS * GRS + lane * GRS),
+                               gi + (((int64_t)(row0 + lane) * L + l) * gi_dirs + (gi_dirs == 2 ? dir : 0)) * G3, G3 * 8, full + 8 * s);
+            }
+        }
+        g_cluster_sync();
+        return;
+    }
+    const uint32_t hb_remote = g_mapa(g_smem_u32(hbuf), crank ^ 1u);
+    const uint32_t hfull_remote = g_mapa(hfull, crank ^ 1u);
+    double hold[2];
+    hold[0] = jok ? hbuf[gid * GHS + j0] : 0.0;
+    hold[1] = jok ? hbuf[gid * GHS + j0 + 1] : 0.0;
+
+    for (int t = 0; t < L; ++t) {
+        const int l = dir ? L - 1 - t : t;
+        const double* hc = hbuf + (t & 1) * GC_ROWS * GHS;
+        const int nb = (t + 1) & 1;
+        const int hn_off = nb * GC_ROWS * GHS + gid * GHS + j0;
+        GRU_TRACE(0);
+        if (t > 0) g_mbar_wait(hfull + 8 * (t & 1), (uint32_t)((t - 1) >> 1) & 1u);    // h(t-1): my warps' halves and the partner's
+        GRU_TRACE(1);
+        double acc[3][2];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) acc[g][0] = bh[g][0], acc[g][1] = bh[g][1];
+#pragma unroll
+        for (int ks = 0; ks < 15; ++ks) {
+            const double a = hc[gid * GHS + 4 * ks + tig];
+            double b[3];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) b[g] = wt[(4 * ks + tig) * GWS + g * GH + jb];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) dmma_8x8x4(acc[g][0], acc[g][1], a, b[g]);
+        }
+        const int s = t % GF2_STAGES;
+        GRU_TRACE(2);
+        g_mbar_wait(full + 8 * s, (uint32_t)(t / GF2_STAGES) & 1u);
+        GRU_TRACE(3);
+        const double* gs = ring + (int64_t)s * STAGE_ROWS * GRS;
+        double hv[2] = {0.0, 0.0}, rv[2], zv[2], nv[2], qv[2];
+        if (jok) {
+            double xr[2], xz[2], xn[2];
+            double2 ar, az, an;
+            if (UV) {
+                const double* up = ubuf + gid * GRS;
+                const double2 ur = *reinterpret_cast<const double2*>(up + j0);
+                const double2 uz = *reinterpret_cast<const double2*>(up + GH + j0);
+                const double2 un = *reinterpret_cast<const double2*>(up + 2 * GH + j0);
+                const double2 vr = *reinterpret_cast<const double2*>(gs + j0);
+                const double2 vz = *reinterpret_cast<const double2*>(gs + GH + j0);
+                const double2 vn = *reinterpret_cast<const double2*>(gs + 2 * GH + j0);
+                ar = make_double2(ur.x + vr.x, ur.y + vr.y);
+                az = make_double2(uz.x + vz.x, uz.y + vz.y);
+                an = make_double2(un.x + vn.x, un.y + vn.y);
+            } else {
+                ar = *reinterpret_cast<const double2*>(gs + gid * GRS + j0);
+                az = *reinterpret_cast<const double2*>(gs + gid * GRS + GH + j0);
+                an = *reinterpret_cast<const double2*>(gs + gid * GRS + 2 * GH + j0);
+            }
+            xr[0] = ar.x, xr[1] = ar.y, xz[0] = az.x, xz[1] = az.y, xn[0] = an.x, xn[1] = an.y;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                qv[e] = acc[2][e];                                   // the accumulators started from b_hh
+                xr[e] += acc[0][e];
+                xz[e] += acc[1][e];
+                rv[e] = gru_sigmoid(xr[e], etab);
+                zv[e] = gru_sigmoid(xz[e], etab);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double gn = fma(rv[e], qv[e], xn[e]);
+                nv[e] = gru_tanh(gn, etab);
+                hv[e] = fma(zv[e], hold[e] - nv[e], nv[e]);
+                hv[e] = fma(0.0, (xr[e] + xz[e]) + gn, hv[e]);       // a NaN pre-activation reaches h (see gru_fwd2_kernel)
+                hold[e] = hv[e];
+            }
+            if (t + 1 < L) {                                         // (nobody reads the last h from shared memory)
+                *reinterpret_cast<double2*>(hbuf + hn_off) = make_double2(hv[0], hv[1]);
+                g_st_async(hb_remote + (uint32_t)hn_off * 8u, hv[0], hv[1], hfull_remote + 8u * nb);
+            }
+        }
+        GRU_TRACE(4);
+        __syncwarp();
+        if (lane == 0) {
+            if (t + 1 < L) {
+                if (warp == 0) g_mbar_expect_tx(hfull + 8 * nb, rx_bytes);      // an arrival that also announces the partner's bytes
+                else g_mbar_arrive(hfull + 8 * nb);
+            }
+            g_mbar_arrive(empty + 8 * s);                                       // this warp has read ring stage s
+        }
+        GRU_TRACE(6);
+        if (jok && gid < nrows) {
+            const int64_t site = (int64_t)(row0 + gid) * L + l;
+            *reinterpret_cast<double2*>(out + site * (2 * GH) + dir * GH + j0) = make_double2(hv[0], hv[1]);
+            if (gates) {
+                double* gp = gates + (site * 2 + dir) * (4 * GH) + j0;
+                *reinterpret_cast<double2*>(gp) = make_double2(rv[0], rv[1]);
+                *reinterpret_cast<double2*>(gp + GH) = make_double2(zv[0], zv[1]);
+                *reinterpret_cast<double2*>(gp + 2 * GH) = make_double2(nv[0], nv[1]);
+                *reinterpret_cast<double2*>(gp + 3 * GH) = make_double2(qv[0], qv[1]);
+            }
+        }
+        GRU_TRACE(5);
+    }
+    g_cluster_sync();              // nobody leaves while its partner could still be addressed
+}
+
+__host__ __device__ constexpr int gbc_smem() { return 2 * GC_ROWS * GDS * 8 + GB_STAGES * GC_ROWS * GB_ROW_STRIDE * 8 + 64; }
+
+__global__ void __launch_bounds__(GC_THREADS, 1) gru_bwdc_kernel(const double* __restrict__ dout, const double* __restrict__ out,
+                                                                 const double* __restrict__ gates, const double* __restrict__ whh,
+                                                                 const double* __restrict__ h0, int n, int L,
+                                                                 double* __restrict__ dgi, double* __restrict__ dh0, int dgi_dirs,
+                                                                 int dout_last)
+{
+    constexpr int RS = GB_ROW_STRIDE;
+    extern __shared__ __align__(16) uint8_t gsm[];
+    double* dgh = reinterpret_cast<double*>(gsm);                                    // [2][8][180]
+    double* ring = dgh + 2 * GC_ROWS * GDS;                                           // [stages][8][312]
+    const uint32_t full = g_smem_u32(gsm + gbc_smem() - 64);
+    const uint32_t empty = full + 8 * GB_STAGES;
+    const uint32_t dfull = empty + 8 * GB_STAGES;                                     // [2] dgh buffer complete (all 180 columns)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    const uint32_t crank = g_cluster_ctarank();
+    const bool producer = warp == GC_NW;
+    const int wg = (int)crank * GC_NW + warp;
+    const int dir = blockIdx.y;
+    const int row0 = (blockIdx.x / GC_CL) * GC_ROWS;
+    const int nrows = min(GC_ROWS, n - row0);
+    const int j0 = wg * 8 + 2 * tig;
+    const bool jok = !producer && j0 < GH;
+    const int jb = wg * 8 + gid;
+    const double* W = whh + (int64_t)dir * G3 * GH;
+    const uint32_t rx_bytes = 3u * GC_ROWS * 8u * (crank == 0 ? (uint32_t)GC_UNITS1 : 8u * GC_NW);
+
+    if (tid == 0) {
+        for (int s = 0; s < GB_STAGES; ++s) {
+            g_mbar_init(full + 8 * s, 1);
+            g_mbar_init(empty + 8 * s, GC_NW);
+        }
+        for (int b = 0; b < 2; ++b) g_mbar_init(dfull + 8 * b, GC_NW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    g_cluster_sync();
+
+    // backward step tb = 0..L-1 handles forward step t = L-1-tb, i.e. position l = dir ? tb : L-1-tb
+    if (producer) {                // saved gates + h_prev of the 8 rows, one copy per lane
+        for (int tb = 0; tb < L; ++tb) {
+            const int s = tb % GB_STAGES;
+            const int t = L - 1 - tb;
+            const int l = dir ? L - 1 - t : t;
+            const int lp = dir ? l + 1 : l - 1;       // position of h_prev (outside [0,L): h0)
+            if (tb >= GB_STAGES) g_mbar_wait(empty + 8 * s, (uint32_t)(tb / GB_STAGES - 1) & 1u);
+            if (lane == 0) g_mbar_expect_tx(full + 8 * s, (uint32_t)nrows * GB_ROW_BYTES);
+            __syncwarp();
+            const int rr = lane >> 1;
+            if (lane < 2 * GC_ROWS && rr < nrows) {
+                const int64_t row = row0 + rr;
+                double* dst = ring + (int64_t)s * GC_ROWS * RS + rr * RS;
+                if (lane & 1) {
+                    const double* hp = t == 0 ? h0 + ((int64_t)dir * n + row) * GH : out + (row * L + lp) * (2 * GH) + dir * GH;
+                    g_bulk_g2s(g_smem_u32(dst + 4 * GH), hp, GH * 8, full + 8 * s);
+                } else {
+                    g_bulk_g2s(g_smem_u32(dst), gates + ((row * L + l) * 2 + dir) * (4 * GH), 4 * GH * 8, full + 8 * s);
+                }
+            }
+        }
+        g_cluster_sync();
+        return;
+    }
+    double B[45];                                 // B[k][n] = W_hh[c = 4 ks + tig][j = jb]
+#pragma unroll
+    for (int ks = 0; ks < 45; ++ks) B[ks] = jb < GH ? W[(int64_t)(4 * ks + tig) * GH + jb] : 0.0;
+    const uint32_t dg_remote = g_mapa(g_smem_u32(dgh), crank ^ 1u);
+    const uint32_t dfull_remote = g_mapa(dfull, crank ^ 1u);
+    double dh[2] = {0.0, 0.0};
+    const bool rok = jok && gid < nrows;
+    double2 dOn;
+    {
+        const int l0 = dir ? 0 : L - 1;            // position of backward step 0
+        const double* src = dout_last ? dout + (int64_t)(row0 + gid) * (2 * GH) + dir * GH + j0
+                                      : dout + ((int64_t)(row0 + gid) * L + l0) * (2 * GH) + dir * GH + j0;
+        dOn = (rok && !(dout_last && l0 != L - 1)) ? *reinterpret_cast<const double2*>(src) : make_double2(0.0, 0.0);
+    }
+
+    for (int tb = 0; tb < L; ++tb) {
+        const int t = L - 1 - tb;
+        const int l = dir ? L - 1 - t : t;
+        GRU_TRACE_B(0);
+        const double2 dO = dOn;                    // requested a whole step ago (see gru_bwd_kernel)
+        if (tb + 1 < L) {
+            const int ln = dir ? l + 1 : l - 1;
+            if (dout_last) {
+                dOn = (rok && ln == L - 1) ? *reinterpret_cast<const double2*>(dout + (int64_t)(row0 + gid) * (2 * GH) + dir * GH + j0)
+                                           : make_double2(0.0, 0.0);
+            } else {
+                dOn = rok ? *reinterpret_cast<const double2*>(dout + ((int64_t)(row0 + gid) * L + ln) * (2 * GH) + dir * GH + j0)
+                          : make_double2(0.0, 0.0);
+            }
+        }
+        const int s = tb % GB_STAGES, b = tb & 1;
+        const int dg_off = b * GC_ROWS * GDS + gid * GDS + j0;
+        GRU_TRACE_B(2);
+        g_mbar_wait(full + 8 * s, (uint32_t)(tb / GB_STAGES) & 1u);
+        GRU_TRACE_B(3);
+        const double* gs = ring + (int64_t)s * GC_ROWS * RS + gid * RS;
+        double dr[2], dz[2], dn[2], dq[2];
+        if (jok) {
+            const double2 rr = *reinterpret_cast<const double2*>(gs + j0);
+            const double2 zz = *reinterpret_cast<const double2*>(gs + GH + j0);
+            const double2 nn = *reinterpret_cast<const double2*>(gs + 2 * GH + j0);
+            const double2 qq = *reinterpret_cast<const double2*>(gs + 3 * GH + j0);
+            const double2 hp = *reinterpret_cast<const double2*>(gs + 4 * GH + j0);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double rv = e ? rr.y : rr.x, zv = e ? zz.y : zz.x, nv = e ? nn.y : nn.x, qv = e ? qq.y : qq.x;
+                const double hv = e ? hp.y : hp.x;
+                const double d = (e ? dO.y : dO.x) + dh[e];
+                dn[e] = d * (1.0 - zv) * (1.0 - nv * nv);
+                dz[e] = d * (hv - nv) * zv * (1.0 - zv);
+                dr[e] = dn[e] * qv * rv * (1.0 - rv);
+                dq[e] = dn[e] * rv;
+                dh[e] = d * zv;
+            }
+            *reinterpret_cast<double2*>(dgh + dg_off) = make_double2(dr[0], dr[1]);
+            *reinterpret_cast<double2*>(dgh + dg_off + GH) = make_double2(dz[0], dz[1]);
+            *reinterpret_cast<double2*>(dgh + dg_off + 2 * GH) = make_double2(dq[0], dq[1]);
+            g_st_async(dg_remote + (uint32_t)dg_off * 8u, dr[0], dr[1], dfull_remote + 8u * b);
+            g_st_async(dg_remote + (uint32_t)(dg_off + GH) * 8u, dz[0], dz[1], dfull_remote + 8u * b);
+            g_st_async(dg_remote + (uint32_t)(dg_off + 2 * GH) * 8u, dq[0], dq[1], dfull_remote + 8u * b);
+        }
+        GRU_TRACE_B(4);
+        __syncwarp();
+        if (lane == 0) {
+            if (warp == 0) g_mbar_expect_tx(dfull + 8 * b, rx_bytes);          // an arrival that also announces the partner's bytes
+            else g_mbar_arrive(dfull + 8 * b);
+            g_mbar_arrive(empty + 8 * s);                                      // this warp has read ring stage s
+        }
+        GRU_TRACE_B(1);
+        if (rok) {
+            double* gp = dgi + (((int64_t)(row0 + gid) * L + l) * dgi_dirs + (dgi_dirs == 2 ? dir : 0)) * G3 + j0;
+            *reinterpret_cast<double2*>(gp) = make_double2(dr[0], dr[1]);
+            *reinterpret_cast<double2*>(gp + GH) = make_double2(dz[0], dz[1]);
+            *reinterpret_cast<double2*>(gp + 2 * GH) = make_double2(dn[0], dn[1]);
+        }
+        GRU_TRACE_B(7);
+        g_mbar_wait(dfull + 8 * b, (uint32_t)(tb >> 1) & 1u);                  // all 180 columns of dgh(tb) are here
+        GRU_TRACE_B(5);
+        // dh_prev[:, own units] = dh z + dgh W_hh[:, own units]: three independent accumulation chains (a single chain of 45
+        // dependent DMMAs is latency-bound with one warp per sub-partition)
+        const double* dg = dgh + b * GC_ROWS * GDS + gid * GDS + tig;
+        double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int ks = 0; ks < 45; ks += 3) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dmma_8x8x4(acc[c][0], acc[c][1], dg[4 * (ks + c)], B[ks + c]);
+        }
+        dh[0] += (acc[0][0] + acc[1][0]) + acc[2][0];
+        dh[1] += (acc[0][1] + acc[1][1]) + acc[2][1];
+        GRU_TRACE_B(6);
+    }
+    if (dh0 && rok) *reinterpret_cast<double2*>(dh0 + ((int64_t)dir * n + row0 + gid) * GH + j0) = make_double2(dh[0], dh[1]);
+    g_cluster_sync();              // nobody leaves while its partner could still be addressed
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Weight gradients of the recurrence: dW_hh[dir] = sum_p dgh[p]^T h_prev[p], db_hh[dir] = sum_p dgh[p] over all
 // (sequence, step) pairs p, with dgh = dgi except that the n-part is multiplied by r.  A [180 x 60] += [180 x K][K x 60]
 // product with K = n L, split over the grid along K; every CTA keeps its partial product in registers (fp64 mma.sync
@@ -742,10 +1143,6 @@ constexpr int GW_SMEM = GW_STAGES * GW_STAGE_BYTES + 64;
 constexpr int GW_MT = 23;                                      // 184 = 23 m-tiles cover the 180 gate columns
 
 constexpr int GW_THREADS = GTHREADS + 64;      // 8 consumer warps (one 8-column group of [h_prev | 1] each) + 2 producer warps
-__device__ __forceinline__ void g_mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 
 // Warps 8 and 9 only issue the bulk copies (96 per 32-pair stage, ~60 cycles of issue each: on the consumer warps they
 // cost 1.4 k of the 8.9 k cycles of a stage, profiles/r01/trace_gru_v6.txt); the consumers never leave the DMMA loop:
@@ -887,6 +1284,64 @@ static int gru_pick_mt(int n, int ndir = 2)
     return 4;
 }
 
+// Pairs of CTAs per 8-row group (gru_fwdc_kernel / gru_bwdc_kernel) whenever the pairs of ALL row groups and directions
+// are resident at once; DRP_GRU_CLUSTER=0 switches the form off, =1 forces it for any size.
+static bool gru_use_cluster(int n, int ndir)
+{
+    static int mode = -1, n_sm = 0;
+    if (mode < 0) {
+        const char* e = getenv("DRP_GRU_CLUSTER");
+        mode = e ? (atoi(e) ? 1 : 0) : 2;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    if (mode != 2) return mode == 1;
+    if (getenv("DRP_GRU_ROWS")) return false;                       // an explicit rows-per-CTA request means the classic kernels
+    return ndir * ((n + GC_ROWS - 1) / GC_ROWS) * GC_CL <= n_sm;
+}
+
+template <typename... KArgs, typename... Args>
+static void gru_cluster_launch(void (*kern)(KArgs...), int n, int ndir, int smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(((n + GC_ROWS - 1) / GC_ROWS) * GC_CL, ndir);
+    cfg.blockDim = dim3(GC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = GC_CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, args...);                        // an error stays in cudaGetLastError for drp_launch_status
+}
+
+template <bool UV>
+static void gru_fwdc_launch(const double* gi, const double* v, const double* whh, const double* bhh, const double* h0, int n,
+                            int L, double* out, double* gates, cudaStream_t st, int ndir)
+{
+    constexpr int smem = gfc_smem(UV);
+    if (drp_first_on_device(60 + (int)UV)) {
+        cudaFuncSetAttribute(gru_fwdc_kernel<UV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }
+    DRP_LAUNCH(DRP_K_GRU_FWD, 2.0 * (double)n * L * ndir * G3 * GH, st);
+    gru_cluster_launch(gru_fwdc_kernel<UV>, n, ndir, smem, st, gi, v, whh, bhh, h0, n, L, out, gates, ndir);
+}
+
+static void gru_bwdc_launch(const double* dout, const double* out, const double* gates, const double* whh, const double* h0,
+                            int n, int L, double* dgi, double* dh0, int ndir, int dgi_dirs, cudaStream_t st, int dout_last)
+{
+    constexpr int smem = gbc_smem();
+    if (drp_first_on_device(62)) {
+        cudaFuncSetAttribute(gru_bwdc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }
+    DRP_LAUNCH(DRP_K_GRU_BWD, 2.0 * (double)n * L * ndir * G3 * GH, st);
+    gru_cluster_launch(gru_bwdc_kernel, n, ndir, smem, st, dout, out, gates, whh, h0, n, L, dgi, dh0, dgi_dirs, dout_last);
+}
+
 static int gru_fwd_generation()
 {
     static int gen = 0;
@@ -954,6 +1409,10 @@ DRP_API int drp_gru_fwd_f64(const double* gi, const double* whh, const double* b
     if (H != GH) return -7;
     if (!out) return -8;
     cudaStream_t st = (cudaStream_t)stream;
+    if (gru_use_cluster(n, 2)) {
+        gru_fwdc_launch<false>(gi, nullptr, whh, bhh, h0, n, L, out, gates, st, 2);
+        return drp_launch_status();
+    }
     switch (gru_pick_mt(n)) {
         case 1: gru_fwd_launch<false, 1>(gi, nullptr, whh, bhh, h0, n, L, out, gates, st); break;
         case 2: gru_fwd_launch<false, 2>(gi, nullptr, whh, bhh, h0, n, L, out, gates, st); break;
@@ -972,6 +1431,10 @@ DRP_API int drp_gru_fwd_dir0_f64(const double* gi0, const double* whh, const dou
     if (H != GH) return -7;
     if (!out) return -8;
     cudaStream_t st = (cudaStream_t)stream;
+    if (gru_use_cluster(n, 1)) {
+        gru_fwdc_launch<false>(gi0, nullptr, whh, bhh, h0, n, L, out, gates, st, 1);
+        return drp_launch_status();
+    }
     switch (gru_pick_mt(n, 1)) {
         case 1: gru_fwd_launch<false, 1>(gi0, nullptr, whh, bhh, h0, n, L, out, gates, st, 1); break;
         case 2: gru_fwd_launch<false, 2>(gi0, nullptr, whh, bhh, h0, n, L, out, gates, st, 1); break;
@@ -989,6 +1452,10 @@ DRP_API int drp_gru_fwd_uv_f64(const double* U, const double* V, const double* w
     if (H != GH) return -8;
     if (!out) return -9;
     cudaStream_t st = (cudaStream_t)stream;
+    if (gru_use_cluster(n, 2)) {
+        gru_fwdc_launch<true>(U, V, whh, bhh, h0, n, L, out, gates, st, 2);
+        return drp_launch_status();
+    }
     switch (gru_pick_mt(n)) {
         case 1: gru_fwd_launch<true, 1>(U, V, whh, bhh, h0, n, L, out, gates, st); break;
         case 2: gru_fwd_launch<true, 2>(U, V, whh, bhh, h0, n, L, out, gates, st); break;
@@ -1005,6 +1472,10 @@ static int gru_bwd_dispatch(const double* dout, const double* out, const double*
     if (H != GH) return -8;
     if (!dgi) return -9;
     cudaStream_t st = (cudaStream_t)stream;
+    if (gru_use_cluster(n, ndir)) {
+        gru_bwdc_launch(dout, out, gates, whh, h0, n, L, dgi, dh0, ndir, dgi_dirs, st, dout_last);
+        return drp_launch_status();
+    }
     switch (gru_pick_mt(n, ndir)) {
         case 1: gru_bwd_launch<1>(dout, out, gates, whh, h0, n, L, dgi, dh0, ndir, dgi_dirs, st, dout_last); break;
         case 2: gru_bwd_launch<2>(dout, out, gates, whh, h0, n, L, dgi, dh0, ndir, dgi_dirs, st, dout_last); break;

@@ -85,12 +85,26 @@ class Trace_ELBO:
         return "Trace_ELBO()"
 
 
-def _recover_generator(device, rng_state):
-    """A capture that dies half-way leaves the device's default generator in capture mode (every later random draw would
-    raise).  Swap in a fresh generator state carrying the seed / offset the capture started from."""
+def _recover_generator(device, rng_state) -> bool:
+    """A capture that dies half-way leaves the device's default generator state in capture mode, with a non-zero
+    intra-graph offset (every later random draw, and every replay of a graph captured EARLIER with that state, would
+    raise).  A trivial capture that succeeds runs the generator's capture prologue / epilogue and so puts the very same state
+    object back in order; the seed / offset the failed capture started from are then restored.  Returns True if that worked
+    (earlier graphs remain usable).  Otherwise a fresh state object is swapped in — eager draws work again, but graphs that
+    registered the old one must be dropped — and the function returns False."""
     try:
         torch.cuda.synchronize(device)
     except Exception:       # noqa: BLE001 - the error of the failed capture may surface here once more
+        pass
+    try:
+        dummy = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(dummy):
+            torch.zeros(1, device=device)
+        del dummy
+        torch.cuda.set_rng_state(rng_state, device)
+        torch.cuda.synchronize(device)
+        return True
+    except Exception:       # noqa: BLE001
         pass
     try:
         fresh = torch.Generator(device=device)
@@ -99,6 +113,7 @@ def _recover_generator(device, rng_state):
         torch.cuda.default_generators[idx].graphsafe_set_state(fresh)
     except Exception:       # noqa: BLE001 - best effort
         pass
+    return False
 
 
 class _CapturedStep:
@@ -131,6 +146,7 @@ class SVI:
         self.step_prologue = None          # callable run at the start of every step (host-fed steps enqueue their copies there)
         self._graphs = {}                  # key -> _CapturedStep | number of eager steps so far | False (not capturable)
         self._capture_failures = 0
+        self._capture_stream = None
         self.last_step_was_replay = False
 
     # ---------------------------------------------------------------------------------------------------------------
@@ -203,8 +219,14 @@ class SVI:
         # per SM for milliseconds) gets SMs ahead of the prior's chain on the (default-priority) side stream whenever both have
         # a kernel pending.  The other order starves the recurrences behind the persistent tcgen05 update kernels: 26-33 ms per
         # 2,000-leaf step instead of 22.4 (profiles/r02/bench_graph_v1_c4.json).
-        prio = int(os.environ.get("DRP_GRAPH_PRIORITY", "-2"))
-        stream = torch.cuda.Stream(device=device, priority=prio) if prio != 0 else None
+        # ONE capture stream per SVI object: the parameters' AccumulateGrad nodes are bound to the stream they were created on
+        # and live as long as any captured step's traces do, so a second capture (other argument tensors) on another stream
+        # would hand the engine a stream mismatch - a cross-stream wait onto a stream outside the capture, which breaks it
+        # now and then (profiles/r02/gpu_session24.sh: the second of two alternating argument sets)
+        if self._capture_stream is None or self._capture_stream.device != device:
+            prio = int(os.environ.get("DRP_GRAPH_PRIORITY", "-2"))
+            self._capture_stream = torch.cuda.Stream(device=device, priority=prio)
+        stream = self._capture_stream
         try:
             with torch.cuda.graph(cs.graph, stream=stream):
                 loss, flag, params = self._evaluate(args, {})
@@ -214,7 +236,8 @@ class SVI:
             cs.infos = ops.end_deferred(token)
         except BaseException:
             ops.end_deferred(token)
-            _recover_generator(device, rng_state)
+            if not _recover_generator(device, rng_state):
+                self._graphs = {k: (self.graph_warmup if isinstance(v, _CapturedStep) else v) for k, v in self._graphs.items()}
             raise
         cs.static_args = args                  # the tensors the graph reads
         cs.params = params

@@ -93,6 +93,10 @@ class Run(SimpleNamespace):
                 lo = min(rows, shard.rank * per)
                 self._patristic_rows = (lo, min(rows, lo + per), per, gathered,
                                         torch.zeros((per, cols), dtype=gathered.dtype, device=self.device))
+                # the pipelined form (`prefetch=`) gathers on the copy stream WHILE the previous step's graph, which holds
+                # all-reduces of the run's communicator, executes: it needs a communicator of its own
+                self._prefetch_group = dist.new_group(ranks=list(range(shard.world)), backend="nccl")
+        self._slots, self._pending = None, None
         return host
 
     def _leaf_rows(self):
@@ -113,8 +117,72 @@ class Run(SimpleNamespace):
             total += rows * (v.numel() // v.shape[0]) * v.element_size()
         return int(total)
 
-    def step_from_host(self, host) -> float:
+    # ---- pipelined form: the NEXT step's inputs cross PCIe while this step computes ---------------------------------
+    def _slot(self, k: int):
+        """Staging set k (0 / 1) of the pipelined host-fed step: device copies of the inputs, plus — sharded — the
+        buffers of the row-sharded patristic copy."""
+        if self._slots is None:
+            self._slots = [None, None]
+            self._slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+        if self._slots[k] is None:
+            st = {name: torch.empty_like(v) for name, v in self._staging.items()}
+            for name, v in self._staging.items():        # rows this rank never copies stay valid
+                st[name].copy_(v)
+            pr = self._patristic_rows
+            if pr is not None:
+                gathered = torch.zeros_like(pr[3])
+                gathered[: st["patristic"].shape[0]].copy_(self._staging["patristic"])
+                st["patristic"] = gathered[: st["patristic"].shape[0]]
+                st["_gathered"], st["_mine"] = gathered, torch.zeros_like(pr[4])
+            self._slots[k] = st
+        return self._slots[k]
+
+    def _enqueue_copy(self, host, k: int):
+        """Copy the host inputs into staging set k on the copy stream; `_slot_ready[k]` fires when they have landed.  The
+        set's previous reader has finished: every step ends with the host reading its loss."""
+        st, cs = self._slot(k), self._copy_stream
+        lo, hi = self._leaf_rows()
+        cs.wait_stream(torch.cuda.current_stream())       # idle between steps; orders the set's initialisation before the copy
+        with torch.cuda.stream(cs):
+            pr = self._patristic_rows
+            if pr is None:
+                st["patristic"].copy_(host["patristic"], non_blocking=True)
+            else:
+                import torch.distributed as dist
+                r_lo, r_hi = pr[0], pr[1]
+                if r_hi > r_lo:
+                    st["_mine"][: r_hi - r_lo].copy_(host["patristic"][r_lo:r_hi], non_blocking=True)
+                dist.all_gather_into_tensor(st["_gathered"], st["_mine"], group=self._prefetch_group)
+            if "blosum" in host:
+                st["blosum"][lo:hi].copy_(host["blosum"][lo:hi], non_blocking=True)
+            st["dataset"][lo:hi].copy_(host["dataset"][lo:hi], non_blocking=True)
+            self._slot_ready[k].record(cs)
+
+    def _pipelined_step(self, host, prefetch) -> float:
+        pend, self._pending = self._pending, None
+        if pend is not None and pend[1] is host:
+            k = pend[0]                                   # already on its way (or landed): issued during the previous step
+        else:
+            k = 0 if pend is None else 1 - pend[0]
+            self._enqueue_copy(host, k)
+        if prefetch is not None:                          # enqueued BEFORE this step's launch: the two overlap
+            self._enqueue_copy(prefetch, 1 - k)
+            self._pending = (1 - k, prefetch)
+        torch.cuda.current_stream().wait_event(self._slot_ready[k])
+        st = self._slots[k]
+        return self.svi.step(st["dataset"], st["patristic"], None, st.get("blosum"), None, None)
+
+    def step_from_host(self, host, prefetch=None) -> float:
         """H2D of the step inputs (pinned, asynchronous) -> svi.step -> loss back to the host as a float.
+
+        `prefetch`: the host inputs of the NEXT call (the next batch of the caller's loader; may be `host` itself).  Their
+        copy is enqueued on the copy stream before this step is launched and lands in the other of two staging sets while
+        this step computes — the loop S/train.py:73-75 with a pinned, double-buffered loader; the next call must then pass
+        that same object as `host` and must not have modified it in between.  Each staging set gets its own captured graph
+        (no copies inside); every step still moves its full inputs across PCIe, one step early.
+
 
         The copies run on a copy stream and every consumer waits for its own input only (event waits on the stream that reads
         it, no host synchronisation): the patristic matrix is awaited by the stream that assembles the covariances (the
@@ -123,8 +191,11 @@ class Run(SimpleNamespace):
         networks ran.  Of the first two the SMALLER goes first: on one GPU that is the matrix (the factorisation then has
         the machine to itself while the 168 MB BLOSUM tensor crosses PCIe), on a leaf-sharded rank it is the rank's slice of
         the BLOSUM tensor (the recurrences are the critical path there and must not queue behind 32 MB of matrix)."""
-        if getattr(self, "_copy_stream", None) is None:
-            self._copy_stream = torch.cuda.Stream(device=self.device)
+        if prefetch is not None or getattr(self, "_pending", None) is not None:
+            return self._pipelined_step(host, prefetch)
+        if getattr(self, "_events", None) is None:
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
             self._events = {k: torch.cuda.Event() for k in ("patristic", "blosum", "dataset")}
             self._armed = False
             real_model, real_guide = self.svi.model, self.svi.guide

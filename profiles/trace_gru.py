@@ -19,11 +19,16 @@ if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) fo
 if not torch.cuda.is_available():
     print("built", out)
     sys.exit(0)
-if len(sys.argv) > 1:
+# argv: rows per CTA (8 / 16 / 32), or "cluster" for the CTA-pair kernels (gru_fwdc_kernel / gru_bwdc_kernel); then n
+cluster = len(sys.argv) > 1 and sys.argv[1] == "cluster"
+if cluster:
+    os.environ["DRP_GRU_CLUSTER"] = "1"
+elif len(sys.argv) > 1:
     os.environ["DRP_GRU_ROWS"] = sys.argv[1]
+    os.environ["DRP_GRU_CLUSTER"] = "0"
 lib = ctypes.CDLL(out)
 dev = torch.device("cuda:0")
-n, L, H = 2000, 500, 60
+n, L, H = (int(sys.argv[2]) if len(sys.argv) > 2 else 2000), 500, 60
 g = torch.Generator(device=dev).manual_seed(0)
 gi = torch.randn(n, L, 2, 3 * H, dtype=torch.float64, device=dev, generator=g)
 whh = torch.randn(2, 3 * H, H, dtype=torch.float64, device=dev, generator=g) * 0.1
@@ -43,7 +48,14 @@ torch.cuda.synchronize()
 buf = (ctypes.c_longlong * (8 * 64 * 2))()
 assert lib.drp_gru_trace_read(buf) == 0
 t = np.frombuffer(buf, dtype=np.int64).reshape(2, 64, 8)
-print(f"# gru_fwd n={n} L={L}: {a.elapsed_time(b):.3f} ms = {a.elapsed_time(b) * 1e6 / L:.0f} ns/step; rows/CTA = {os.environ.get('DRP_GRU_ROWS', 'auto')}")
+print(f"# gru_fwd n={n} L={L}: {a.elapsed_time(b):.3f} ms = {a.elapsed_time(b) * 1e6 / L:.0f} ns/step; rows/CTA = {'8 per CTA pair' if cluster else os.environ.get('DRP_GRU_ROWS', 'auto')}")
+if cluster:
+    order = [0, 1, 2, 3, 4, 6, 5]
+    print("# cycles per phase (mean over steps 200..263): wait h (both halves) | product | wait gi | gates + h stores (local, st.async) | mbarrier arrivals | global stores | step total")
+    for w, name in ((0, "warp 0"), (1, "warp 3")):
+        d = np.diff(t[w][:, order], axis=1).astype(np.float64)
+        step = np.diff(t[w, :, 0]).astype(np.float64)
+        print(name, " ".join(f"{v:8.0f}" for v in d.mean(0)), f"| step {step.mean():8.0f} (min {step.min():.0f} max {step.max():.0f})")
 print("# cycles per phase (mean over steps 200..263): issue | product | (to wait) | wait gi | gates+stores | barrier | step total")
 for w, name in ((0, "warp 0"), (1, "warp 8/7")):
     d = np.diff(t[w, :, :6], axis=1).astype(np.float64)            # [64, 5]
@@ -65,6 +77,13 @@ torch.cuda.synchronize()
 assert lib.drp_gru_trace_read(buf) == 0
 t = np.frombuffer(buf, dtype=np.int64).reshape(2, 64, 8)
 print(f"# gru_bwd n={n} L={L}: {a.elapsed_time(b):.3f} ms = {a.elapsed_time(b) * 1e6 / L:.0f} ns/step")
+if cluster:
+    order = [0, 2, 3, 4, 1, 7, 5, 6]
+    print("# cycles per phase: dout loads issued | wait ring | gates + dgh stores (local, st.async) | mbarrier arrivals | global stores | wait dgh (both halves) | product | step total")
+    for w, name in ((0, "warp 0"), (1, "warp 3")):
+        d = np.diff(t[w][:, order], axis=1).astype(np.float64)
+        step = np.diff(t[w, :, 0]).astype(np.float64)
+        print(name, " ".join(f"{v:8.0f}" for v in d.mean(0)), f"| step {step.mean():8.0f}")
 print("# cycles per phase: issue | dout loads issued | wait ring | gates+stores | barrier 1 | product | barrier 2 | step total")
 for w, name in ((0, "warp 0"), (1, "warp 7")):
     d = np.diff(t[w, :, :8], axis=1).astype(np.float64)

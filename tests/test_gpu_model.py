@@ -189,6 +189,49 @@ def test_host_fed_step_equals_resident_step(cuda, guide):
         assert abs(la - lb) <= 1e-10 * abs(la), (la, lb)
 
 
+@pytest.mark.parametrize("guide", ["delta_map", "variational"])
+def test_pipelined_host_fed_steps(cuda, guide):
+    """`Run.step_from_host(host, prefetch=next)`: the next step's inputs are copied into the other staging set while this
+    step runs.  Two different data sets alternate (so a step that read the wrong set, or a set before its copy landed, shows
+    up in the loss); eight steps cover the eager steps, the capture and the replay of BOTH sets' graphs.  Same trajectory
+    as resident steps on the same alternation."""
+    n, L = 450, 30
+    torch.manual_seed(0)
+    problem, run_a, _ = _pair(n, L, guide, cuda)
+    torch.manual_seed(0)
+    _, run_b, _ = _pair(n, L, guide, cuda)
+    host0 = run_b.make_host_inputs()
+    pin = lambda t: t.clone().pin_memory()
+    host1 = {k: pin(v) for k, v in host0.items()}
+    g = torch.Generator().manual_seed(11)
+    perm = torch.randperm(n, generator=g)
+    host1["dataset"] = pin(host0["dataset"][perm])                    # other leaves' sequences under the same tree
+    if "blosum" in host1:
+        host1["blosum"] = pin(host0["blosum"][perm])
+    scaled = host0["patristic"].clone()
+    scaled[1:, 1:] *= 1.25                                            # (row / column 0 hold the node indices)
+    host1["patristic"] = pin(scaled)
+    hosts = [host0, host1]
+    dev = [{k: v.to(cuda) for k, v in h.items()} for h in hosts]
+    torch.manual_seed(5)
+    want = []
+    for k in range(8):
+        d = dev[k % 2]
+        want.append(run_a.svi.step(d["dataset"], d["patristic"], None, d.get("blosum"), None, None))
+    torch.manual_seed(5)
+    got = []
+    for k in range(8):
+        got.append(run_b.step_from_host(hosts[k % 2], prefetch=hosts[(k + 1) % 2] if k < 7 else None))
+    assert run_b.svi.last_step_was_replay
+    assert got == pytest.approx(want, rel=1e-10)
+    # a call whose inputs were NOT announced still works (copied on the spot), and the plain form afterwards too
+    torch.manual_seed(6)
+    w2 = [run_a.svi.step(dev[0]["dataset"], dev[0]["patristic"], None, dev[0].get("blosum"), None, None) for _ in range(2)]
+    torch.manual_seed(6)
+    g2 = [run_b.step_from_host(host0, prefetch=host1), run_b.step_from_host(host0)]
+    assert g2 == pytest.approx(w2, rel=1e-10)
+
+
 @pytest.mark.parametrize("guide,n,L", [("delta_map", 19, 225), ("variational", 60, 40), ("variational", 450, 24)])
 def test_graph_replay_walks_the_eager_trajectory(cuda, guide, n, L):
     """after two eager steps `svi.step` is captured in a CUDA graph and replayed.  Same losses,
@@ -276,6 +319,34 @@ def test_graph_replay_raises_before_the_update(cuda):
     run.patristic_matrix_train[1:, 1:].div_(-50.0)
     l1, l2 = run.step(), run.step()                        # the graph is still usable afterwards
     assert run.svi.last_step_was_replay and l1 == l1 and l2 < l1 + abs(l1) and run.optim.step_count == steps + 2
+
+
+def test_failed_capture_leaves_earlier_graphs_usable(cuda):
+    """A capture that dies half-way (here: a step prologue that synchronises the device, which no capture tolerates) must
+    not take the graphs captured before it down with it: the default generator's state is put back in order, the run
+    continues eagerly for that call pattern and the first graph keeps replaying on the eager trajectory (the variational
+    guide draws inside the graph)."""
+    torch.manual_seed(0)
+    _, run_e, _ = _pair(60, 20, "variational", cuda, cuda_graph=False)
+    torch.manual_seed(0)
+    _, run_g, _ = _pair(60, 20, "variational", cuda, cuda_graph=True)
+    bad = lambda: torch.cuda.synchronize()
+
+    def walk(run):
+        torch.manual_seed(9)
+        out = [run.step() for _ in range(4)]                          # graph run: eager, eager, capture + replay, replay
+        run.svi.step_prologue = bad
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out += [run.step() for _ in range(4)]                     # third of these tries to capture and fails
+        run.svi.step_prologue = None
+        out += [run.step() for _ in range(3)]
+        return out
+
+    import warnings
+    want, got = walk(run_e), walk(run_g)
+    assert run_g.svi.last_step_was_replay and run_g.svi._capture_failures >= 1
+    assert got == pytest.approx(want, rel=1e-11)
 
 
 @pytest.mark.parametrize("guide", ["delta_map", "variational"])
