@@ -22,6 +22,7 @@
 #include "instrument.cuh"
 #include "factor.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -739,12 +740,17 @@ __global__ void __launch_bounds__(GTHREADS, 1) gru_bwd_kernel(const double* __re
 // pipe however few rows there are (profiles/r02/trace_gru_rows8.txt), plus the gate arithmetic of 8 x 60 elements.  Here CTA
 // c of the pair owns hidden units 32 c .. 32 c + 31 (four warps, one per SM sub-partition: 45 DMMAs each) and the matching
 // half of the gate arithmetic.  What the other half needs - the new h (forward), dgh (backward) - goes into BOTH CTAs'
-// shared memory: a plain store at home and `st.async` into the partner, which signals the partner's mbarrier with the bytes
-// it delivers.  One mbarrier per operand buffer collects the four local warps' arrivals and the partner's bytes, so a step
-// has a single wait and no fence (a barrier.cluster per step costs 1.3-1.6 k cycles here: its release is a MEMBAR.GPU that
-// waits for the step's global stores, profiles/r02/trace_gru_cluster_v1.txt).  The operand buffers are double-buffered and
-// nothing else is needed: whoever writes buffer b for step t + 2 has consumed everything the readers of step t produced
-// AFTER reading it.  A fifth warp per CTA issues the TMA copies, up to two steps ahead (full / empty mbarriers).
+// shared memory: a plain store at home and `st.async` into the partner, which completes bytes on the partner's mbarrier.
+// No fence and no barrier.cluster inside the loop (one per step costs 1.3-1.6 k cycles here: its release is a MEMBAR.GPU
+// that waits for the step's global stores, profiles/r02/trace_gru_cluster_v1.txt).  Per operand buffer one mbarrier
+// collects the four local warps' arrivals and one the partner's bytes; the product multiplies the columns written at home
+// first and the partner's - ~450 cycles of DSMEM + mbarrier latency away - second, by which time they have arrived.
+// The operand buffers are double-buffered and nothing else is needed: whoever writes buffer b for step t + 2 has consumed
+// everything the readers of step t produced AFTER reading it.  A fifth warp per CTA issues the TMA copies, up to two
+// steps ahead (full / empty mbarriers).  Per step at 250 rows: 2.30 k cycles forward, 2.07 k backward, against 3.24 k /
+// 2.93 k for one 8-row CTA (profiles/r02/trace_gru_cluster_v3.txt, trace_gru_rows8.txt).  Splitting the reduction
+// dimension over a second warp per sub-partition does not help: the fp64 pipe of a sub-partition takes a DMMA every
+// ~17 cycles whoever issues it, and the extra exchange costs more than the single warp's 22 (trace_gru_cluster_v4_8warps.txt).
 // Same arguments and layouts as gru_fwd2_kernel / gru_bwd_kernel; rows per cluster: 8.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int GC_CL = 2;                      // CTAs per cluster
@@ -799,7 +805,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_fwdc_kernel(const double* _
     double* etab = reinterpret_cast<double*>(gsm + gfc_smem(UV) - 256);
     const uint32_t full = g_smem_u32(gsm + gfc_smem(UV) - 320);                       // [stages]  ring stage landed
     const uint32_t empty = full + 8 * GF2_STAGES;                                     // [stages]  ring stage read by the 4 warps
-    const uint32_t hfull = empty + 8 * GF2_STAGES;                                    // [2]       h buffer complete (both halves)
+    const uint32_t hloc = empty + 8 * GF2_STAGES;                                     // [2]       h buffer: this CTA's half written
+    const uint32_t hrem = hloc + 16;                                                  // [2]       h buffer: the partner's half landed
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
     const uint32_t crank = g_cluster_ctarank();
     const bool producer = warp == GC_NW;
@@ -830,7 +837,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_fwdc_kernel(const double* _
             g_mbar_init(full + 8 * s, 1);
             g_mbar_init(empty + 8 * s, GC_NW);
         }
-        for (int b = 0; b < 2; ++b) g_mbar_init(hfull + 8 * b, GC_NW);      // warp 0's arrival carries the partner's byte count
+        for (int b = 0; b < 2; ++b) {
+            g_mbar_init(hloc + 8 * b, GC_NW);
+            g_mbar_init(hrem + 8 * b, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -869,101 +879,124 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_fwdc_kernel(const double* _
         return;
     }
     const uint32_t hb_remote = g_mapa(g_smem_u32(hbuf), crank ^ 1u);
-    const uint32_t hfull_remote = g_mapa(hfull, crank ^ 1u);
+    const uint32_t hrem_remote = g_mapa(hrem, crank ^ 1u);
     double hold[2];
     hold[0] = jok ? hbuf[gid * GHS + j0] : 0.0;
     hold[1] = jok ? hbuf[gid * GHS + j0 + 1] : 0.0;
 
-    for (int t = 0; t < L; ++t) {
-        const int l = dir ? L - 1 - t : t;
-        const double* hc = hbuf + (t & 1) * GC_ROWS * GHS;
-        const int nb = (t + 1) & 1;
-        const int hn_off = nb * GC_ROWS * GHS + gid * GHS + j0;
-        GRU_TRACE(0);
-        if (t > 0) g_mbar_wait(hfull + 8 * (t & 1), (uint32_t)((t - 1) >> 1) & 1u);    // h(t-1): my warps' halves and the partner's
-        GRU_TRACE(1);
-        double acc[3][2];
+    // CR = rank in the pair, as a compile-time constant: the k-steps of the recurrent product that read this CTA's OWN half
+    // of h (written by its four warps: a local barrier away) go first, the partner's half - ~450 cycles of DSMEM + mbarrier
+    // latency away - second, by which time it has normally arrived.  Six accumulation chains (gate x k parity).
+    auto run = [&](auto cr_tag) {
+        constexpr int CR = decltype(cr_tag)::value;
+        constexpr int LK0 = CR ? 8 : 0, LKN = CR ? 7 : 8, RK0 = CR ? 0 : 8, RKN = 15 - LKN;
+        for (int t = 0; t < L; ++t) {
+            const int l = dir ? L - 1 - t : t;
+            const double* hc = hbuf + (t & 1) * GC_ROWS * GHS;
+            const int nb = (t + 1) & 1;
+            const int hn_off = nb * GC_ROWS * GHS + gid * GHS + j0;
+            const uint32_t hpar = (uint32_t)((t - 1) >> 1) & 1u;
+            GRU_TRACE(0);
+            if (t > 0) g_mbar_wait(hloc + 8 * (t & 1), hpar);                  // h(t-1), this CTA's half
+            GRU_TRACE(1);
+            double acc[2][3][2];
 #pragma unroll
-        for (int g = 0; g < 3; ++g) acc[g][0] = bh[g][0], acc[g][1] = bh[g][1];
+            for (int g = 0; g < 3; ++g) acc[0][g][0] = bh[g][0], acc[0][g][1] = bh[g][1], acc[1][g][0] = acc[1][g][1] = 0.0;
 #pragma unroll
-        for (int ks = 0; ks < 15; ++ks) {
-            const double a = hc[gid * GHS + 4 * ks + tig];
-            double b[3];
+            for (int i = 0; i < LKN; ++i) {
+                const int ks = LK0 + i;
+                const double a = hc[gid * GHS + 4 * ks + tig];
+                double b[3];
 #pragma unroll
-            for (int g = 0; g < 3; ++g) b[g] = wt[(4 * ks + tig) * GWS + g * GH + jb];
+                for (int g = 0; g < 3; ++g) b[g] = wt[(4 * ks + tig) * GWS + g * GH + jb];
 #pragma unroll
-            for (int g = 0; g < 3; ++g) dmma_8x8x4(acc[g][0], acc[g][1], a, b[g]);
+                for (int g = 0; g < 3; ++g) dmma_8x8x4(acc[i & 1][g][0], acc[i & 1][g][1], a, b[g]);
+            }
+            GRU_TRACE(7);
+            if (t > 0) g_mbar_wait(hrem + 8 * (t & 1), hpar);                  // h(t-1), the partner's half
+#pragma unroll
+            for (int i = 0; i < RKN; ++i) {
+                const int ks = RK0 + i;
+                const double a = hc[gid * GHS + 4 * ks + tig];
+                double b[3];
+#pragma unroll
+                for (int g = 0; g < 3; ++g) b[g] = wt[(4 * ks + tig) * GWS + g * GH + jb];
+#pragma unroll
+                for (int g = 0; g < 3; ++g) dmma_8x8x4(acc[(LKN + i) & 1][g][0], acc[(LKN + i) & 1][g][1], a, b[g]);
+            }
+            const int s = t % GF2_STAGES;
+            GRU_TRACE(2);
+            g_mbar_wait(full + 8 * s, (uint32_t)(t / GF2_STAGES) & 1u);
+            GRU_TRACE(3);
+            const double* gs = ring + (int64_t)s * STAGE_ROWS * GRS;
+            double hv[2] = {0.0, 0.0}, rv[2], zv[2], nv[2], qv[2];
+            if (jok) {
+                double xr[2], xz[2], xn[2];
+                double2 ar, az, an;
+                if (UV) {
+                    const double* up = ubuf + gid * GRS;
+                    const double2 ur = *reinterpret_cast<const double2*>(up + j0);
+                    const double2 uz = *reinterpret_cast<const double2*>(up + GH + j0);
+                    const double2 un = *reinterpret_cast<const double2*>(up + 2 * GH + j0);
+                    const double2 vr = *reinterpret_cast<const double2*>(gs + j0);
+                    const double2 vz = *reinterpret_cast<const double2*>(gs + GH + j0);
+                    const double2 vn = *reinterpret_cast<const double2*>(gs + 2 * GH + j0);
+                    ar = make_double2(ur.x + vr.x, ur.y + vr.y);
+                    az = make_double2(uz.x + vz.x, uz.y + vz.y);
+                    an = make_double2(un.x + vn.x, un.y + vn.y);
+                } else {
+                    ar = *reinterpret_cast<const double2*>(gs + gid * GRS + j0);
+                    az = *reinterpret_cast<const double2*>(gs + gid * GRS + GH + j0);
+                    an = *reinterpret_cast<const double2*>(gs + gid * GRS + 2 * GH + j0);
+                }
+                xr[0] = ar.x, xr[1] = ar.y, xz[0] = az.x, xz[1] = az.y, xn[0] = an.x, xn[1] = an.y;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    qv[e] = acc[0][2][e] + acc[1][2][e];                 // the accumulators started from b_hh
+                    xr[e] += acc[0][0][e] + acc[1][0][e];
+                    xz[e] += acc[0][1][e] + acc[1][1][e];
+                    rv[e] = gru_sigmoid(xr[e], etab);
+                    zv[e] = gru_sigmoid(xz[e], etab);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double gn = fma(rv[e], qv[e], xn[e]);
+                    nv[e] = gru_tanh(gn, etab);
+                    hv[e] = fma(zv[e], hold[e] - nv[e], nv[e]);
+                    hv[e] = fma(0.0, (xr[e] + xz[e]) + gn, hv[e]);   // a NaN pre-activation reaches h (see gru_fwd2_kernel)
+                    hold[e] = hv[e];
+                }
+                if (t + 1 < L) {                                     // (nobody reads the last h from shared memory)
+                    *reinterpret_cast<double2*>(hbuf + hn_off) = make_double2(hv[0], hv[1]);
+                    g_st_async(hb_remote + (uint32_t)hn_off * 8u, hv[0], hv[1], hrem_remote + 8u * nb);
+                }
+            }
+            GRU_TRACE(4);
+            __syncwarp();
+            if (lane == 0) {
+                if (t + 1 < L) {
+                    g_mbar_arrive(hloc + 8 * nb);
+                    if (warp == 0) g_mbar_expect_tx(hrem + 8 * nb, rx_bytes);  // the only arrival: announces the partner's bytes
+                }
+                g_mbar_arrive(empty + 8 * s);                                   // this warp has read ring stage s
+            }
+            GRU_TRACE(6);
+            if (jok && gid < nrows) {
+                const int64_t site = (int64_t)(row0 + gid) * L + l;
+                *reinterpret_cast<double2*>(out + site * (2 * GH) + dir * GH + j0) = make_double2(hv[0], hv[1]);
+                if (gates) {
+                    double* gp = gates + (site * 2 + dir) * (4 * GH) + j0;
+                    *reinterpret_cast<double2*>(gp) = make_double2(rv[0], rv[1]);
+                    *reinterpret_cast<double2*>(gp + GH) = make_double2(zv[0], zv[1]);
+                    *reinterpret_cast<double2*>(gp + 2 * GH) = make_double2(nv[0], nv[1]);
+                    *reinterpret_cast<double2*>(gp + 3 * GH) = make_double2(qv[0], qv[1]);
+                }
+            }
+            GRU_TRACE(5);
         }
-        const int s = t % GF2_STAGES;
-        GRU_TRACE(2);
-        g_mbar_wait(full + 8 * s, (uint32_t)(t / GF2_STAGES) & 1u);
-        GRU_TRACE(3);
-        const double* gs = ring + (int64_t)s * STAGE_ROWS * GRS;
-        double hv[2] = {0.0, 0.0}, rv[2], zv[2], nv[2], qv[2];
-        if (jok) {
-            double xr[2], xz[2], xn[2];
-            double2 ar, az, an;
-            if (UV) {
-                const double* up = ubuf + gid * GRS;
-                const double2 ur = *reinterpret_cast<const double2*>(up + j0);
-                const double2 uz = *reinterpret_cast<const double2*>(up + GH + j0);
-                const double2 un = *reinterpret_cast<const double2*>(up + 2 * GH + j0);
-                const double2 vr = *reinterpret_cast<const double2*>(gs + j0);
-                const double2 vz = *reinterpret_cast<const double2*>(gs + GH + j0);
-                const double2 vn = *reinterpret_cast<const double2*>(gs + 2 * GH + j0);
-                ar = make_double2(ur.x + vr.x, ur.y + vr.y);
-                az = make_double2(uz.x + vz.x, uz.y + vz.y);
-                an = make_double2(un.x + vn.x, un.y + vn.y);
-            } else {
-                ar = *reinterpret_cast<const double2*>(gs + gid * GRS + j0);
-                az = *reinterpret_cast<const double2*>(gs + gid * GRS + GH + j0);
-                an = *reinterpret_cast<const double2*>(gs + gid * GRS + 2 * GH + j0);
-            }
-            xr[0] = ar.x, xr[1] = ar.y, xz[0] = az.x, xz[1] = az.y, xn[0] = an.x, xn[1] = an.y;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                qv[e] = acc[2][e];                                   // the accumulators started from b_hh
-                xr[e] += acc[0][e];
-                xz[e] += acc[1][e];
-                rv[e] = gru_sigmoid(xr[e], etab);
-                zv[e] = gru_sigmoid(xz[e], etab);
-            }
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const double gn = fma(rv[e], qv[e], xn[e]);
-                nv[e] = gru_tanh(gn, etab);
-                hv[e] = fma(zv[e], hold[e] - nv[e], nv[e]);
-                hv[e] = fma(0.0, (xr[e] + xz[e]) + gn, hv[e]);       // a NaN pre-activation reaches h (see gru_fwd2_kernel)
-                hold[e] = hv[e];
-            }
-            if (t + 1 < L) {                                         // (nobody reads the last h from shared memory)
-                *reinterpret_cast<double2*>(hbuf + hn_off) = make_double2(hv[0], hv[1]);
-                g_st_async(hb_remote + (uint32_t)hn_off * 8u, hv[0], hv[1], hfull_remote + 8u * nb);
-            }
-        }
-        GRU_TRACE(4);
-        __syncwarp();
-        if (lane == 0) {
-            if (t + 1 < L) {
-                if (warp == 0) g_mbar_expect_tx(hfull + 8 * nb, rx_bytes);      // an arrival that also announces the partner's bytes
-                else g_mbar_arrive(hfull + 8 * nb);
-            }
-            g_mbar_arrive(empty + 8 * s);                                       // this warp has read ring stage s
-        }
-        GRU_TRACE(6);
-        if (jok && gid < nrows) {
-            const int64_t site = (int64_t)(row0 + gid) * L + l;
-            *reinterpret_cast<double2*>(out + site * (2 * GH) + dir * GH + j0) = make_double2(hv[0], hv[1]);
-            if (gates) {
-                double* gp = gates + (site * 2 + dir) * (4 * GH) + j0;
-                *reinterpret_cast<double2*>(gp) = make_double2(rv[0], rv[1]);
-                *reinterpret_cast<double2*>(gp + GH) = make_double2(zv[0], zv[1]);
-                *reinterpret_cast<double2*>(gp + 2 * GH) = make_double2(nv[0], nv[1]);
-                *reinterpret_cast<double2*>(gp + 3 * GH) = make_double2(qv[0], qv[1]);
-            }
-        }
-        GRU_TRACE(5);
-    }
+    };
+    if (crank == 0) run(std::integral_constant<int, 0>{});
+    else run(std::integral_constant<int, 1>{});
     g_cluster_sync();              // nobody leaves while its partner could still be addressed
 }
 
@@ -981,7 +1014,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_bwdc_kernel(const double* _
     double* ring = dgh + 2 * GC_ROWS * GDS;                                           // [stages][8][312]
     const uint32_t full = g_smem_u32(gsm + gbc_smem() - 64);
     const uint32_t empty = full + 8 * GB_STAGES;
-    const uint32_t dfull = empty + 8 * GB_STAGES;                                     // [2] dgh buffer complete (all 180 columns)
+    const uint32_t dloc = empty + 8 * GB_STAGES;                                      // [2] dgh buffer: this CTA's columns written
+    const uint32_t drem = dloc + 16;                                                  // [2] dgh buffer: the partner's columns landed
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
     const uint32_t crank = g_cluster_ctarank();
     const bool producer = warp == GC_NW;
@@ -1000,7 +1034,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_bwdc_kernel(const double* _
             g_mbar_init(full + 8 * s, 1);
             g_mbar_init(empty + 8 * s, GC_NW);
         }
-        for (int b = 0; b < 2; ++b) g_mbar_init(dfull + 8 * b, GC_NW);
+        for (int b = 0; b < 2; ++b) {
+            g_mbar_init(dloc + 8 * b, GC_NW);
+            g_mbar_init(drem + 8 * b, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -1036,7 +1073,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_bwdc_kernel(const double* _
 #pragma unroll
     for (int ks = 0; ks < 45; ++ks) B[ks] = jb < GH ? W[(int64_t)(4 * ks + tig) * GH + jb] : 0.0;
     const uint32_t dg_remote = g_mapa(g_smem_u32(dgh), crank ^ 1u);
-    const uint32_t dfull_remote = g_mapa(dfull, crank ^ 1u);
+    const uint32_t drem_remote = g_mapa(drem, crank ^ 1u);
     double dh[2] = {0.0, 0.0};
     const bool rok = jok && gid < nrows;
     double2 dOn;
@@ -1047,82 +1084,100 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_bwdc_kernel(const double* _
         dOn = (rok && !(dout_last && l0 != L - 1)) ? *reinterpret_cast<const double2*>(src) : make_double2(0.0, 0.0);
     }
 
-    for (int tb = 0; tb < L; ++tb) {
-        const int t = L - 1 - tb;
-        const int l = dir ? L - 1 - t : t;
-        GRU_TRACE_B(0);
-        const double2 dO = dOn;                    // requested a whole step ago (see gru_bwd_kernel)
-        if (tb + 1 < L) {
-            const int ln = dir ? l + 1 : l - 1;
-            if (dout_last) {
-                dOn = (rok && ln == L - 1) ? *reinterpret_cast<const double2*>(dout + (int64_t)(row0 + gid) * (2 * GH) + dir * GH + j0)
-                                           : make_double2(0.0, 0.0);
-            } else {
-                dOn = rok ? *reinterpret_cast<const double2*>(dout + ((int64_t)(row0 + gid) * L + ln) * (2 * GH) + dir * GH + j0)
-                          : make_double2(0.0, 0.0);
+    // CR = rank in the pair at compile time (W_hh sits in registers: static indices): the columns of dgh this CTA's own
+    // warps wrote are multiplied first, the partner's - still in flight - second; six accumulation chains
+    auto run = [&](auto cr_tag) {
+        constexpr int CR = decltype(cr_tag)::value;
+        constexpr int LK0 = CR ? 8 : 0, LKN = CR ? 7 : 8, RK0 = CR ? 0 : 8, RKN = 15 - LKN;
+        for (int tb = 0; tb < L; ++tb) {
+            const int t = L - 1 - tb;
+            const int l = dir ? L - 1 - t : t;
+            GRU_TRACE_B(0);
+            const double2 dO = dOn;                    // requested a whole step ago (see gru_bwd_kernel)
+            if (tb + 1 < L) {
+                const int ln = dir ? l + 1 : l - 1;
+                if (dout_last) {
+                    dOn = (rok && ln == L - 1) ? *reinterpret_cast<const double2*>(dout + (int64_t)(row0 + gid) * (2 * GH) + dir * GH + j0)
+                                               : make_double2(0.0, 0.0);
+                } else {
+                    dOn = rok ? *reinterpret_cast<const double2*>(dout + ((int64_t)(row0 + gid) * L + ln) * (2 * GH) + dir * GH + j0)
+                              : make_double2(0.0, 0.0);
+                }
             }
-        }
-        const int s = tb % GB_STAGES, b = tb & 1;
-        const int dg_off = b * GC_ROWS * GDS + gid * GDS + j0;
-        GRU_TRACE_B(2);
-        g_mbar_wait(full + 8 * s, (uint32_t)(tb / GB_STAGES) & 1u);
-        GRU_TRACE_B(3);
-        const double* gs = ring + (int64_t)s * GC_ROWS * RS + gid * RS;
-        double dr[2], dz[2], dn[2], dq[2];
-        if (jok) {
-            const double2 rr = *reinterpret_cast<const double2*>(gs + j0);
-            const double2 zz = *reinterpret_cast<const double2*>(gs + GH + j0);
-            const double2 nn = *reinterpret_cast<const double2*>(gs + 2 * GH + j0);
-            const double2 qq = *reinterpret_cast<const double2*>(gs + 3 * GH + j0);
-            const double2 hp = *reinterpret_cast<const double2*>(gs + 4 * GH + j0);
+            const int s = tb % GB_STAGES, b = tb & 1;
+            const int dg_off = b * GC_ROWS * GDS + gid * GDS + j0;
+            const uint32_t dpar = (uint32_t)(tb >> 1) & 1u;
+            GRU_TRACE_B(2);
+            g_mbar_wait(full + 8 * s, (uint32_t)(tb / GB_STAGES) & 1u);
+            GRU_TRACE_B(3);
+            const double* gs = ring + (int64_t)s * GC_ROWS * RS + gid * RS;
+            double dr[2], dz[2], dn[2], dq[2];
+            if (jok) {
+                const double2 rr = *reinterpret_cast<const double2*>(gs + j0);
+                const double2 zz = *reinterpret_cast<const double2*>(gs + GH + j0);
+                const double2 nn = *reinterpret_cast<const double2*>(gs + 2 * GH + j0);
+                const double2 qq = *reinterpret_cast<const double2*>(gs + 3 * GH + j0);
+                const double2 hp = *reinterpret_cast<const double2*>(gs + 4 * GH + j0);
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const double rv = e ? rr.y : rr.x, zv = e ? zz.y : zz.x, nv = e ? nn.y : nn.x, qv = e ? qq.y : qq.x;
-                const double hv = e ? hp.y : hp.x;
-                const double d = (e ? dO.y : dO.x) + dh[e];
-                dn[e] = d * (1.0 - zv) * (1.0 - nv * nv);
-                dz[e] = d * (hv - nv) * zv * (1.0 - zv);
-                dr[e] = dn[e] * qv * rv * (1.0 - rv);
-                dq[e] = dn[e] * rv;
-                dh[e] = d * zv;
+                for (int e = 0; e < 2; ++e) {
+                    const double rv = e ? rr.y : rr.x, zv = e ? zz.y : zz.x, nv = e ? nn.y : nn.x, qv = e ? qq.y : qq.x;
+                    const double hv = e ? hp.y : hp.x;
+                    const double d = (e ? dO.y : dO.x) + dh[e];
+                    dn[e] = d * (1.0 - zv) * (1.0 - nv * nv);
+                    dz[e] = d * (hv - nv) * zv * (1.0 - zv);
+                    dr[e] = dn[e] * qv * rv * (1.0 - rv);
+                    dq[e] = dn[e] * rv;
+                    dh[e] = d * zv;
+                }
+                *reinterpret_cast<double2*>(dgh + dg_off) = make_double2(dr[0], dr[1]);
+                *reinterpret_cast<double2*>(dgh + dg_off + GH) = make_double2(dz[0], dz[1]);
+                *reinterpret_cast<double2*>(dgh + dg_off + 2 * GH) = make_double2(dq[0], dq[1]);
+                g_st_async(dg_remote + (uint32_t)dg_off * 8u, dr[0], dr[1], drem_remote + 8u * b);
+                g_st_async(dg_remote + (uint32_t)(dg_off + GH) * 8u, dz[0], dz[1], drem_remote + 8u * b);
+                g_st_async(dg_remote + (uint32_t)(dg_off + 2 * GH) * 8u, dq[0], dq[1], drem_remote + 8u * b);
             }
-            *reinterpret_cast<double2*>(dgh + dg_off) = make_double2(dr[0], dr[1]);
-            *reinterpret_cast<double2*>(dgh + dg_off + GH) = make_double2(dz[0], dz[1]);
-            *reinterpret_cast<double2*>(dgh + dg_off + 2 * GH) = make_double2(dq[0], dq[1]);
-            g_st_async(dg_remote + (uint32_t)dg_off * 8u, dr[0], dr[1], dfull_remote + 8u * b);
-            g_st_async(dg_remote + (uint32_t)(dg_off + GH) * 8u, dz[0], dz[1], dfull_remote + 8u * b);
-            g_st_async(dg_remote + (uint32_t)(dg_off + 2 * GH) * 8u, dq[0], dq[1], dfull_remote + 8u * b);
-        }
-        GRU_TRACE_B(4);
-        __syncwarp();
-        if (lane == 0) {
-            if (warp == 0) g_mbar_expect_tx(dfull + 8 * b, rx_bytes);          // an arrival that also announces the partner's bytes
-            else g_mbar_arrive(dfull + 8 * b);
-            g_mbar_arrive(empty + 8 * s);                                      // this warp has read ring stage s
-        }
-        GRU_TRACE_B(1);
-        if (rok) {
-            double* gp = dgi + (((int64_t)(row0 + gid) * L + l) * dgi_dirs + (dgi_dirs == 2 ? dir : 0)) * G3 + j0;
-            *reinterpret_cast<double2*>(gp) = make_double2(dr[0], dr[1]);
-            *reinterpret_cast<double2*>(gp + GH) = make_double2(dz[0], dz[1]);
-            *reinterpret_cast<double2*>(gp + 2 * GH) = make_double2(dn[0], dn[1]);
-        }
-        GRU_TRACE_B(7);
-        g_mbar_wait(dfull + 8 * b, (uint32_t)(tb >> 1) & 1u);                  // all 180 columns of dgh(tb) are here
-        GRU_TRACE_B(5);
-        // dh_prev[:, own units] = dh z + dgh W_hh[:, own units]: three independent accumulation chains (a single chain of 45
-        // dependent DMMAs is latency-bound with one warp per sub-partition)
-        const double* dg = dgh + b * GC_ROWS * GDS + gid * GDS + tig;
-        double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+            GRU_TRACE_B(4);
+            __syncwarp();
+            if (lane == 0) {
+                g_mbar_arrive(dloc + 8 * b);
+                if (warp == 0) g_mbar_expect_tx(drem + 8 * b, rx_bytes);       // the only arrival: announces the partner's bytes
+                g_mbar_arrive(empty + 8 * s);                                  // this warp has read ring stage s
+            }
+            GRU_TRACE_B(1);
+            if (rok) {
+                double* gp = dgi + (((int64_t)(row0 + gid) * L + l) * dgi_dirs + (dgi_dirs == 2 ? dir : 0)) * G3 + j0;
+                *reinterpret_cast<double2*>(gp) = make_double2(dr[0], dr[1]);
+                *reinterpret_cast<double2*>(gp + GH) = make_double2(dz[0], dz[1]);
+                *reinterpret_cast<double2*>(gp + 2 * GH) = make_double2(dn[0], dn[1]);
+            }
+            GRU_TRACE_B(7);
+            // dh_prev[:, own units] = dh z + dgh W_hh[:, own units]
+            const double* dg = dgh + b * GC_ROWS * GDS + gid * GDS + tig;
+            double acc[6][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+            g_mbar_wait(dloc + 8 * b, dpar);                                   // the columns this CTA's warps wrote
 #pragma unroll
-        for (int ks = 0; ks < 45; ks += 3) {
+            for (int g = 0; g < 3; ++g)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) dmma_8x8x4(acc[c][0], acc[c][1], dg[4 * (ks + c)], B[ks + c]);
+                for (int i = 0; i < LKN; ++i) {
+                    const int ks = g * 15 + LK0 + i, c = (g * LKN + i) % 6;
+                    dmma_8x8x4(acc[c][0], acc[c][1], dg[4 * ks], B[ks]);
+                }
+            GRU_TRACE_B(5);
+            g_mbar_wait(drem + 8 * b, dpar);                                   // the partner's columns
+#pragma unroll
+            for (int g = 0; g < 3; ++g)
+#pragma unroll
+                for (int i = 0; i < RKN; ++i) {
+                    const int ks = g * 15 + RK0 + i, c = (3 * LKN + g * RKN + i) % 6;
+                    dmma_8x8x4(acc[c][0], acc[c][1], dg[4 * ks], B[ks]);
+                }
+            dh[0] += ((acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0])) + (acc[4][0] + acc[5][0]);
+            dh[1] += ((acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1])) + (acc[4][1] + acc[5][1]);
+            GRU_TRACE_B(6);
         }
-        dh[0] += (acc[0][0] + acc[1][0]) + acc[2][0];
-        dh[1] += (acc[0][1] + acc[1][1]) + acc[2][1];
-        GRU_TRACE_B(6);
-    }
+    };
+    if (crank == 0) run(std::integral_constant<int, 0>{});
+    else run(std::integral_constant<int, 1>{});
     if (dh0 && rok) *reinterpret_cast<double2*>(dh0 + ((int64_t)dir * n + row0 + gid) * GH + j0) = make_double2(dh[0], dh[1]);
     g_cluster_sync();              // nobody leaves while its partner could still be addressed
 }

@@ -50,8 +50,8 @@ assert lib.drp_gru_trace_read(buf) == 0
 t = np.frombuffer(buf, dtype=np.int64).reshape(2, 64, 8)
 print(f"# gru_fwd n={n} L={L}: {a.elapsed_time(b):.3f} ms = {a.elapsed_time(b) * 1e6 / L:.0f} ns/step; rows/CTA = {'8 per CTA pair' if cluster else os.environ.get('DRP_GRU_ROWS', 'auto')}")
 if cluster:
-    order = [0, 1, 2, 3, 4, 6, 5]
-    print("# cycles per phase (mean over steps 200..263): wait h (both halves) | product | wait gi | gates + h stores (local, st.async) | mbarrier arrivals | global stores | step total")
+    order = [0, 1, 7, 2, 3, 4, 6, 5]
+    print("# cycles per phase (mean over steps 200..263): wait own half of h | product, own half | wait partner's half + product | wait gi | gates + h stores (local, st.async) | mbarrier arrivals | global stores | step total")
     for w, name in ((0, "warp 0"), (1, "warp 3")):
         d = np.diff(t[w][:, order], axis=1).astype(np.float64)
         step = np.diff(t[w, :, 0]).astype(np.float64)
@@ -79,7 +79,7 @@ t = np.frombuffer(buf, dtype=np.int64).reshape(2, 64, 8)
 print(f"# gru_bwd n={n} L={L}: {a.elapsed_time(b):.3f} ms = {a.elapsed_time(b) * 1e6 / L:.0f} ns/step")
 if cluster:
     order = [0, 2, 3, 4, 1, 7, 5, 6]
-    print("# cycles per phase: dout loads issued | wait ring | gates + dgh stores (local, st.async) | mbarrier arrivals | global stores | wait dgh (both halves) | product | step total")
+    print("# cycles per phase: dout loads issued | wait ring | gates + dgh stores (local, st.async) | mbarrier arrivals | global stores | wait own columns + product | wait partner's columns + product | step total")
     for w, name in ((0, "warp 0"), (1, "warp 3")):
         d = np.diff(t[w][:, order], axis=1).astype(np.float64)
         step = np.diff(t[w, :, 0]).astype(np.float64)

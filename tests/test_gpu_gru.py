@@ -29,10 +29,19 @@ def _ref_and_ours(n, L, I, seed, cuda):
     return ref, got
 
 
-@pytest.mark.parametrize("rows", [8, 16, 32])          # sequences per CTA (DRP_GRU_ROWS overrides the one-wave heuristic)
+def _rows_per_cta(monkeypatch, rows):
+    """DRP_GRU_ROWS overrides the one-wave heuristic (8 / 16 / 32 sequences per CTA, classic kernels); "pair" leaves the
+    choice to the library, which runs this few rows on CTA pairs (gru_fwdc_kernel / gru_bwdc_kernel)."""
+    if rows == "pair":
+        monkeypatch.delenv("DRP_GRU_ROWS", raising=False)
+    else:
+        monkeypatch.setenv("DRP_GRU_ROWS", str(rows))
+
+
+@pytest.mark.parametrize("rows", [8, 16, 32, "pair"])
 @pytest.mark.parametrize("n,L,I", [(1, 1, 21), (5, 7, 51), (37, 23, 51), (64, 40, 21), (130, 33, 51)])
 def test_gru_matches_torch(cuda, monkeypatch, n, L, I, rows):
-    monkeypatch.setenv("DRP_GRU_ROWS", str(rows))
+    _rows_per_cta(monkeypatch, rows)
     ref, got = _ref_and_ours(n, L, I, seed=n + L, cuda=cuda)
     for k in ref:
         scale = ref[k].abs().max().clamp_min(1e-30)
@@ -40,9 +49,21 @@ def test_gru_matches_torch(cuda, monkeypatch, n, L, I, rows):
         assert err < 1e-11, (k, err)
 
 
-@pytest.mark.parametrize("rows", [8, 16, 32])
+@pytest.mark.parametrize("n,L,I", [(8, 2, 21), (9, 3, 51), (16, 4, 21), (250, 61, 51), (296, 5, 21)])
+def test_gru_on_cta_pairs_edge_shapes(cuda, monkeypatch, n, L, I):
+    """The CTA-pair kernels at the edges of their pipelines: one, two and three steps past the prologue (two TMA stages,
+    two operand buffers), full and ragged last row groups, the largest size the pairs are chosen for (296 rows)."""
+    _rows_per_cta(monkeypatch, "pair")
+    ref, got = _ref_and_ours(n, L, I, seed=n + L, cuda=cuda)
+    for k in ref:
+        scale = ref[k].abs().max().clamp_min(1e-30)
+        err = float((ref[k] - got[k]).abs().max() / scale)
+        assert err < 1e-11, (k, err)
+
+
+@pytest.mark.parametrize("rows", [8, 16, 32, "pair"])
 def test_no_grad_path_and_structured_decoder(cuda, monkeypatch, rows):
-    monkeypatch.setenv("DRP_GRU_ROWS", str(rows))
+    _rows_per_cta(monkeypatch, rows)
     from draupnir_asr_b200.models_utils import RNNDecoder_Tiling
     torch.manual_seed(3)
     n, L, z, A = 45, 31, 30, 21
