@@ -72,13 +72,13 @@ DRP_API const char* drp_timing_class_name(int k)
         "syrk_kernel", "trsm_kernel", "potf2_kernel", "ou_assemble_kernel", "small_reductions", "cat_fwd_bwd_kernel",
         "lca_patristic_kernel", "misc", "oz_syrk_kernel", "oz_slice_kernel", "gru_fwd2_kernel", "gru_bwd_kernel",
         "gru_wgrad_kernel", "tall_gemm_kernel", "gram_tn_kernel", "gru_input_sums_kernel", "ou_grad_kernel",
-        "ou_symv_tile_kernel", "ou_cov_fwd_kernel"};
+        "ou_symv_tile_kernel", "ou_cov_fwd_kernel", "potrf_diag_kernel", "panel_solve_kernel"};
     return (k >= 0 && k < DRP_K_CLASSES) ? names[k] : "";
 }
 DRP_API int drp_timing_class_is_flops(int k)
 {
     return k == DRP_K_SYRK || k == DRP_K_TRSM || k == DRP_K_POTF2 || k == DRP_K_SYRK_TC || k == DRP_K_GRU_FWD ||
-           k == DRP_K_GRU_BWD || k == DRP_K_GRU_WGRAD;
+           k == DRP_K_GRU_BWD || k == DRP_K_GRU_WGRAD || k == DRP_K_POTRF_DIAG || k == DRP_K_PANEL_SOLVE;
 }
 
 // Cumulative number of kernels this library has launched (all classes).

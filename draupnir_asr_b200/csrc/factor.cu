@@ -58,24 +58,23 @@ __device__ __forceinline__ double potf2_rsqrt(double x)
     return y;
 }
 
-__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb,
-                                                    int32_t* __restrict__ info)
+// 1 / x for x > 0: MUFU.RCP64H seed (>= 20 bits) and ONE fourth-order correction, y (1 + e)(1 + e^2) with e = 1 - x y: three
+// dependent fp64 operations behind the seed.  This is the chain every column of the panel factorisation waits for.
+__device__ __forceinline__ double potf2_rcp(double x)
 {
-    __shared__ double Lp[NB][4];                   // the current panel of L
-    __shared__ int sbad;
-    double* A = Mb + (int64_t)blockIdx.x * bs + (int64_t)c0 * ld + c0;
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    const double y1 = fma(y, e, y), e2 = e * e;
+    return fma(y1, e2, y1);
+}
+
+// Factor the register-distributed 64 x 64 block `a` (thread (ty, tx) = (tid & 15, tid >> 4) holds rows 4 ty.., columns 4 tx..)
+// in place.  `*sbad` (shared, zeroed by the caller before a barrier) receives 1 + the first column with a non-positive pivot.
+// Ends with a barrier.
+__device__ __forceinline__ void potf2_regs(double (&a)[4][4], double (*Lp)[4], int* sbad)
+{
     const int tid = threadIdx.x, tx = tid >> 4, ty = tid & 15, lane = tid & 31;
-    if (tid == 0) sbad = 0;
-    double a[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = 4 * ty + r, j = 4 * tx + k;
-            // rows / columns beyond nb: identity, so the elimination is a no-op there
-            a[r][k] = (i < nb && j <= i) ? A[(int64_t)i * ld + j] : (i == j ? 1.0 : 0.0);
-        }
-    __syncthreads();
     for (int cb = 0; cb < NB / 4; ++cb) {
         if (tx == cb) {                                            // one half-warp: lanes (cb & 1) * 16 + ty
             const unsigned mask = (cb & 1) ? 0xffff0000u : 0x0000ffffu;
@@ -84,20 +83,25 @@ __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ Mb, int
             for (int cc = 0; cc < 4; ++cc) {
                 const int c = 4 * cb + cc;
                 const double piv = __shfl_sync(mask, a[cc][cc], lane_d);
-                if (ty == 0 && !(piv > 0.0) && sbad == 0) sbad = c + 1;
+                double ack[4];                                     // unscaled column entries A[4 cb + k][c]: on their way
+#pragma unroll                                                     // before either chain below has finished
+                for (int k = cc + 1; k < 4; ++k) ack[k] = __shfl_sync(mask, a[k][cc], lane_d);
+                if (ty == 0 && !(piv > 0.0) && *sbad == 0) *sbad = c + 1;
+                // two independent chains from the pivot: 1 / piv, which the remaining columns of the panel wait for
+                // (a_rk -= (a_rc / piv) a_kc: seed + 3 + 2 dependent operations per column), and 1 / sqrt(piv) for the stored
+                // column of L, which nothing in the panel waits for
+                const double ip = potf2_rcp(piv);
                 const double rd = potf2_rsqrt(piv);
-                double lv[4];
+#pragma unroll
+                for (int k = cc + 1; k < 4; ++k) {                 // remaining columns of the panel (rows <= c: never read)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) a[r][k] = fma(-(a[r][cc] * ip), ack[k], a[r][k]);
+                }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const int i = 4 * ty + r;
-                    lv[r] = i > c ? a[r][cc] * rd : (i == c ? piv * rd : 0.0);
-                    if (i >= c) a[r][cc] = lv[r];
-                }
-#pragma unroll
-                for (int k = cc + 1; k < 4; ++k) {                 // remaining columns of the panel
-                    const double lck = __shfl_sync(mask, lv[k], lane_d);       // L[4 cb + k][c]
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) a[r][k] = fma(-lv[r], lck, a[r][k]);
+                    const double lv = i > c ? a[r][cc] * rd : (i == c ? piv * rd : 0.0);
+                    if (i >= c) a[r][cc] = lv;
                 }
             }
 #pragma unroll
@@ -127,6 +131,27 @@ __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ Mb, int
         }
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb,
+                                                    int32_t* __restrict__ info)
+{
+    __shared__ double Lp[NB][4];                   // the current panel of L
+    __shared__ int sbad;
+    double* A = Mb + (int64_t)blockIdx.x * bs + (int64_t)c0 * ld + c0;
+    const int tid = threadIdx.x, tx = tid >> 4, ty = tid & 15;
+    if (tid == 0) sbad = 0;
+    double a[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = 4 * ty + r, j = 4 * tx + k;
+            // rows / columns beyond nb: identity, so the elimination is a no-op there
+            a[r][k] = (i < nb && j <= i) ? A[(int64_t)i * ld + j] : (i == j ? 1.0 : 0.0);
+        }
+    __syncthreads();
+    potf2_regs(a, Lp, &sbad);
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -152,6 +177,7 @@ struct TrsmSlice {
     int32_t* scl;
     int* counter;
     int Rpad, S;
+    int KBN;            // 128-column k-blocks of the sliced panel (panel_solve_kernel only; trsm_kernel slices 64 columns)
 };
 
 __global__ void __launch_bounds__(PR) trsm_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb, int R,
@@ -386,6 +412,362 @@ __global__ void gate_kernel(const double* __restrict__ cond, const double* __res
     zmap[1] = nf;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused panel kernels (round 2): one panel of W <= 256 columns in TWO launches instead of the chain
+// potf2 -> trsm -> in-panel update -> potf2 -> trsm ... of the 64-column steps.
+//
+//   potrf_diag_kernel   one CTA per matrix factors the whole W x W diagonal block: per 64-column block the register
+//                       potf2, then every remaining row of the diagonal region is solved by substitution (thread per
+//                       row) WHILE 64 other threads run the same substitution on the identity, i.e. invert the factored
+//                       64 x 64 block; the in-region trailing blocks are updated on the fp64 tensor pipe.  The block
+//                       inverses Y_jj go to the workspace.
+//   panel_solve_kernel  the rows below the diagonal region are independent of each other once the diagonal region is
+//                       factored: a CTA owns 64 rows and runs the whole blocked forward substitution for them,
+//                       X_j = (B_j - sum_{i<j} X_i L_ji^T) Y_jj^T, as 64 x 64 x 64 products on the fp64 tensor pipe.
+//                       Multiplying by the explicit inverse leaves a residual of ~cond(L_jj) eps, harmless for the
+//                       matrices that take the split-integer update anyway (cond <= 3.4e5, backward error 2e-11); every
+//                       other matrix (the precision gate's fp64 list, callers without a bound) gets one step of
+//                       fixed-precision refinement, X += (B - X L_jj^T) Y_jj^T, which restores the backward error of a
+//                       substitution (Skeel).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GLD = 68;            // row stride of the 64 x 64 operand tiles (conflict-free mma fragments, 16-byte rows)
+constexpr int GT = NB * GLD;       // doubles per tile
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// 64 x 64 tile <- global rows (asynchronously): entry (r, c) = src[r * ld + c] for r < nr, c < nc (and c <= r if `lower`),
+// otherwise `ident` ? (r == c) : 0.  All 256 threads; coalesced 8-byte copies.
+__device__ __forceinline__ void tile_load_async(double* dst, const double* src, int64_t ld, int nr, int nc, bool lower, bool ident)
+{
+    const int c = threadIdx.x & 63, rb = threadIdx.x >> 6;
+#pragma unroll 4
+    for (int r = rb; r < NB; r += 4) {
+        if (r < nr && c < nc && (!lower || c <= r)) cp_async8(dst + r * GLD + c, src + (int64_t)r * ld + c);
+        else dst[r * GLD + c] = (ident && r == c) ? 1.0 : 0.0;
+    }
+}
+
+// acc += As[rows 16 wm ..][k] * Bs[cols 32 wn ..][k] over k < 64 ("NT" product of two row-major tiles); 8 warps = 4 x 2.
+// acc[i][j][0/1] = entry (16 wm + 8 i + gid, 32 wn + 8 j + 2 tig + 0/1).
+// LOWER: Bs is lower triangular (a diagonal block of L or of its inverse), so output columns [8 q, 8 q + 8) only see
+// k < 8 q + 8 - 44 % of the tensor instructions of a full product are skipped (warp-uniform predicates).
+template <bool LOWER>
+__device__ __forceinline__ void blk_gemm_nt(double (&acc)[2][4][2], const double* As, const double* Bs)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+    const int wn = warp & 1;
+    const double* ap = As + ((warp >> 1) * 16 + gid) * GLD + tig;
+    const double* bp = Bs + (wn * 32 + gid) * GLD + tig;
+    const int kend = LOWER ? wn * 32 + 32 : NB;
+#pragma unroll 4
+    for (int k = 0; k < kend; k += 4) {
+        double a[2], b[4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a[i] = ap[i * 8 * GLD + k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = bp[j * 8 * GLD + k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (LOWER && k >= wn * 32 + 8 * j + 8) continue;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+}
+__device__ __forceinline__ void acc_zero(double (&acc)[2][4][2])
+{
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+}
+
+// x <- x L^-T for one row in registers: L (lower, row stride GLD) and invd = 1 / diag(L) in shared memory (broadcast reads).
+__device__ __forceinline__ void row_solve(double (&x)[NB], const double* Ls, const double* invd)
+{
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        const double* lc = Ls + c * GLD;
+        double a0 = x[c], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int p = 0; p + 3 < c; p += 4) {
+            const double2 l01 = *reinterpret_cast<const double2*>(lc + p);
+            const double2 l23 = *reinterpret_cast<const double2*>(lc + p + 2);
+            a0 = fma(-x[p], l01.x, a0);
+            a1 = fma(-x[p + 1], l01.y, a1);
+            a2 = fma(-x[p + 2], l23.x, a2);
+            a3 = fma(-x[p + 3], l23.y, a3);
+        }
+#pragma unroll
+        for (int p = c & ~3; p < c; ++p) a0 = fma(-x[p], lc[p], a0);
+        x[c] = ((a0 + a1) + (a2 + a3)) * invd[c];
+    }
+}
+
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* Mb, int64_t ld, int64_t bs, int c0, int W,
+                                                         int32_t* __restrict__ info, double* __restrict__ linv)
+{
+    extern __shared__ __align__(16) double sm[];
+    double* Ld = sm;                   // factored diagonal block: zeros above the diagonal, identity beyond its nb columns
+    double* Yd = Ld + GT;              // its inverse
+    double* T = Yd + GT;               // up to three tiles: rows of the diagonal region below the block (block column j)
+    __shared__ double Lp[NB][4];
+    __shared__ double invd[NB];
+    __shared__ int sbad;
+    const int tid = threadIdx.x, tx = tid >> 4, ty = tid & 15;
+    double* A = Mb + (int64_t)blockIdx.x * bs + (int64_t)c0 * ld + c0;
+    double* Yg = linv + (int64_t)blockIdx.x * (4 * NB * NB);
+    const int nblk = (W + NB - 1) / NB;
+    for (int j = 0; j < nblk; ++j) {
+        const int nbj = min(NB, W - NB * j);
+        const int nbelow = W - NB * (j + 1);                        // rows of the region below this block (<= 192)
+        double* Ajj = A + (int64_t)(NB * j) * ld + NB * j;
+        // rows below, block column j: on their way to shared memory while the diagonal block is factored
+        for (int t = 0; t * NB < nbelow; ++t)
+            tile_load_async(T + t * GT, Ajj + (int64_t)(NB * (t + 1)) * ld, ld, nbelow - t * NB, NB, false, false);
+        if (tid == 0) sbad = 0;
+        {
+            double a[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = 4 * ty + r, q = 4 * tx + k;
+                    a[r][k] = (i < nbj && q <= i) ? Ajj[(int64_t)i * ld + q] : (i == q ? 1.0 : 0.0);
+                }
+            __syncthreads();
+            potf2_regs(a, Lp, &sbad);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = 4 * ty + r, q = 4 * tx + k;
+                    if (i < nbj && q <= i) Ajj[(int64_t)i * ld + q] = a[r][k];
+                    Ld[i * GLD + q] = q <= i ? a[r][k] : 0.0;
+                }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (tid == 0 && sbad && sbad <= nbj && info) atomicCAS(info + blockIdx.x, 0, c0 + NB * j + sbad);
+        if (tid < NB) invd[tid] = 1.0 / Ld[tid * GLD + tid];
+        __syncthreads();
+        {   // threads 0..63: row t of the identity -> column t of Y = L^-1; threads 64..: one row of the region below
+            const int rr = tid - NB;
+            const bool inv_row = tid < NB;
+            if (inv_row || rr < nbelow) {
+                double x[NB];
+                double* trow = T + (rr >> 6) * GT + (rr & 63) * GLD;
+                if (inv_row) {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) x[c] = (c == tid) ? 1.0 : 0.0;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NB; c += 2) {
+                        const double2 v = *reinterpret_cast<const double2*>(trow + c);
+                        x[c] = v.x;
+                        x[c + 1] = v.y;
+                    }
+                }
+                row_solve(x, Ld, invd);
+                if (inv_row) {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) Yd[c * GLD + tid] = x[c];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(trow + c) = make_double2(x[c], x[c + 1]);
+                }
+            }
+        }
+        __syncthreads();
+        {   // the inverse to the workspace, the solved rows back to the matrix (coalesced)
+            const int c = tid & 63, rb = tid >> 6;
+            for (int r = rb; r < NB; r += 4) Yg[(j * NB + r) * NB + c] = Yd[r * GLD + c];
+            for (int r = rb; r < nbelow; r += 4)
+                Ajj[(int64_t)(NB + r) * ld + c] = T[(r >> 6) * GT + (r & 63) * GLD + c];
+        }
+        // trailing blocks of the diagonal region: A_ik -= A_ij A_kj^T for j < k <= i
+        const int lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3, wm = warp >> 1, wn = warp & 1;
+        for (int i = j + 1; i < nblk; ++i)
+            for (int k = j + 1; k <= i; ++k) {
+                if (i == k && 32 * wn > 16 * wm + 15) continue;               // this warp's window lies above the diagonal
+                double acc[2][4][2];
+                acc_zero(acc);
+                blk_gemm_nt<false>(acc, T + (i - j - 1) * GT, T + (k - j - 1) * GT);
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii) {
+                    const int row = NB * i + wm * 16 + ii * 8 + gid;
+                    if (row >= W) continue;
+                    double* crow = A + (int64_t)row * ld;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int col = NB * k + wn * 32 + jj * 8 + 2 * tig;
+                        if (col <= row && col < W) crow[col] -= acc[ii][jj][0];
+                        if (col + 1 <= row && col + 1 < W) crow[col + 1] -= acc[ii][jj][1];
+                    }
+                }
+            }
+        __syncthreads();               // the block's global writes are visible to its own later reads
+    }
+}
+
+__global__ void __launch_bounds__(256) panel_solve_kernel(double* Mb, int64_t ld, int64_t bs, int c0, int W, int R,
+                                                          const double* __restrict__ linv, const int* __restrict__ zmap,
+                                                          int z, int refine_all, const TrsmSlice sl)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int nblk = (W + NB - 1) / NB;
+    double* X = sm;                    // nblk tiles: this CTA's 64 rows of the panel
+    double* Lt = sm + nblk * GT;       // the block of L (or of the inverse) being multiplied
+    const int zz = blockIdx.y, tid = threadIdx.x;
+    double* A = Mb + (int64_t)zz * bs;
+    const double* Yg = linv + (int64_t)zz * (4 * NB * NB);
+    const int r0 = c0 + W + blockIdx.x * NB;
+    const int nrows = max(0, min(NB, R - r0));     // 0: a CTA past the last row, there to write the zero rows of the slice buffer
+    bool refine = refine_all != 0;
+    if (!refine && zmap) {             // on the precision gate's fp64 list?
+        const int nf = zmap[1];
+        for (int q = 0; q < nf; ++q) refine |= (zmap[2 + z + q] == zz);
+    }
+    for (int j = 0; j < nblk; ++j)
+        tile_load_async(X + j * GT, A + (int64_t)r0 * ld + c0 + NB * j, ld, nrows, W - NB * j, false, false);
+    const int lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3, wm = warp >> 1, wn = warp & 1;
+    for (int j = 0; j < (nrows > 0 ? nblk : 0); ++j) {
+        const int nbj = min(NB, W - NB * j);
+        double* Xj = X + j * GT;
+        const double* Ljrow = A + (int64_t)(c0 + NB * j) * ld + c0;            // row block j of the factored region
+        double acc[2][4][2];
+        if (j > 0) {
+            acc_zero(acc);
+            for (int i = 0; i < j; ++i) {
+                __syncthreads();                                               // Lt free
+                tile_load_async(Lt, Ljrow + NB * i, ld, nbj, NB, false, false);
+                cp_async_wait_all();
+                __syncthreads();
+                blk_gemm_nt<false>(acc, X + i * GT, Lt);
+            }
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    double2* p = reinterpret_cast<double2*>(Xj + (wm * 16 + ii * 8 + gid) * GLD + wn * 32 + jj * 8 + 2 * tig);
+                    double2 v = *p;
+                    v.x -= acc[ii][jj][0];
+                    v.y -= acc[ii][jj][1];
+                    *p = v;
+                }
+        }
+        __syncthreads();
+        tile_load_async(Lt, Yg + j * NB * NB, NB, NB, NB, false, false);
+        cp_async_wait_all();
+        __syncthreads();
+        acc_zero(acc);
+        blk_gemm_nt<true>(acc, Xj, Lt);                                              // X0 = B Y^T
+        if (refine) {
+            double b[2][4][2], res[2][4][2];
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const double2 v = *reinterpret_cast<const double2*>(Xj + (wm * 16 + ii * 8 + gid) * GLD + wn * 32 + jj * 8 + 2 * tig);
+                    b[ii][jj][0] = v.x;
+                    b[ii][jj][1] = v.y;
+                }
+            __syncthreads();                                                   // every read of B and of Y is done
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    *reinterpret_cast<double2*>(Xj + (wm * 16 + ii * 8 + gid) * GLD + wn * 32 + jj * 8 + 2 * tig) =
+                        make_double2(acc[ii][jj][0], acc[ii][jj][1]);
+            tile_load_async(Lt, Ljrow + NB * j, ld, nbj, nbj, true, true);     // L_jj
+            cp_async_wait_all();
+            __syncthreads();
+            acc_zero(res);
+            blk_gemm_nt<true>(res, Xj, Lt);                                          // X0 L^T
+            __syncthreads();
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    *reinterpret_cast<double2*>(Xj + (wm * 16 + ii * 8 + gid) * GLD + wn * 32 + jj * 8 + 2 * tig) =
+                        make_double2(b[ii][jj][0] - res[ii][jj][0], b[ii][jj][1] - res[ii][jj][1]);
+            tile_load_async(Lt, Yg + j * NB * NB, NB, NB, NB, false, false);
+            cp_async_wait_all();
+            __syncthreads();
+            blk_gemm_nt<true>(acc, Xj, Lt);                                          // X0 + (B - X0 L^T) Y^T
+        }
+        __syncthreads();                                                       // every read of the tile is done
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+            const int r = wm * 16 + ii * 8 + gid;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int c = wn * 32 + jj * 8 + 2 * tig;
+                *reinterpret_cast<double2*>(Xj + r * GLD + c) = make_double2(acc[ii][jj][0], acc[ii][jj][1]);
+                if (r < nrows) {
+                    double* g = A + (int64_t)(r0 + r) * ld + c0 + NB * j + c;
+                    if (c < nbj) g[0] = acc[ii][jj][0];
+                    if (c + 1 < nbj) g[1] = acc[ii][jj][1];
+                }
+            }
+        }
+    }
+    if (sl.sl == nullptr) return;
+    // ---- the solved rows ARE the panel of the trailing update that follows (all W columns on chip, so the row scale is
+    //      known): its int8 slices go out from shared memory in the layout of oz_slice_kernel (ozaki.cu), bit-identical
+    cp_async_wait_all();
+    __syncthreads();
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) sl.counter[0] = sl.counter[1] = 0;
+    const int NS = sl.S, KBN = sl.KBN;
+    const long long hi = (1LL << (8 * NS - 1)) - 1;
+    uint8_t* dst = sl.sl + (int64_t)zz * sl.sl_bs;
+    for (int it = 0; it < NB / 8; ++it) {
+        const int i = warp * (NB / 8) + it;                        // row inside the CTA
+        const int rr = blockIdx.x * NB + i;                        // row of the slice buffer (relative to c0 + W)
+        double xv[8];
+        double m = 0.0;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+            const int tile = 2 * kb + (lane >> 4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double v = tile < nblk ? X[tile * GT + i * GLD + 4 * (lane & 15) + q] : 0.0;   // rows >= nrows are zeros
+                xv[kb * 4 + q] = v;
+                m = fmax(m, fabs(v));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        int e = 0;
+        if (m > 0.0 && m < 1e300) frexp(m, &e);
+        if (lane == 0) sl.scl[(int64_t)zz * sl.Rpad + rr] = e;
+        const int sh = 8 * NS - 1 - e;
+        const int chunk = ((lane >> 2) ^ (rr & 7)) << 4;           // 16-byte chunk of the row after the 128B swizzle
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+            if (kb >= KBN) break;
+            long long Xq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const long long v = __double2ll_rn(scalbn(xv[kb * 4 + q], sh));
+                Xq[q] = v > hi ? hi : (v < -hi - 1 ? -hi - 1 : v);
+            }
+            for (int t = 0; t < NS; ++t) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) w |= (uint32_t)((Xq[q] >> (8 * (NS - 1 - t))) & 0xFF) << (8 * q);
+                *reinterpret_cast<uint32_t*>(dst + ((int64_t)(t * KBN + kb) * sl.Rpad + rr) * 128 + chunk + ((4 * lane) & 15)) = w;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 #include <stdlib.h>
@@ -461,6 +843,19 @@ static bool fused_slicing()
     return v != 0;
 }
 
+// Fused panel kernels (potrf_diag + panel_solve) instead of the 64-column chain: DRP_PANEL_WIDTH = 0 (off: potf2 / trsm
+// steps), 64, 128 (default) or 256 columns per fused panel.  They need the workspace (block inverses).
+static int panel_width()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DRP_PANEL_WIDTH");
+        v = e ? atoi(e) : 128;
+        if (v != 0 && v != 64 && v != 128 && v != 256) v = 128;
+    }
+    return v;
+}
+
 static bool lookahead_enabled()
 {
     static int v = -1;
@@ -493,10 +888,20 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
                    int32_t* info, void* ws, int64_t ws_bytes, const DrpGate& gate, const DrpAux* aux, cudaStream_t st)
 {
     if (drp_first_on_device(1)) cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM);
+    if (drp_first_on_device(2)) {
+        cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * GT * (int)sizeof(double));
+        cudaFuncSetAttribute(panel_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * GT * (int)sizeof(double));
+    }
     if (info) cudaMemsetAsync(info, 0, sizeof(int32_t) * z, st);
     const bool gated = gate.cond != nullptr || (gate.sf != nullptr && gate.sn != nullptr);
     const bool tensor_path = gated && ws != nullptr && drp_ozaki_slices() != 0 && ws_bytes >= drp_ozaki_workspace_bytes(R_full, z)
                              && R_full >= 384 + NB;                 // smaller matrices never reach a qualifying update
+    // the block inverses of the fused panel kernels live at the very end of the workspace
+    double* linv = nullptr;
+    if (ws != nullptr && panel_width() != 0 && ws_bytes >= drp_linv_bytes(z) + drp_zmap_bytes(z)) {
+        ws_bytes -= drp_linv_bytes(z);
+        linv = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + ws_bytes + 15) & ~(uintptr_t)15);
+    }
     const int NBO = outer_block(R_full, tensor_path);
     void* tws = tensor_path ? ws : nullptr;
     int* zmap = nullptr;
@@ -516,10 +921,39 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
         const int R = grow_base > 0 ? min(R_full, grow_base + C1) : R_full;
         // inside the outer panel: 64-wide steps; with the tensor path the panel is split again into 128-wide
         // sub-panels so that only 64-column-wide updates are left to the fp64 mma.sync kernel
-        const int NBM = (tensor_path && W > 2 * NB) ? 2 * NB : W;
+        bool outer_sliced = false;
+        const int NBM = linv ? min(W, panel_width()) : (tensor_path && W > 2 * NB) ? 2 * NB : W;
         for (int Q0 = C0; Q0 < C1 && rc == 0; Q0 += NBM) {
             const int Q1 = min(Q0 + NBM, C1);
-            for (int c0 = Q0; c0 < Q1 && rc == 0; c0 += NB) {
+            bool inner_sliced = false;
+            if (linv) {                // the whole sub-panel in two launches (fused panel kernels)
+                const int Wq = Q1 - Q0, nblk = (Wq + NB - 1) / NB;
+                {
+                    DRP_LAUNCH(DRP_K_POTRF_DIAG, (double)z * Wq * Wq * Wq / 3.0, st);
+                    potrf_diag_kernel<<<z, 256, (2 + (nblk > 1 ? nblk - 1 : 1)) * GT * sizeof(double), st>>>(M, ld, bs, Q0, Wq, info, linv);
+                }
+                const int below = R - Q1;
+                if (below > 0) {
+                    // the trailing update that consumes exactly this launch's columns takes its slices from it: the update
+                    // inside the outer panel (Q1 < C1), or the update of the rest of the matrix when the outer panel is one piece
+                    TrsmSlice psl{nullptr, 0, nullptr, nullptr, 0, 0, 0};
+                    int gx = (below + NB - 1) / NB;
+                    if (fused_slicing() && tws != nullptr && !look && (Q1 < C1 || Q0 == C0)) {
+                        DrpOzLayout lay;
+                        const bool inner = Q1 < C1;
+                        if (drp_ozaki_layout(z, Wq, Q1, R, inner ? min(col_limit, C1) : col_limit, drp_ozaki_slices(), tws, ws_bytes,
+                                             inner ? 1 : 0, &lay) && lay.rb == Q1 && lay.Rpad >= below) {
+                            psl = TrsmSlice{lay.sl, lay.sl_bs, lay.scl, lay.counter, lay.Rpad, drp_ozaki_slices(), lay.KBN};
+                            gx = lay.Rpad / NB;
+                            (inner ? inner_sliced : outer_sliced) = true;
+                        }
+                    }
+                    DRP_LAUNCH(DRP_K_PANEL_SOLVE, (double)z * below * Wq * Wq, st);
+                    panel_solve_kernel<<<dim3(gx, z), 256, (nblk + 1) * GT * sizeof(double), st>>>(
+                        M, ld, bs, Q0, Wq, R, linv, zmap, z, tensor_path ? 0 : 1, psl);
+                }
+            }
+            for (int c0 = Q0; c0 < Q1 && rc == 0 && !linv; c0 += NB) {
                 const int nb = min(NB, Q1 - c0);
                 const int c1 = c0 + nb;
                 {
@@ -546,7 +980,8 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
                 }
             }
             if (Q1 < C1 && rc == 0)                                                                     // rest of the outer panel
-                rc = trailing_update(M, ld, bs, z, Q0, Q1 - Q0, Q1, R, Q1, min(col_limit, C1), tws, ws_bytes, zmap, 1, 1, 0, st);
+                rc = trailing_update(M, ld, bs, z, Q0, Q1 - Q0, Q1, R, Q1, min(col_limit, C1), tws, ws_bytes, zmap, inner_sliced ? 0 : 1,
+                                     1, 0, st);
         }
         if (rc) break;
         // ---- rest of the matrix
@@ -565,7 +1000,7 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
             cudaEventRecord(aux->ev_join, aux->stream);
             pending_b = true;
         } else {
-            rc = trailing_update(M, ld, bs, z, C0, W, C1, R, C1, col_limit, tws, ws_bytes, zmap, 1, 0, 0, st);
+            rc = trailing_update(M, ld, bs, z, C0, W, C1, R, C1, col_limit, tws, ws_bytes, zmap, outer_sliced ? 0 : 1, 0, 0, st);
         }
     }
     if (pending_b) cudaStreamWaitEvent(st, aux->ev_join, 0);        // the auxiliary stream is joined before anything follows

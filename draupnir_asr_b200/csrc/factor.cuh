@@ -52,6 +52,7 @@ bool drp_ozaki_layout(int z, int K, int c1, int R, int col_hi, int S, void* ws, 
 // zmap (device, nullable = all z matrices): [0] number of matrices on the tensor path, [1] number on the fp64 path,
 // [2 .. 2+z) indices of the former, [2+z .. 2+2z) indices of the latter
 int64_t drp_zmap_bytes(int z);
+int64_t drp_linv_bytes(int z);
 int drp_ozaki_syrk(double* M, int64_t ld, int64_t bs, int z, int k0, int K, int c1, int R, int col_lo, int col_hi, int S,
                    void* ws, int64_t ws_bytes, const int* zmap, int do_slice, int buffer, int counter_idx, cudaStream_t st);
 // factor.cu: the fp64 mma.sync trailing update (also exported for kernel-vs-kernel parity tests); with a zmap only the

@@ -24,7 +24,9 @@ enum DrpKernelClass {
     DRP_K_OU_GRAD = 16,  // ou_grad_kernel / ou_cov_bwd_kernel: hyper-parameter gradient sums     work = bytes
     DRP_K_SYMV = 17,     // ou_symv_tile_kernel: alpha = K^-1 x from the stored inverse           work = bytes
     DRP_K_OU_COV = 18,   // ou_cov_fwd_kernel: dense [z,n,n] OU covariance (OUKernel_Fast.forward)            work = bytes
-    DRP_K_CLASSES = 19
+    DRP_K_POTRF_DIAG = 19,  // potrf_diag_kernel: W x W diagonal region of a panel (potf2 + in-region solves/updates)   work = flops
+    DRP_K_PANEL_SOLVE = 20, // panel_solve_kernel: blocked forward substitution of the rows below, fp64 mma.sync        work = flops
+    DRP_K_CLASSES = 21
 };
 
 // Call right before / after a kernel launch of class `k` doing `work` algorithmic flops or bytes.

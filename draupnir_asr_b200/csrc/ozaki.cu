@@ -716,8 +716,12 @@ static int64_t oz_buffer_bytes(int R_full, int z)
 // former are still being multiplied) and the precision gate's index lists at the very end.
 int64_t drp_ozaki_workspace_bytes(int R_full, int z)
 {
-    return 2 * oz_buffer_bytes(R_full, z) + drp_zmap_bytes(z);
+    return 2 * oz_buffer_bytes(R_full, z) + drp_zmap_bytes(z) + drp_linv_bytes(z);
 }
+
+// Inverses of the (up to four) 64 x 64 diagonal blocks of the panel being factored, per matrix (factor.cu: fused panel
+// kernels); the last region of the workspace.
+int64_t drp_linv_bytes(int z) { return (int64_t)z * 4 * DRP_NB * DRP_NB * 8 + 256; }
 
 // Largest condition-number bound a matrix may have to take the split-integer update: eps_S * cond <= 1e-5 with the
 // backward error eps_S ~ 2^-(8S-13) |K| of a whole factorisation (S = 6: 2.9e-11; measured < 2e-11 at 1,100-1,500 leaves).

@@ -33,9 +33,12 @@ def test_argument_validation_without_a_gpu():
     assert lib.drp_cat_loglik_fwd_f64(None, None, 1, 10, 21, None, None, None, None) == -1
     assert lib.drp_ou_workspace_ld(19, 19) == 40 and lib.drp_ou_workspace_ld(2000, 2000) == 4008
     assert lib.drp_ou_workspace_elems(19, 0, 30) == 30 * 20 * 24 + (lib.drp_factor_workspace_bytes(20, 30) + 7) // 8
-    assert lib.drp_factor_workspace_bytes(2000, 30) == 2 * ((30 * 2176 * (12 * 128 + 8) + 2048 + 1023) // 1024 * 1024) + 256
+    # two slice buffers + the precision gate's index lists + the block inverses of the fused panel kernels (4 x 64 x 64 per matrix)
+    assert lib.drp_factor_workspace_bytes(2000, 30) == (2 * ((30 * 2176 * (12 * 128 + 8) + 2048 + 1023) // 1024 * 1024) + 256
+                                                        + 30 * 4 * 64 * 64 * 8 + 256)
     assert lib.drp_ozaki_cond_limit_f64() == 1e-5 * 2.0 ** 35
-    assert lib.drp_timing_classes() == 19 and lib.drp_timing_class_name(8) == b"oz_syrk_kernel"
+    assert lib.drp_timing_classes() == 21 and lib.drp_timing_class_name(8) == b"oz_syrk_kernel"
+    assert lib.drp_timing_class_name(19) == b"potrf_diag_kernel" and lib.drp_timing_class_name(20) == b"panel_solve_kernel"
     assert lib.drp_gru_hidden_size() == 60
     assert lib.drp_gru_fwd_f64(None, None, None, None, 4, 4, 60, None, None, None) == -1
     assert lib.drp_cat_loglik_partials(257) == 2

@@ -196,3 +196,60 @@ print("RESULT", " ".join(repr(float(v)) for v in list(lp.detach().cpu()) + list(
         line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][0]
         outs.append(np.array([float(v) for v in line.split()[1:]]))
     np.testing.assert_allclose(outs[0], outs[1], rtol=1e-12, atol=0)
+
+
+def test_fused_panel_widths_agree(cuda):
+    """csrc/factor.cu: a panel is factored by two fused kernels (potrf_diag_kernel: the W x W diagonal region in one CTA per
+    matrix; panel_solve_kernel: blocked forward substitution of the rows below on the fp64 tensor pipe, with the explicit
+    block inverses and one refinement step for matrices off the tensor path).  DRP_PANEL_WIDTH selects W = 64 / 128 (default)
+    / 256 or 0 = the potf2 / trsm chain of 64-column steps.  Every setting, in a child process each, must give the same
+    prior (values + gradients, tensor path and small-matrix path), the same conditional moments with ragged widths, and
+    LAPACK-level factors of the ill-conditioned matrices the precision gate keeps on the fp64 kernels."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch, numpy as np
+sys.path.insert(0, %r)
+from draupnir_asr_b200 import ops, synthetic as S
+from oracle import draupnir_oracle as O
+out = []
+for n in (450, 90, 200):                      # tensor path (901 rows); one ragged panel; 128 + 72 columns
+    t = S.random_tree(n, seed=2)
+    Dh = S.patristic_host(t)
+    D = torch.from_numpy(Dh[np.ix_(t.leaves, t.leaves)]).cuda()
+    g = torch.Generator().manual_seed(n)
+    sf, sn, lam = (torch.rand(3, generator=g, dtype=torch.float64).add(0.5).cuda().requires_grad_(True) for _ in range(3))
+    x = torch.randn(3, n, generator=g, dtype=torch.float64).cuda().requires_grad_(True)
+    lp = ops.ou_prior_logp(D, sf, sn, lam, x)
+    lp.sum().backward()
+    out += list(lp.detach().cpu()) + list(sf.grad.cpu()) + list(sn.grad.cpu()) + list(lam.grad.cpu()) + [x.grad.norm().cpu()]
+    if n != 450:
+        Df = torch.from_numpy(Dh).cuda()
+        leaf = torch.as_tensor(t.leaves); internal = torch.as_tensor([i for i in range(Dh.shape[0]) if i not in set(t.leaves)])
+        mean, cov = ops.ou_conditional(Df, leaf, internal, sf.detach(), sn.detach(), lam.detach(), x.detach(), jitter=0.0)
+        out += [mean.norm().cpu(), mean[1, 3].cpu(), cov.norm().cpu(), cov[2].diagonal().sum().cpu()]
+n = 1100
+t = S.random_tree(n, seed=2)
+D = torch.from_numpy(S.patristic_host(t)[np.ix_(t.leaves, t.leaves)])
+sf = torch.tensor([1.3, 0.9, 1.1], dtype=torch.float64)
+sn = torch.tensor([0.6, 2e-4, 1e-3], dtype=torch.float64)
+lam = torch.tensor([0.9, 1.4, 0.7], dtype=torch.float64)
+K = O.ou_covariance(D, sf, sn, lam)
+L = ops.potrf(K.cuda(), cond_bound=ops.ou_cond_bound(sf, sn, n)).cpu()
+back = ((L @ L.transpose(-1, -2) - K).abs().amax((1, 2)) / K.abs().amax((1, 2))).tolist()
+assert back[0] < 2e-11 and back[1] < 2e-15 and back[2] < 2e-15, back
+out += [L[1].diagonal().log().sum(), L[2].diagonal().log().sum()]
+torch.cuda.synchronize()
+print("RESULT", " ".join(repr(float(v)) for v in out))
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for w in ("0", "64", "128", "256"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DRP_PANEL_WIDTH=w), capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, (w, r.stderr[-2000:])
+        line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][0]
+        outs[w] = np.array([float(v) for v in line.split()[1:]])
+    for w in ("64", "128", "256"):
+        # different blockings of the same fp64 elimination (plus the 2e-11 tensor-path updates at n = 450)
+        np.testing.assert_allclose(outs[w], outs["0"], rtol=1e-6, atol=1e-9, err_msg=f"DRP_PANEL_WIDTH={w}")
