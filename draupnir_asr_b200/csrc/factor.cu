@@ -856,6 +856,20 @@ static int panel_width()
     return v;
 }
 
+// Slices of the next update written by panel_solve_kernel itself (instead of oz_slice_kernel re-reading the solved rows).
+// Parity-identical; measured at 2,000 leaves on one B200 the slicing work moves from one kernel into the other (slicing
+// 0.78 -> 0.45 ms, panel solve 1.27 -> 1.63 ms per step) and the replayed step is 0.1 ms SLOWER (21.47 vs 21.35 ms), so it
+// is opt-in (DRP_PANEL_SLICING=1).
+static bool panel_slicing()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DRP_PANEL_SLICING");
+        v = e ? atoi(e) : 0;
+    }
+    return v != 0;
+}
+
 static bool lookahead_enabled()
 {
     static int v = -1;
@@ -938,7 +952,7 @@ int drp_factor_run(double* M, int64_t ld, int64_t bs, int z, int nfactor, int R_
                     // inside the outer panel (Q1 < C1), or the update of the rest of the matrix when the outer panel is one piece
                     TrsmSlice psl{nullptr, 0, nullptr, nullptr, 0, 0, 0};
                     int gx = (below + NB - 1) / NB;
-                    if (fused_slicing() && tws != nullptr && !look && (Q1 < C1 || Q0 == C0)) {
+                    if (panel_slicing() && tws != nullptr && !look && (Q1 < C1 || Q0 == C0)) {
                         DrpOzLayout lay;
                         const bool inner = Q1 < C1;
                         if (drp_ozaki_layout(z, Wq, Q1, R, inner ? min(col_limit, C1) : col_limit, drp_ozaki_slices(), tws, ws_bytes,

@@ -244,12 +244,15 @@ torch.cuda.synchronize()
 print("RESULT", " ".join(repr(float(v)) for v in out))
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
-    for w in ("0", "64", "128", "256"):
-        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DRP_PANEL_WIDTH=w), capture_output=True, text=True,
-                           timeout=600)
+    for w in ("0", "64", "128", "256", "128s", "256s"):         # "s": the solve kernel also writes the next update's slices
+        env = dict(os.environ, DRP_PANEL_WIDTH=w.rstrip("s"), DRP_PANEL_SLICING="1" if w.endswith("s") else "0")
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, (w, r.stderr[-2000:])
         line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][0]
         outs[w] = np.array([float(v) for v in line.split()[1:]])
+    # slices written by the solve kernel are bit-identical to oz_slice_kernel's
+    np.testing.assert_array_equal(outs["128s"], outs["128"])
+    np.testing.assert_array_equal(outs["256s"], outs["256"])
     for w in ("64", "128", "256"):
         # different blockings of the same fp64 elimination (plus the 2e-11 tensor-path updates at n = 450)
         np.testing.assert_allclose(outs[w], outs["0"], rtol=1e-6, atol=1e-9, err_msg=f"DRP_PANEL_WIDTH={w}")
