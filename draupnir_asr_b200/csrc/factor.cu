@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "factor.cuh"
 #include "instrument.cuh"
+#include "slice.cuh"
 
 namespace {
 
@@ -72,7 +73,15 @@ __device__ __forceinline__ double potf2_rcp(double x)
 // Factor the register-distributed 64 x 64 block `a` (thread (ty, tx) = (tid & 15, tid >> 4) holds rows 4 ty.., columns 4 tx..)
 // in place.  `*sbad` (shared, zeroed by the caller before a barrier) receives 1 + the first column with a non-positive pivot.
 // Ends with a barrier.
-__device__ __forceinline__ void potf2_regs(double (&a)[4][4], double (*Lp)[4], int* sbad)
+// The panel in shared memory: row r of the 64 x 4 panel at LP_ROW(r) doubles - 32 bytes per row plus 16 bytes after every
+// fourth row.  The rank-4 update reads rows 4 ty .. 4 ty + 3 with 16-byte loads, lane = ty: at a plain 32-byte row stride the
+// eight lanes of a quarter-warp are 128 bytes apart, i.e. on the SAME four banks (a 8-way conflict on each of the 8 loads
+// per thread and panel: the ncu source page showed the update phase waiting on shared memory); with the shift they are 144
+// bytes apart and cover all 32 banks.
+#define LP_ROW(r) ((r) * 4 + 2 * ((r) >> 2))
+constexpr int LP_ELEMS = NB * 4 + 2 * (NB / 4);
+
+__device__ __forceinline__ void potf2_regs(double (&a)[4][4], double* Lp, int* sbad)
 {
     const int tid = threadIdx.x, tx = tid >> 4, ty = tid & 15, lane = tid & 31;
     for (int cb = 0; cb < NB / 4; ++cb) {
@@ -107,7 +116,7 @@ __device__ __forceinline__ void potf2_regs(double (&a)[4][4], double (*Lp)[4], i
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) Lp[4 * ty + r][k] = (4 * ty + r >= 4 * cb + k) ? a[r][k] : 0.0;
+                for (int k = 0; k < 4; ++k) Lp[LP_ROW(4 * ty + r) + k] = (4 * ty + r >= 4 * cb + k) ? a[r][k] : 0.0;
         }
         __syncthreads();
         if (tx > cb) {                                             // rank-4 update of the trailing blocks
@@ -116,8 +125,8 @@ __device__ __forceinline__ void potf2_regs(double (&a)[4][4], double (*Lp)[4], i
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    lr[r][q] = Lp[4 * ty + r][q];
-                    lc[r][q] = Lp[4 * tx + r][q];
+                    lr[r][q] = Lp[LP_ROW(4 * ty + r) + q];
+                    lc[r][q] = Lp[LP_ROW(4 * tx + r) + q];
                 }
 #pragma unroll
             for (int r = 0; r < 4; ++r)
@@ -136,7 +145,7 @@ __device__ __forceinline__ void potf2_regs(double (&a)[4][4], double (*Lp)[4], i
 __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ Mb, int64_t ld, int64_t bs, int c0, int nb,
                                                     int32_t* __restrict__ info)
 {
-    __shared__ double Lp[NB][4];                   // the current panel of L
+    __shared__ __align__(16) double Lp[LP_ELEMS];   // the current panel of L
     __shared__ int sbad;
     double* A = Mb + (int64_t)blockIdx.x * bs + (int64_t)c0 * ld + c0;
     const int tid = threadIdx.x, tx = tid >> 4, ty = tid & 15;
@@ -256,7 +265,6 @@ __global__ void __launch_bounds__(PR) trsm_kernel(double* __restrict__ Mb, int64
     if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) sl.counter[0] = sl.counter[1] = 0;
     const int warp = tid >> 5, lane = tid & 31, hl = lane & 15, sub = lane >> 4;
     const int NS = sl.S;
-    const long long hi = (1LL << (8 * NS - 1)) - 1;
     uint8_t* dst = sl.sl + (int64_t)blockIdx.y * sl.sl_bs;
     for (int it = 0; it < PR / 8; ++it) {
         const int i = warp * (PR / 4) + 2 * it + sub;            // row inside the CTA
@@ -273,20 +281,11 @@ __global__ void __launch_bounds__(PR) trsm_kernel(double* __restrict__ Mb, int64
         int e = 0;
         if (m > 0.0 && m < 1e300) frexp(m, &e);
         if (hl == 0) sl.scl[(int64_t)blockIdx.y * sl.Rpad + rr] = e;
-        const int sh = 8 * NS - 1 - e;
         long long Xq[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const long long q = __double2ll_rn(scalbn(xv[j], sh));
-            Xq[j] = q > hi ? hi : (q < -hi - 1 ? -hi - 1 : q);
-        }
+        drp_quant4(xv, m, e, NS, Xq);
         const int chunk = ((hl >> 2) ^ (rr & 7)) << 4;           // 16-byte chunk of the row after the 128B swizzle
-        for (int t = 0; t < NS; ++t) {
-            uint32_t w = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) w |= (uint32_t)((Xq[j] >> (8 * (NS - 1 - t))) & 0xFF) << (8 * j);
-            *reinterpret_cast<uint32_t*>(dst + ((int64_t)t * sl.Rpad + rr) * 128 + chunk + ((4 * hl) & 15)) = w;
-        }
+        for (int t = 0; t < NS; ++t)
+            *reinterpret_cast<uint32_t*>(dst + ((int64_t)t * sl.Rpad + rr) * 128 + chunk + ((4 * hl) & 15)) = drp_pick4(Xq, NS - 1 - t);
     }
 }
 
@@ -494,19 +493,30 @@ __device__ __forceinline__ void row_solve(double (&x)[NB], const double* Ls, con
 #pragma unroll
     for (int c = 0; c < NB; ++c) {
         const double* lc = Ls + c * GLD;
-        double a0 = x[c], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        // EIGHT accumulation chains: in potrf_diag_kernel this runs on one or two warps per SM sub-partition, a pure
+        // dependent-latency chain of 64 stages
+        double a0 = x[c], a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
 #pragma unroll
-        for (int p = 0; p + 3 < c; p += 4) {
+        for (int p = 0; p + 7 < c; p += 8) {
             const double2 l01 = *reinterpret_cast<const double2*>(lc + p);
             const double2 l23 = *reinterpret_cast<const double2*>(lc + p + 2);
+            const double2 l45 = *reinterpret_cast<const double2*>(lc + p + 4);
+            const double2 l67 = *reinterpret_cast<const double2*>(lc + p + 6);
             a0 = fma(-x[p], l01.x, a0);
             a1 = fma(-x[p + 1], l01.y, a1);
             a2 = fma(-x[p + 2], l23.x, a2);
             a3 = fma(-x[p + 3], l23.y, a3);
+            a4 = fma(-x[p + 4], l45.x, a4);
+            a5 = fma(-x[p + 5], l45.y, a5);
+            a6 = fma(-x[p + 6], l67.x, a6);
+            a7 = fma(-x[p + 7], l67.y, a7);
         }
 #pragma unroll
-        for (int p = c & ~3; p < c; ++p) a0 = fma(-x[p], lc[p], a0);
-        x[c] = ((a0 + a1) + (a2 + a3)) * invd[c];
+        for (int p = c & ~7; p < c; ++p) {
+            if ((p & 1) == 0) a0 = fma(-x[p], lc[p], a0);
+            else a1 = fma(-x[p], lc[p], a1);
+        }
+        x[c] = (((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7))) * invd[c];
     }
 }
 
@@ -517,7 +527,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* Mb, int64_t ld,
     double* Ld = sm;                   // factored diagonal block: zeros above the diagonal, identity beyond its nb columns
     double* Yd = Ld + GT;              // its inverse
     double* T = Yd + GT;               // up to three tiles: rows of the diagonal region below the block (block column j)
-    __shared__ double Lp[NB][4];
+    __shared__ __align__(16) double Lp[LP_ELEMS];
     __shared__ double invd[NB];
     __shared__ int sbad;
     const int tid = threadIdx.x, tx = tid >> 4, ty = tid & 15;
@@ -725,7 +735,6 @@ __global__ void __launch_bounds__(256) panel_solve_kernel(double* Mb, int64_t ld
     __syncthreads();
     if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) sl.counter[0] = sl.counter[1] = 0;
     const int NS = sl.S, KBN = sl.KBN;
-    const long long hi = (1LL << (8 * NS - 1)) - 1;
     uint8_t* dst = sl.sl + (int64_t)zz * sl.sl_bs;
     for (int it = 0; it < NB / 8; ++it) {
         const int i = warp * (NB / 8) + it;                        // row inside the CTA
@@ -747,23 +756,16 @@ __global__ void __launch_bounds__(256) panel_solve_kernel(double* Mb, int64_t ld
         int e = 0;
         if (m > 0.0 && m < 1e300) frexp(m, &e);
         if (lane == 0) sl.scl[(int64_t)zz * sl.Rpad + rr] = e;
-        const int sh = 8 * NS - 1 - e;
         const int chunk = ((lane >> 2) ^ (rr & 7)) << 4;           // 16-byte chunk of the row after the 128B swizzle
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
             if (kb >= KBN) break;
             long long Xq[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const long long v = __double2ll_rn(scalbn(xv[kb * 4 + q], sh));
-                Xq[q] = v > hi ? hi : (v < -hi - 1 ? -hi - 1 : v);
-            }
-            for (int t = 0; t < NS; ++t) {
-                uint32_t w = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) w |= (uint32_t)((Xq[q] >> (8 * (NS - 1 - t))) & 0xFF) << (8 * q);
-                *reinterpret_cast<uint32_t*>(dst + ((int64_t)(t * KBN + kb) * sl.Rpad + rr) * 128 + chunk + ((4 * lane) & 15)) = w;
-            }
+            const double xk[4] = {xv[kb * 4], xv[kb * 4 + 1], xv[kb * 4 + 2], xv[kb * 4 + 3]};
+            drp_quant4(xk, m, e, NS, Xq);
+            for (int t = 0; t < NS; ++t)
+                *reinterpret_cast<uint32_t*>(dst + ((int64_t)(t * KBN + kb) * sl.Rpad + rr) * 128 + chunk + ((4 * lane) & 15)) =
+                    drp_pick4(Xq, NS - 1 - t);
         }
     }
 }

@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "instrument.cuh"
 #include "factor.cuh"
+#include "slice.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -273,24 +274,18 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     int e = 0;
     if (m > 0.0 && m < 1e300) frexp(m, &e);
     if (lane == 0) scl[(int64_t)zz * Rpad + rr] = e;
-    const int sh = 8 * S - 1 - e;
-    const long long hi = (1LL << (8 * S - 1)) - 1;
     uint8_t* dst = sl + (int64_t)zz * sl_bs;
     const int chunk = ((lane >> 2) ^ (rr & 7)) << 4;       // 16-byte chunk of the row after the 128B swizzle
-    for (int kb = 0; kb < KBN; ++kb) {
-        long long X[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            long long q = __double2ll_rn(scalbn(x[kb * 4 + j], sh));
-            X[j] = q > hi ? hi : (q < -hi - 1 ? -hi - 1 : q);
-        }
+    for (int kb = 0; kb < 2; ++kb) {
+        if (kb >= KBN) break;
+        long long X[4];
+        const double xk[4] = {x[kb * 4], x[kb * 4 + 1], x[kb * 4 + 2], x[kb * 4 + 3]};
+        drp_quant4(xk, m, e, S, X);
 #pragma unroll
         for (int t = 0; t < S; ++t) {
-            uint32_t w = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) w |= (uint32_t)((X[j] >> (8 * (S - 1 - t))) & 0xFF) << (8 * j);
             const int64_t off = ((int64_t)(t * KBN + kb) * Rpad + rr) * OZ_ROWB + chunk + ((4 * lane) & 15);
-            *reinterpret_cast<uint32_t*>(dst + off) = w;
+            *reinterpret_cast<uint32_t*>(dst + off) = drp_pick4(X, S - 1 - t);
         }
     }
 }
