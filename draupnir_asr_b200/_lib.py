@@ -59,6 +59,7 @@ SIGNATURES = {
     "drp_gru_wgrad_workspace_elems": (_i64, []),
     "drp_gru_wgrad_f64": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),
     "drp_gram_workspace_elems": (_i64, [_i32, _i32]),
+    "drp_gram_tn_supported": (_i32, [_i32, _i32]),
     "drp_gram_tn_f64": (_i32, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _i64, _p]),
     "drp_tall_gemm_f64": (_i32, [_p, _p, _p, _i64, _i32, _i32, _p, _p]),
     "drp_site_logp_workspace_elems": (_i64, []),

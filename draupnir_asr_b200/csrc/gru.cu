@@ -1736,21 +1736,54 @@ DRP_API int drp_gru_wgrad_dir0_f64(const double* dgi0, const double* gates, cons
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int GG_ROWS = 32;                      // K-rows per pipeline stage
 constexpr int GG_STAGES = 3;
-constexpr int GG_MAX_TILES = 12;                 // accumulator tiles (8x8) per warp
+constexpr int GG_MI = 3, GG_NI = 5;              // accumulator tiles (8x8) per warp: a block of up to 3 x 5
 
+// How the mt_n x nt_n grid of 8x8 output tiles is cut into 8 rectangular blocks, one per warp: wm_n warps along m (8, 4, 2
+// or 1), 8 / wm_n along n, each block at most GG_MI x GG_NI tiles; 0 if no cut fits.  Among the cuts that fit, the one with
+// the fewest fragment loads per k-step (mi + ni).
+__host__ __device__ inline int gg_warp_cut(int mt_n, int nt_n)
+{
+    int best = 0, cost = 1 << 30;
+    for (int wm = 8; wm >= 1; wm >>= 1) {
+        const int wn = 8 / wm, mi = (mt_n + wm - 1) / wm, ni = (nt_n + wn - 1) / wn;
+        if (mi <= GG_MI && ni <= GG_NI && mi + ni < cost) best = wm, cost = mi + ni;
+    }
+    return best;
+}
+// K-rows per pipeline stage: ~48 KB per stage (three stages in flight), at least 32 and at most 128 rows, a multiple of 16.
+// With narrow operands (21 + 21 columns) 32-row stages are 10 KB and the loop is bound by its per-iteration overhead.
+__host__ __device__ inline int gg_stage_rows(int M, int N)
+{
+    int r = (48 * 1024) / ((M + N) * 8);
+    r = r > 128 ? 128 : (r < 32 ? 32 : r);
+    return r & ~15;
+}
+
+// Every warp owns a RECTANGULAR block of tiles, so that per k-step it loads mi A-fragments and ni B-fragments for mi x ni
+// tensor instructions (the first version dealt tiles round-robin: two shared-memory loads per instruction, and shared-memory
+// bandwidth - 283 KB per 32-row block at M = 180 - was a third bound next to the DMMA pipe and HBM, all three ~2.2 k cycles
+// per block, 4.9 k measured).
+template <int MI, int NI>
 __global__ void __launch_bounds__(GTHREADS, 1) gram_tn_kernel(const double* __restrict__ A, const double* __restrict__ B,
-                                                              int64_t K, int M, int N, double* __restrict__ part)
+                                                              int64_t K, int M, int N, double* __restrict__ part, int rows,
+                                                              int wm_n)
 {
     extern __shared__ __align__(16) uint8_t gsm[];
     const int NE = N + 1;                                        // + the ones column (column sums of A)
-    const int mt_n = (M + 7) / 8, nt_n = (NE + 7) / 8, tiles = mt_n * nt_n;
-    const int stage_elems = GG_ROWS * (M + N);
+    const int mt_n = (M + 7) / 8, nt_n = (NE + 7) / 8;
+    const int stage_elems = rows * (M + N);
     double* ring = reinterpret_cast<double*>(gsm);
     const uint32_t bars = g_smem_u32(gsm + (size_t)GG_STAGES * stage_elems * 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
-    const int64_t nblk = (K + GG_ROWS - 1) / GG_ROWS;
+    const int wn_n = 8 / wm_n;
+    const int mt0 = (warp / wn_n) * MI, nt0 = (warp % wn_n) * NI;   // this warp's MI x NI block of tiles
+    bool vm[MI], vn[NI];                                         // warp-uniform: which tiles of the block exist (edge warps)
+#pragma unroll
+    for (int i = 0; i < MI; ++i) vm[i] = mt0 + i < mt_n;
+#pragma unroll
+    for (int j = 0; j < NI; ++j) vn[j] = nt0 + j < nt_n;
+    const int64_t nblk = (K + rows - 1) / rows;
     const int64_t b0 = nblk * blockIdx.x / gridDim.x, b1 = nblk * (blockIdx.x + 1) / gridDim.x;
     if (tid == 0) {
         for (int s = 0; s < GG_STAGES; ++s) g_mbar_init(bars + 8 * s, 1);
@@ -1760,15 +1793,17 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tn_kernel(const double* __re
     __syncthreads();
     auto issue = [&](int64_t blk) {                              // one thread: two contiguous bulk copies
         const int s = (int)((blk - b0) % GG_STAGES);
-        if (K - blk * GG_ROWS < GG_ROWS) return;               // ragged last block: loaded with plain loads by the consumer
+        if (K - blk * rows < rows) return;                       // ragged last block: loaded with plain loads by the consumer
         double* dst = ring + (int64_t)s * stage_elems;
-        g_mbar_expect_tx(bars + 8 * s, (uint32_t)GG_ROWS * (M + N) * 8);
-        g_bulk_g2s(g_smem_u32(dst), A + blk * GG_ROWS * M, (uint32_t)GG_ROWS * M * 8, bars + 8 * s);
-        g_bulk_g2s(g_smem_u32(dst + GG_ROWS * M), B + blk * GG_ROWS * N, (uint32_t)GG_ROWS * N * 8, bars + 8 * s);
+        g_mbar_expect_tx(bars + 8 * s, (uint32_t)rows * (M + N) * 8);
+        g_bulk_g2s(g_smem_u32(dst), A + blk * rows * M, (uint32_t)rows * M * 8, bars + 8 * s);
+        g_bulk_g2s(g_smem_u32(dst + rows * M), B + blk * rows * N, (uint32_t)rows * N * 8, bars + 8 * s);
     };
-    double acc[GG_MAX_TILES][2];
+    double acc[MI][NI][2];
 #pragma unroll
-    for (int i = 0; i < GG_MAX_TILES; ++i) acc[i][0] = acc[i][1] = 0.0;
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     if (tid == 0)
         for (int64_t blk = b0; blk < min(b1, b0 + GG_STAGES - 1); ++blk) issue(blk);
     for (int64_t blk = b0; blk < b1; ++blk) {
@@ -1776,41 +1811,46 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tn_kernel(const double* __re
         const int s = it % GG_STAGES;
         if (tid == 0 && blk + GG_STAGES - 1 < b1) issue(blk + GG_STAGES - 1);    // its stage was drained in iteration it-1
         double* sa = ring + (int64_t)s * stage_elems;
-        double* sb = sa + GG_ROWS * M;
-        const int valid = (int)min((int64_t)GG_ROWS, K - blk * GG_ROWS);
-        if (valid == GG_ROWS) {
+        double* sb = sa + rows * M;
+        const int valid = (int)min((int64_t)rows, K - blk * rows);
+        if (valid == rows) {
             g_mbar_wait(bars + 8 * s, (uint32_t)(it / GG_STAGES) & 1u);
         } else {                                                 // ragged last block (no 16-byte size guarantee): plain loads, zero fill
-            const double* ga = A + blk * GG_ROWS * M;
-            const double* gb = B + blk * GG_ROWS * N;
-            for (int idx = tid; idx < GG_ROWS * M; idx += GTHREADS) sa[idx] = idx < valid * M ? ga[idx] : 0.0;
-            for (int idx = tid; idx < GG_ROWS * N; idx += GTHREADS) sb[idx] = idx < valid * N ? gb[idx] : 0.0;
+            const double* ga = A + blk * rows * M;
+            const double* gb = B + blk * rows * N;
+            for (int idx = tid; idx < rows * M; idx += GTHREADS) sa[idx] = idx < valid * M ? ga[idx] : 0.0;
+            for (int idx = tid; idx < rows * N; idx += GTHREADS) sb[idx] = idx < valid * N ? gb[idx] : 0.0;
             __syncthreads();
         }
+#pragma unroll 4
+        for (int ks = 0; ks < rows / 4; ++ks) {                  // rows is a multiple of 16
+            const int k = 4 * ks + tig;
+            double a[MI], b[NI];
 #pragma unroll
-        for (int i = 0; i < GG_MAX_TILES; ++i) {
-            const int tile = warp + 8 * i;                        // warp-uniform
-            if (tile >= tiles) break;
-            const int mt = tile / nt_n, nt = tile - mt * nt_n;
-            const int m = 8 * mt + gid, nn = 8 * nt + gid;
-#pragma unroll
-            for (int ks = 0; ks < GG_ROWS / 4; ++ks) {
-                const int k = 4 * ks + tig;
-                const double a = m < M ? sa[k * M + m] : 0.0;
-                const double b = nn < N ? sb[k * N + nn] : (nn == N && k < valid ? 1.0 : 0.0);
-                dmma_8x8x4(acc[i][0], acc[i][1], a, b);
+            for (int i = 0; i < MI; ++i) {
+                const int m = 8 * (mt0 + i) + gid;
+                a[i] = (vm[i] && m < M) ? sa[k * M + m] : 0.0;
             }
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                const int nn = 8 * (nt0 + j) + gid;
+                b[j] = !vn[j] ? 0.0 : (nn < N ? sb[k * N + nn] : (nn == N && k < valid ? 1.0 : 0.0));
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);   // tiles that do not exist add zeros
         }
         __syncthreads();                                          // stage s drained before it is refilled
     }
     double* dst = part + (int64_t)blockIdx.x * (mt_n * 8) * (nt_n * 8);
 #pragma unroll
-    for (int i = 0; i < GG_MAX_TILES; ++i) {
-        const int tile = warp + 8 * i;
-        if (tile >= tiles) break;
-        const int mt = tile / nt_n, nt = tile - mt * nt_n;
-        *reinterpret_cast<double2*>(dst + (int64_t)(8 * mt + gid) * (nt_n * 8) + 8 * nt + 2 * tig) = make_double2(acc[i][0], acc[i][1]);
-    }
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j)
+            if (vm[i] && vn[j])
+                *reinterpret_cast<double2*>(dst + (int64_t)(8 * (mt0 + i) + gid) * (nt_n * 8) + 8 * (nt0 + j) + 2 * tig) =
+                    make_double2(acc[i][j][0], acc[i][j][1]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1970,6 +2010,15 @@ DRP_API int64_t drp_gram_workspace_elems(int M, int N)
     return (int64_t)n_sm * (((M + 7) / 8) * 8) * (((N + 1 + 7) / 8) * 8);
 }
 
+// Does drp_gram_tn_f64 take the shape (M, N)?  (The 8x8 output tiles must split into 8 blocks of at most 3 x 5 and three
+// pipeline stages must fit in shared memory.)
+DRP_API int drp_gram_tn_supported(int M, int N)
+{
+    if (M <= 0 || N <= 0 || M > 192 || N > 192) return 0;
+    if (gg_warp_cut((M + 7) / 8, (N + 1 + 7) / 8) == 0) return 0;
+    return GG_STAGES * gg_stage_rows(M, N) * (M + N) * 8 + 64 <= 200 * 1024;
+}
+
 // C [M,N] = A^T B and colsum [M] = sum_k A[k][:] (nullable) for A [K,M], B [K,N], both row-major contiguous fp64.
 DRP_API int drp_gram_tn_f64(const double* A, const double* B, int64_t K, int M, int N, double* C, double* colsum, double* ws,
                             int64_t ws_elems, void* stream)
@@ -1978,24 +2027,33 @@ DRP_API int drp_gram_tn_f64(const double* A, const double* B, int64_t K, int M, 
     if (K <= 0) return -3;
     if (M <= 0 || N <= 0 || M > 192 || N > 192) return -4;
     if (!C) return -6;
-    const int tiles = ((M + 7) / 8) * ((N + 1 + 7) / 8);
-    if (tiles > 8 * GG_MAX_TILES) return -4;
+    const int wm_n = gg_warp_cut((M + 7) / 8, (N + 1 + 7) / 8);
+    if (wm_n == 0) return -4;
+    const int rows = gg_stage_rows(M, N);
     cudaStream_t st = (cudaStream_t)stream;
     static int n_sm = 148;
     if (drp_first_on_device(57)) {
         int dev = 0;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-        cudaFuncSetAttribute(gram_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }
-    const int smem = GG_STAGES * GG_ROWS * (M + N) * 8 + 64;
+    const int wn_n = 8 / wm_n, mi = ((M + 7) / 8 + wm_n - 1) / wm_n, ni = ((N + 1 + 7) / 8 + wn_n - 1) / wn_n;
+    void (*kern)(const double*, const double*, int64_t, int, int, double*, int, int) = nullptr;
+#define GG_CASE(a, b) if (mi == a && ni == b) kern = gram_tn_kernel<a, b>;
+    GG_CASE(1, 1) GG_CASE(1, 2) GG_CASE(1, 3) GG_CASE(1, 4) GG_CASE(1, 5)
+    GG_CASE(2, 1) GG_CASE(2, 2) GG_CASE(2, 3) GG_CASE(2, 4) GG_CASE(2, 5)
+    GG_CASE(3, 1) GG_CASE(3, 2) GG_CASE(3, 3) GG_CASE(3, 4) GG_CASE(3, 5)
+#undef GG_CASE
+    if (!kern) return -4;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // idempotent, ~1 us
+    const int smem = GG_STAGES * rows * (M + N) * 8 + 64;
     if (smem > 200 * 1024) return -4;
-    const int64_t nblk = (K + GG_ROWS - 1) / GG_ROWS;
+    const int64_t nblk = (K + rows - 1) / rows;
     const int grid = (int)(nblk < n_sm ? nblk : n_sm);
     if (!ws || ws_elems < (int64_t)grid * (((M + 7) / 8) * 8) * (((N + 1 + 7) / 8) * 8)) return -8;
     {
         DRP_LAUNCH(DRP_K_GRAM, (double)K * (M + N) * 8.0, st);
-        gram_tn_kernel<<<grid, GTHREADS, smem, st>>>(A, B, K, M, N, ws);
+        kern<<<grid, GTHREADS, smem, st>>>(A, B, K, M, N, ws, rows, wm_n);
     }
     {
         DRP_LAUNCH(DRP_K_GRAM, (double)grid * M * (N + 1) * 8.0, st);

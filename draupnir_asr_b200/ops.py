@@ -697,10 +697,9 @@ def gram_tn(A: torch.Tensor, B: torch.Tensor):
     _req(A, "A"), _req(B, "B")
     K, M = A.shape
     N = B.shape[1]
-    tiles = ((M + 7) // 8) * ((N + 8) // 8)
     if B.shape[0] != K:
         raise RuntimeError(f"gram_tn: A has {K} rows, B has {B.shape[0]}")
-    if _GRAM_OFF or M > 192 or N > 192 or tiles > 96 or 3 * 32 * (M + N) * 8 + 64 > 200 * 1024:
+    if _GRAM_OFF or not lib.drp_gram_tn_supported(M, N):
         return A.t() @ B, A.sum(0)                  # shapes outside the kernel's range (never on the DRAUPNIR path): cuBLAS
     A, B = _aligned16(A.contiguous()), _aligned16(B.contiguous())
     C = torch.empty((M, N), dtype=torch.float64, device=A.device)

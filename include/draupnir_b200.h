@@ -169,6 +169,8 @@ int drp_gru_wgrad_f64(const double* dgi, const double* gates, const double* out,
 /* ---- weight / bias gradients of the dense layers around the recurrences (autograd of nn.Linear: S/models_utils.py:54-65,
  *      93-99):  C [M,N] = A^T B, colsum [M] = sum_k A[k][:] (nullable) for A [K,M], B [K,N], M, N <= 192, K arbitrary ------ */
 int64_t drp_gram_workspace_elems(int M, int N);
+/* 1 if drp_gram_tn_f64 takes the shape (its 8x8 output tiles split into 8 warp blocks of <= 3 x 5, stages fit), else 0.   */
+int drp_gram_tn_supported(int M, int N);
 int drp_gram_tn_f64(const double* A, const double* B, int64_t K, int M, int N, double* C, double* colsum, double* ws,
                     int64_t ws_elems, void* stream);
 
