@@ -71,7 +71,11 @@ int drp_ou_cov_bwd_f64(const double* D, int64_t ldd, int n, const double* lam, i
  * cond_bound[z] <= drp_ozaki_cond_limit() (1e-5 / 2^-(8S-13): 3.4e5 for S = 6; DRP_OZAKI_COND_LIMIT overrides), decided
  * on the device.  Every other matrix — and every matrix when cond_bound is NULL — gets fp64 (mma.sync) updates, i.e. the
  * accuracy of the LAPACK routine the reference calls.  The OU entry points below derive the bound from the
- * hyper-parameters themselves: (nodes * sf^2 + sn^2) / sn^2.                                                        */
+ * hyper-parameters themselves: (nodes * sf^2 + sn^2) / sn^2.
+ * With a workspace every 128-column panel is also factored by two fused kernels (whole diagonal region in one CTA per
+ * matrix; row-independent blocked substitution of the rows below on the fp64 tensor pipe, with one refinement step for the
+ * matrices off the tensor path) instead of a chain of 64-column potf2 / trsm / update steps; the workspace's tail holds the
+ * inverses of the 64 x 64 diagonal blocks (DRP_PANEL_WIDTH = 0 keeps the chain).                                       */
 int64_t drp_factor_workspace_bytes(int rows, int z);
 double drp_ozaki_cond_limit_f64(void);
 /* Look-ahead (every entry point that factorises takes the same three arguments): aux_stream, ev_fork, ev_join — a second
