@@ -240,41 +240,49 @@ __global__ void __launch_bounds__(256) ou_symv_finish_kernel(double* __restrict_
 //   part[z][r] = ( sum_c G_rc E_rc , sum_c G_rc E_rc D_rc , G_rr )   over the full row r (by symmetry 2x lower).
 // K^-1 is read once from the factored matrix (-M[n+1+i][n+1+j], lower), E is recomputed from D.
 // alpha comes from the dense [z][n] copy (coalesced; the column M[n+1+c][n] it was read from before costs a 32-byte sector
-// per entry - three times the traffic of the K^-1 row itself), and the three sums share ONE block reduction.
+// per entry - three times the traffic of the K^-1 row itself).  One WARP per row, eight rows per CTA, the row walked with
+// four independent loads in flight per lane: with one CTA per row (60,000 CTAs, <= 8 dependent load -> exp iterations per
+// thread and a block reduction each) the kernel ran at 24 % of the DRAM rate (ncu, profiles/r02/ncu_last_c4.summary.txt);
+// a CTA walking eight rows with all its threads one after the other was slower still.
+// part [z][nblk][3], nblk = ceil(n / OU_GRAD_ROWS).
+constexpr int OU_GRAD_ROWS = 8;
 __global__ void __launch_bounds__(256) ou_grad_kernel(const double* __restrict__ M, int64_t ld, int64_t bs, int n,
                                                       const double* __restrict__ D, int64_t ldd,
                                                       const double* __restrict__ lam, const double* __restrict__ alpha,
                                                       double* __restrict__ part)
 {
     __shared__ double red[3][8];
-    const int r = blockIdx.x, zz = blockIdx.y;
+    const int zz = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r = blockIdx.x * OU_GRAD_ROWS + w;
     const double* A = M + (int64_t)zz * bs;
     const double* al = alpha + (int64_t)zz * n;
     const double nil = -1.0 / lam[zz];
-    const double ar = al[r];
-    const double* krow = A + (int64_t)(n + 1 + r) * ld + n + 1;
-    const double* drow = D + (int64_t)r * ldd;
     double sE = 0.0, sED = 0.0, gd = 0.0;
-    for (int c = threadIdx.x; c <= r; c += blockDim.x) {
-        const double g = 0.5 * (ar * al[c] + krow[c]);       // krow = -Kinv
-        const double d = drow[c];
-        const double w = (c == r) ? 1.0 : 2.0;
-        const double t = w * g * drp_exp(d * nil);
-        sE += t;
-        sED += t * d;
-        if (c == r) gd = g;
+    if (r < n) {
+        const double ar = al[r];
+        const double* krow = A + (int64_t)(n + 1 + r) * ld + n + 1;
+        const double* drow = D + (int64_t)r * ldd;
+#pragma unroll 4
+        for (int c = lane; c <= r; c += 32) {
+            const double g = 0.5 * (ar * al[c] + krow[c]);       // krow = -Kinv
+            const double d = drow[c];
+            const double wgt = (c == r) ? 1.0 : 2.0;
+            const double t = wgt * g * drp_exp(d * nil);
+            sE += t;
+            sED += t * d;
+            if (c == r) gd = g;
+        }
     }
     sE = warp_sum(sE);
     sED = warp_sum(sED);
     gd = warp_sum(gd);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) red[0][w] = sE, red[1][w] = sED, red[2][w] = gd;
     __syncthreads();
     if (threadIdx.x < 3) {
         double v = 0.0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) v += red[threadIdx.x][q];
-        part[((int64_t)zz * n + r) * 3 + threadIdx.x] = v;
+        part[((int64_t)zz * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = v;
     }
 }
 
@@ -396,11 +404,11 @@ DRP_API int drp_ou_prior_f64(const double* D, int64_t ldd, int n, const double* 
         }
         {
             DRP_LAUNCH(DRP_K_OU_GRAD, ((double)z * n * n * 4.0 + (double)n * n * 4.0), st);
-            ou_grad_kernel<<<dim3(n, z), 256, 0, st>>>(M, ld, bs, n, D, ldd, lam, alpha, part);
+            ou_grad_kernel<<<dim3((n + OU_GRAD_ROWS - 1) / OU_GRAD_ROWS, z), 256, 0, st>>>(M, ld, bs, n, D, ldd, lam, alpha, part);
         }
         {
             DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 24.0), st);
-            reduce3_kernel<<<z, 256, 0, st>>>(part, n, gsum);
+            reduce3_kernel<<<z, 256, 0, st>>>(part, (n + OU_GRAD_ROWS - 1) / OU_GRAD_ROWS, gsum);
         }
     }
     return drp_launch_status();
@@ -466,11 +474,11 @@ DRP_API int drp_ou_prior_apply_f64(const double* D, int64_t ldd, int n, const do
     }
     {
         DRP_LAUNCH(DRP_K_OU_GRAD, ((double)z * n * n * 4.0 + (double)n * n * 4.0), st);
-        ou_grad_kernel<<<dim3(n, z), 256, 0, st>>>(M, ld, bs, n, D, ldd, lam, alpha, part);
+        ou_grad_kernel<<<dim3((n + OU_GRAD_ROWS - 1) / OU_GRAD_ROWS, z), 256, 0, st>>>(M, ld, bs, n, D, ldd, lam, alpha, part);
     }
     {
         DRP_LAUNCH(DRP_K_REDUCE, ((double)z * n * 24.0), st);
-        reduce3_kernel<<<z, 256, 0, st>>>(part, n, gsum);
+        reduce3_kernel<<<z, 256, 0, st>>>(part, (n + OU_GRAD_ROWS - 1) / OU_GRAD_ROWS, gsum);
     }
     return drp_launch_status();
 }
