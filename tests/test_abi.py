@@ -39,6 +39,11 @@ def test_argument_validation_without_a_gpu():
     assert lib.drp_ozaki_cond_limit_f64() == 1e-5 * 2.0 ** 35
     assert lib.drp_timing_classes() == 21 and lib.drp_timing_class_name(8) == b"oz_syrk_kernel"
     assert lib.drp_timing_class_name(19) == b"potrf_diag_kernel" and lib.drp_timing_class_name(20) == b"panel_solve_kernel"
+    # every weight-gradient shape of the DRAUPNIR networks (M = rows of dY, N = rows of X) is taken by the split-K kernel
+    for M, N in ((180, 21), (21, 120), (21, 21), (120, 21), (21, 180), (60, 60), (30, 60), (1, 1), (64, 64)):
+        assert lib.drp_gram_tn_supported(M, N) == 1, (M, N)
+    for M, N in ((193, 21), (21, 193), (192, 192), (0, 5)):
+        assert lib.drp_gram_tn_supported(M, N) == 0, (M, N)
     assert lib.drp_gru_hidden_size() == 60
     assert lib.drp_gru_fwd_f64(None, None, None, None, 4, 4, 60, None, None, None) == -1
     assert lib.drp_cat_loglik_partials(257) == 2
