@@ -4,7 +4,6 @@ import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from draupnir_asr_b200 import ops, synthetic as S
-from oracle import draupnir_oracle as O
 n = 1100
 t = S.random_tree(n, seed=2)
 Dh = S.patristic_host(t)
@@ -12,7 +11,7 @@ D = torch.from_numpy(Dh[np.ix_(t.leaves, t.leaves)])
 sf = torch.tensor([1.3, 0.9, 1.1], dtype=torch.float64)
 sn = torch.tensor([0.6, 2e-4, 1e-3], dtype=torch.float64)
 lam = torch.tensor([0.9, 1.4, 0.7], dtype=torch.float64)
-K = O.ou_covariance(D, sf, sn, lam)
+K = sf[:, None, None] ** 2 * torch.exp(-D[None] / lam[:, None, None]) + (sn[:, None, None] ** 2) * torch.eye(n, dtype=torch.float64)   # S/models_utils.py:303-311
 Kg = K.cuda()
 cb = ops.ou_cond_bound(sf, sn, n)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
